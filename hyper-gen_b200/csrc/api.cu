@@ -1,0 +1,426 @@
+// api.cu — the extern "C" boundary declared in include/hypergen_b200.h: context, host-buffer
+// entry points (H2D / D2H inside), device-pointer entry points (inputs resident in HBM).
+// Replaces the cudarc plumbing of reference src/sketch_cuda.rs:52-60,119-166.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "hg_common.cuh"
+
+uint32_t hg_kmer_tile_positions();
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void hg_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int hg_cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  hg_set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return HG_E_CUDA;
+}
+
+extern "C" const char *hg_last_error(void) { return g_err; }
+extern "C" const char *hg_version(void) { return "hypergen_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+extern "C" int hg_init(int device, hg_ctx **out) {
+  if (!out) { hg_set_error("hg_init: out is NULL"); return HG_E_INVALID; }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    hg_set_error("hg_init: no CUDA device (%s); this library has no CPU fallback",
+                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return HG_E_CUDA;
+  }
+  if (device < 0 || device >= n) { hg_set_error("hg_init: device %d out of range (%d)", device, n); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(device));
+  hg_ctx *c = new hg_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  cudaDeviceProp prop;
+  HG_CUDA(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  HG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  HG_CUDA(cudaMalloc(&c->d_status, 4 * sizeof(uint32_t)));
+  HG_CUDA(cudaMemset(c->d_status, 0, 4 * sizeof(uint32_t)));
+  *out = c;
+  return HG_OK;
+}
+
+extern "C" void hg_destroy(hg_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 8; i++) if (c->d_scratch[i]) cudaFree(c->d_scratch[i]);
+  for (int i = 0; i < 4; i++) if (c->h_pinned[i]) cudaFreeHost(c->h_pinned[i]);
+  if (c->d_status) cudaFree(c->d_status);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int hg_sync(hg_ctx *c) {
+  if (!c) { hg_set_error("hg_sync: ctx is NULL"); return HG_E_INVALID; }
+  HG_CUDA(cudaStreamSynchronize(c->stream));
+  return HG_OK;
+}
+
+extern "C" uint64_t hg_stream_handle(hg_ctx *c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
+extern "C" uint64_t hg_launch_count(hg_ctx *c) { return c ? c->launches : 0; }
+
+int hg_scratch(hg_ctx *c, int slot, size_t bytes, void **out) {
+  if (bytes == 0) bytes = 256;
+  if (c->d_scratch_bytes[slot] < bytes) {
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->d_scratch[slot]) HG_CUDA(cudaFree(c->d_scratch[slot]));
+    c->d_scratch[slot] = nullptr;
+    c->d_scratch_bytes[slot] = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    HG_CUDA(cudaMalloc(&c->d_scratch[slot], want));
+    c->d_scratch_bytes[slot] = want;
+  }
+  *out = c->d_scratch[slot];
+  return HG_OK;
+}
+
+int hg_pinned(hg_ctx *c, int slot, size_t bytes, void **out) {
+  if (bytes == 0) bytes = 256;
+  if (c->h_pinned_bytes[slot] < bytes) {
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->h_pinned[slot]) HG_CUDA(cudaFreeHost(c->h_pinned[slot]));
+    c->h_pinned[slot] = nullptr;
+    c->h_pinned_bytes[slot] = 0;
+    size_t want = bytes + bytes / 8 + 4096;
+    HG_CUDA(cudaMallocHost(&c->h_pinned[slot], want));
+    c->h_pinned_bytes[slot] = want;
+  }
+  *out = c->h_pinned[slot];
+  return HG_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// sketch
+// ---------------------------------------------------------------------------------------
+static int check_params(const hg_sketch_params *p) {
+  if (!p) { hg_set_error("params is NULL"); return HG_E_INVALID; }
+  if (p->ksize == 0 || p->ksize > 32) { hg_set_error("ksize %u out of range 1..32", (unsigned)p->ksize); return HG_E_INVALID; }
+  if (p->scaled == 0) { hg_set_error("scaled must be >= 1"); return HG_E_INVALID; }
+  if (p->hv_d == 0 || p->hv_d % 256 != 0) {
+    hg_set_error("hv_d %u must be a positive multiple of 256 (BitPacker8x block, src/hd.rs:147)", p->hv_d);
+    return HG_E_INVALID;
+  }
+  return HG_OK;
+}
+
+struct SketchPlan {
+  std::vector<hg_genome_desc> desc;
+  uint64_t total_slots = 0;
+  uint32_t n_tiles = 0;
+  uint32_t max_slots = 0;
+};
+
+static int make_plan(const uint64_t *seg_off, uint32_t n, const hg_sketch_params *p, SketchPlan &pl) {
+  const uint32_t tile = hg_kmer_tile_positions();
+  pl.desc.resize(n);
+  uint64_t slots_total = 0, tiles_total = 0;
+  for (uint32_t g = 0; g < n; g++) {
+    if (seg_off[g + 1] < seg_off[g]) { hg_set_error("seg_off not monotone at %u", g); return HG_E_INVALID; }
+    const uint64_t len = seg_off[g + 1] - seg_off[g];
+    const uint64_t n_kmers = len >= p->ksize ? len - p->ksize + 1 : 0;
+    // open-addressing table at <= 50 % load for the expected FracMinHash sample size
+    uint64_t want = 2 * (len / p->scaled + 1) + 32, slots = 64;
+    while (slots < want) slots <<= 1;
+    if (slots > (1ull << 31)) { hg_set_error("genome %u too large for one table", g); return HG_E_UNSUPPORTED; }
+    hg_genome_desc &d = pl.desc[g];
+    d.seq_begin = seg_off[g];
+    d.seq_len = len;
+    d.table_begin = slots_total;
+    d.table_mask = (uint32_t)(slots - 1);
+    d.first_tile = (uint32_t)tiles_total;
+    slots_total += slots;
+    tiles_total += (n_kmers + tile - 1) / tile;
+    if (slots > pl.max_slots) pl.max_slots = (uint32_t)slots;
+    if (tiles_total > 0x7fffffffull) { hg_set_error("batch too large: split it"); return HG_E_UNSUPPORTED; }
+  }
+  pl.total_slots = slots_total;
+  pl.n_tiles = (uint32_t)tiles_total;
+  return HG_OK;
+}
+
+// stage the plan, clear the tables and hash every genome; tables/counts stay in scratch 2/3
+static int run_hash_stage(hg_ctx *c, const uint8_t *d_seq, const SketchPlan &pl, uint32_t n,
+                          const hg_sketch_params *p, hg_genome_desc **d_desc_out, uint64_t **d_tables_out,
+                          uint32_t **d_counts_out) {
+  void *d_desc, *d_tables, *d_counts, *h_desc;
+  int rc;
+  if ((rc = hg_scratch(c, 1, sizeof(hg_genome_desc) * n, &d_desc))) return rc;
+  if ((rc = hg_scratch(c, 2, pl.total_slots * 8, &d_tables))) return rc;
+  if ((rc = hg_scratch(c, 3, sizeof(uint32_t) * n, &d_counts))) return rc;
+  if ((rc = hg_pinned(c, 0, sizeof(hg_genome_desc) * n, &h_desc))) return rc;
+  memcpy(h_desc, pl.desc.data(), sizeof(hg_genome_desc) * n);
+  HG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(hg_genome_desc) * n, cudaMemcpyHostToDevice, c->stream));
+  HG_CUDA(cudaMemsetAsync(d_tables, 0xFF, pl.total_slots * 8, c->stream));
+  HG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n, c->stream));
+  HG_CUDA(cudaMemsetAsync(c->d_status, 0, 4 * sizeof(uint32_t), c->stream));
+  if ((rc = hg_launch_kmer_hash(c, d_seq, (const hg_genome_desc *)d_desc, n, pl.n_tiles, p, (uint64_t *)d_tables,
+                                (uint32_t *)d_counts)))
+    return rc;
+  *d_desc_out = (hg_genome_desc *)d_desc;
+  *d_tables_out = (uint64_t *)d_tables;
+  *d_counts_out = (uint32_t *)d_counts;
+  return HG_OK;
+}
+
+static int status_to_rc(const uint32_t *st) {
+  if (st[0]) { hg_set_error("a genome's hash table overflowed (more distinct sampled hashes than 2x the FracMinHash expectation)"); return HG_E_CAPACITY; }
+  if (st[1]) { hg_set_error("a sketch needs hv_quant_bits = 16: outside the reference's representable range (src/hd.rs:140)"); return HG_E_RANGE; }
+  return HG_OK;
+}
+
+extern "C" int hg_sketch_batch_dev(hg_ctx *c, const uint8_t *d_seq, const uint64_t *seg_off, uint32_t n,
+                                   const hg_sketch_params *p, int16_t *d_hv, uint8_t *d_packed,
+                                   uint8_t *d_quant_bits, int32_t *d_norm2, uint32_t *d_n_hashes) {
+  if (!c || !seg_off || (!d_seq && n && seg_off[n] > 0)) { hg_set_error("hg_sketch_batch_dev: NULL argument"); return HG_E_INVALID; }
+  if (!d_quant_bits || !d_norm2 || !d_n_hashes) { hg_set_error("hg_sketch_batch_dev: quant_bits/norm2/n_hashes are required"); return HG_E_INVALID; }
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (n == 0) return HG_OK;
+  HG_CUDA(cudaSetDevice(c->device));
+  SketchPlan pl;
+  if ((rc = make_plan(seg_off, n, p, pl))) return rc;
+  hg_genome_desc *d_desc; uint64_t *d_tables; uint32_t *d_counts;
+  if ((rc = run_hash_stage(c, d_seq, pl, n, p, &d_desc, &d_tables, &d_counts))) return rc;
+  return hg_launch_encode(c, d_desc, n, d_tables, d_counts, p->hv_d, d_hv, d_packed, d_quant_bits, d_norm2, d_n_hashes);
+}
+
+extern "C" int hg_sketch_status(hg_ctx *c) {
+  if (!c) { hg_set_error("ctx is NULL"); return HG_E_INVALID; }
+  HG_CUDA(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(c->h_status), cudaMemcpyDeviceToHost, c->stream));
+  HG_CUDA(cudaStreamSynchronize(c->stream));
+  return status_to_rc(c->h_status);
+}
+
+extern "C" int hg_sketch_batch(hg_ctx *c, const uint8_t *seq, const uint64_t *seg_off, uint32_t n,
+                               const hg_sketch_params *p, int16_t *hv, uint8_t *packed, uint8_t *quant_bits,
+                               int32_t *norm2, uint32_t *n_hashes) {
+  if (!c || !seg_off) { hg_set_error("hg_sketch_batch: NULL argument"); return HG_E_INVALID; }
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (n == 0) return HG_OK;
+  if (!seq && seg_off[n] > 0) { hg_set_error("hg_sketch_batch: seq is NULL"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(c->device));
+  const uint64_t lo = seg_off[0], hi = seg_off[n];
+  const uint32_t D = p->hv_d;
+  void *d_seq, *d_hv = nullptr, *d_packed, *d_small;
+  if ((rc = hg_scratch(c, 0, hi - lo + 64, &d_seq))) return rc;
+  if (hv && (rc = hg_scratch(c, 4, (size_t)n * D * 2, &d_hv))) return rc;
+  if ((rc = hg_scratch(c, 5, (size_t)n * D * 2, &d_packed))) return rc;
+  if ((rc = hg_scratch(c, 6, (size_t)n * 12, &d_small))) return rc;
+  uint8_t *d_bits = (uint8_t *)d_small + (size_t)n * 8;
+  int32_t *d_norm = (int32_t *)d_small;
+  uint32_t *d_nh = (uint32_t *)d_small + n;
+  // copy exactly the bytes the batch spans; keep the caller's alignment modulo 16 so that
+  // the kernel's aligned 16-byte loads see the same layout either way
+  const uint64_t shift = (uint64_t)((uintptr_t)(seq + lo) & 15);
+  HG_CUDA(cudaMemcpyAsync((uint8_t *)d_seq + shift, seq + lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
+  std::vector<uint64_t> rel(n + 1);
+  for (uint32_t g = 0; g <= n; g++) rel[g] = seg_off[g] - lo + shift;
+  rc = hg_sketch_batch_dev(c, (const uint8_t *)d_seq, rel.data(), n, p, (int16_t *)d_hv, (uint8_t *)d_packed, d_bits,
+                           d_norm, d_nh);
+  if (rc) return rc;
+  if (hv) HG_CUDA(cudaMemcpyAsync(hv, d_hv, (size_t)n * D * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (packed) HG_CUDA(cudaMemcpyAsync(packed, d_packed, (size_t)n * D * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (quant_bits) HG_CUDA(cudaMemcpyAsync(quant_bits, d_bits, n, cudaMemcpyDeviceToHost, c->stream));
+  if (norm2) HG_CUDA(cudaMemcpyAsync(norm2, d_norm, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (n_hashes) HG_CUDA(cudaMemcpyAsync(n_hashes, d_nh, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  return hg_sketch_status(c);
+}
+
+extern "C" int hg_kmer_hash(hg_ctx *c, const uint8_t *seq, const uint64_t *seg_off, uint32_t n,
+                            const hg_sketch_params *p, uint64_t *hashes, uint64_t cap, uint64_t *hash_off) {
+  if (!c || !seg_off || !hash_off) { hg_set_error("hg_kmer_hash: NULL argument"); return HG_E_INVALID; }
+  int rc = check_params(p);
+  if (rc) return rc;
+  hash_off[0] = 0;
+  if (n == 0) return HG_OK;
+  if (!seq && seg_off[n] > 0) { hg_set_error("hg_kmer_hash: seq is NULL"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(c->device));
+  const uint64_t lo = seg_off[0], hi = seg_off[n];
+  void *d_seq;
+  if ((rc = hg_scratch(c, 0, hi - lo + 64, &d_seq))) return rc;
+  const uint64_t shift = (uint64_t)((uintptr_t)(seq + lo) & 15);
+  HG_CUDA(cudaMemcpyAsync((uint8_t *)d_seq + shift, seq + lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
+  std::vector<uint64_t> rel(n + 1);
+  for (uint32_t g = 0; g <= n; g++) rel[g] = seg_off[g] - lo + shift;
+  SketchPlan pl;
+  if ((rc = make_plan(rel.data(), n, p, pl))) return rc;
+  hg_genome_desc *d_desc; uint64_t *d_tables; uint32_t *d_counts;
+  if ((rc = run_hash_stage(c, (const uint8_t *)d_seq, pl, n, p, &d_desc, &d_tables, &d_counts))) return rc;
+  if ((rc = hg_launch_sort_tables(c, d_desc, n, d_tables, pl.max_slots))) return rc;
+  std::vector<uint32_t> counts(n);
+  HG_CUDA(cudaMemcpyAsync(counts.data(), d_counts, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = hg_sketch_status(c))) return rc;  // synchronises
+  uint64_t total = 0;
+  for (uint32_t g = 0; g < n; g++) { total += counts[g]; hash_off[g + 1] = total; }
+  if (total > cap || (!hashes && total)) { hg_set_error("hg_kmer_hash: need room for %llu hashes", (unsigned long long)total); return HG_E_CAPACITY; }
+  for (uint32_t g = 0; g < n; g++)
+    if (counts[g])
+      HG_CUDA(cudaMemcpyAsync(hashes + hash_off[g], d_tables + pl.desc[g].table_begin, (size_t)counts[g] * 8,
+                              cudaMemcpyDeviceToHost, c->stream));
+  HG_CUDA(cudaStreamSynchronize(c->stream));
+  return HG_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// sketch format
+// ---------------------------------------------------------------------------------------
+extern "C" int hg_unpack_dev(hg_ctx *c, const uint8_t *d_packed, uint64_t row_stride, const uint8_t *d_bits,
+                             uint32_t n, uint32_t hv_d, int16_t *d_hv) {
+  if (!c || !d_packed || !d_bits || !d_hv) { hg_set_error("hg_unpack_dev: NULL argument"); return HG_E_INVALID; }
+  if (hv_d == 0 || hv_d % 256 != 0 || row_stride % 4 != 0) { hg_set_error("hg_unpack_dev: hv_d %% 256 or row_stride %% 4"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(c->device));
+  return hg_launch_unpack(c, d_packed, row_stride, d_bits, n, hv_d, d_hv);
+}
+
+extern "C" int hg_unpack(hg_ctx *c, const uint8_t *packed, uint64_t row_stride, const uint8_t *bits, uint32_t n,
+                         uint32_t hv_d, int16_t *hv) {
+  if (!c || !packed || !bits || !hv) { hg_set_error("hg_unpack: NULL argument"); return HG_E_INVALID; }
+  if (n == 0) return HG_OK;
+  for (uint32_t g = 0; g < n; g++)
+    if (bits[g] < 1 || bits[g] > 16 || (uint64_t)bits[g] * hv_d / 8 > row_stride) {
+      hg_set_error("hg_unpack: sketch %u has hv_quant_bits %u (row_stride %llu)", g, (unsigned)bits[g], (unsigned long long)row_stride);
+      return HG_E_INVALID;
+    }
+  HG_CUDA(cudaSetDevice(c->device));
+  int rc;
+  void *d_p, *d_b, *d_h;
+  if ((rc = hg_scratch(c, 5, (size_t)n * row_stride, &d_p))) return rc;
+  if ((rc = hg_scratch(c, 6, n, &d_b))) return rc;
+  if ((rc = hg_scratch(c, 4, (size_t)n * hv_d * 2, &d_h))) return rc;
+  HG_CUDA(cudaMemcpyAsync(d_p, packed, (size_t)n * row_stride, cudaMemcpyHostToDevice, c->stream));
+  HG_CUDA(cudaMemcpyAsync(d_b, bits, n, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = hg_unpack_dev(c, (const uint8_t *)d_p, row_stride, (const uint8_t *)d_b, n, hv_d, (int16_t *)d_h))) return rc;
+  HG_CUDA(cudaMemcpyAsync(hv, d_h, (size_t)n * hv_d * 2, cudaMemcpyDeviceToHost, c->stream));
+  HG_CUDA(cudaStreamSynchronize(c->stream));
+  return HG_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// dist
+// ---------------------------------------------------------------------------------------
+static const int32_t HG_TC_MAX_ABS = 8127;  // |x| <= 8127 splits into two s8 limbs (x = 128 h + l)
+
+extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref, uint32_t i0,
+                           const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry, uint32_t j0,
+                           uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path, hg_hit *d_hits,
+                           uint64_t cap, unsigned long long *d_n_hits) {
+  if (!c || !d_n_hits) { hg_set_error("hg_dist_dev: NULL argument"); return HG_E_INVALID; }
+  if ((n_ref && (!d_ref || !d_ref_norm)) || (n_qry && (!d_qry || !d_qry_norm)) || (cap && !d_hits)) {
+    hg_set_error("hg_dist_dev: NULL argument"); return HG_E_INVALID;
+  }
+  if (hv_d == 0 || hv_d % 256 != 0) { hg_set_error("hg_dist_dev: hv_d %u must be a multiple of 256", hv_d); return HG_E_INVALID; }
+  if (path < 0 || path > 2) { hg_set_error("hg_dist_dev: path %d", path); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(c->device));
+  HG_CUDA(cudaMemsetAsync(d_n_hits, 0, sizeof(unsigned long long), c->stream));
+  if (n_ref == 0 || n_qry == 0) return HG_OK;
+
+  int use = path;
+  if (use == 0) {
+    // tensor path only when every element fits the int8 limb split; this costs one read of
+    // both matrices (HBM-bound, ~0.1 ms per GB) and one 4-byte D2H
+    void *d_max;
+    int rc;
+    if ((rc = hg_scratch(c, 7, 256, &d_max))) return rc;
+    int32_t m1 = 0, m2 = 0;
+    if ((rc = hg_launch_absmax(c, d_ref, (uint64_t)n_ref * hv_d, (int32_t *)d_max))) return rc;
+    HG_CUDA(cudaMemcpyAsync(&m1, d_max, 4, cudaMemcpyDeviceToHost, c->stream));
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    if (d_qry != d_ref) {
+      if ((rc = hg_launch_absmax(c, d_qry, (uint64_t)n_qry * hv_d, (int32_t *)d_max))) return rc;
+      HG_CUDA(cudaMemcpyAsync(&m2, d_max, 4, cudaMemcpyDeviceToHost, c->stream));
+      HG_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    const int32_t m = m1 > m2 ? m1 : m2;
+    if (m > HG_TC_MAX_ABS) {
+      use = 1;
+      snprintf(c->dist_reason, sizeof(c->dist_reason),
+               "SIMT: max |hv| = %d exceeds the 13-bit budget (%d) of the int8 limb split", m, HG_TC_MAX_ABS);
+    } else if ((uint64_t)n_ref * n_qry < 128ull * 128ull) {
+      use = 1;
+      snprintf(c->dist_reason, sizeof(c->dist_reason), "SIMT: %u x %u pairs do not fill one 128x128 tensor tile", n_ref, n_qry);
+    } else {
+      use = 2;
+      snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor: max |hv| = %d fits two s8 limbs; tcgen05 kind::i8", m);
+    }
+  } else {
+    snprintf(c->dist_reason, sizeof(c->dist_reason), "%s: forced by caller", use == 1 ? "SIMT" : "tensor");
+  }
+  c->dist_path = use;
+  if (use == 2)
+    return hg_launch_dist_tc(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th,
+                             symmetric, d_hits, cap, d_n_hits);
+  return hg_launch_dist_simt(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th,
+                             symmetric, d_hits, cap, d_n_hits);
+}
+
+extern "C" int hg_dist_last_path(hg_ctx *c) { return c ? c->dist_path : 0; }
+extern "C" const char *hg_dist_last_reason(hg_ctx *c) { return c ? c->dist_reason : ""; }
+
+extern "C" int hg_dist(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uint32_t n_ref, const int16_t *qry,
+                       const int32_t *qry_norm, uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th,
+                       int symmetric, int path, hg_hit *hits, uint64_t cap, uint64_t *n_hits) {
+  if (!c || !n_hits) { hg_set_error("hg_dist: NULL argument"); return HG_E_INVALID; }
+  *n_hits = 0;
+  if ((n_ref && (!ref || !ref_norm)) || (n_qry && (!qry || !qry_norm)) || (cap && !hits)) {
+    hg_set_error("hg_dist: NULL argument"); return HG_E_INVALID;
+  }
+  if (n_ref == 0 || n_qry == 0) return HG_OK;
+  HG_CUDA(cudaSetDevice(c->device));
+  int rc;
+  const bool same = (ref == qry && ref_norm == qry_norm && n_ref == n_qry);
+  const size_t rb = (size_t)n_ref * hv_d * 2, qb = same ? 0 : (size_t)n_qry * hv_d * 2;
+  void *d_mat, *d_norm, *d_hits, *d_cnt;
+  if ((rc = hg_scratch(c, 4, rb + qb + 512, &d_mat))) return rc;
+  if ((rc = hg_scratch(c, 6, ((size_t)n_ref + n_qry) * 4 + 256, &d_norm))) return rc;
+  if ((rc = hg_scratch(c, 5, cap * sizeof(hg_hit) + 256, &d_hits))) return rc;
+  if ((rc = hg_scratch(c, 3, 256, &d_cnt))) return rc;
+  int16_t *d_ref = (int16_t *)d_mat;
+  const size_t rb_al = (rb + 255) & ~(size_t)255;
+  int16_t *d_qry = same ? d_ref : (int16_t *)((uint8_t *)d_mat + rb_al);
+  int32_t *d_rn = (int32_t *)d_norm, *d_qn = same ? d_rn : d_rn + n_ref;
+  HG_CUDA(cudaMemcpyAsync(d_ref, ref, rb, cudaMemcpyHostToDevice, c->stream));
+  HG_CUDA(cudaMemcpyAsync(d_rn, ref_norm, (size_t)n_ref * 4, cudaMemcpyHostToDevice, c->stream));
+  if (!same) {
+    HG_CUDA(cudaMemcpyAsync(d_qry, qry, qb, cudaMemcpyHostToDevice, c->stream));
+    HG_CUDA(cudaMemcpyAsync(d_qn, qry_norm, (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  rc = hg_dist_dev(c, d_ref, d_rn, n_ref, 0, d_qry, d_qn, n_qry, 0, hv_d, ksize, ani_th, symmetric, path,
+                   (hg_hit *)d_hits, cap, (unsigned long long *)d_cnt);
+  if (rc) return rc;
+  unsigned long long cnt = 0;
+  HG_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
+  HG_CUDA(cudaStreamSynchronize(c->stream));
+  *n_hits = cnt;
+  if (cnt > cap) {
+    hg_set_error("hg_dist: %llu pairs pass the threshold, capacity is %llu", cnt, (unsigned long long)cap);
+    return HG_E_CAPACITY;
+  }
+  if (cnt) {
+    HG_CUDA(cudaMemcpyAsync(hits, d_hits, cnt * sizeof(hg_hit), cudaMemcpyDeviceToHost, c->stream));
+    HG_CUDA(cudaStreamSynchronize(c->stream));
+    // the device appends in arbitrary order; hand back a deterministic (i, j) order
+    std::sort(hits, hits + cnt, [](const hg_hit &a, const hg_hit &b) { return a.i != b.i ? a.i < b.i : a.j < b.j; });
+  }
+  return HG_OK;
+}

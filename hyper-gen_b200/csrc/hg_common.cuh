@@ -1,0 +1,186 @@
+// hg_common.cuh — shared declarations for the sm_100a HyperGen hot path.
+// Arithmetic building blocks restate, for the device, the functions the reference defines in
+// src/cuda_kernel.cu:71-246 (t1ha2), the wyhash crate's wyrng (call sites src/hd.rs:44,51)
+// and glibc's logf (behind f32::ln in src/dist.rs:154).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hypergen_b200.h"
+
+#define HG_EMPTY_SLOT 0xFFFFFFFFFFFFFFFFull
+
+// ---------------------------------------------------------------------------------------
+// t1ha2_atonce (length <= 32) on pre-assembled little-endian words.
+//   reference: cuda_kernel.cu:196-246 (switch), :136-141 mixup64, :149-153 final64.
+// ---------------------------------------------------------------------------------------
+namespace hg {
+
+__host__ __device__ constexpr uint64_t t1_p0() { return 0xEC99BF0D8372CAABull; }
+__host__ __device__ constexpr uint64_t t1_p1() { return 0x82434FE90EDCEF39ull; }
+__host__ __device__ constexpr uint64_t t1_p2() { return 0xD4F06DB99D67BE4Bull; }
+__host__ __device__ constexpr uint64_t t1_p3() { return 0xBD9CACC22C6E9571ull; }
+__host__ __device__ constexpr uint64_t t1_p4() { return 0x9C06FAF4D023E3ABull; }
+__host__ __device__ constexpr uint64_t t1_p5() { return 0xC060724A8424F345ull; }
+__host__ __device__ constexpr uint64_t t1_p6() { return 0xCB5AF53AE3AAAC31ull; }
+
+__device__ __forceinline__ uint64_t rot64(uint64_t v, unsigned s) { return (v >> s) | (v << (64 - s)); }
+
+__device__ __forceinline__ void mixup64(uint64_t &a, uint64_t &b, uint64_t v, uint64_t prime) {
+  const uint64_t t = b + v;
+  a ^= t * prime;
+  b += __umul64hi(t, prime);
+}
+
+__device__ __forceinline__ uint64_t final64(uint64_t a, uint64_t b) {
+  const uint64_t x = (a + rot64(b, 41)) * t1_p0();
+  const uint64_t y = (rot64(a, 23) + b) * t1_p6();
+  const uint64_t v = x ^ y;
+  return (v * t1_p5()) ^ __umul64hi(v, t1_p5());
+}
+
+// NW = ceil(K / 8) words; word m holds bytes 8m..8m+7 of the k-mer, little-endian, the last
+// one zero-extended (tail64_le_unaligned, cuda_kernel.cu:155-194).
+template <int K>
+__device__ __forceinline__ uint64_t t1ha2_kmer(const uint64_t (&w)[(K + 7) / 8], uint64_t seed) {
+  uint64_t a = seed, b = (uint64_t)K;
+  int m = 0;
+  if (K > 24) mixup64(a, b, w[m++], t1_p4());
+  if (K > 16) mixup64(b, a, w[m++], t1_p3());
+  if (K > 8) mixup64(a, b, w[m++], t1_p2());
+  if (K > 0) mixup64(b, a, w[m++], t1_p1());
+  return final64(a, b);
+}
+
+// ---------------------------------------------------------------------------------------
+// WyRng word i (0-based) of the generator seeded with h: the state advances by a constant,
+// so the i-th output is a closed form of (h, i) — no sequential dependency (hd.rs:44,51).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t wyrng_word(uint64_t h, uint32_t i) {
+  const uint64_t s = h + (uint64_t)(i + 1) * 0xa0761d6478bd642full;
+  const uint64_t t = s ^ 0xe7037ed1a0b428dbull;
+  return (s * t) ^ __umul64hi(s, t);
+}
+
+// ---------------------------------------------------------------------------------------
+// glibc logf (FMA ifunc variant), bit-for-bit: double-precision table + polynomial, one
+// final rounding to float.  Restated in oracle/hg_oracle.c:hgo_logf_glibc and checked there
+// against the host libm over every positive float.
+// ---------------------------------------------------------------------------------------
+static __device__ __constant__ double c_logf_tab[32] = {
+    0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2, 0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2,
+    0x1.49539f0f010b0p+0, -0x1.01eae7f513a67p-2, 0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3,
+    0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3, 0x1.25e227b0b8ea0p+0, -0x1.1aa2bc79c8100p-3,
+    0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4, 0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4,
+    0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5, 0x1.0000000000000p+0, 0x0.0p+0,
+    0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5,  0x1.ca4b31f026aa0p-1, 0x1.c5e53aa362eb4p-4,
+    0x1.b2036576afce6p-1, 0x1.526e57720db08p-3,  0x1.9c2d163a1aa2dp-1, 0x1.bc2860d224770p-3,
+    0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2,  0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2};
+
+__device__ __forceinline__ float logf_glibc(float x) {
+  uint32_t ix = __float_as_uint(x);
+  if (ix == 0x3f800000u) return 0.0f;
+  if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
+    if (ix * 2 == 0) return __uint_as_float(0xff800000u);  // -inf
+    if (ix == 0x7f800000u) return x;
+    if ((ix & 0x80000000u) || ix * 2 >= 0xff000000u) return __uint_as_float(0x7fc00000u);
+    ix = __float_as_uint(__fmul_rn(x, 8388608.0f));  // subnormal: scale by 2^23
+    ix -= 23u << 23;
+  }
+  const uint32_t tmp = ix - 0x3f330000u;
+  const uint32_t i = (tmp >> 19) & 15;
+  const int k = (int)tmp >> 23;
+  const uint32_t iz = ix - (tmp & 0xff800000u);
+  const double z = (double)__uint_as_float(iz);
+  const double invc = c_logf_tab[2 * i], logc = c_logf_tab[2 * i + 1];
+  const double r = __fma_rn(z, invc, -1.0);
+  const double y0 = __fma_rn((double)k, 0x1.62e42fefa39efp-1, logc);
+  const double r2 = __dmul_rn(r, r);
+  double y = __fma_rn(r, 0x1.5575b0be00b6ap-2, -0x1.ffffef20a4123p-2);
+  y = __fma_rn(r2, -0x1.00ea348b88334p-2, y);
+  y = __fma_rn(r2, y, __dadd_rn(y0, r));
+  return __double2float_rn(y);
+}
+
+// compute_pairwise_ani after the dot product: src/dist.rs:153-160, every operation a
+// correctly rounded f32 op exactly as rustc emits it (no contraction, no fast-math).
+__device__ __forceinline__ float ani_from_dot(int32_t dot, int32_t norm2_r, int32_t norm2_q, float ksize_f) {
+  const int32_t den = (int32_t)((uint32_t)norm2_r + (uint32_t)norm2_q - (uint32_t)dot);
+  const float jaccard = __fdiv_rn(__int2float_rn(dot), __int2float_rn(den));
+  float t = __fdiv_rn(1.0f, jaccard);
+  t = __fadd_rn(t, 1.0f);
+  t = __fdiv_rn(2.0f, t);
+  float ani = __fadd_rn(1.0f, __fdiv_rn(logf_glibc(t), ksize_f));
+  if (ani != ani) return 0.0f;
+  ani = ani < 1.0f ? ani : 1.0f;  // f32::min(1.0)
+  ani = ani > 0.0f ? ani : 0.0f;  // f32::max(0.0)
+  return __fmul_rn(ani, 100.0f);
+}
+
+}  // namespace hg
+
+// ---------------------------------------------------------------------------------------
+// host-side plumbing shared by the .cu files
+// ---------------------------------------------------------------------------------------
+struct hg_ctx {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  unsigned long long launches;
+  // grow-only device scratch
+  void *d_scratch[8];
+  size_t d_scratch_bytes[8];
+  // pinned host scratch
+  void *h_pinned[4];
+  size_t h_pinned_bytes[4];
+  // last dist decision
+  int dist_path;
+  char dist_reason[160];
+  // status words of the last sketch batch (device + host copy)
+  uint32_t *d_status;  // [0] table overflow, [1] quant range overflow
+  uint32_t h_status[4];
+};
+
+void hg_set_error(const char *fmt, ...);
+int hg_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define HG_CUDA(call)                                                   \
+  do {                                                                  \
+    cudaError_t e__ = (call);                                           \
+    if (e__ != cudaSuccess) return hg_cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+// scratch slot `slot` grown to at least `bytes` (contents not preserved)
+int hg_scratch(hg_ctx *ctx, int slot, size_t bytes, void **out);
+int hg_pinned(hg_ctx *ctx, int slot, size_t bytes, void **out);
+
+// ---- kernel launchers (all asynchronous on ctx->stream) ----
+
+struct hg_genome_desc {   // per genome, device-visible
+  uint64_t seq_begin;     // byte offset of the genome in the sequence buffer
+  uint64_t seq_len;       // bases
+  uint64_t table_begin;   // first slot of this genome's hash table
+  uint32_t table_mask;    // slots - 1 (slots is a power of two)
+  uint32_t first_tile;    // index of this genome's first tile in the launch
+};
+
+int hg_launch_kmer_hash(hg_ctx *ctx, const uint8_t *d_seq, const hg_genome_desc *d_desc,
+                        uint32_t n_genomes, uint32_t n_tiles, const hg_sketch_params *p,
+                        uint64_t *d_tables, uint32_t *d_counts);
+int hg_launch_sort_tables(hg_ctx *ctx, const hg_genome_desc *d_desc, uint32_t n_genomes,
+                          uint64_t *d_tables, uint32_t max_slots);
+int hg_launch_encode(hg_ctx *ctx, const hg_genome_desc *d_desc, uint32_t n_genomes,
+                     const uint64_t *d_tables, const uint32_t *d_counts, uint32_t hv_d,
+                     int16_t *d_hv, uint8_t *d_packed, uint8_t *d_quant_bits, int32_t *d_norm2,
+                     uint32_t *d_n_hashes);
+int hg_launch_unpack(hg_ctx *ctx, const uint8_t *d_packed, uint64_t row_stride,
+                     const uint8_t *d_quant_bits, uint32_t n, uint32_t hv_d, int16_t *d_hv);
+int hg_launch_dist_simt(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref,
+                        uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
+                        uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
+                        hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits);
+int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref,
+                      uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
+                      uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
+                      hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits);
+// max |hv| over a device matrix (decides the dist path); result in *d_out (int32)
+int hg_launch_absmax(hg_ctx *ctx, const int16_t *d_hv, uint64_t n_elems, int32_t *d_out);

@@ -1,0 +1,227 @@
+"""ctypes binding of include/hypergen_b200.h — the stub a host language adds on its side.
+
+Every function here is a 1:1 call into the C ABI; there is no Python or CPU implementation
+of the hot path behind it.  If the shared library (or a CUDA device) is missing the calls
+fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+HG_OK, HG_E_INVALID, HG_E_CUDA, HG_E_CAPACITY, HG_E_RANGE, HG_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+EXPORTS = [
+    "hg_init", "hg_destroy", "hg_sync", "hg_last_error", "hg_version", "hg_stream_handle", "hg_launch_count",
+    "hg_kmer_hash", "hg_sketch_batch", "hg_sketch_batch_dev", "hg_sketch_status", "hg_unpack", "hg_unpack_dev",
+    "hg_dist", "hg_dist_dev", "hg_dist_last_path", "hg_dist_last_reason",
+]
+
+
+class SketchParams(C.Structure):
+    """struct hg_sketch_params (reference knobs: src/types.rs:97-113, FileSketch fields)."""
+    _fields_ = [("scaled", C.c_uint64), ("seed", C.c_uint64), ("hv_d", C.c_uint32), ("ksize", C.c_uint8),
+                ("canonical", C.c_uint8), ("reserved", C.c_uint8 * 2)]
+
+
+HIT_DTYPE = np.dtype([("i", np.uint32), ("j", np.uint32), ("dot", np.int32), ("ani", np.float32)])
+
+
+class HyperGenError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("hypergen_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library (building it first if the sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _build.needs_build():
+        _build.build()
+    L = C.CDLL(lib_path())
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    pp = C.POINTER(SketchParams)
+    L.hg_init.restype = i32; L.hg_init.argtypes = [i32, C.POINTER(vp)]
+    L.hg_destroy.restype = None; L.hg_destroy.argtypes = [vp]
+    L.hg_sync.restype = i32; L.hg_sync.argtypes = [vp]
+    L.hg_last_error.restype = C.c_char_p; L.hg_last_error.argtypes = []
+    L.hg_version.restype = C.c_char_p; L.hg_version.argtypes = []
+    L.hg_stream_handle.restype = u64; L.hg_stream_handle.argtypes = [vp]
+    L.hg_launch_count.restype = u64; L.hg_launch_count.argtypes = [vp]
+    L.hg_kmer_hash.restype = i32; L.hg_kmer_hash.argtypes = [vp, vp, vp, u32, pp, vp, u64, vp]
+    L.hg_sketch_batch.restype = i32; L.hg_sketch_batch.argtypes = [vp, vp, vp, u32, pp, vp, vp, vp, vp, vp]
+    L.hg_sketch_batch_dev.restype = i32; L.hg_sketch_batch_dev.argtypes = [vp, vp, vp, u32, pp, vp, vp, vp, vp, vp]
+    L.hg_sketch_status.restype = i32; L.hg_sketch_status.argtypes = [vp]
+    L.hg_unpack.restype = i32; L.hg_unpack.argtypes = [vp, vp, u64, vp, u32, u32, vp]
+    L.hg_unpack_dev.restype = i32; L.hg_unpack_dev.argtypes = [vp, vp, u64, vp, u32, u32, vp]
+    L.hg_dist.restype = i32
+    L.hg_dist.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, u32, C.c_float, i32, i32, vp, u64, C.POINTER(u64)]
+    L.hg_dist_dev.restype = i32
+    L.hg_dist_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp, u32, u32, u32, u32, C.c_float, i32, i32, vp, u64, vp]
+    L.hg_dist_last_path.restype = i32; L.hg_dist_last_path.argtypes = [vp]
+    L.hg_dist_last_reason.restype = C.c_char_p; L.hg_dist_last_reason.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != HG_OK:
+        raise HyperGenError(rc, load().hg_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a) -> int:
+    """host numpy array / device pointer int / None -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    return a.ctypes.data
+
+
+def make_params(k=21, scaled=1500, seed=123, canonical=True, hv_d=4096) -> SketchParams:
+    return SketchParams(scaled=scaled, seed=seed, hv_d=hv_d, ksize=k, canonical=int(bool(canonical)))
+
+
+class Context:
+    """hg_ctx: one CUDA device + stream (replaces CudaDevice::new(0), sketch_cuda.rs:52)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(load().hg_init(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            load().hg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- plumbing --
+    def sync(self):
+        _check(load().hg_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(load().hg_stream_handle(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(load().hg_launch_count(self._h))
+
+    # -- stage 1 --
+    def kmer_hash(self, seq: np.ndarray, seg_off: np.ndarray, params: SketchParams):
+        """hg_kmer_hash: per-genome sorted unique sampled hashes -> (hashes, hash_off)."""
+        seq = np.ascontiguousarray(seq, np.uint8)
+        off = np.ascontiguousarray(seg_off, np.uint64)
+        n = off.size - 1
+        hash_off = np.zeros(n + 1, np.uint64)
+        total_len = int(off[-1] - off[0]) if n else 0
+        cap = total_len // max(int(params.scaled), 1) * 2 + 4096 * max(n, 1)
+        hashes = np.empty(cap, np.uint64)
+        rc = load().hg_kmer_hash(self._h, _ptr(seq) if seq.size else None, _ptr(off), n, C.byref(params),
+                                 _ptr(hashes), cap, _ptr(hash_off))
+        if rc == HG_E_CAPACITY and int(hash_off[-1]) > cap:
+            cap = int(hash_off[-1])
+            hashes = np.empty(cap, np.uint64)
+            rc = load().hg_kmer_hash(self._h, _ptr(seq), _ptr(off), n, C.byref(params), _ptr(hashes), cap,
+                                     _ptr(hash_off))
+        _check(rc)
+        return hashes[: int(hash_off[-1])].copy(), hash_off
+
+    def sketch_batch(self, seq: np.ndarray, seg_off: np.ndarray, params: SketchParams, want_hv: bool = True):
+        """hg_sketch_batch with host buffers -> dict(hv, packed, quant_bits, norm2, n_hashes)."""
+        seq = np.ascontiguousarray(seq, np.uint8)
+        off = np.ascontiguousarray(seg_off, np.uint64)
+        n = off.size - 1
+        D = int(params.hv_d)
+        hv = np.empty((n, D), np.int16) if want_hv else None
+        packed = np.empty((n, 2 * D), np.uint8)
+        qb = np.empty(n, np.uint8)
+        norm2 = np.empty(n, np.int32)
+        nh = np.empty(n, np.uint32)
+        _check(load().hg_sketch_batch(self._h, _ptr(seq) if seq.size else None, _ptr(off), n, C.byref(params),
+                                      _ptr(hv), _ptr(packed), _ptr(qb), _ptr(norm2), _ptr(nh)))
+        return dict(hv=hv, packed=packed, quant_bits=qb, norm2=norm2, n_hashes=nh)
+
+    def sketch_batch_dev(self, d_seq: int, seg_off: np.ndarray, params: SketchParams, d_hv, d_packed,
+                         d_quant_bits: int, d_norm2: int, d_n_hashes: int):
+        """hg_sketch_batch_dev: device pointers (ints), asynchronous on self.stream."""
+        off = np.ascontiguousarray(seg_off, np.uint64)
+        _check(load().hg_sketch_batch_dev(self._h, d_seq, _ptr(off), off.size - 1, C.byref(params), d_hv, d_packed,
+                                          d_quant_bits, d_norm2, d_n_hashes))
+
+    def sketch_status(self):
+        _check(load().hg_sketch_status(self._h))
+
+    # -- format --
+    def unpack(self, packed: np.ndarray, quant_bits: np.ndarray, hv_d: int) -> np.ndarray:
+        packed = np.ascontiguousarray(packed, np.uint8)
+        qb = np.ascontiguousarray(quant_bits, np.uint8)
+        n = qb.size
+        hv = np.empty((n, hv_d), np.int16)
+        _check(load().hg_unpack(self._h, _ptr(packed), packed.shape[1], _ptr(qb), n, hv_d, _ptr(hv)))
+        return hv
+
+    def unpack_dev(self, d_packed: int, row_stride: int, d_quant_bits: int, n: int, hv_d: int, d_hv: int):
+        _check(load().hg_unpack_dev(self._h, d_packed, row_stride, d_quant_bits, n, hv_d, d_hv))
+
+    # -- stage 2 --
+    def dist(self, ref_hv, ref_norm2, qry_hv, qry_norm2, ksize=21, ani_th=85.0, symmetric=False, path=0,
+             cap=None) -> np.ndarray:
+        """hg_dist with host buffers -> structured array of hits (i, j, dot, ani), sorted by (i, j)."""
+        r = np.ascontiguousarray(ref_hv, np.int16)
+        rn = np.ascontiguousarray(ref_norm2, np.int32)
+        same = qry_hv is ref_hv
+        q = r if same else np.ascontiguousarray(qry_hv, np.int16)
+        qn = rn if same and qry_norm2 is ref_norm2 else np.ascontiguousarray(qry_norm2, np.int32)
+        R, D = r.shape
+        Q = q.shape[0]
+        if cap is None:
+            cap = max(1024, R * Q // 64)
+        while True:
+            hits = np.empty(cap, HIT_DTYPE)
+            n_hits = C.c_uint64(0)
+            rc = load().hg_dist(self._h, _ptr(r), _ptr(rn), R, _ptr(q), _ptr(qn), Q, D, ksize, ani_th,
+                                int(symmetric), path, _ptr(hits), cap, C.byref(n_hits))
+            if rc == HG_E_CAPACITY and n_hits.value > cap:
+                cap = int(n_hits.value)
+                continue
+            _check(rc)
+            return hits[: n_hits.value].copy()
+
+    def dist_dev(self, d_ref, d_ref_norm2, n_ref, i0, d_qry, d_qry_norm2, n_qry, j0, hv_d, ksize, ani_th,
+                 symmetric, path, d_hits, cap, d_n_hits):
+        _check(load().hg_dist_dev(self._h, d_ref, d_ref_norm2, n_ref, i0, d_qry, d_qry_norm2, n_qry, j0, hv_d, ksize,
+                                  ani_th, int(symmetric), path, d_hits, cap, d_n_hits))
+
+    @property
+    def dist_last_path(self) -> int:
+        return int(load().hg_dist_last_path(self._h))
+
+    @property
+    def dist_last_reason(self) -> str:
+        return load().hg_dist_last_reason(self._h).decode()

@@ -1,0 +1,157 @@
+/*
+ * hypergen_b200.h — C ABI of the B200-native (sm_100a) HyperGen sketch -> dist hot path.
+ *
+ * This header takes the place of the reference's src/cuda_kernel.h (an empty include
+ * guard, cuda_kernel.h:1-4) and the library behind it replaces the PTX-JIT boundary of
+ * src/sketch_cuda.rs:52-60,119-166 (cudarc htod_copy / launch / sync_reclaim) plus the CPU
+ * stages that followed it.  Every entry point names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every buffer it passes in;
+ *   - every function returns HG_OK (0) or a negative hg_status, never throws or aborts
+ *     (the reference panics: `unwrap()` + panic="abort", Cargo.toml:67-70);
+ *     hg_last_error() returns a thread-local message for the last failure;
+ *   - "_dev" variants take DEVICE pointers (inputs/outputs resident in HBM) and run
+ *     asynchronously on the context's stream — call hg_sync() before reading results;
+ *     the plain variants take HOST pointers and include the H2D / D2H copies;
+ *   - there is no CPU fallback: without a CUDA device hg_init fails with HG_E_CUDA.
+ */
+#ifndef HYPERGEN_B200_H
+#define HYPERGEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define HG_API
+#else
+#define HG_API __attribute__((visibility("default")))
+#endif
+
+typedef enum hg_status {
+  HG_OK = 0,
+  HG_E_INVALID = -1,     /* bad argument (NULL pointer, k = 0 or > 32, hv_d % 256 != 0 ...) */
+  HG_E_CUDA = -2,        /* CUDA runtime / driver error, message in hg_last_error()        */
+  HG_E_CAPACITY = -3,    /* caller's output buffer too small; required size is reported    */
+  HG_E_RANGE = -4,       /* a sketch needs hv_quant_bits = 16, which the reference's own
+                            offset arithmetic cannot represent (src/hd.rs:140)              */
+  HG_E_UNSUPPORTED = -5  /* valid for the reference but outside this build  */
+} hg_status;
+
+typedef struct hg_ctx hg_ctx; /* one CUDA device, one stream, grow-only device scratch */
+
+/* The knobs that reach the kernels: FileSketch fields ksize/scaled/canonical/seed/hv_d
+ * (src/types.rs:224-235; defaults src/types.rs:97-113: k=21 seed=123 scaled=1500 hv_d=4096). */
+typedef struct hg_sketch_params {
+  uint64_t scaled;   /* FracMinHash: keep h < u64::MAX / scaled (src/sketch.rs:73)          */
+  uint64_t seed;     /* t1ha2 seed (src/sketch.rs:74)                                       */
+  uint32_t hv_d;     /* HV dimension, multiple of 256 (BitPacker8x block, src/hd.rs:147)    */
+  uint8_t ksize;     /* 1..32 (t1ha2_atonce in src/cuda_kernel.cu:196-246 covers <= 32)     */
+  uint8_t canonical; /* as the reference GPU path (src/cuda_kernel.cu:306-314); the CPU path
+                        is always canonical (src/sketch.rs:89)                              */
+  uint8_t reserved[2];
+} hg_sketch_params;
+
+/* One reported pair: indices into the ref / query arrays, the exact i32 dot product and
+ * the f32 ANI of src/dist.rs:139-161. */
+typedef struct hg_hit {
+  uint32_t i;
+  uint32_t j;
+  int32_t dot;
+  float ani;
+} hg_hit;
+
+/* ---- context ---------------------------------------------------------------------- */
+
+/* Replaces CudaDevice::new(0) + load_ptx (src/sketch_cuda.rs:52-60).  `device` is a CUDA
+ * ordinal; multi-GPU hosts create one context per device (one process per GPU). */
+HG_API int hg_init(int device, hg_ctx **out);
+HG_API void hg_destroy(hg_ctx *ctx);
+HG_API int hg_sync(hg_ctx *ctx);
+HG_API const char *hg_last_error(void);
+HG_API const char *hg_version(void);
+/* cudaStream_t of the context as an integer handle, so a host framework (torch) can order
+ * its own work against it. */
+HG_API uint64_t hg_stream_handle(hg_ctx *ctx);
+/* number of kernel launches issued through this context so far (bench `gpu_launches`) */
+HG_API uint64_t hg_launch_count(hg_ctx *ctx);
+
+/* ---- stage 1: sketch -------------------------------------------------------------- */
+
+/* Stage hook = extract_kmer_t1ha2_cuda (src/sketch_cuda.rs:119-166) for a batch: the set of
+ * sampled canonical k-mer hashes of each genome, SORTED ascending and de-duplicated (the
+ * reference builds a HashSet, src/sketch_cuda.rs:158-163; unlike it, nothing is dropped
+ * when a 512-k-mer chunk yields more than 8 samples, and h == 0 is kept).
+ *   seq      concatenated sequence bytes, genome g = seq[seg_off[g] .. seg_off[g+1])
+ *            (what fastx_reader::read_merge_seq returns, src/fastx_reader.rs:6-29)
+ *   hash_off n_genomes+1 prefix offsets into `hashes` (written)
+ *   hashes   capacity `cap` u64; on HG_E_CAPACITY hash_off[n_genomes] holds the need. */
+HG_API int hg_kmer_hash(hg_ctx *ctx, const uint8_t *seq, const uint64_t *seg_off, uint32_t n_genomes,
+                        const hg_sketch_params *p, uint64_t *hashes, uint64_t cap, uint64_t *hash_off);
+
+/* The whole per-file body of sketch_cuda (src/sketch_cuda.rs:79-100) for a batch of files:
+ * k-mer hash set -> encode_hash_hd_avx2 layout (src/hd.rs:15-92) -> compute_hv_l2_norm
+ * (src/dist.rs:132-137) -> compress_hd_sketch (src/hd.rs:116-157).
+ *   hv         optional (NULL ok) n_genomes x hv_d int16, the uncompressed sketch HVs
+ *   packed     n_genomes rows of 2*hv_d bytes; row g holds quant_bits[g]*hv_d/8 valid
+ *              bytes = FileSketch.hv reinterpreted as bytes (src/hd.rs:155-157)
+ *   quant_bits FileSketch.hv_quant_bits, norm2 FileSketch.hv_norm_2, n_hashes set sizes */
+HG_API int hg_sketch_batch(hg_ctx *ctx, const uint8_t *seq, const uint64_t *seg_off, uint32_t n_genomes,
+                           const hg_sketch_params *p, int16_t *hv, uint8_t *packed,
+                           uint8_t *quant_bits, int32_t *norm2, uint32_t *n_hashes);
+
+/* Same with `d_seq` and every output in device memory; seg_off stays a HOST array (the
+ * tile schedule is built from it).  Asynchronous on the context stream. */
+HG_API int hg_sketch_batch_dev(hg_ctx *ctx, const uint8_t *d_seq, const uint64_t *seg_off,
+                               uint32_t n_genomes, const hg_sketch_params *p, int16_t *d_hv,
+                               uint8_t *d_packed, uint8_t *d_quant_bits, int32_t *d_norm2,
+                               uint32_t *d_n_hashes);
+/* After hg_sync(): HG_OK, or HG_E_RANGE / HG_E_CAPACITY if any genome of the last
+ * hg_sketch_batch_dev overflowed (never silently truncated). */
+HG_API int hg_sketch_status(hg_ctx *ctx);
+
+/* ---- sketch format ---------------------------------------------------------------- */
+
+/* decompress_hd_sketch (src/hd.rs:184-212) for n sketches on the GPU: packed rows of
+ * `row_stride` bytes -> n x hv_d int16.  Host pointers. */
+HG_API int hg_unpack(hg_ctx *ctx, const uint8_t *packed, uint64_t row_stride, const uint8_t *quant_bits,
+                     uint32_t n, uint32_t hv_d, int16_t *hv);
+HG_API int hg_unpack_dev(hg_ctx *ctx, const uint8_t *d_packed, uint64_t row_stride,
+                         const uint8_t *d_quant_bits, uint32_t n, uint32_t hv_d, int16_t *d_hv);
+
+/* ---- stage 2: dist ---------------------------------------------------------------- */
+
+/* compute_hv_ani + the threshold filter of dump_ani_file (src/dist.rs:231-294,
+ * src/utils.rs:274-285): every (ref i, query j) pair — only j > i when `symmetric`
+ * (same ref/query sketch file, src/dist.rs:13,253-265) — gets the exact i32 dot, the ANI
+ * of src/dist.rs:153-160, and is reported iff ani >= ani_th.  Hits come back sorted by
+ * (i, j).  If more than `cap` pairs pass, returns HG_E_CAPACITY with *n_hits = need.
+ *   path: 0 = auto (tcgen05 int8 limb path when every |hv| fits 13 bits, else SIMT),
+ *         1 = force SIMT (CUDA-core) path, 2 = force tensor path. */
+HG_API int hg_dist(hg_ctx *ctx, const int16_t *ref_hv, const int32_t *ref_norm2, uint32_t n_ref,
+                   const int16_t *qry_hv, const int32_t *qry_norm2, uint32_t n_qry, uint32_t hv_d,
+                   uint32_t ksize, float ani_th, int symmetric, int path, hg_hit *hits, uint64_t cap,
+                   uint64_t *n_hits);
+
+/* Device-resident variant: HVs/norms/hits in HBM, hit order unspecified (atomic append),
+ * *d_n_hits counts every passing pair even beyond cap.  (i, j) are offset by i0 / j0 so a
+ * row shard of a larger ref matrix reports global indices; with `symmetric` the filter is
+ * global_j > global_i.  Asynchronous on the context stream. */
+HG_API int hg_dist_dev(hg_ctx *ctx, const int16_t *d_ref_hv, const int32_t *d_ref_norm2, uint32_t n_ref,
+                       uint32_t i0, const int16_t *d_qry_hv, const int32_t *d_qry_norm2,
+                       uint32_t n_qry, uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th,
+                       int symmetric, int path, hg_hit *d_hits, uint64_t cap,
+                       unsigned long long *d_n_hits);
+
+/* Which path the last hg_dist / hg_dist_dev took (1 SIMT, 2 tensor) and why. */
+HG_API int hg_dist_last_path(hg_ctx *ctx);
+HG_API const char *hg_dist_last_reason(hg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPERGEN_B200_H */
