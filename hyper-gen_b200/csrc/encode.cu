@@ -152,7 +152,10 @@ encode_kernel(const hg_genome_desc *__restrict__ desc, const uint64_t *__restric
   if (lane == 0) { s_red[0][warp] = mn; s_red[1][warp] = mx; s_red[2][warp] = (int)sq; }
   __syncthreads();
   if (warp == 0) {
-    mn = warp_min(s_red[0][lane]); mx = warp_max(s_red[1][lane]); sq = warp_sum((uint32_t)s_red[2][lane]);
+    const bool in = lane < EN_WARPS;
+    mn = warp_min(in ? s_red[0][lane] : 32767);
+    mx = warp_max(in ? s_red[1][lane] : -32768);
+    sq = warp_sum(in ? (uint32_t)s_red[2][lane] : 0u);
     if (lane == 0) { s_red[0][0] = mn; s_red[1][0] = mx; s_red[2][0] = (int)sq; }
   }
   __syncthreads();

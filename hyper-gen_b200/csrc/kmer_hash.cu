@@ -201,9 +201,9 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
         constexpr uint32_t LUT = 0x54434741u;
         const int nb = (K - 8 * m) < 8 ? (K - 8 * m) : 8;  // bases in this word
         uint32_t x = (uint32_t)(y >> (16 * m)) & 0xFFFFu;
-        x = (x * 0x101u) & 0x00FF00FFu;
-        x = (x * 0x11u) & 0x0F0F0F0Fu;
-        x = (x * 0x5u) & 0x33333333u;
+        x = (x | (x << 8)) & 0x00FF00FFu;
+        x = (x | (x << 4)) & 0x0F0F0F0Fu;
+        x = (x | (x << 2)) & 0x33333333u;
         if (nb < 8) x |= 0x44444444u << (4 * nb);         // bytes past the k-mer read as zero
         const uint32_t lo = __byte_perm(LUT, 0u, x);
         const uint32_t hi = __byte_perm(LUT, 0u, x >> 16);
