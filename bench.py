@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's configs, on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Headline (`metric`/`value`): genomes sketched per second, config[1] of BASELINE.json —
+1,000 synthetic 5 Mbp genomes, k=21 scaled=1500 D=4096 per GPU (weak scaling: every rank
+sketches its own 1,000 genomes, no collective on the data path).  A "step" is one pass of
+the sketch hot path (k-mer hash -> set -> HV encode -> norm -> quantise -> bit-pack) over the
+whole batch with the sequence bytes already resident in HBM.  `e2e` is the same pass through
+the host-pointer C-ABI call (pinned host buffers, H2D of the FASTA bytes and D2H of the
+sketches inside the timed region).  The `dist` object carries the second half of the
+metric: ANI pairs/s for the all-vs-all over 10,000 sketches (config[2]), ref rows sharded
+over the ranks, queries broadcast and hits gathered with NCCL.
+
+`--impl reference` times the reference's CPU path restated in C (oracle/hg_oracle.c — the
+Rust crate cannot be built here: no cargo/rustc) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, SCALED, SEED, HV_D = 21, 1500, 123, 4096
+GENOME_LEN = 5_000_000
+# algorithmic bytes of the k-mer hash kernel per genome: 1 B per base read + 8 B per sampled
+# hash written — n ~= L / scaled
+ALG_BYTES_PER_GENOME = GENOME_LEN + 8 * (GENOME_LEN // SCALED)
+# integer instructions the k-mer kernel executes per k-mer (ncu smsp__inst_executed /
+# k-mers, profiles/): used only for the auxiliary INT32 roofline
+KMER_INST_PER_KMER = float(os.environ.get("HG_KMER_INST_PER_KMER", "150"))
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, 50 ms period)."""
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+            return self
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def _run(self):
+        nv = self._nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        med = statistics.median(self.samples) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_sketch_baseline(seq_host: np.ndarray, n_avail: int, seconds_hint: float = 10.0):
+    """The restated reference CPU path (oracle, `kind: port`) on a bounded sample, all cores."""
+    import oracle as O  # the checker / baseline: never on the product path
+    cores = os.cpu_count() or 1
+    O.set_threads(cores)
+    # ~0.15 s per 5 Mbp genome per core: size the sample for roughly seconds_hint of wall time
+    n = int(min(n_avail, max(cores, cores * seconds_hint / 0.15)))
+    off = np.arange(n + 1, dtype=np.uint64) * np.uint64(GENOME_LEN)
+    t0 = time.perf_counter()
+    O.sketch_batch(seq_host[: n * GENOME_LEN], off, k=K, scaled=SCALED, seed=SEED, hv_d=HV_D, want_hv=False)
+    dt = time.perf_counter() - t0
+    return dict(value=n / dt, unit="genomes/s", cores=cores, kind="port",
+                sample="%d of the step's 5 Mbp genomes, oracle/hg_oracle.c (C restatement of src/sketch.rs:35-52), %d threads, %.1f s"
+                % (n, cores, dt))
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU algorithm on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import torch
+    from hypergen_b200 import synth
+    cores = os.cpu_count() or 1
+    import oracle as O
+    O.set_threads(cores)
+    n = int(min(args.genomes, max(cores, 2 * cores)))
+    seq, off = synth.family_batch(n, GENOME_LEN, device="cpu")
+    seq = seq.numpy()
+    times = []
+    for step in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.sketch_batch(seq, off, k=K, scaled=SCALED, seed=SEED, hv_d=HV_D, want_hv=False)
+        if step >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = n * len(times) / total
+    line = {
+        "impl": "reference", "metric": "genomes sketched/sec (5 Mbp, k=21, D=4096)", "value": value, "unit": "genomes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "sketch %d synthetic 5 Mbp genomes per step (bounded sample of config[1]), k=21 scaled=1500 D=4096, CPU" % n},
+        "cpu_baseline": {"value": value, "unit": "genomes/s", "cores": cores, "kind": "port",
+                         "sample": "%d genomes per step; oracle/hg_oracle.c restates src/sketch.rs:35-52 (Rust crate not buildable here: no cargo)" % n},
+        "e2e": {"value": value, "unit": "genomes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genomes", type=int, default=1000, help="genomes per GPU per step (config[1]: 1000)")
+    ap.add_argument("--dist-n", type=int, default=10000, help="sketches in the all-vs-all (config[2]: 10000)")
+    ap.add_argument("--no-dist", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
+        # convenience: relaunch under torchrun exactly as the driver does
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import hypergen_b200 as hg
+    from hypergen_b200 import multigpu, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peaks = load_peaks()
+    ctx = hg.Context(local_rank)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    params = hg.make_params(k=K, scaled=SCALED, seed=SEED, canonical=True, hv_d=HV_D)
+    n = args.genomes
+
+    # ---------------- workload: this rank's genomes, generated on the GPU ----------------
+    seq_dev, seg_off = synth.family_batch(n, GENOME_LEN, device=dev, first=rank * n)
+    d_packed = torch.empty((n, 2 * HV_D), dtype=torch.uint8, device=dev)
+    d_bits = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_norm = torch.empty(n, dtype=torch.int32, device=dev)
+    d_nh = torch.empty(n, dtype=torch.int32, device=dev)
+    d_hv = torch.empty((n, HV_D), dtype=torch.int16, device=dev)
+    torch.cuda.synchronize()
+
+    def sketch_step():
+        ctx.sketch_batch_dev(seq_dev.data_ptr(), seg_off, params, d_hv.data_ptr(), d_packed.data_ptr(),
+                             d_bits.data_ptr(), d_norm.data_ptr(), d_nh.data_ptr())
+
+    # ---------------- device-resident timing (`value`) ----------------
+    ctx.set_profiling(True)
+    for _ in range(args.warmup):
+        sketch_step()
+    ctx.sync()
+    ctx.sketch_status()
+    sampler = ClockSampler(local_rank).start()
+    barrier()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = []
+    with torch.cuda.stream(ext):
+        e0.record()
+        for _ in range(args.steps):
+            sketch_step()
+            stage.append(ctx.stage_ms())  # syncs the stream: < 20 us against a ~30 ms step
+        e1.record()
+    e1.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launches - l0
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    ctx.sketch_status()
+    value = world * n * args.steps / (dev_ms * 1e-3)
+    kmer_ms = statistics.mean(s[1] for s in stage)
+    enc_ms = statistics.mean(s[2] for s in stage)
+    stg_ms = statistics.mean(s[0] for s in stage)
+    achieved_gbs = n * ALG_BYTES_PER_GENOME / (kmer_ms * 1e-3) / 1e9
+    kmers_per_s = n * (GENOME_LEN - K + 1) / (kmer_ms * 1e-3)
+
+    # ---------------- end to end through the host-pointer C ABI ----------------
+    seq_host = torch.empty(n * GENOME_LEN, dtype=torch.uint8, pin_memory=True)
+    seq_host.copy_(seq_dev)
+    h_packed = torch.empty((n, 2 * HV_D), dtype=torch.uint8, pin_memory=True)
+    h_bits = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_norm = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    h_nh = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    torch.cuda.synchronize()
+    lib = hg.ffi.load()
+    import ctypes as C
+
+    def e2e_step():
+        rc = lib.hg_sketch_batch(ctx._h, seq_host.data_ptr(), seg_off.ctypes.data, n, C.byref(params), None,
+                                 h_packed.data_ptr(), h_bits.data_ptr(), h_norm.data_ptr(), h_nh.data_ptr())
+        if rc != 0:
+            raise RuntimeError(lib.hg_last_error().decode())
+
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()  # synchronous: returns after the D2H of the sketches
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * n * e2e_steps / e2e_s
+    h2d = int(n * GENOME_LEN + (n + 1) * 8 + n * 40)
+    d2h = int(n * 2 * HV_D + n * 9)
+    # sanity: the e2e results equal the device-resident ones
+    assert torch.equal(h_norm, d_norm.cpu()) and torch.equal(h_bits, d_bits.cpu())
+
+    line = {
+        "metric": "genomes sketched/sec (5 Mbp, k=21, D=4096)", "value": value, "unit": "genomes/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "sketch %d synthetic 5 Mbp genomes per GPU per step (BASELINE configs[1]), k=21 scaled=1500 D=4096"
+                               % n, "genomes_per_gpu": n, "genome_bp": GENOME_LEN, "k": K, "scaled": SCALED, "hv_d": HV_D,
+                   "l2": "inputs (%.1f GB per step) larger than L2" % (n * GENOME_LEN / 1e9), "parallelism": "genomes sharded, no collective"},
+        "e2e": {"value": e2e_value, "unit": "genomes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                "h2d_gbs": world * h2d * e2e_steps / e2e_s / 1e9},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "kmer_hash_kernel<21,true>", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                     "alg_bytes_per_launch": n * ALG_BYTES_PER_GENOME, "ms_per_launch": kmer_ms,
+                     "note": "bit-exact t1ha2 makes this kernel INT32-issue bound, not HBM bound (SURVEY.md 8d): see roofline_int32"},
+        "stages_ms": {"staging_memset": stg_ms, "kmer_hash": kmer_ms, "encode_pack": enc_ms},
+    }
+
+    # auxiliary INT32 roofline (denominator measured live with the library's probe kernels)
+    try:
+        int_peak = ctx.int_peak(2)
+        line["roofline_int32"] = {"bound": "int32_issue", "achieved": kmers_per_s * KMER_INST_PER_KMER * 1.0,
+                                  "peak": int_peak, "unit": "lane-instr/s", "frac": kmers_per_s * KMER_INST_PER_KMER / int_peak,
+                                  "kmers_per_s": kmers_per_s, "inst_per_kmer": KMER_INST_PER_KMER,
+                                  "peak_imad_only": ctx.int_peak(0), "peak_alu_only": ctx.int_peak(1)}
+    except Exception as ex:  # pragma: no cover
+        line["roofline_int32"] = {"error": str(ex)}
+
+    # ---------------- dist: all-vs-all ANI over dist_n sketches ----------------
+    if not args.no_dist:
+        line["dist"] = bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, max_over_ranks, peaks)
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_sketch_baseline(seq_host.numpy(), n)
+    elif rank == 0:
+        line["cpu_baseline"] = None
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, max_over_ranks, peaks):
+    import torch
+    import torch.distributed as dist
+    nq = args.dist_n
+    D = HV_D
+    # sketches with controlled Jaccard, encoded on the GPU from hash sets (rank 0), then broadcast
+    if rank == 0:
+        sets = synth.hash_sets_family(nq)
+        off = np.zeros(nq + 1, np.uint64)
+        off[1:] = np.cumsum([len(s) for s in sets])
+        hashes = torch.from_numpy(np.concatenate(sets).view(np.int64)).to(dev)
+        hv = torch.empty((nq, D), dtype=torch.int16, device=dev)
+        bits = torch.empty(nq, dtype=torch.uint8, device=dev)
+        norm = torch.empty(nq, dtype=torch.int32, device=dev)
+        ctx.encode_sets_dev(hashes.data_ptr(), off, D, hv.data_ptr(), None, bits.data_ptr(), norm.data_ptr())
+        ctx.sync()
+        del hashes
+    else:
+        hv = norm = None
+    cap = 4_000_000
+    d_hits = torch.empty(cap * 16, dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    bounds = multigpu.triangle_rows(nq, world, align=128)
+    a, b = bounds[rank], bounds[rank + 1]
+    n_pairs = nq * (nq - 1) // 2
+
+    def step():
+        """broadcast queries -> local shard -> hits gathered on rank 0; returns device ms"""
+        nonlocal hv, norm
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        if world > 1:
+            hv, norm = multigpu.broadcast_queries(hv, norm, (nq, D), dev)
+            torch.cuda.current_stream().synchronize()
+        with torch.cuda.stream(ext):
+            ctx.dist_dev(hv[a:b].data_ptr(), norm[a:b].data_ptr(), b - a, a, hv.data_ptr(), norm.data_ptr(), nq, 0, D, K,
+                         85.0, True, 0, d_hits.data_ptr(), cap, d_cnt.data_ptr())
+        ctx.sync()
+        cnt = int(d_cnt.item())
+        local = np.frombuffer(d_hits[: min(cnt, cap) * 16].cpu().numpy().tobytes(), dtype=hg.ffi.HIT_DTYPE)
+        allh = multigpu.gather_hits(local, dev) if world > 1 else local
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1), ctx.stage_ms()[3], (allh.size if allh is not None else 0)
+
+    ctx.set_profiling(True)
+    for _ in range(3):
+        step()
+    steps = max(5, args.steps)
+    tot_ms, kern_ms, n_hits = 0.0, [], 0
+    barrier()
+    for _ in range(steps):
+        flush.fill_(1)  # inputs (82 MB) fit in L2: flush it between timed iterations
+        barrier()
+        ms, kms, n_hits = step()
+        tot_ms += max_over_ranks(ms)
+        kern_ms.append(max_over_ranks(kms))
+    kms = statistics.mean(kern_ms)
+    out = {
+        "metric": "ANI pairs/sec (all-vs-all, D=4096, ani_th=85)", "unit": "pairs/s",
+        "value": n_pairs * steps / (tot_ms * 1e-3), "kernel_value": n_pairs / (kms * 1e-3),
+        "ms_per_step": tot_ms / steps, "kernel_ms": kms, "steps": steps, "hits": int(n_hits), "pairs": n_pairs,
+        "config": {"workload": "all-vs-all dist over %d synthetic sketches (BASELINE configs[2]), D=4096, ani_th=85" % nq,
+                   "rows_per_rank": [bounds[r + 1] - bounds[r] for r in range(world)], "l2": "flushed between iterations"},
+        "path": ctx.dist_last_path, "path_reason": ctx.dist_last_reason,
+    }
+    alg_ops = 2.0 * D * n_pairs
+    int8_peak = 2.0 * peaks["bf16_tflops"]  # kind::i8 runs at twice the bf16 MMA rate
+    out["roofline"] = {"bound": "tensor", "achieved": alg_ops / (kms * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s",
+                       "frac": alg_ops / (kms * 1e-3) / 1e12 / int8_peak,
+                       "note": "algorithmic 2*D ops per pair; peak = 2 x measured bf16 (int8 MMA rate); the limb split executes 3x these MACs"}
+    # e2e through the host-pointer call (N=1 only: H2D of both matrices, D2H of the hits)
+    if world == 1:
+        hv_h = hv.cpu().numpy()
+        norm_h = norm.cpu().numpy()
+        ctx.dist(hv_h, norm_h, hv_h, norm_h, ksize=K, ani_th=85.0, symmetric=True, cap=cap)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            hits = ctx.dist(hv_h, norm_h, hv_h, norm_h, ksize=K, ani_th=85.0, symmetric=True, cap=cap)
+        dt = (time.perf_counter() - t0) / reps
+        out["e2e"] = {"value": n_pairs / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(hv_h.nbytes + norm_h.nbytes),
+                      "d2h_bytes_per_step": int(hits.nbytes + 8), "ms_per_step": dt * 1e3}
+    return out
+
+
+if __name__ == "__main__":
+    main()

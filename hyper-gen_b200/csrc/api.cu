@@ -55,6 +55,7 @@ extern "C" int hg_init(int device, hg_ctx **out) {
   HG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   HG_CUDA(cudaMalloc(&c->d_status, 4 * sizeof(uint32_t)));
   HG_CUDA(cudaMemset(c->d_status, 0, 4 * sizeof(uint32_t)));
+  for (int i = 0; i < 8; i++) HG_CUDA(cudaEventCreate(&c->ev[i]));
   *out = c;
   return HG_OK;
 }
@@ -66,6 +67,7 @@ extern "C" void hg_destroy(hg_ctx *c) {
   for (int i = 0; i < 8; i++) if (c->d_scratch[i]) cudaFree(c->d_scratch[i]);
   for (int i = 0; i < 4; i++) if (c->h_pinned[i]) cudaFreeHost(c->h_pinned[i]);
   if (c->d_status) cudaFree(c->d_status);
+  for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -78,6 +80,53 @@ extern "C" int hg_sync(hg_ctx *c) {
 
 extern "C" uint64_t hg_stream_handle(hg_ctx *c) { return c ? (uint64_t)(uintptr_t)c->stream : 0; }
 extern "C" uint64_t hg_launch_count(hg_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int hg_set_profiling(hg_ctx *c, int enabled) {
+  if (!c) { hg_set_error("ctx is NULL"); return HG_E_INVALID; }
+  c->prof = enabled != 0;
+  c->ev_used = 0;
+  return HG_OK;
+}
+
+extern "C" int hg_stage_ms(hg_ctx *c, float out_ms[4]) {
+  if (!c || !out_ms) { hg_set_error("hg_stage_ms: NULL argument"); return HG_E_INVALID; }
+  HG_CUDA(cudaStreamSynchronize(c->stream));
+  const int pairs[4][2] = {{0, 1}, {1, 2}, {2, 3}, {4, 5}};
+  for (int s = 0; s < 4; s++) {
+    out_ms[s] = -1.0f;
+    const int a = pairs[s][0], b = pairs[s][1];
+    if ((c->ev_used >> a & 1) && (c->ev_used >> b & 1)) HG_CUDA(cudaEventElapsedTime(&out_ms[s], c->ev[a], c->ev[b]));
+  }
+  return HG_OK;
+}
+
+extern "C" int hg_int_peak(hg_ctx *c, int which, double *lane_ops_per_s) {
+  if (!c || !lane_ops_per_s) { hg_set_error("hg_int_peak: NULL argument"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(c->device));
+  void *d_sink;
+  int rc;
+  if ((rc = hg_scratch(c, 7, 256, &d_sink))) return rc;
+  const uint32_t blocks = (uint32_t)c->sm_count * 8, iters = 4096;
+  if ((rc = hg_launch_int_peak(c, which, 64, (uint32_t *)d_sink, blocks))) return rc;  // warm-up
+  cudaEvent_t e0, e1;
+  HG_CUDA(cudaEventCreate(&e0));
+  HG_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    HG_CUDA(cudaEventRecord(e0, c->stream));
+    if ((rc = hg_launch_int_peak(c, which, iters, (uint32_t *)d_sink, blocks))) return rc;
+    HG_CUDA(cudaEventRecord(e1, c->stream));
+    HG_CUDA(cudaEventSynchronize(e1));
+    float ms;
+    HG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double per_thread = (double)iters * 64.0 * (which == 2 ? 2.0 : 1.0);
+  *lane_ops_per_s = per_thread * 256.0 * blocks / (best * 1e-3);
+  return HG_OK;
+}
 
 int hg_scratch(hg_ctx *c, int slot, size_t bytes, void **out) {
   if (bytes == 0) bytes = 256;
@@ -148,6 +197,8 @@ static int make_plan(const uint64_t *seg_off, uint32_t n, const hg_sketch_params
     d.table_begin = slots_total;
     d.table_mask = (uint32_t)(slots - 1);
     d.first_tile = (uint32_t)tiles_total;
+    d.table_slots = (uint32_t)slots;
+    d.pad_ = 0;
     slots_total += slots;
     tiles_total += (n_kmers + tile - 1) / tile;
     if (slots > pl.max_slots) pl.max_slots = (uint32_t)slots;
@@ -169,13 +220,17 @@ static int run_hash_stage(hg_ctx *c, const uint8_t *d_seq, const SketchPlan &pl,
   if ((rc = hg_scratch(c, 3, sizeof(uint32_t) * n, &d_counts))) return rc;
   if ((rc = hg_pinned(c, 0, sizeof(hg_genome_desc) * n, &h_desc))) return rc;
   memcpy(h_desc, pl.desc.data(), sizeof(hg_genome_desc) * n);
+  c->ev_used = 0;
+  HG_PROF(c, 0);
   HG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(hg_genome_desc) * n, cudaMemcpyHostToDevice, c->stream));
   HG_CUDA(cudaMemsetAsync(d_tables, 0xFF, pl.total_slots * 8, c->stream));
   HG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n, c->stream));
   HG_CUDA(cudaMemsetAsync(c->d_status, 0, 4 * sizeof(uint32_t), c->stream));
+  HG_PROF(c, 1);
   if ((rc = hg_launch_kmer_hash(c, d_seq, (const hg_genome_desc *)d_desc, n, pl.n_tiles, p, (uint64_t *)d_tables,
                                 (uint32_t *)d_counts)))
     return rc;
+  HG_PROF(c, 2);
   *d_desc_out = (hg_genome_desc *)d_desc;
   *d_tables_out = (uint64_t *)d_tables;
   *d_counts_out = (uint32_t *)d_counts;
@@ -201,7 +256,68 @@ extern "C" int hg_sketch_batch_dev(hg_ctx *c, const uint8_t *d_seq, const uint64
   if ((rc = make_plan(seg_off, n, p, pl))) return rc;
   hg_genome_desc *d_desc; uint64_t *d_tables; uint32_t *d_counts;
   if ((rc = run_hash_stage(c, d_seq, pl, n, p, &d_desc, &d_tables, &d_counts))) return rc;
-  return hg_launch_encode(c, d_desc, n, d_tables, d_counts, p->hv_d, d_hv, d_packed, d_quant_bits, d_norm2, d_n_hashes);
+  rc = hg_launch_encode(c, d_desc, n, d_tables, d_counts, p->hv_d, d_hv, d_packed, d_quant_bits, d_norm2, d_n_hashes);
+  HG_PROF(c, 3);
+  return rc;
+}
+
+// ---- stage hook: encode from explicit hash sets (hd.rs:15 takes a HashSet) ----
+extern "C" int hg_encode_sets_dev(hg_ctx *c, const uint64_t *d_hashes, const uint64_t *hash_off, uint32_t n,
+                                  uint32_t hv_d, int16_t *d_hv, uint8_t *d_packed, uint8_t *d_quant_bits,
+                                  int32_t *d_norm2) {
+  if (!c || !hash_off || !d_quant_bits || !d_norm2) { hg_set_error("hg_encode_sets_dev: NULL argument"); return HG_E_INVALID; }
+  if (hv_d == 0 || hv_d % 256 != 0) { hg_set_error("hv_d %u must be a positive multiple of 256", hv_d); return HG_E_INVALID; }
+  if (n == 0) return HG_OK;
+  HG_CUDA(cudaSetDevice(c->device));
+  std::vector<hg_genome_desc> desc(n);
+  for (uint32_t g = 0; g < n; g++) {
+    if (hash_off[g + 1] < hash_off[g] || hash_off[g + 1] - hash_off[g] > 0x7fffffffull) { hg_set_error("hash_off invalid at %u", g); return HG_E_INVALID; }
+    memset(&desc[g], 0, sizeof(hg_genome_desc));
+    desc[g].table_begin = hash_off[g];
+    desc[g].table_slots = (uint32_t)(hash_off[g + 1] - hash_off[g]);
+  }
+  void *d_desc, *h_desc;
+  int rc;
+  if ((rc = hg_scratch(c, 1, sizeof(hg_genome_desc) * n, &d_desc))) return rc;
+  if ((rc = hg_pinned(c, 0, sizeof(hg_genome_desc) * n, &h_desc))) return rc;
+  memcpy(h_desc, desc.data(), sizeof(hg_genome_desc) * n);
+  c->ev_used = 0;
+  HG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(hg_genome_desc) * n, cudaMemcpyHostToDevice, c->stream));
+  HG_CUDA(cudaMemsetAsync(c->d_status, 0, 4 * sizeof(uint32_t), c->stream));
+  HG_PROF(c, 2);
+  rc = hg_launch_encode(c, (const hg_genome_desc *)d_desc, n, d_hashes, nullptr, hv_d, d_hv, d_packed, d_quant_bits,
+                        d_norm2, nullptr);
+  HG_PROF(c, 3);
+  return rc;
+}
+
+extern "C" int hg_encode_sets(hg_ctx *c, const uint64_t *hashes, const uint64_t *hash_off, uint32_t n, uint32_t hv_d,
+                              int16_t *hv, uint8_t *packed, uint8_t *quant_bits, int32_t *norm2) {
+  if (!c || !hash_off) { hg_set_error("hg_encode_sets: NULL argument"); return HG_E_INVALID; }
+  if (n == 0) return HG_OK;
+  if (hv_d == 0 || hv_d % 256 != 0) { hg_set_error("hv_d %u must be a positive multiple of 256", hv_d); return HG_E_INVALID; }
+  const uint64_t total = hash_off[n] - hash_off[0];
+  if (total && !hashes) { hg_set_error("hg_encode_sets: hashes is NULL"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(c->device));
+  int rc;
+  void *d_hashes, *d_hv = nullptr, *d_packed = nullptr, *d_small;
+  if ((rc = hg_scratch(c, 2, total * 8 + 64, &d_hashes))) return rc;
+  if (hv && (rc = hg_scratch(c, 4, (size_t)n * hv_d * 2, &d_hv))) return rc;
+  if (packed && (rc = hg_scratch(c, 5, (size_t)n * hv_d * 2, &d_packed))) return rc;
+  if ((rc = hg_scratch(c, 6, (size_t)n * 12, &d_small))) return rc;
+  uint8_t *d_bits = (uint8_t *)d_small + (size_t)n * 8;
+  int32_t *d_norm = (int32_t *)d_small;
+  HG_CUDA(cudaMemcpyAsync(d_hashes, hashes + hash_off[0], total * 8, cudaMemcpyHostToDevice, c->stream));
+  std::vector<uint64_t> rel(n + 1);
+  for (uint32_t g = 0; g <= n; g++) rel[g] = hash_off[g] - hash_off[0];
+  if ((rc = hg_encode_sets_dev(c, (const uint64_t *)d_hashes, rel.data(), n, hv_d, (int16_t *)d_hv, (uint8_t *)d_packed,
+                               d_bits, d_norm)))
+    return rc;
+  if (hv) HG_CUDA(cudaMemcpyAsync(hv, d_hv, (size_t)n * hv_d * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (packed) HG_CUDA(cudaMemcpyAsync(packed, d_packed, (size_t)n * hv_d * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (quant_bits) HG_CUDA(cudaMemcpyAsync(quant_bits, d_bits, n, cudaMemcpyDeviceToHost, c->stream));
+  if (norm2) HG_CUDA(cudaMemcpyAsync(norm2, d_norm, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  return hg_sketch_status(c);
 }
 
 extern "C" int hg_sketch_status(hg_ctx *c) {
@@ -367,11 +483,17 @@ extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref
     snprintf(c->dist_reason, sizeof(c->dist_reason), "%s: forced by caller", use == 1 ? "SIMT" : "tensor");
   }
   c->dist_path = use;
+  c->ev_used &= ~(3 << 4);
+  HG_PROF(c, 4);
+  int rc2;
   if (use == 2)
-    return hg_launch_dist_tc(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th,
-                             symmetric, d_hits, cap, d_n_hits);
-  return hg_launch_dist_simt(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th,
-                             symmetric, d_hits, cap, d_n_hits);
+    rc2 = hg_launch_dist_tc(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th,
+                            symmetric, d_hits, cap, d_n_hits);
+  else
+    rc2 = hg_launch_dist_simt(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th,
+                              symmetric, d_hits, cap, d_n_hits);
+  HG_PROF(c, 5);
+  return rc2;
 }
 
 extern "C" int hg_dist_last_path(hg_ctx *c) { return c ? c->dist_path : 0; }

@@ -61,8 +61,8 @@ encode_kernel(const hg_genome_desc *__restrict__ desc, const uint64_t *__restric
   const uint32_t g = blockIdx.x;
   const hg_genome_desc gd = desc[g];
   const uint64_t *table = tables + gd.table_begin;
-  const uint32_t slots = gd.table_mask + 1;
-  const uint32_t n = counts[g];  // distinct sampled hashes (sketch.rs: kmer_hash_set.len())
+  const uint32_t slots = gd.table_slots;
+  const uint32_t n = counts ? counts[g] : slots;  // dense list mode: every slot is a hash  // distinct sampled hashes (sketch.rs: kmer_hash_set.len())
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (uint32_t d = tid; d < 64 * CP; d += EN_THREADS) s_cnt[d] = 0;
@@ -75,11 +75,11 @@ encode_kernel(const hg_genome_desc *__restrict__ desc, const uint64_t *__restric
     if (tid == 0) s_m = 0;
     __syncthreads();
     // ---- stage the non-empty slots of this slice, compacted ----
-    for (uint32_t s = base + tid; s < base + EN_BATCH && s < slots; s += EN_THREADS) {
-      const uint64_t h = table[s];
+    const uint32_t lim = min(base + EN_BATCH, (slots + 31u) & ~31u);  // warp-uniform trip count
+    for (uint32_t s = base + tid; s < lim; s += EN_THREADS) {
+      const uint64_t h = s < slots ? table[s] : HG_EMPTY_SLOT;
       const bool have = h != HG_EMPTY_SLOT;
       const uint32_t bal = __ballot_sync(0xffffffffu, have);
-      // (the loop trip count is warp-uniform: slots and EN_BATCH are multiples of 32)
       uint32_t pos = 0;
       if (lane == 0 && bal) pos = atomicAdd(&s_m, (uint32_t)__popc(bal));
       pos = __shfl_sync(0xffffffffu, pos, 0);
@@ -169,7 +169,7 @@ encode_kernel(const hg_genome_desc *__restrict__ desc, const uint64_t *__restric
   if (tid == 0) {
     out_bits[g] = (uint8_t)b;
     out_norm2[g] = (int32_t)sq;
-    out_n[g] = n;
+    if (out_n) out_n[g] = n;
   }
   if (out_hv) {
     uint32_t *dst = reinterpret_cast<uint32_t *>(out_hv + (size_t)g * hv_d);

@@ -139,7 +139,21 @@ struct hg_ctx {
   // status words of the last sketch batch (device + host copy)
   uint32_t *d_status;  // [0] table overflow, [1] quant range overflow
   uint32_t h_status[4];
+  // optional stage timing (hg_set_profiling): events on ctx->stream around each stage
+  int prof;
+  cudaEvent_t ev[8];
+  int ev_used;           // which stage boundaries were recorded in the last call
 };
+
+// stage boundaries: 0 start, 1 after staging/memsets, 2 after k-mer hash, 3 after encode,
+// 4 dist start, 5 dist end
+#define HG_PROF(ctx, idx)                                              \
+  do {                                                                 \
+    if ((ctx)->prof) {                                                 \
+      cudaEventRecord((ctx)->ev[idx], (ctx)->stream);                  \
+      (ctx)->ev_used |= 1 << (idx);                                    \
+    }                                                                  \
+  } while (0)
 
 void hg_set_error(const char *fmt, ...);
 int hg_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
@@ -159,8 +173,10 @@ struct hg_genome_desc {   // per genome, device-visible
   uint64_t seq_begin;     // byte offset of the genome in the sequence buffer
   uint64_t seq_len;       // bases
   uint64_t table_begin;   // first slot of this genome's hash table
-  uint32_t table_mask;    // slots - 1 (slots is a power of two)
+  uint32_t table_mask;    // slots - 1 (slots is a power of two) — used by the inserts
   uint32_t first_tile;    // index of this genome's first tile in the launch
+  uint32_t table_slots;   // slots the encoder scans (== mask + 1, or a dense list length)
+  uint32_t pad_;
 };
 
 int hg_launch_kmer_hash(hg_ctx *ctx, const uint8_t *d_seq, const hg_genome_desc *d_desc,
@@ -182,5 +198,6 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
                       uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
                       uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
                       hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits);
+int hg_launch_int_peak(hg_ctx *ctx, int which, uint32_t iters, uint32_t *d_sink, uint32_t blocks);
 // max |hv| over a device matrix (decides the dist path); result in *d_out (int32)
 int hg_launch_absmax(hg_ctx *ctx, const int16_t *d_hv, uint64_t n_elems, int32_t *d_out);

@@ -17,6 +17,7 @@ HG_OK, HG_E_INVALID, HG_E_CUDA, HG_E_CAPACITY, HG_E_RANGE, HG_E_UNSUPPORTED = 0,
 
 EXPORTS = [
     "hg_init", "hg_destroy", "hg_sync", "hg_last_error", "hg_version", "hg_stream_handle", "hg_launch_count",
+    "hg_set_profiling", "hg_stage_ms", "hg_int_peak", "hg_encode_sets", "hg_encode_sets_dev",
     "hg_kmer_hash", "hg_sketch_batch", "hg_sketch_batch_dev", "hg_sketch_status", "hg_unpack", "hg_unpack_dev",
     "hg_dist", "hg_dist_dev", "hg_dist_last_path", "hg_dist_last_reason",
 ]
@@ -61,6 +62,11 @@ def load() -> C.CDLL:
     L.hg_version.restype = C.c_char_p; L.hg_version.argtypes = []
     L.hg_stream_handle.restype = u64; L.hg_stream_handle.argtypes = [vp]
     L.hg_launch_count.restype = u64; L.hg_launch_count.argtypes = [vp]
+    L.hg_set_profiling.restype = i32; L.hg_set_profiling.argtypes = [vp, i32]
+    L.hg_stage_ms.restype = i32; L.hg_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.hg_int_peak.restype = i32; L.hg_int_peak.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    L.hg_encode_sets.restype = i32; L.hg_encode_sets.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp, vp]
+    L.hg_encode_sets_dev.restype = i32; L.hg_encode_sets_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp, vp]
     L.hg_kmer_hash.restype = i32; L.hg_kmer_hash.argtypes = [vp, vp, vp, u32, pp, vp, u64, vp]
     L.hg_sketch_batch.restype = i32; L.hg_sketch_batch.argtypes = [vp, vp, vp, u32, pp, vp, vp, vp, vp, vp]
     L.hg_sketch_batch_dev.restype = i32; L.hg_sketch_batch_dev.argtypes = [vp, vp, vp, u32, pp, vp, vp, vp, vp, vp]
@@ -132,6 +138,20 @@ class Context:
     def launches(self) -> int:
         return int(load().hg_launch_count(self._h))
 
+    def set_profiling(self, enabled: bool):
+        _check(load().hg_set_profiling(self._h, int(enabled)))
+
+    def stage_ms(self):
+        """device ms of the last call's stages: [staging, kmer_hash, encode, dist] (-1 = not run)"""
+        out = (C.c_float * 4)()
+        _check(load().hg_stage_ms(self._h, out))
+        return [float(x) for x in out]
+
+    def int_peak(self, which: int = 2) -> float:
+        v = C.c_double(0)
+        _check(load().hg_int_peak(self._h, which, C.byref(v)))
+        return v.value
+
     # -- stage 1 --
     def kmer_hash(self, seq: np.ndarray, seg_off: np.ndarray, params: SketchParams):
         """hg_kmer_hash: per-genome sorted unique sampled hashes -> (hashes, hash_off)."""
@@ -173,6 +193,25 @@ class Context:
         off = np.ascontiguousarray(seg_off, np.uint64)
         _check(load().hg_sketch_batch_dev(self._h, d_seq, _ptr(off), off.size - 1, C.byref(params), d_hv, d_packed,
                                           d_quant_bits, d_norm2, d_n_hashes))
+
+    def encode_sets(self, sets, hv_d: int = 4096, want_hv: bool = True):
+        """hg_encode_sets: list of unique-u64 arrays -> dict(hv, packed, quant_bits, norm2)."""
+        n = len(sets)
+        off = np.zeros(n + 1, np.uint64)
+        off[1:] = np.cumsum([len(x) for x in sets])
+        hashes = np.ascontiguousarray(np.concatenate(sets) if n and int(off[-1]) else np.zeros(0), np.uint64)
+        hv = np.empty((n, hv_d), np.int16) if want_hv else None
+        packed = np.empty((n, 2 * hv_d), np.uint8)
+        qb = np.empty(n, np.uint8)
+        norm2 = np.empty(n, np.int32)
+        _check(load().hg_encode_sets(self._h, _ptr(hashes) if hashes.size else None, _ptr(off), n, hv_d, _ptr(hv),
+                                     _ptr(packed), _ptr(qb), _ptr(norm2)))
+        return dict(hv=hv, packed=packed, quant_bits=qb, norm2=norm2)
+
+    def encode_sets_dev(self, d_hashes: int, hash_off: np.ndarray, hv_d: int, d_hv, d_packed, d_quant_bits, d_norm2):
+        off = np.ascontiguousarray(hash_off, np.uint64)
+        _check(load().hg_encode_sets_dev(self._h, d_hashes, _ptr(off), off.size - 1, hv_d, d_hv, d_packed,
+                                         d_quant_bits, d_norm2))
 
     def sketch_status(self):
         _check(load().hg_sketch_status(self._h))

@@ -1,0 +1,112 @@
+"""One process per GPU: how the two stages shard.
+
+  * sketch — genomes are independent (the reference already treats files as independent
+    rayon tasks, src/sketch.rs:35): greedy longest-first partition of the files over the
+    ranks, no collective on the data path.
+  * dist   — the ref sketch matrix is row-sharded, the query HVs + norms are broadcast, every
+    rank runs the fused kernel on its R_r x Q block and the (sparse) hit lists are gathered.
+    For the symmetric all-vs-all case the row boundaries are chosen so every rank owns the
+    same number of upper-triangle pairs.
+
+The collective logic is independent of the device: it takes a `compute` callback, so the
+same code runs under NCCL on GPUs and under gloo on CPU tensors in the tests.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .ffi import HIT_DTYPE
+
+
+def partition_greedy(sizes, n_ranks: int) -> list[list[int]]:
+    """Longest-first assignment of items (genome files by byte size) to the least-loaded rank."""
+    order = sorted(range(len(sizes)), key=lambda i: (-int(sizes[i]), i))
+    load = [0] * n_ranks
+    out: list[list[int]] = [[] for _ in range(n_ranks)]
+    for i in order:
+        r = min(range(n_ranks), key=lambda t: (load[t], t))
+        out[r].append(i)
+        load[r] += int(sizes[i])
+    for lst in out:
+        lst.sort()
+    return out
+
+
+def even_rows(n: int, n_ranks: int) -> list[int]:
+    """Boundaries a_0..a_N of a contiguous row split with sizes differing by at most one."""
+    return [(n * r) // n_ranks for r in range(n_ranks + 1)]
+
+
+def triangle_rows(n: int, n_ranks: int, align: int = 1) -> list[int]:
+    """Row boundaries such that each shard [a_r, a_{r+1}) holds ~1/N of the pairs (i, j > i)."""
+    total = n * (n - 1) // 2
+    bounds = [0]
+    for r in range(1, n_ranks):
+        target = total * r / n_ranks
+        # pairs in rows [0, a) = a*(n-1) - a*(a-1)/2  -> solve the quadratic for a
+        a = (2 * n - 1 - math.sqrt(max((2 * n - 1) ** 2 - 8 * target, 0.0))) / 2
+        a = int(round(a / align)) * align
+        bounds.append(min(max(a, bounds[-1]), n))
+    bounds.append(n)
+    return bounds
+
+
+def pairs_in_rows(n: int, a: int, b: int) -> int:
+    f = lambda x: x * (n - 1) - x * (x - 1) // 2
+    return f(b) - f(a)
+
+
+def broadcast_queries(qry_hv: torch.Tensor | None, qry_norm: torch.Tensor | None, shape, device, src: int = 0):
+    """Rank `src` owns the query HVs (n x D int16) and norms (n int32); everyone gets a copy."""
+    rank = dist.get_rank()
+    n, d = shape
+    if rank != src:
+        qry_hv = torch.empty((n, d), dtype=torch.int16, device=device)
+        qry_norm = torch.empty((n,), dtype=torch.int32, device=device)
+    dist.broadcast(qry_hv, src=src)
+    dist.broadcast(qry_norm, src=src)
+    return qry_hv, qry_norm
+
+
+def gather_hits(local_hits: np.ndarray, device, dst: int = 0) -> np.ndarray | None:
+    """Variable-length hit lists -> one array on rank `dst` (sorted by (i, j)); None elsewhere."""
+    world = dist.get_world_size()
+    cnt = torch.tensor([local_hits.size], dtype=torch.int64, device=device)
+    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    counts = [int(c.item()) for c in counts]
+    mx = max(max(counts), 1)
+    buf = torch.zeros(mx * HIT_DTYPE.itemsize, dtype=torch.uint8, device=device)
+    if local_hits.size:
+        raw = torch.from_numpy(np.frombuffer(local_hits.tobytes(), dtype=np.uint8).copy())
+        buf[: raw.numel()] = raw.to(device)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    if dist.get_rank() != dst:
+        return None
+    parts = [np.frombuffer(bufs[r].cpu().numpy().tobytes(), dtype=HIT_DTYPE)[: counts[r]] for r in range(world)]
+    allh = np.concatenate(parts) if parts else np.zeros(0, HIT_DTYPE)
+    return allh[np.lexsort((allh["j"], allh["i"]))]
+
+
+def dist_sharded(compute, ref_hv, ref_norm, qry_hv, qry_norm, n_ref: int, n_qry: int, hv_d: int, symmetric: bool,
+                 device, bounds=None) -> np.ndarray | None:
+    """Row-shard the refs, broadcast the queries, compute locally, gather the hits on rank 0.
+
+    ref_hv / ref_norm: this rank's view of the FULL ref matrix or None (then the shard is taken
+    from the broadcast queries — the all-vs-all case where ref == query).
+    compute(ref_block, ref_norm_block, i0, qry_hv, qry_norm) -> np.ndarray[HIT_DTYPE]
+    """
+    rank, world = dist.get_rank(), dist.get_world_size()
+    qry_hv, qry_norm = broadcast_queries(qry_hv, qry_norm, (n_qry, hv_d), device)
+    if bounds is None:
+        bounds = triangle_rows(n_ref, world) if symmetric else even_rows(n_ref, world)
+    a, b = bounds[rank], bounds[rank + 1]
+    if ref_hv is None:
+        ref_hv, ref_norm = qry_hv, qry_norm
+    local = compute(ref_hv[a:b], ref_norm[a:b], a, qry_hv, qry_norm) if b > a else np.zeros(0, HIT_DTYPE)
+    return gather_hits(local, device)

@@ -79,6 +79,15 @@ HG_API const char *hg_version(void);
 HG_API uint64_t hg_stream_handle(hg_ctx *ctx);
 /* number of kernel launches issued through this context so far (bench `gpu_launches`) */
 HG_API uint64_t hg_launch_count(hg_ctx *ctx);
+/* Measurement support.  hg_set_profiling(ctx, 1) records CUDA events on the context stream
+ * around every stage; after hg_sync(), hg_stage_ms() returns the device time of the last
+ * call's stages in ms: [0] staging + table clears, [1] k-mer hash kernel, [2] encode kernel,
+ * [3] dist kernel(s).  Entries that did not run are -1. */
+HG_API int hg_set_profiling(hg_ctx *ctx, int enabled);
+HG_API int hg_stage_ms(hg_ctx *ctx, float out_ms[4]);
+/* Dependent-free integer issue-rate probe used as the INT32 roofline denominator:
+ * which = 0 IMAD chain mix, 1 LOP3/IADD3/SHF mix, 2 both interleaved.  Returns lane-ops/s. */
+HG_API int hg_int_peak(hg_ctx *ctx, int which, double *lane_ops_per_s);
 
 /* ---- stage 1: sketch -------------------------------------------------------------- */
 
@@ -113,6 +122,17 @@ HG_API int hg_sketch_batch_dev(hg_ctx *ctx, const uint8_t *d_seq, const uint64_t
 /* After hg_sync(): HG_OK, or HG_E_RANGE / HG_E_CAPACITY if any genome of the last
  * hg_sketch_batch_dev overflowed (never silently truncated). */
 HG_API int hg_sketch_status(hg_ctx *ctx);
+
+/* Stage hook = hd::encode_hash_hd_avx2 + compute_hv_l2_norm + compress_hd_sketch
+ * (src/hd.rs:15-92,116-157, src/dist.rs:132-137) from explicit hash SETS (unique values,
+ * as the reference's HashSet argument): set g = hashes[hash_off[g] .. hash_off[g+1]).
+ * Host pointers; outputs as hg_sketch_batch. */
+HG_API int hg_encode_sets(hg_ctx *ctx, const uint64_t *hashes, const uint64_t *hash_off, uint32_t n_sets,
+                          uint32_t hv_d, int16_t *hv, uint8_t *packed, uint8_t *quant_bits, int32_t *norm2);
+/* Same with `d_hashes` and the outputs in device memory (hash_off stays on the host). */
+HG_API int hg_encode_sets_dev(hg_ctx *ctx, const uint64_t *d_hashes, const uint64_t *hash_off,
+                              uint32_t n_sets, uint32_t hv_d, int16_t *d_hv, uint8_t *d_packed,
+                              uint8_t *d_quant_bits, int32_t *d_norm2);
 
 /* ---- sketch format ---------------------------------------------------------------- */
 
