@@ -181,7 +181,7 @@ struct SketchPlan {
 
 static int make_plan(const uint64_t *seg_off, uint32_t n, const hg_sketch_params *p, SketchPlan &pl) {
   const uint32_t tile = hg_kmer_tile_positions();
-  pl.desc.resize(n);
+  pl.desc.resize(n + 1);  // + sentinel
   uint64_t slots_total = 0, tiles_total = 0;
   for (uint32_t g = 0; g < n; g++) {
     if (seg_off[g + 1] < seg_off[g]) { hg_set_error("seg_off not monotone at %u", g); return HG_E_INVALID; }
@@ -204,6 +204,8 @@ static int make_plan(const uint64_t *seg_off, uint32_t n, const hg_sketch_params
     if (slots > pl.max_slots) pl.max_slots = (uint32_t)slots;
     if (tiles_total > 0x7fffffffull) { hg_set_error("batch too large: split it"); return HG_E_UNSUPPORTED; }
   }
+  memset(&pl.desc[n], 0, sizeof(hg_genome_desc));
+  pl.desc[n].first_tile = (uint32_t)tiles_total;  // sentinel: ends the kernel's forward walk
   pl.total_slots = slots_total;
   pl.n_tiles = (uint32_t)tiles_total;
   return HG_OK;
@@ -215,14 +217,14 @@ static int run_hash_stage(hg_ctx *c, const uint8_t *d_seq, const SketchPlan &pl,
                           uint32_t **d_counts_out) {
   void *d_desc, *d_tables, *d_counts, *h_desc;
   int rc;
-  if ((rc = hg_scratch(c, 1, sizeof(hg_genome_desc) * n, &d_desc))) return rc;
+  if ((rc = hg_scratch(c, 1, sizeof(hg_genome_desc) * (n + 1), &d_desc))) return rc;
   if ((rc = hg_scratch(c, 2, pl.total_slots * 8, &d_tables))) return rc;
   if ((rc = hg_scratch(c, 3, sizeof(uint32_t) * n, &d_counts))) return rc;
-  if ((rc = hg_pinned(c, 0, sizeof(hg_genome_desc) * n, &h_desc))) return rc;
-  memcpy(h_desc, pl.desc.data(), sizeof(hg_genome_desc) * n);
+  if ((rc = hg_pinned(c, 0, sizeof(hg_genome_desc) * (n + 1), &h_desc))) return rc;
+  memcpy(h_desc, pl.desc.data(), sizeof(hg_genome_desc) * (n + 1));
   c->ev_used = 0;
   HG_PROF(c, 0);
-  HG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(hg_genome_desc) * n, cudaMemcpyHostToDevice, c->stream));
+  HG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(hg_genome_desc) * (n + 1), cudaMemcpyHostToDevice, c->stream));
   HG_CUDA(cudaMemsetAsync(d_tables, 0xFF, pl.total_slots * 8, c->stream));
   HG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n, c->stream));
   HG_CUDA(cudaMemsetAsync(c->d_status, 0, 4 * sizeof(uint32_t), c->stream));
@@ -486,10 +488,15 @@ extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref
   c->ev_used &= ~(3 << 4);
   HG_PROF(c, 4);
   int rc2;
-  if (use == 2)
+  if (use == 2) {
     rc2 = hg_launch_dist_tc(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th,
                             symmetric, d_hits, cap, d_n_hits);
-  else
+    if (rc2 == HG_E_UNSUPPORTED && path == 0) {  // shape outside the tensor kernel's tiling: exact SIMT path
+      use = c->dist_path = 1;
+      snprintf(c->dist_reason, sizeof(c->dist_reason), "SIMT: tensor kernel declined this shape (%s)", hg_last_error());
+    }
+  }
+  if (use != 2)
     rc2 = hg_launch_dist_simt(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th,
                               symmetric, d_hits, cap, d_n_hits);
   HG_PROF(c, 5);

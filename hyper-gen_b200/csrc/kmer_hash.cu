@@ -6,12 +6,13 @@
 // (src/sketch.rs:71-98).  Design (not the reference's one-thread-per-512-k-mers walk):
 //   * one CTA per tile of 8192 k-mer start positions of ONE genome; the tile's bytes
 //     (+ k-1 halo) are read once with aligned, coalesced 16-byte loads, converted SWAR-style
-//     to 2-bit codes + a validity bit per base, and staged in 3 KB of shared memory;
-//   * each thread then owns 32 consecutive start positions: rolling forward / reverse-
-//     complement 2-bit k-mers in registers, canonical = min() on the packed value (same order
-//     as the reference's byte compare, cuda_kernel.cu:84-89,306-311), expansion of the chosen
-//     k-mer back to its upper-case ASCII bytes with PRMT table lookups (the hash is defined
-//     over the ASCII k-mer, sketch.rs:90), t1ha2_atonce in registers, threshold compare;
+//     to nibble codes + a validity bit per base, and staged in 5 KB of shared memory;
+//   * each thread then owns 32 consecutive start positions: the forward and reverse-
+//     complement k-mers roll in registers one NIBBLE per base (first base in the low nibble),
+//     canonical = lexicographic min via BREV'd unsigned compares (same order as the
+//     reference's byte compare, cuda_kernel.cu:84-89,306-311), and the chosen k-mer becomes
+//     its upper-case ASCII bytes with two PRMT table lookups per 8 bases (the hash is defined
+//     over the ASCII k-mer, sketch.rs:90); t1ha2_atonce in registers; threshold compare;
 //   * the rare survivors (1/scaled) are inserted into the genome's open-addressing table in
 //     HBM with atomicCAS, which both removes duplicates (the reference keeps a set) and has
 //     no per-thread capacity cliff (the reference drops hits beyond 8 per thread,
@@ -20,10 +21,12 @@
 
 namespace {
 
-constexpr int KH_THREADS = 256;
+constexpr int KH_THREADS = 128;
+constexpr int KH_WARPS = KH_THREADS / 32;
 constexpr int KH_PPT = 32;                       // k-mer start positions per thread
-constexpr int KH_TILE = KH_THREADS * KH_PPT;     // start positions per CTA
+constexpr int KH_TILE = 32 * KH_PPT;             // start positions per WARP tile
 constexpr int KH_CHUNKS = (KH_TILE + 64) / 16;   // 16-base chunks staged per tile (halo + align)
+constexpr int KH_MIN_CTAS = 12;                  // 48 resident warps per SM (<= 40 registers)
 
 __device__ __forceinline__ uint4 ld_stream16(const void *p) {
   uint4 r;
@@ -33,16 +36,29 @@ __device__ __forceinline__ uint4 ld_stream16(const void *p) {
   return r;
 }
 
-// 4 ASCII bytes -> 8 bits of 2-bit codes (A0 C1 G2 T3, base 0 in the low bits) and 4
-// validity bits (only A,C,G,T in either case are valid — cuda_kernel.cu:277-296).
-__device__ __forceinline__ void encode4(uint32_t w, uint32_t &codes8, uint32_t &valid4) {
+// raw PRMT: selector nibbles are always < 8 here, so the masking __byte_perm adds is not needed
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// Nibble code of a base (one nibble per base everywhere below):  A=2  C=6  G=1  T=5, 0 = "no
+// base".  Chosen so that (i) complement is XOR 7, (ii) the bit-reversed nibbles order as
+// A<C<G<T, so BREV turns "first base in the low nibble" words into unsigned-comparable keys,
+// and (iii) every code is a PRMT selector (< 8) into an 8-byte ASCII table with 0 -> 0x00.
+//
+// 4 ASCII bytes -> 16 bits of nibble codes (base 0 in the low nibble) + 4 validity bits
+// (only A,C,G,T in either case are bases — cuda_kernel.cu:277-296).
+__device__ __forceinline__ void encode4(uint32_t w, uint32_t &nib16, uint32_t &valid4) {
   const uint32_t u = w & 0xDFDFDFDFu;                               // fold case
   const uint32_t code = ((u >> 1) ^ (u >> 2)) & 0x03030303u;        // per byte: A0 C1 G2 T3
-  codes8 = (code * 0x01041040u) >> 24;                              // gather the four fields
-  // re-expand the codes to upper-case ASCII and compare: anything else is not a base
   const uint32_t sel = (code | (code >> 12)) & 0xFFFFu;             // nibbles: b0 b2 b1 b3
-  const uint32_t expect = __byte_perm(0x54474341u, 0u, sel);        // 'A','C','G','T'
-  const uint32_t have = __byte_perm(u, 0u, 0x3120u);                // same byte order
+  const uint32_t nib = prmt(0x05010602u, 0u, sel);           // bytes n0 n2 n1 n3
+  nib16 = (nib | (nib >> 12)) & 0xFFFFu;                            // n0 n1 n2 n3
+  // re-expand the codes to upper-case ASCII and compare: anything else is not a base
+  const uint32_t expect = prmt(0x54474341u, 0u, sel);        // 'A','C','G','T'
+  const uint32_t have = prmt(u, 0u, 0x3120u);                // same byte order
   const uint32_t d = expect ^ have;
   const uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
   const uint32_t ok = (nz ^ 0x80808080u) >> 7;                      // flags at bits 0,8,16,24
@@ -51,6 +67,11 @@ __device__ __forceinline__ void encode4(uint32_t w, uint32_t &codes8, uint32_t &
 
 __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
   return __funnelshift_r(lo, hi, s);
+}
+
+// reverse the bit order inside every nibble (undoes what BREV does to the codes)
+__device__ __forceinline__ uint32_t rev_in_nibble(uint32_t x) {
+  return ((x & 0x11111111u) << 3) | ((x & 0x22222222u) << 1) | ((x >> 1) & 0x22222222u) | ((x >> 3) & 0x11111111u);
 }
 
 // Insert h into the genome's table (linear probing).  Duplicates collapse: F3 set semantics.
@@ -72,69 +93,69 @@ __device__ __noinline__ void table_insert(uint64_t *__restrict__ table, uint32_t
 }
 
 template <int K, bool CANON>
-__global__ void __launch_bounds__(KH_THREADS)
+__global__ void __launch_bounds__(KH_THREADS, KH_MIN_CTAS)
 kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restrict__ desc,
-                 uint32_t n_genomes, uint64_t threshold, uint64_t seed,
+                 uint32_t n_genomes, uint32_t n_tiles, uint64_t threshold, uint64_t seed,
                  uint64_t *__restrict__ tables, uint32_t *__restrict__ counts,
-                 uint32_t *__restrict__ status) {
-  constexpr int NW = (K + 7) / 8;
-  __shared__ uint32_t s_codes[KH_CHUNKS + 4];
-  __shared__ uint32_t s_valid[KH_CHUNKS / 2 + 4];  // 16 bits per chunk
-  __shared__ uint32_t s_genome;
+                 uint32_t *__restrict__ status, uint32_t lut_lo, uint32_t lut_hi,
+                 const uint32_t *__restrict__ cta_genome) {
+  constexpr int NW = (K + 7) / 8;          // nibble words == t1ha2 input words (8 bases each)
+  constexpr int LASTN = K - 8 * (NW - 1);  // bases in the last word, 1..8
+  constexpr uint32_t LASTMASK = LASTN == 8 ? 0xFFFFFFFFu : ((1u << (4 * LASTN)) - 1u);
+  // every warp owns a private staging area and runs on its own: no CTA-wide barrier anywhere
+  __shared__ uint32_t s_nib_all[KH_WARPS][KH_CHUNKS * 2 + 8];    // 8 bases per word
+  __shared__ uint32_t s_valid_all[KH_WARPS][KH_CHUNKS / 2 + 4];  // 16 bits per chunk
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t *s_nib = s_nib_all[warp];
+  uint32_t *s_valid = s_valid_all[warp];
+  uint16_t *s_valid16 = reinterpret_cast<uint16_t *>(s_valid);
 
-  // ---- which genome does this tile belong to (binary search over first_tile) ----
-  if (threadIdx.x == 0) {
-    uint32_t lo = 0, hi = n_genomes - 1;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi + 1) >> 1;
-      if (desc[mid].first_tile <= blockIdx.x) lo = mid; else hi = mid - 1;
-    }
-    s_genome = lo;
-  }
-  __syncthreads();
-  const uint32_t g = s_genome;
+  // One tile per warp, 8 consecutive tiles per CTA.  cta_genome[] (written by tile_map_kernel)
+  // names the genome of the CTA's first tile; the warp walks the sorted first_tile column
+  // forward from there (desc[n_genomes] is a sentinel holding the tile count).
+  const uint32_t tile = blockIdx.x * KH_WARPS + warp;
+  if (tile >= n_tiles) return;
+  uint32_t g = cta_genome[blockIdx.x];
+  while (desc[g + 1].first_tile <= tile) ++g;  // warp-uniform, usually zero steps
+  {
   const hg_genome_desc gd = desc[g];
-  const uint64_t tile_base = (uint64_t)(blockIdx.x - gd.first_tile) * KH_TILE;  // first start position
-  uint64_t need_end = tile_base + KH_TILE + (K - 1);                            // bases [tile_base, need_end)
+  const uint64_t tile_base = (uint64_t)(tile - gd.first_tile) * KH_TILE;  // first start position
+  uint64_t need_end = tile_base + KH_TILE + (K - 1);                      // bases [tile_base, need_end)
   if (need_end > gd.seq_len) need_end = gd.seq_len;
 
-  // ---- phase A: bytes -> 2-bit codes + validity, staged in shared memory ----
+  // ---- phase A: bytes -> nibble codes + validity, staged in this warp's shared memory ----
   const uintptr_t p_lo = (uintptr_t)(seq + gd.seq_begin + tile_base);
   const uintptr_t p_hi = (uintptr_t)(seq + gd.seq_begin + need_end);
   const uintptr_t p_al = p_lo & ~(uintptr_t)15;
   const uint32_t sh = (uint32_t)(p_lo - p_al);  // 0..15 bases of alignment slack
-  uint16_t *s_valid16 = reinterpret_cast<uint16_t *>(s_valid);
-  for (int c = threadIdx.x; c < KH_CHUNKS + 4; c += KH_THREADS) {
+  for (int c = lane; c < KH_CHUNKS + 4; c += 32) {
     const uintptr_t pc = p_al + (uintptr_t)16 * c;
-    uint32_t codes = 0, valid = 0;
+    uint32_t n0 = 0, n1 = 0, valid = 0;
     if (c < KH_CHUNKS && pc < p_hi && pc + 16 > p_lo) {
       const uint4 v = ld_stream16(reinterpret_cast<const void *>(pc));
-      uint32_t c8, v4;
-      encode4(v.x, c8, v4); codes = c8;        valid = v4;
-      encode4(v.y, c8, v4); codes |= c8 << 8;  valid |= v4 << 4;
-      encode4(v.z, c8, v4); codes |= c8 << 16; valid |= v4 << 8;
-      encode4(v.w, c8, v4); codes |= c8 << 24; valid |= v4 << 12;
+      uint32_t n16, v4;
+      encode4(v.x, n16, v4); n0 = n16;        valid = v4;
+      encode4(v.y, n16, v4); n0 |= n16 << 16; valid |= v4 << 4;
+      encode4(v.z, n16, v4); n1 = n16;        valid |= v4 << 8;
+      encode4(v.w, n16, v4); n1 |= n16 << 16; valid |= v4 << 12;
       // bytes of this chunk outside [p_lo, p_hi) belong to someone else (or nobody)
       const int first = pc < p_lo ? (int)(p_lo - pc) : 0;
       const int last = pc + 16 > p_hi ? (int)(p_hi - pc) : 16;
       valid &= ((1u << last) - 1u) & ~((1u << first) - 1u);
     }
-    s_codes[c] = codes;
+    s_nib[2 * c] = n0;
+    s_nib[2 * c + 1] = n1;
     s_valid16[c] = (uint16_t)valid;
   }
-  __syncthreads();
+  __syncwarp();
 
   // ---- phase B: 32 start positions per thread ----
-  const int t = threadIdx.x;
-  // 64 bases of codes starting at this thread's first base
-  uint32_t cw[4];
-  {
-    const uint32_t a0 = s_codes[2 * t], a1 = s_codes[2 * t + 1], a2 = s_codes[2 * t + 2],
-                   a3 = s_codes[2 * t + 3], a4 = s_codes[2 * t + 4];
-    const uint32_t s2 = 2 * sh;
-    cw[0] = funnel_r(a0, a1, s2); cw[1] = funnel_r(a1, a2, s2);
-    cw[2] = funnel_r(a2, a3, s2); cw[3] = funnel_r(a3, a4, s2);
-  }
+  const int t = lane;
+  const uint32_t nb0 = sh + 32u * t;  // this thread's first base, as a nibble index into s_nib
+  auto window8 = [&](uint32_t nib_off) -> uint32_t {  // 8 consecutive bases starting at nib_off
+    const uint32_t idx = nib_off >> 3;
+    return funnel_r(s_nib[idx], s_nib[idx + 1], (nib_off & 7u) * 4u);
+  };
   uint64_t v;
   {
     const uint32_t b0 = s_valid[t], b1 = s_valid[t + 1], b2 = s_valid[t + 2];
@@ -152,81 +173,150 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
     }
   }
   const uint32_t kv32 = (uint32_t)kv;
-  if (kv32 == 0) return;
+  if (kv32 != 0) {
 
-  constexpr uint64_t KMASK = (K == 32) ? ~0ull : ((1ull << (2 * K)) - 1ull);
-  const uint64_t codes_lo = (uint64_t)cw[0] | ((uint64_t)cw[1] << 32);  // bases 0..31, LSB first
-
-  // rolling state after the first K-1 bases: fwd is MSB-first (oldest base on top) so that an
-  // unsigned compare is the lexicographic compare; rc holds the reverse complement likewise.
-  uint64_t fwd = 0, rc = 0;
-  if constexpr (K > 1) {
-    constexpr uint64_t PMASK = (K == 1) ? 0ull : ((1ull << (2 * (K - 1))) - 1ull);
-    const uint64_t x = codes_lo & PMASK;                       // bases 0..K-2, base i at bits 2i
-    rc = ((~x) & PMASK) << 2;                                  // complement, base i at 2(i+1)
-    uint64_t y = __brevll(x) >> (64 - 2 * (K - 1));            // order reversed, bit pairs swapped
-    fwd = ((y & 0x5555555555555555ull) << 1) | ((y >> 1) & 0x5555555555555555ull);
+  // Rolling state, one nibble per base, FIRST base of the k-mer in the LOW nibble of word 0
+  // (the byte order t1ha2 reads).  F = forward strand, R = reverse complement.  Before each
+  // step F holds the previous k-mer; the step drops its first base and appends the new one.
+  uint32_t F[NW], R[NW];
+  {
+    // X = the first K-1 bases of the window, nibble i = base i
+    uint32_t X[NW];
+#pragma unroll
+    for (int m = 0; m < NW; ++m) {
+      constexpr int P = K - 1;
+      const int have = P - 8 * m;  // bases of X that live in word m
+      X[m] = have <= 0 ? 0u : (window8(nb0 + 8 * m) & (have >= 8 ? 0xFFFFFFFFu : ((1u << (4 * (have & 7))) - 1u)));
+    }
+    // F = X << 4 (so that the first step's shift-right puts base i at nibble i)
+#pragma unroll
+    for (int m = NW - 1; m >= 0; --m) F[m] = (X[m] << 4) | (m > 0 ? (X[m - 1] >> 28) : 0u);
+    // R: nibble i = complement(base[K-2-i]), i < K-1.  Complement = XOR 7 on real bases.
+    if (CANON) {
+      constexpr int P = K - 1;
+      uint32_t Y[NW];
+#pragma unroll
+      for (int m = 0; m < NW; ++m) {
+        const int have = P - 8 * m;
+        const uint32_t cm = have <= 0 ? 0u : (have >= 8 ? 0x77777777u : (0x77777777u & ((1u << (4 * (have & 7))) - 1u)));
+        Y[m] = X[m] ^ cm;
+      }
+      // reverse the nibble order of the whole NW-word value, then shift the P used nibbles down
+      uint32_t V[NW + 1];
+#pragma unroll
+      for (int m = 0; m < NW; ++m) V[m] = rev_in_nibble(__brev(Y[NW - 1 - m]));
+      V[NW] = 0;
+      constexpr int SHB = 4 * (8 * NW - P);  // bits to shift right
+      constexpr int SW = SHB / 32, SB = SHB % 32;
+#pragma unroll
+      for (int m = 0; m < NW; ++m) {
+        const uint32_t lo = (m + SW) <= NW ? V[(m + SW) <= NW ? (m + SW) : NW] : 0u;
+        const uint32_t hi = (m + SW + 1) <= NW ? V[(m + SW + 1) <= NW ? (m + SW + 1) : NW] : 0u;
+        R[m] = SB ? funnel_r(lo, hi, SB) : lo;
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < NW; ++m) R[m] = 0;
+    }
   }
 
   uint64_t *table = tables + gd.table_begin;
   uint32_t *count = counts + g;
 
-  // the 32 incoming bases (window positions K-1 .. K+30), LSB first
-  uint32_t up[2];
-  {
-    constexpr int S = 2 * (K - 1);  // bit offset of base K-1 in the 128-bit code window
-    const uint32_t q0 = cw[0], q1 = cw[1], q2 = cw[2], q3 = cw[3];
-    if constexpr (S < 32) { up[0] = funnel_r(q0, q1, S);      up[1] = funnel_r(q1, q2, S); (void)q3; }
-    else                  { up[0] = funnel_r(q1, q2, S - 32); up[1] = funnel_r(q2, q3, S - 32); (void)q0; }
-  }
-
 #pragma unroll 1
   for (int o = 0; o < KH_PPT / 8; ++o) {
-    const uint32_t in16 = ((o & 2) ? up[1] : up[0]) >> (16 * (o & 1));
+    const uint32_t in32 = window8(nb0 + (K - 1) + 8 * o);  // the 8 incoming bases
+    const uint32_t in32c = in32 ^ 0x77777777u;             // their complements
     const uint32_t kv8 = kv32 >> (8 * o);
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
-      const uint32_t c = (in16 >> (2 * jj)) & 3u;
-      fwd = ((fwd << 2) | c) & KMASK;
-      rc = (rc >> 2) | ((uint64_t)(3u - c) << (2 * (K - 1)));
-      const uint64_t canon = CANON ? (fwd < rc ? fwd : rc) : fwd;
-
-      // ASCII expansion: reverse so base 0 sits in the low bits (bit pairs come out swapped,
-      // which the lookup table absorbs: 0->'A' 1->'G' 2->'C' 3->'T'), spread each 2-bit
-      // field to a nibble, and let PRMT pick the bytes.
-      const uint64_t y = __brevll(canon) >> (64 - 2 * K);
+      // ---- roll the forward strand: drop the low nibble, append at nibble K-1 ----
+#pragma unroll
+      for (int m = 0; m + 1 < NW; ++m) F[m] = funnel_r(F[m], F[m + 1], 4);
+      {
+        constexpr int TO = 4 * (LASTN - 1);
+        const int from = 4 * jj;
+        const uint32_t moved = TO >= from ? (in32 << (TO - from)) : (in32 >> (from - TO));
+        F[NW - 1] = (F[NW - 1] >> 4) | (moved & (0xFu << TO));
+      }
+      uint32_t C[NW];
+      if (CANON) {
+        // ---- roll the reverse complement: shift up one nibble, new complement at nibble 0 ----
+#pragma unroll
+        for (int m = NW - 1; m > 0; --m) R[m] = __funnelshift_l(R[m - 1], R[m], 4);
+        R[0] = (R[0] << 4) | ((in32c >> (4 * jj)) & 0xFu);
+        if (LASTN < 8) R[NW - 1] &= LASTMASK;
+        // ---- canonical = lexicographic min: compare the bit-reversed words, word 0 first ----
+        // borrow chain over the bit-reversed words, least significant (last) word first:
+        // mask = all ones iff F < R
+        uint32_t a[NW], b[NW], mask;
+#pragma unroll
+        for (int m = 0; m < NW; ++m) { a[m] = __brev(F[m]); b[m] = __brev(R[m]); }
+        if (NW == 1) {
+          asm("{.reg .u32 t; sub.cc.u32 t, %1, %2; subc.u32 %0, 0, 0;}" : "=r"(mask) : "r"(a[0]), "r"(b[0]));
+        } else if (NW == 2) {
+          asm("{.reg .u32 t; sub.cc.u32 t, %1, %2; subc.cc.u32 t, %3, %4; subc.u32 %0, 0, 0;}"
+              : "=r"(mask) : "r"(a[1]), "r"(b[1]), "r"(a[0]), "r"(b[0]));
+        } else if (NW == 3) {
+          asm("{.reg .u32 t; sub.cc.u32 t, %1, %2; subc.cc.u32 t, %3, %4; subc.cc.u32 t, %5, %6; subc.u32 %0, 0, 0;}"
+              : "=r"(mask) : "r"(a[2]), "r"(b[2]), "r"(a[1]), "r"(b[1]), "r"(a[0]), "r"(b[0]));
+        } else {
+          asm("{.reg .u32 t; sub.cc.u32 t, %1, %2; subc.cc.u32 t, %3, %4; subc.cc.u32 t, %5, %6; subc.cc.u32 t, %7, %8; subc.u32 %0, 0, 0;}"
+              : "=r"(mask) : "r"(a[NW - 1]), "r"(b[NW - 1]), "r"(a[NW > 2 ? 2 : 0]), "r"(b[NW > 2 ? 2 : 0]), "r"(a[1]), "r"(b[1]), "r"(a[0]), "r"(b[0]));
+        }
+#pragma unroll
+        for (int m = 0; m < NW; ++m) C[m] = (F[m] & mask) | (R[m] & ~mask);
+      } else {
+#pragma unroll
+        for (int m = 0; m < NW; ++m) C[m] = F[m];
+      }
+      // ---- ASCII expansion: each nibble is a PRMT selector into {0,'G','A',0,0,'T','C',0} ----
       uint64_t w[NW];
 #pragma unroll
       for (int m = 0; m < NW; ++m) {
-        constexpr uint32_t LUT = 0x54434741u;
-        const int nb = (K - 8 * m) < 8 ? (K - 8 * m) : 8;  // bases in this word
-        uint32_t x = (uint32_t)(y >> (16 * m)) & 0xFFFFu;
-        x = (x | (x << 8)) & 0x00FF00FFu;
-        x = (x | (x << 4)) & 0x0F0F0F0Fu;
-        x = (x | (x << 2)) & 0x33333333u;
-        if (nb < 8) x |= 0x44444444u << (4 * nb);         // bytes past the k-mer read as zero
-        const uint32_t lo = __byte_perm(LUT, 0u, x);
-        const uint32_t hi = __byte_perm(LUT, 0u, x >> 16);
+        const uint32_t lo = prmt(lut_lo, lut_hi, C[m]);
+        const uint32_t hi = prmt(lut_lo, lut_hi, C[m] >> 16);
         w[m] = (uint64_t)lo | ((uint64_t)hi << 32);
       }
       const uint64_t h = hg::t1ha2_kmer<K>(w, seed);
       if (h < threshold && ((kv8 >> jj) & 1u)) table_insert(table, gd.table_mask, h, count, status);
     }
   }
+  }  // kv32 != 0
+  }
+}
+
+// cta_genome[c] = genome that owns tile c * KH_WARPS: one warp per genome fills its range.
+__global__ void tile_map_kernel(const hg_genome_desc *__restrict__ desc, uint32_t n_genomes,
+                                uint32_t *__restrict__ cta_genome) {
+  const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= n_genomes) return;
+  const uint32_t c0 = (desc[g].first_tile + KH_WARPS - 1) / KH_WARPS;
+  const uint32_t c1 = (desc[g + 1].first_tile + KH_WARPS - 1) / KH_WARPS;
+  for (uint32_t c = c0 + lane; c < c1; c += 32) cta_genome[c] = g;
+}
+
+template <int K, bool CANON>
+int launch_kc(hg_ctx *ctx, uint32_t n_tiles, const uint8_t *d_seq, const hg_genome_desc *d_desc, uint32_t n_genomes,
+              uint64_t threshold, uint64_t seed, uint64_t *d_tables, uint32_t *d_counts) {
+  const uint32_t grid = (n_tiles + KH_WARPS - 1) / KH_WARPS;
+  void *d_map;
+  int rc = hg_scratch(ctx, 7, (size_t)grid * 4 + 256, &d_map);
+  if (rc) return rc;
+  tile_map_kernel<<<(n_genomes * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_desc, n_genomes, (uint32_t *)d_map);
+  kmer_hash_kernel<K, CANON><<<grid, KH_THREADS, 0, ctx->stream>>>(d_seq, d_desc, n_genomes, n_tiles, threshold, seed,
+                                                                   d_tables, d_counts, ctx->d_status, 0x00414700u,
+                                                                   0x00435400u, (const uint32_t *)d_map);
+  ctx->launches += 2;
+  HG_CUDA(cudaGetLastError());
+  return HG_OK;
 }
 
 template <int K>
 int launch_k(hg_ctx *ctx, bool canon, uint32_t n_tiles, const uint8_t *d_seq, const hg_genome_desc *d_desc,
              uint32_t n_genomes, uint64_t threshold, uint64_t seed, uint64_t *d_tables, uint32_t *d_counts) {
-  if (canon)
-    kmer_hash_kernel<K, true><<<n_tiles, KH_THREADS, 0, ctx->stream>>>(d_seq, d_desc, n_genomes, threshold,
-                                                                       seed, d_tables, d_counts, ctx->d_status);
-  else
-    kmer_hash_kernel<K, false><<<n_tiles, KH_THREADS, 0, ctx->stream>>>(d_seq, d_desc, n_genomes, threshold,
-                                                                        seed, d_tables, d_counts, ctx->d_status);
-  ctx->launches++;
-  HG_CUDA(cudaGetLastError());
-  return HG_OK;
+  return canon ? launch_kc<K, true>(ctx, n_tiles, d_seq, d_desc, n_genomes, threshold, seed, d_tables, d_counts)
+               : launch_kc<K, false>(ctx, n_tiles, d_seq, d_desc, n_genomes, threshold, seed, d_tables, d_counts);
 }
 
 }  // namespace
