@@ -64,7 +64,7 @@ extern "C" void hg_destroy(hg_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (int i = 0; i < 8; i++) if (c->d_scratch[i]) cudaFree(c->d_scratch[i]);
+  for (int i = 0; i < 12; i++) if (c->d_scratch[i]) cudaFree(c->d_scratch[i]);
   for (int i = 0; i < 4; i++) if (c->h_pinned[i]) cudaFreeHost(c->h_pinned[i]);
   if (c->d_status) cudaFree(c->d_status);
   for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);

@@ -2,6 +2,8 @@
 // Jaccard -> ANI (reference src/dist.rs:153-160) -> `ani >= ani_th` filter
 // (src/utils.rs:274-285) -> compacted append of (i, j, dot, ani).
 #pragma once
+#include <math.h>
+
 #include "hg_common.cuh"
 
 namespace hg {
@@ -13,6 +15,7 @@ struct DistEpilogue {
   uint32_t i0, j0;  // global index offsets of this shard
   float ksize_f;
   float ani_th;
+  float jmin;  // conservative Jaccard pre-filter (0 = off): pairs below it cannot reach ani_th
   int symmetric;
   hg_hit *__restrict__ hits;
   unsigned long long cap;
@@ -29,8 +32,16 @@ __device__ __forceinline__ void dist_emit(const DistEpilogue &e, bool live, uint
     gi = e.i0 + li;
     gj = e.j0 + lj;
     if (!e.symmetric || gj > gi) {  // dist.rs:253-265: only j > i when ref == query
-      ani = ani_from_dot(dot, e.ref_norm[li], e.qry_norm[lj], e.ksize_f);
-      keep = ani >= e.ani_th;
+      const int32_t nr = e.ref_norm[li], nq = e.qry_norm[lj];
+      bool cand = true;
+      if (e.jmin > 0.0f) {  // cheap monotone bound first; the exact f32 sequence decides
+        const int32_t den = (int32_t)((uint32_t)nr + (uint32_t)nq - (uint32_t)dot);
+        cand = den <= 0 || __int2float_rn(dot) >= e.jmin * __int2float_rn(den);
+      }
+      if (cand) {
+        ani = ani_from_dot(dot, nr, nq, e.ksize_f);
+        keep = ani >= e.ani_th;
+      }
     }
   }
   const uint32_t bal = __ballot_sync(0xffffffffu, keep);
@@ -47,6 +58,17 @@ __device__ __forceinline__ void dist_emit(const DistEpilogue &e, bool live, uint
       e.hits[idx] = h;
     }
   }
+}
+
+// Host: the Jaccard value below which ANI (dist.rs:154) cannot reach ani_th, lowered by a safety
+// margin (0.01 ANI points and 0.1 % relative) that dwarfs every f32 rounding in the exact path.
+inline float dist_jmin(float ani_th, uint32_t ksize) {
+  const double a = (double)ani_th / 100.0 - 1e-4;
+  if (!(a > 0.0)) return 0.0f;            // everything (ani >= 0 always) must be evaluated exactly
+  if (a >= 1.0) return 1e30f;             // ani is clamped to 100: nothing can pass, J bound irrelevant
+  const double E = exp((double)ksize * (a - 1.0));  // 2J/(1+J) = E
+  const double J = E / (2.0 - E);
+  return (float)(J * (1.0 - 1e-3));
 }
 
 }  // namespace hg

@@ -128,8 +128,8 @@ struct hg_ctx {
   cudaStream_t stream;
   unsigned long long launches;
   // grow-only device scratch
-  void *d_scratch[8];
-  size_t d_scratch_bytes[8];
+  void *d_scratch[12];
+  size_t d_scratch_bytes[12];
   // pinned host scratch
   void *h_pinned[4];
   size_t h_pinned_bytes[4];
