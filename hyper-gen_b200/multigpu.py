@@ -67,8 +67,9 @@ def broadcast_queries(qry_hv: torch.Tensor | None, qry_norm: torch.Tensor | None
     if rank != src:
         qry_hv = torch.empty((n, d), dtype=torch.int16, device=device)
         qry_norm = torch.empty((n,), dtype=torch.int32, device=device)
-    dist.broadcast(qry_hv, src=src)
-    dist.broadcast(qry_norm, src=src)
+    # moved as raw bytes: NCCL does not care, and gloo has no int16 kernels
+    dist.broadcast(qry_hv.view(torch.uint8), src=src)
+    dist.broadcast(qry_norm.view(torch.uint8), src=src)
     return qry_hv, qry_norm
 
 
