@@ -73,23 +73,32 @@ def broadcast_queries(qry_hv: torch.Tensor | None, qry_norm: torch.Tensor | None
     return qry_hv, qry_norm
 
 
-def gather_hits(local_hits: np.ndarray, device, dst: int = 0) -> np.ndarray | None:
-    """Variable-length hit lists -> one array on rank `dst` (sorted by (i, j)); None elsewhere."""
+def gather_hits(local_hits, device, dst: int = 0, count: int | None = None) -> np.ndarray | None:
+    """Variable-length hit lists -> one array on rank `dst` (sorted by (i, j)); None elsewhere.
+
+    `local_hits` is either a numpy HIT_DTYPE array or a uint8 torch tensor already on `device`
+    holding `count` packed hg_hit records (the CUDA path: nothing touches the host until rank
+    `dst` reads the gathered buffer once)."""
     world = dist.get_world_size()
-    cnt = torch.tensor([local_hits.size], dtype=torch.int64, device=device)
-    counts = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(counts, cnt)
-    counts = [int(c.item()) for c in counts]
+    isz = HIT_DTYPE.itemsize
+    if isinstance(local_hits, np.ndarray):
+        count = int(local_hits.size)
+        raw = torch.from_numpy(np.frombuffer(local_hits.tobytes(), dtype=np.uint8).copy()).to(device)
+    else:
+        raw = local_hits[: count * isz]
+    cnt = torch.tensor([count], dtype=torch.int64, device=device)
+    counts = torch.zeros(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(counts, cnt)
+    counts = counts.tolist()  # one host read: sizes the second collective
     mx = max(max(counts), 1)
-    buf = torch.zeros(mx * HIT_DTYPE.itemsize, dtype=torch.uint8, device=device)
-    if local_hits.size:
-        raw = torch.from_numpy(np.frombuffer(local_hits.tobytes(), dtype=np.uint8).copy())
-        buf[: raw.numel()] = raw.to(device)
-    bufs = [torch.zeros_like(buf) for _ in range(world)]
-    dist.all_gather(bufs, buf)
+    buf = torch.zeros(mx * isz, dtype=torch.uint8, device=device)
+    buf[: raw.numel()] = raw
+    allbuf = torch.empty(world * mx * isz, dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(allbuf, buf)
     if dist.get_rank() != dst:
         return None
-    parts = [np.frombuffer(bufs[r].cpu().numpy().tobytes(), dtype=HIT_DTYPE)[: counts[r]] for r in range(world)]
+    host = allbuf.cpu().numpy()
+    parts = [np.frombuffer(host[r * mx * isz:(r * mx + counts[r]) * isz].tobytes(), dtype=HIT_DTYPE) for r in range(world)]
     allh = np.concatenate(parts) if parts else np.zeros(0, HIT_DTYPE)
     return allh[np.lexsort((allh["j"], allh["i"]))]
 
