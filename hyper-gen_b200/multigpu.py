@@ -74,7 +74,8 @@ def broadcast_queries(qry_hv: torch.Tensor | None, qry_norm: torch.Tensor | None
 
 
 def gather_hits(local_hits, device, dst: int = 0, count: int | None = None) -> np.ndarray | None:
-    """Variable-length hit lists -> one array on rank `dst` (sorted by (i, j)); None elsewhere.
+    """Variable-length hit lists -> one array on rank `dst` (rank order, unsorted — the output
+    stage orders hits, dist.reference_output_order); None elsewhere.
 
     `local_hits` is either a numpy HIT_DTYPE array or a uint8 torch tensor already on `device`
     holding `count` packed hg_hit records (the CUDA path: nothing touches the host until rank
@@ -99,8 +100,7 @@ def gather_hits(local_hits, device, dst: int = 0, count: int | None = None) -> n
         return None
     host = allbuf.cpu().numpy()
     parts = [np.frombuffer(host[r * mx * isz:(r * mx + counts[r]) * isz].tobytes(), dtype=HIT_DTYPE) for r in range(world)]
-    allh = np.concatenate(parts) if parts else np.zeros(0, HIT_DTYPE)
-    return allh[np.lexsort((allh["j"], allh["i"]))]
+    return np.concatenate(parts) if parts else np.zeros(0, HIT_DTYPE)
 
 
 def dist_sharded(compute, ref_hv, ref_norm, qry_hv, qry_norm, n_ref: int, n_qry: int, hv_d: int, symmetric: bool,
