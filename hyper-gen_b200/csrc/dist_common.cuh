@@ -16,6 +16,7 @@ struct DistEpilogue {
   float ksize_f;
   float ani_th;
   float jmin;  // conservative Jaccard pre-filter (0 = off): pairs below it cannot reach ani_th
+  float cfrac; // jmin / (1 + jmin): dot >= cfrac * (norm_r + norm_q) is the same bound, division-free
   int symmetric;
   hg_hit *__restrict__ hits;
   unsigned long long cap;

@@ -103,6 +103,7 @@ int hg_launch_dist_simt(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_
   ep.n_ref = n_ref; ep.n_qry = n_qry; ep.i0 = i0; ep.j0 = j0;
   ep.ksize_f = (float)ksize; ep.ani_th = ani_th; ep.symmetric = symmetric;
   ep.jmin = hg::dist_jmin(ani_th, ksize);
+  ep.cfrac = ep.jmin > 0.0f ? (float)((double)ep.jmin / (1.0 + (double)ep.jmin)) : 0.0f;
   ep.hits = d_hits; ep.cap = cap; ep.n_hits = d_n_hits;
   const uint32_t gx = (n_qry + DS_TILE - 1) / DS_TILE, gy_total = (n_ref + DS_TILE - 1) / DS_TILE;
   // gridDim.y <= 65535: slice the rows if a shard is taller than 4.19 M sketches

@@ -12,10 +12,11 @@
 // is accumulated as three s32 accumulators (the two cross products share one), each < 2^31
 // for D <= 32768.  The recombination wraps in i32 exactly like the reference's i32 sum.
 //
-// One CTA per 128 x 128 output tile, 6 warps: warp 0 issues TMA loads of the four 128 x 128 B
+// One CTA per 128 x 128 output tile, 10 warps: warp 0 issues TMA loads of the four 128 x 128 B
 // operand tiles (128B-swizzled, K-major) through a 3-stage mbarrier ring, one thread of warp 1
-// issues the tcgen05.mma stream and commits stage releases, warps 2-5 drain the three TMEM
-// accumulators with tcgen05.ld and run the shared epilogue (dist_common.cuh).
+// issues the tcgen05.mma stream and commits stage releases, warps 2-9 drain the three TMEM
+// accumulators with tcgen05.ld, apply a division-free bound and run the shared exact epilogue
+// (dist_common.cuh) only where a pair can reach the threshold.
 #include <cuda.h>
 
 #include "dist_common.cuh"
@@ -26,8 +27,9 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 128;  // BK in bytes == int8 ele
 constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = 128 * TC_BK;            // one operand tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;     // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_EPI_WARPS = 8;                      // two per TMEM lane quarter, half the columns each
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*col bounds*/;
 constexpr uint32_t TC_TMEM_COLS = 512;
 
 // instruction descriptor, kind::i8: D = s32, A = B = signed 8-bit, both K-major, M = 128, N = 128
@@ -155,24 +157,61 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
       umma_commit(accum_bar);       // all accumulators final
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> exact i32 dot -> ANI -> filter -> append =====
+    // ===== epilogue: TMEM -> registers -> exact i32 dot -> bound test -> (rare) ANI + append =====
+    // Cheap per-element test first: ani >= ani_th implies dot >= cfrac * (norm_r + norm_q)
+    // (dist_common.cuh), split into a per-row and a per-column integer so that an element
+    // costs two shift-adds, one add and one compare.  Only 16-column chunks in which some
+    // lane passes run the exact f32 ANI sequence and the compacted append.
+    const int ew = warp - 2;                 // 0..7
+    const uint32_t q = warp & 3;             // TMEM lane quarter this warp may read
+    const int half = (ew >> 2);              // which 64 columns this warp drains
+    int32_t *s_tq = reinterpret_cast<int32_t *>(aligned + TC_STAGES * TC_STAGE_BYTES + 256);
+    const bool use_bound = ep.cfrac > 0.0f;
+    {  // per-column bounds, one column per epilogue thread of the first four warps
+      const int t = threadIdx.x - 64;
+      if (t < TC_BN) {
+        const uint32_t lj = col0 + t;
+        int32_t v = INT32_MIN;  // out-of-range / degenerate columns always go to the exact path
+        if (use_bound && lj < ep.n_qry) {
+          const int32_t nq = ep.qry_norm[lj];
+          if (nq > 0) v = __float2int_rd(ep.cfrac * __int2float_rz(nq)) - 1;
+        }
+        s_tq[t] = v;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");  // epilogue warps only
+    const uint32_t li = row0 + q * 32 + lane;
+    const bool row_live = li < ep.n_ref;
+    int32_t tr = INT32_MIN / 2;
+    if (use_bound && row_live) {
+      const int32_t nr = ep.ref_norm[li];
+      if (nr > 0) tr = __float2int_rd(ep.cfrac * __int2float_rz(nr)) - 1;
+    }
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t q = warp & 3;  // TMEM lane quarter this warp may read
-    const uint32_t li = row0 + q * 32 + lane;
     const uint32_t taddr = tmem_base + ((q * 32u) << 16);
 #pragma unroll 1
-    for (int c = 0; c < TC_BN; c += 16) {
+    for (int c = half * (TC_BN / 2); c < (half + 1) * (TC_BN / 2); c += 16) {
       uint32_t hh[16], cr[16], ll[16];
       tmem_ld16(taddr + 0 * TC_BN + c, hh);
       tmem_ld16(taddr + 1 * TC_BN + c, cr);
       tmem_ld16(taddr + 2 * TC_BN + c, ll);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      int32_t dot[16];
+      bool any = false;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int32_t dot = (int32_t)((hh[j] << 14) + (cr[j] << 7) + ll[j]);  // wrapping i32, as dist.rs:147-151
-        const uint32_t lj = col0 + c + j;
-        hg::dist_emit(ep, li < ep.n_ref && lj < ep.n_qry, li, lj, dot);
+        dot[j] = (int32_t)((((hh[j] << 7) + cr[j]) << 7) + ll[j]);  // wrapping i32, as dist.rs:147-151
+        const int32_t tq = s_tq[c + j];
+        // tq = INT32_MIN or tr = INT32_MIN / 2 make the sum so negative that the pair is a candidate
+        any |= dot[j] >= (int32_t)((uint32_t)tr + (uint32_t)tq) || tq == INT32_MIN || tr == INT32_MIN / 2;
+      }
+      if (__any_sync(0xffffffffu, any && row_live)) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t lj = col0 + c + j;
+          hg::dist_emit(ep, row_live && lj < ep.n_qry, li, lj, dot[j]);
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -287,6 +326,7 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
     ep.ksize_f = (float)ksize;
     ep.ani_th = ani_th;
     ep.jmin = hg::dist_jmin(ani_th, ksize);
+  ep.cfrac = ep.jmin > 0.0f ? (float)((double)ep.jmin / (1.0 + (double)ep.jmin)) : 0.0f;
     ep.symmetric = symmetric;
     ep.hits = d_hits;
     ep.cap = cap;
