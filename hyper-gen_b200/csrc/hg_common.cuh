@@ -143,6 +143,9 @@ struct hg_ctx {
   int prof;
   cudaEvent_t ev[8];
   int ev_used;           // which stage boundaries were recorded in the last call
+  // H2D pipeline of the host-pointer sketch entry
+  cudaStream_t copy_stream;
+  cudaEvent_t ev_copied[2], ev_done[2];
 };
 
 // stage boundaries: 0 start, 1 after staging/memsets, 2 after k-mer hash, 3 after encode,

@@ -322,6 +322,7 @@ int launch_k(hg_ctx *ctx, bool canon, uint32_t n_tiles, const uint8_t *d_seq, co
 }  // namespace
 
 uint32_t hg_kmer_tile_positions() { return KH_TILE; }
+uint32_t hg_kmer_tiles_per_cta() { return KH_WARPS; }
 
 int hg_launch_kmer_hash(hg_ctx *ctx, const uint8_t *d_seq, const hg_genome_desc *d_desc, uint32_t n_genomes,
                         uint32_t n_tiles, const hg_sketch_params *p, uint64_t *d_tables, uint32_t *d_counts) {
