@@ -83,5 +83,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_SRC = os.path.join(HERE, "host", "hyper_gen.cpp")
+HOST_BIN = os.path.join(HERE, "bin", "hyper-gen")
+
+
+def build_host(force: bool = False) -> str:
+    """The C++ host (hyper-gen sketch / dist CLI) on top of the C ABI."""
+    build(force=False)
+    if (not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) > os.path.getmtime(HOST_SRC)
+            and os.path.getmtime(HOST_BIN) > os.path.getmtime(LIB)):
+        return HOST_BIN
+    os.makedirs(os.path.dirname(HOST_BIN), exist_ok=True)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-pthread", HOST_SRC, "-o", HOST_BIN, "-L" + HERE, "-lhypergen_b200",
+           "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

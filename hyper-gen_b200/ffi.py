@@ -50,9 +50,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if _build.needs_build():
-        _build.build()
-    L = C.CDLL(lib_path())
+    override = os.environ.get("HG_LIB")  # kernel-variant experiments only
+    if override:
+        L = C.CDLL(override)
+    else:
+        if _build.needs_build():
+            _build.build()
+        L = C.CDLL(lib_path())
     vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
     pp = C.POINTER(SketchParams)
     L.hg_init.restype = i32; L.hg_init.argtypes = [i32, C.POINTER(vp)]

@@ -1,0 +1,311 @@
+// hyper_gen.cpp — the host side of the hot path in C++, above the C ABI (include/hypergen_b200.h).
+//
+// The reference's host is Rust; no Rust toolchain exists in this image, so the drivers that sit
+// on top of the FFI are mirrored here with the same names, arguments and file formats:
+//
+//   utils::get_fasta_files          src/utils.rs:208-221     *.fna, *.fa, *.fasta (each sorted)
+//   fastx_reader::read_merge_seq    src/fastx_reader.rs:6-29 sequence lines joined, 'N' per header
+//   sketch_cuda::sketch_cuda        src/sketch_cuda.rs:43-117
+//   utils::dump_sketch/load_sketch  src/utils.rs:234-258     bincode 1.x Vec<FileSketch>
+//   dist::dist                      src/dist.rs:11-63
+//   utils::dump_ani_file            src/utils.rs:260-308     stable sort by ANI, reversed, >= threshold
+//
+// CLI (same flags as src/utils.rs:44-126):
+//   hyper-gen sketch -p <dir> -o <out> [-k 21] [-s 1500] [-S 123] [-d 4096] [-C true] [-t 16]
+//   hyper-gen dist   -r <ref sketch> -q <query sketch> -o <out> [-a 85.0]
+// The GPU path is the only path (`-D gpu` is implied): there is no CPU fallback.
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <glob.h>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/hypergen_b200.h"
+
+namespace types {
+
+struct SketchParams {  // src/types.rs:83-113
+  std::string path, out_file;
+  bool canonical = true;
+  uint8_t ksize = 21;
+  uint64_t seed = 123, scaled = 1500;
+  size_t hv_d = 4096;
+  int threads = 16;
+};
+
+struct FileSketch {  // src/types.rs:224-235
+  uint8_t ksize = 21;
+  uint64_t scaled = 1500;
+  bool canonical = true;
+  uint64_t seed = 123;
+  uint64_t hv_d = 4096;
+  uint8_t hv_quant_bits = 16;
+  int32_t hv_norm_2 = 0;
+  std::string file_str;
+  std::vector<int16_t> hv;
+};
+
+struct SketchDist {  // src/types.rs:237-245
+  std::string path_ref_sketch, path_query_sketch, out_file;
+  float ani_threshold = 85.0f;
+};
+
+}  // namespace types
+
+[[noreturn]] static void die(const std::string &msg) {
+  fprintf(stderr, "hyper-gen: %s\n", msg.c_str());
+  exit(1);
+}
+static void check(int rc, const char *what) {
+  if (rc != HG_OK) die(std::string(what) + ": " + hg_last_error());
+}
+
+namespace utils {
+
+std::vector<std::string> get_fasta_files(const std::string &path) {
+  std::vector<std::string> all;
+  for (const char *pat : {"*.fna", "*.fa", "*.fasta"}) {
+    glob_t g;
+    if (glob((path + "/" + pat).c_str(), 0, nullptr, &g) == 0)
+      for (size_t i = 0; i < g.gl_pathc; i++) all.emplace_back(g.gl_pathv[i]);  // glob() sorts
+    globfree(&g);
+  }
+  return all;
+}
+
+template <class T> static void put(std::string &b, T v) { b.append(reinterpret_cast<const char *>(&v), sizeof(T)); }
+
+void dump_sketch(const std::vector<types::FileSketch> &fs, const std::string &out) {
+  std::string b;
+  put<uint64_t>(b, fs.size());
+  for (const auto &s : fs) {
+    put<uint8_t>(b, s.ksize);
+    put<uint64_t>(b, s.scaled);
+    put<uint8_t>(b, s.canonical ? 1 : 0);
+    put<uint64_t>(b, s.seed);
+    put<uint64_t>(b, s.hv_d);
+    put<uint8_t>(b, s.hv_quant_bits);
+    put<int32_t>(b, s.hv_norm_2);
+    put<uint64_t>(b, s.file_str.size());
+    b += s.file_str;
+    put<uint64_t>(b, s.hv.size());
+    b.append(reinterpret_cast<const char *>(s.hv.data()), s.hv.size() * 2);
+  }
+  std::ofstream f(out, std::ios::binary);
+  if (!f) die("Dump sketch file failed!");
+  f.write(b.data(), (std::streamsize)b.size());
+  fprintf(stdout, "Dump sketch file to %s with size %.2f MB\n", out.c_str(), b.size() / 1024.0 / 1024.0);
+}
+
+std::vector<types::FileSketch> load_sketch(const std::string &path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) die("Opening sketch file failed!");
+  std::string d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  size_t pos = 0;
+  auto get = [&](void *out, size_t n) {
+    if (pos + n > d.size()) die("sketch file truncated: " + path);
+    memcpy(out, d.data() + pos, n);
+    pos += n;
+  };
+  uint64_t n;
+  get(&n, 8);
+  std::vector<types::FileSketch> out(n);
+  for (auto &s : out) {
+    uint8_t c;
+    uint64_t len;
+    get(&s.ksize, 1); get(&s.scaled, 8); get(&c, 1); s.canonical = c != 0;
+    get(&s.seed, 8); get(&s.hv_d, 8); get(&s.hv_quant_bits, 1); get(&s.hv_norm_2, 4);
+    get(&len, 8); s.file_str.resize(len); get(&s.file_str[0], len);
+    get(&len, 8); s.hv.resize(len); get(s.hv.data(), len * 2);
+  }
+  return out;
+}
+
+}  // namespace utils
+
+namespace fastx_reader {
+
+std::vector<uint8_t> read_merge_seq(const std::string &file_name) {
+  std::ifstream f(file_name, std::ios::binary);
+  if (!f) die("Opening .fna files failed: " + file_name);
+  std::string d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  std::vector<uint8_t> out;
+  out.reserve(d.size());
+  size_t i = 0;
+  while (i < d.size()) {
+    size_t e = d.find('\n', i);
+    size_t end = e == std::string::npos ? d.size() : e;  // line without its '\n'
+    if (d[i] == '>') {
+      out.push_back('N');
+    } else {
+      size_t le = end;
+      if (le > i && d[le - 1] == '\r') le--;
+      out.insert(out.end(), d.begin() + (long)i, d.begin() + (long)le);
+    }
+    i = e == std::string::npos ? d.size() : e + 1;
+  }
+  return out;
+}
+
+}  // namespace fastx_reader
+
+namespace sketch_cuda {
+
+void sketch_cuda(const types::SketchParams &params) {
+  const auto files = utils::get_fasta_files(params.path);
+  const size_t n_file = files.size();
+  fprintf(stdout, "Start GPU sketching...\n");
+  hg_ctx *ctx = nullptr;
+  check(hg_init(0, &ctx), "hg_init");
+  hg_sketch_params p{};
+  p.scaled = params.scaled; p.seed = params.seed; p.hv_d = (uint32_t)params.hv_d;
+  p.ksize = params.ksize; p.canonical = params.canonical ? 1 : 0;
+  const size_t D = params.hv_d;
+  std::vector<types::FileSketch> all(n_file);
+  const size_t batch_files = 256;
+  for (size_t b0 = 0; b0 < n_file; b0 += batch_files) {
+    const size_t b1 = std::min(n_file, b0 + batch_files), m = b1 - b0;
+    // host FASTA reading in parallel (the reference's rayon par_iter over files)
+    std::vector<std::vector<uint8_t>> seqs(m);
+    {
+      std::vector<std::thread> th;
+      const int nt = std::max(1, std::min<int>(params.threads, (int)m));
+      for (int t = 0; t < nt; t++)
+        th.emplace_back([&, t] { for (size_t i = (size_t)t; i < m; i += (size_t)nt) seqs[i] = fastx_reader::read_merge_seq(files[b0 + i]); });
+      for (auto &x : th) x.join();
+    }
+    std::vector<uint64_t> seg_off(m + 1, 0);
+    for (size_t i = 0; i < m; i++) seg_off[i + 1] = seg_off[i] + seqs[i].size();
+    std::vector<uint8_t> seq(seg_off[m]);
+    for (size_t i = 0; i < m; i++) if (!seqs[i].empty()) memcpy(seq.data() + seg_off[i], seqs[i].data(), seqs[i].size());
+    std::vector<uint8_t> packed(m * 2 * D), bits(m);
+    std::vector<int32_t> norm2(m);
+    std::vector<uint32_t> nh(m);
+    check(hg_sketch_batch(ctx, seq.data(), seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
+                          norm2.data(), nh.data()), "hg_sketch_batch");
+    for (size_t i = 0; i < m; i++) {
+      types::FileSketch &s = all[b0 + i];
+      s.ksize = params.ksize; s.scaled = params.scaled; s.seed = params.seed; s.canonical = params.canonical;
+      s.hv_d = D; s.hv_quant_bits = bits[i]; s.hv_norm_2 = norm2[i]; s.file_str = files[b0 + i];
+      const size_t nbytes = (size_t)bits[i] * D / 8;  // hd.rs:146
+      s.hv.resize(nbytes / 2);
+      memcpy(s.hv.data(), packed.data() + i * 2 * D, nbytes);  // hd.rs:155-157: bytes viewed as i16
+    }
+  }
+  hg_destroy(ctx);
+  utils::dump_sketch(all, params.out_file);
+}
+
+}  // namespace sketch_cuda
+
+namespace dist {
+
+struct Stacked { std::vector<uint8_t> packed, bits; std::vector<int32_t> norm; };
+static Stacked stack(const std::vector<types::FileSketch> &fs, size_t D) {
+  Stacked s;
+  s.packed.assign(fs.size() * 2 * D, 0); s.bits.resize(fs.size()); s.norm.resize(fs.size());
+  for (size_t i = 0; i < fs.size(); i++) {
+    memcpy(s.packed.data() + i * 2 * D, fs[i].hv.data(), std::min(fs[i].hv.size() * 2, 2 * D));
+    s.bits[i] = fs[i].hv_quant_bits; s.norm[i] = fs[i].hv_norm_2;
+  }
+  return s;
+}
+
+void dist(const types::SketchDist &sd) {
+  const bool if_sym = sd.path_ref_sketch == sd.path_query_sketch;  // dist.rs:13
+  auto ref = utils::load_sketch(sd.path_ref_sketch);
+  auto qry = if_sym ? ref : utils::load_sketch(sd.path_query_sketch);
+  if (ref.empty() || qry.empty()) die("empty sketch file");
+  if (ref[0].ksize != qry[0].ksize) die("Ref and query sketches use different kmer sizes!");
+  if (ref[0].hv_d != qry[0].hv_d) die("Ref and query sketches use different HV dimensions!");
+  const size_t D = ref[0].hv_d, R = ref.size(), Q = qry.size();
+  hg_ctx *ctx = nullptr;
+  check(hg_init(0, &ctx), "hg_init");
+  Stacked rs = stack(ref, D);
+  std::vector<int16_t> rhv(R * D), qhv_store;
+  check(hg_unpack(ctx, rs.packed.data(), 2 * D, rs.bits.data(), (uint32_t)R, (uint32_t)D, rhv.data()), "hg_unpack");
+  const int16_t *qhv = rhv.data();
+  const int32_t *qn = rs.norm.data();
+  Stacked qs;
+  if (!if_sym) {
+    qs = stack(qry, D);
+    qhv_store.resize(Q * D);
+    check(hg_unpack(ctx, qs.packed.data(), 2 * D, qs.bits.data(), (uint32_t)Q, (uint32_t)D, qhv_store.data()), "hg_unpack");
+    qhv = qhv_store.data();
+    qn = qs.norm.data();
+  }
+  uint64_t cap = 1 << 20, n_hits = 0;
+  std::vector<hg_hit> hits;
+  for (;;) {
+    hits.resize(cap);
+    const int rc = hg_dist(ctx, rhv.data(), rs.norm.data(), (uint32_t)R, qhv, qn, (uint32_t)Q, (uint32_t)D, ref[0].ksize,
+                           sd.ani_threshold, if_sym ? 1 : 0, 0, hits.data(), cap, &n_hits);
+    if (rc == HG_E_CAPACITY && n_hits > cap) { cap = n_hits; continue; }
+    check(rc, "hg_dist");
+    break;
+  }
+  hits.resize(n_hits);
+  hg_destroy(ctx);
+  // dump_ani_file (utils.rs:262-285): stable ascending sort over the pair enumeration, reversed
+  auto pair_index = [&](const hg_hit &h) -> uint64_t {
+    const uint64_t i = h.i, j = h.j;
+    return if_sym ? i * (Q - 1) - i * (i - 1) / 2 + (j - i - 1) : i * Q + j;
+  };
+  std::sort(hits.begin(), hits.end(), [&](const hg_hit &a, const hg_hit &b) {
+    if (a.ani != b.ani) return a.ani > b.ani;
+    return pair_index(a) > pair_index(b);
+  });
+  std::string csv;
+  char buf[64];
+  for (const auto &h : hits) {
+    csv += ref[h.i].file_str; csv += '\t'; csv += qry[h.j].file_str;
+    snprintf(buf, sizeof(buf), "\t%.3f\n", (double)h.ani);
+    csv += buf;
+  }
+  std::ofstream f(sd.out_file, std::ios::binary);
+  if (!f) die("Dump ANI file failed!");
+  f.write(csv.data(), (std::streamsize)csv.size());
+  const double total = if_sym ? (double)R * (double)(Q - 1) / 2.0 : (double)R * (double)Q;
+  fprintf(stdout, "Output %zu of %.0f ANIs above threshold %.1f to file %s\n", hits.size(), total,
+          (double)sd.ani_threshold, sd.out_file.c_str());
+}
+
+}  // namespace dist
+
+int main(int argc, char **argv) {
+  if (argc < 2) die("usage: hyper-gen <sketch|dist> ...");
+  const std::string mode = argv[1];
+  types::SketchParams sp;
+  types::SketchDist sd;
+  for (int i = 2; i + 1 < argc; i += 2) {
+    const std::string k = argv[i], v = argv[i + 1];
+    if (k == "-p" || k == "--path") sp.path = v;
+    else if (k == "-o" || k == "--out") { sp.out_file = v; sd.out_file = v; }
+    else if (k == "-r" || k == "--path_r") sd.path_ref_sketch = v;
+    else if (k == "-q" || k == "--path_q") sd.path_query_sketch = v;
+    else if (k == "-t" || k == "--thread") sp.threads = atoi(v.c_str());
+    else if (k == "-C" || k == "--canonical") sp.canonical = (v == "true" || v == "1");
+    else if (k == "-k" || k == "--ksize") sp.ksize = (uint8_t)atoi(v.c_str());
+    else if (k == "-S" || k == "--seed") sp.seed = strtoull(v.c_str(), nullptr, 10);
+    else if (k == "-s" || k == "--scaled") sp.scaled = strtoull(v.c_str(), nullptr, 10);
+    else if (k == "-d" || k == "--hv_d") sp.hv_d = strtoull(v.c_str(), nullptr, 10);
+    else if (k == "-a" || k == "--ani_th") sd.ani_threshold = (float)atof(v.c_str());
+    else if (k == "-D" || k == "--device" || k == "-m" || k == "--sketch_method" || k == "-Q" || k == "--quant_scale") {}
+    else die("unknown flag " + k);
+  }
+  if (mode == "sketch") {
+    if (sp.path.empty() || sp.out_file.empty()) die("sketch needs -p and -o");
+    sketch_cuda::sketch_cuda(sp);
+  } else if (mode == "dist") {
+    if (sd.path_ref_sketch.empty() || sd.path_query_sketch.empty() || sd.out_file.empty()) die("dist needs -r -q -o");
+    dist::dist(sd);
+  } else {
+    die("unknown subcommand " + mode);
+  }
+  return 0;
+}

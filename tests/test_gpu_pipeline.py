@@ -66,3 +66,27 @@ def test_encode_sets_hook(ctx, hg, oracle):
             b, packed = oracle.compress_hd_sketch(hv)
             assert got["quant_bits"][t] == b and got["norm2"][t] == oracle.hv_l2_norm_sq(hv)
             assert np.array_equal(got["packed"][t, :packed.size], packed)
+
+
+def test_cpp_host_cli_matches_python_host(ctx, hg, oracle, tmp_path):
+    """The C++ host (hyper-gen sketch / dist) writes the same sketch file and TSV."""
+    import subprocess
+    from hypergen_b200 import synth, sketch, dist, _build
+    exe = _build.build_host()
+    d = tmp_path / "genomes"
+    d.mkdir()
+    for g in range(9):
+        _write_fasta(str(d / ("s%02d.fna" % g)), synth.family_member(g + 20, 120_000).numpy(), "s%d" % g, records=1 + g % 2)
+    out_py, out_cc = str(tmp_path / "py.sketch"), str(tmp_path / "cc.sketch")
+    sketch.sketch(sketch.SketchParams(path=str(d), out_file=out_py, scaled=500, hv_d=1024), ctx=ctx)
+    subprocess.check_call([exe, "sketch", "-p", str(d), "-o", out_cc, "-s", "500", "-d", "1024", "-t", "4"])
+    assert open(out_py, "rb").read() == open(out_cc, "rb").read()
+    tsv_py = dist.dist(dist.SketchDist(out_py, out_py, str(tmp_path / "py.tsv"), ani_threshold=80.0), ctx=ctx)
+    subprocess.check_call([exe, "dist", "-r", out_cc, "-q", out_cc, "-o", str(tmp_path / "cc.tsv"), "-a", "80.0"])
+    assert open(tmp_path / "cc.tsv").read() == tsv_py and tsv_py
+    # ref != query path => full R x Q grid (dist.rs:13)
+    out2 = str(tmp_path / "copy.sketch")
+    open(out2, "wb").write(open(out_cc, "rb").read())
+    tsv2 = dist.dist(dist.SketchDist(out_py, out2, "", ani_threshold=80.0), ctx=ctx)
+    subprocess.check_call([exe, "dist", "-r", out_cc, "-q", out2, "-o", str(tmp_path / "cc2.tsv"), "-a", "80.0"])
+    assert open(tmp_path / "cc2.tsv").read() == tsv2
