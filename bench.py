@@ -108,9 +108,31 @@ def cpu_sketch_baseline(seq_host: np.ndarray, n_avail: int, seconds_hint: float 
     t0 = time.perf_counter()
     O.sketch_batch(seq_host[: n * GENOME_LEN], off, k=K, scaled=SCALED, seed=SEED, hv_d=HV_D, want_hv=False)
     dt = time.perf_counter() - t0
-    return dict(value=n / dt, unit="genomes/s", cores=cores, kind="port",
+    O.set_threads(1)
+    t1 = time.perf_counter()
+    O.sketch_batch(seq_host[: 4 * GENOME_LEN], off[:5], k=K, scaled=SCALED, seed=SEED, hv_d=HV_D, want_hv=False)
+    per_core = 4 / (time.perf_counter() - t1)
+    O.set_threads(cores)
+    return dict(value=n / dt, unit="genomes/s", cores=cores, kind="port", value_1_thread=per_core,
                 sample="%d of the step's 5 Mbp genomes, oracle/hg_oracle.c (C restatement of src/sketch.rs:35-52), %d threads, %.1f s"
                 % (n, cores, dt))
+
+
+def parity_sample(seq_host, packed, bits, norm, n):
+    """Checker leg: the e2e results of a few genomes of the timed batch against the oracle."""
+    import oracle as O
+    pick = sorted(set([0, 1, n // 2, n - 1]))
+    bad = 0
+    for g in pick:
+        s = seq_host[g * GENOME_LEN:(g + 1) * GENOME_LEN]
+        w = O.sketch_batch(s, np.array([0, GENOME_LEN], np.uint64), k=K, scaled=SCALED, seed=SEED, hv_d=HV_D, want_hv=False)
+        nb = int(w["quant_bits"][0]) * HV_D // 8
+        ok = (int(w["quant_bits"][0]) == int(bits[g]) and int(w["norm2"][0]) == int(norm[g])
+              and np.array_equal(w["packed"][0, :nb], packed[g, :nb]))
+        bad += 0 if ok else 1
+    if bad:
+        raise RuntimeError("parity check failed on %d of %d sampled genomes" % (bad, len(pick)))
+    return "ok: %d sampled genomes of the timed batch bit-identical to the oracle (packed HV, bits, norm)" % len(pick)
 
 
 def run_reference(args, rank):
@@ -328,6 +350,7 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_sketch_baseline(seq_host.numpy(), n)
+        line["parity_check"] = parity_sample(seq_host.numpy(), h_packed.numpy(), h_bits.numpy(), h_norm.numpy(), n)
     elif rank == 0:
         line["cpu_baseline"] = None
 
@@ -417,18 +440,33 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
     out["roofline"] = {"bound": "tensor", "achieved": alg_ops / (kms * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s",
                        "frac": alg_ops / (kms * 1e-3) / 1e12 / int8_peak,
                        "note": "algorithmic 2*D ops per pair; peak = 2 x measured bf16 (int8 MMA rate); the limb split executes 3x these MACs"}
-    # e2e through the host-pointer call (N=1 only: H2D of both matrices, D2H of the hits)
+    # e2e through the host-pointer C-ABI call (N=1 only): pinned host matrices in, hits out
     if world == 1:
-        hv_h = hv.cpu().numpy()
-        norm_h = norm.cpu().numpy()
-        ctx.dist(hv_h, norm_h, hv_h, norm_h, ksize=K, ani_th=85.0, symmetric=True, cap=cap)
+        import ctypes as C
+        lib = hg.ffi.load()
+        hv_h = torch.empty((nq, D), dtype=torch.int16, pin_memory=True)
+        norm_h = torch.empty(nq, dtype=torch.int32, pin_memory=True)
+        hv_h.copy_(hv)
+        norm_h.copy_(norm)
+        hits_h = torch.empty(cap * 16, dtype=torch.uint8, pin_memory=True)
+        torch.cuda.synchronize()
+        n_hits_c = C.c_uint64(0)
+
+        def e2e():
+            rc = lib.hg_dist(ctx._h, hv_h.data_ptr(), norm_h.data_ptr(), nq, hv_h.data_ptr(), norm_h.data_ptr(), nq, D, K,
+                             85.0, 1, path_sel[0], hits_h.data_ptr(), cap, C.byref(n_hits_c))
+            if rc != 0:
+                raise RuntimeError(lib.hg_last_error().decode())
+
+        e2e()
         t0 = time.perf_counter()
-        reps = 3
+        reps = 5
         for _ in range(reps):
-            hits = ctx.dist(hv_h, norm_h, hv_h, norm_h, ksize=K, ani_th=85.0, symmetric=True, cap=cap)
+            e2e()
         dt = (time.perf_counter() - t0) / reps
-        out["e2e"] = {"value": n_pairs / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(hv_h.nbytes + norm_h.nbytes),
-                      "d2h_bytes_per_step": int(hits.nbytes + 8), "ms_per_step": dt * 1e3}
+        assert n_hits_c.value == n_hits
+        out["e2e"] = {"value": n_pairs / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(hv_h.numel() * 2 + norm_h.numel() * 4),
+                      "d2h_bytes_per_step": int(n_hits_c.value * 16 + 8), "ms_per_step": dt * 1e3}
     return out
 
 

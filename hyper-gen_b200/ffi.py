@@ -235,7 +235,7 @@ class Context:
     # -- stage 2 --
     def dist(self, ref_hv, ref_norm2, qry_hv, qry_norm2, ksize=21, ani_th=85.0, symmetric=False, path=0,
              cap=None) -> np.ndarray:
-        """hg_dist with host buffers -> structured array of hits (i, j, dot, ani), sorted by (i, j)."""
+        """hg_dist with host buffers -> structured array of hits (i, j, dot, ani), unspecified order."""
         r = np.ascontiguousarray(ref_hv, np.int16)
         rn = np.ascontiguousarray(ref_norm2, np.int32)
         same = qry_hv is ref_hv

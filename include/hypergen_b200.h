@@ -148,8 +148,9 @@ HG_API int hg_unpack_dev(hg_ctx *ctx, const uint8_t *d_packed, uint64_t row_stri
 /* compute_hv_ani + the threshold filter of dump_ani_file (src/dist.rs:231-294,
  * src/utils.rs:274-285): every (ref i, query j) pair — only j > i when `symmetric`
  * (same ref/query sketch file, src/dist.rs:13,253-265) — gets the exact i32 dot, the ANI
- * of src/dist.rs:153-160, and is reported iff ani >= ani_th.  Hits come back sorted by
- * (i, j).  If more than `cap` pairs pass, returns HG_E_CAPACITY with *n_hits = need.
+ * of src/dist.rs:153-160, and is reported iff ani >= ani_th.  The order of the hits is
+ * unspecified (the reference sorts by ANI when it writes its output, src/utils.rs:262-269).
+ * If more than `cap` pairs pass, returns HG_E_CAPACITY with *n_hits = need.
  *   path: 0 = auto (tcgen05 int8 limb path when every |hv| fits 13 bits, else SIMT),
  *         1 = force SIMT (CUDA-core) path, 2 = force tensor path. */
 HG_API int hg_dist(hg_ctx *ctx, const int16_t *ref_hv, const int32_t *ref_norm2, uint32_t n_ref,
