@@ -383,6 +383,7 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
     d_hits = torch.empty(cap * 16, dtype=torch.uint8, device=dev)
     d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    hits_pin = torch.empty(cap * 16, dtype=torch.uint8, pin_memory=True)
     bounds = multigpu.triangle_rows(nq, world, align=128)
     a, b = bounds[rank], bounds[rank + 1]
     n_pairs = nq * (nq - 1) // 2
@@ -404,7 +405,9 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
             if world > 1:
                 allh = multigpu.gather_hits(d_hits, dev, count=cnt)
             else:
-                allh = np.frombuffer(d_hits[: cnt * 16].cpu().numpy().tobytes(), dtype=hg.ffi.HIT_DTYPE)
+                hits_pin[: cnt * 16].copy_(d_hits[: cnt * 16], non_blocking=True)  # D2H of the hit list
+                torch.cuda.current_stream().synchronize()
+                allh = hits_pin[: cnt * 16].numpy().view(hg.ffi.HIT_DTYPE)
             e1.record()
         e1.synchronize()
         return e0.elapsed_time(e1), ctx.stage_ms()[3], (allh.size if allh is not None else 0)
@@ -440,6 +443,19 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
     out["roofline"] = {"bound": "tensor", "achieved": alg_ops / (kms * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s",
                        "frac": alg_ops / (kms * 1e-3) / 1e12 / int8_peak,
                        "note": "algorithmic 2*D ops per pair; peak = 2 x measured bf16 (int8 MMA rate); the limb split executes 3x these MACs"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # CPU port of dist::compute_hv_ani (dist.rs:231-294) on a bounded sample of the same sketches
+        import oracle as O
+        cores = os.cpu_count() or 1
+        O.set_threads(cores)
+        m = min(nq, 3000)
+        hv_s, norm_s = hv[:m].cpu().numpy(), norm[:m].cpu().numpy()
+        t0 = time.perf_counter()
+        ani_s, _ = O.dist_all(hv_s, norm_s, hv_s, norm_s, k=K, symmetric=True, want_dot=False)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": (m * (m - 1) // 2) / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+                               "sample": "all-vs-all over the first %d of the %d sketches (%d pairs), oracle/hg_oracle.c, %d threads, %.1f s"
+                               % (m, nq, m * (m - 1) // 2, cores, dt)}
     # e2e through the host-pointer C-ABI call (N=1 only): pinned host matrices in, hits out
     if world == 1:
         import ctypes as C
