@@ -581,7 +581,6 @@ extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref
   }
   c->dist_path = use;
   c->ev_used &= ~(3 << 4);
-  HG_PROF(c, 4);
   int rc2;
   if (use == 2) {
     rc2 = hg_launch_dist_tc(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th,
@@ -591,10 +590,12 @@ extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref
       snprintf(c->dist_reason, sizeof(c->dist_reason), "SIMT: tensor kernel declined this shape (%s)", hg_last_error());
     }
   }
-  if (use != 2)
+  if (use != 2) {
+    HG_PROF(c, 4);
     rc2 = hg_launch_dist_simt(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th,
                               symmetric, d_hits, cap, d_n_hits);
-  HG_PROF(c, 5);
+    HG_PROF(c, 5);
+  }
   return rc2;
 }
 

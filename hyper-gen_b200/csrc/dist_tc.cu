@@ -19,6 +19,8 @@
 // (dist_common.cuh) only where a pair can reach the threshold.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "dist_common.cuh"
 
 namespace {
@@ -59,6 +61,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+      "l"(map), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // smem matrix descriptor: K-major, 128B swizzle, 8-row atoms 1024 B apart (SBO), version 1
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -82,13 +101,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
 }
 
+// CL = 1: stand-alone CTAs.  CL = 2: 2 x 2 thread-block clusters — the two CTAs of a cluster row
+// share their A (ref) tile and the two of a cluster column their B (query) tile; each CTA loads
+// half of each shared tile and TMA-multicasts it to its peer, halving the L2 -> SM operand
+// traffic that bounds this kernel.
+template <int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_qry,
                uint32_t ref_plane_rows, uint32_t ref_row_base, uint32_t qry_plane_rows, uint32_t hv_d,
                hg::DistEpilogue ep) {
   const uint32_t row0 = blockIdx.y * TC_BM, col0 = blockIdx.x * TC_BN;
-  // symmetric: a tile whose largest global j is not above its smallest global i is empty
-  if (ep.symmetric && (uint64_t)ep.j0 + col0 + TC_BN - 1 <= (uint64_t)ep.i0 + row0) return;
+  // symmetric: a tile (cluster of tiles) whose largest global j is not above its smallest global
+  // i is empty.  The test is uniform over a cluster, so whole clusters leave together.
+  {
+    const uint32_t crow0 = (blockIdx.y / CL) * CL * TC_BM, ccol_end = (blockIdx.x / CL + 1) * CL * TC_BN;
+    if (ep.symmetric && (uint64_t)ep.j0 + ccol_end - 1 <= (uint64_t)ep.i0 + crow0) return;
+  }
+  const bool own_tile_empty = ep.symmetric && (uint64_t)ep.j0 + col0 + TC_BN - 1 <= (uint64_t)ep.i0 + row0;
+  // position inside the cluster: cx along N (blockIdx.x), cy along M (blockIdx.y); rank = cx + CL * cy
+  const uint32_t cx = CL == 1 ? 0u : (blockIdx.x % CL), cy = CL == 1 ? 0u : (blockIdx.y % CL);
+  const uint32_t crank = cx + CL * cy;
+  const uint16_t mask_a = CL == 1 ? 1 : (uint16_t)(((1u << CL) - 1u) << (CL * cy));               // same cluster row
+  const uint16_t mask_b = CL == 1 ? 1 : (uint16_t)((1u << cx) | (1u << (cx + CL)));               // same cluster column
+  const uint16_t mask_e = (uint16_t)(mask_a | mask_b);  // everyone that writes into my stages
+  (void)crank;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle wants 1024 B alignment
@@ -101,7 +137,8 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    // a stage is released when my own MMAs and those of every CTA I multicast into have read it
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL == 1 ? 1 : 2 * CL - 1); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -113,6 +150,7 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // every peer's barriers are initialised before anyone signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t num_kb = hv_d / TC_BK;
@@ -127,10 +165,21 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
         mbar_expect_tx(full_bar(s), TC_STAGE_BYTES);
         const uint32_t st = base + s * TC_STAGE_BYTES;
         const int k0 = (int)(kb * TC_BK);
-        tma_load_2d(st + 0 * TC_TILE_BYTES, &tm_ref, full_bar(s), k0, (int)(ref_row_base + row0));  // ref hi limbs
-        tma_load_2d(st + 1 * TC_TILE_BYTES, &tm_ref, full_bar(s), k0, (int)(ref_plane_rows + ref_row_base + row0));  // ref lo
-        tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_qry, full_bar(s), k0, (int)col0);                    // qry hi limbs
-        tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_qry, full_bar(s), k0, (int)(qry_plane_rows + col0));  // qry lo limbs
+        if (CL == 1) {
+          tma_load_2d(st + 0 * TC_TILE_BYTES, &tm_ref, full_bar(s), k0, (int)(ref_row_base + row0));  // ref hi limbs
+          tma_load_2d(st + 1 * TC_TILE_BYTES, &tm_ref, full_bar(s), k0, (int)(ref_plane_rows + ref_row_base + row0));  // ref lo
+          tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_qry, full_bar(s), k0, (int)col0);                    // qry hi limbs
+          tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_qry, full_bar(s), k0, (int)(qry_plane_rows + col0));  // qry lo limbs
+        } else {
+          // my 1/CL slice of the row-shared A tile and of the column-shared B tile, multicast
+          constexpr int HR = 128 / CL;                     // rows per slice
+          constexpr int HB = HR * TC_BK;                   // bytes per slice
+          const int ar = (int)(ref_row_base + row0 + cx * HR), br = (int)(col0 + cy * HR);
+          tma_load_2d_mc(st + 0 * TC_TILE_BYTES + cx * HB, &tm_ref, full_bar(s), k0, ar, mask_a);
+          tma_load_2d_mc(st + 1 * TC_TILE_BYTES + cx * HB, &tm_ref, full_bar(s), k0, (int)ref_plane_rows + ar, mask_a);
+          tma_load_2d_mc(st + 2 * TC_TILE_BYTES + cy * HB, &tm_qry, full_bar(s), k0, br, mask_b);
+          tma_load_2d_mc(st + 3 * TC_TILE_BYTES + cy * HB, &tm_qry, full_bar(s), k0, (int)qry_plane_rows + br, mask_b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -152,7 +201,8 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
           umma_i8(tmem_base + 1 * TC_BN, a_lo, b_hi, 1u);   //   + Lr.Hq
           umma_i8(tmem_base + 2 * TC_BN, a_lo, b_lo, acc);  // Lr.Lq
         }
-        umma_commit(empty_bar(s));  // the stage is free once these MMAs have read it
+        if (CL == 1) umma_commit(empty_bar(s));  // the stage is free once these MMAs have read it
+        else umma_commit_mc(empty_bar(s), mask_e);
       }
       umma_commit(accum_bar);       // all accumulators final
     }
@@ -191,32 +241,40 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t taddr = tmem_base + ((q * 32u) << 16);
 #pragma unroll 1
-    for (int c = half * (TC_BN / 2); c < (half + 1) * (TC_BN / 2); c += 16) {
+    for (int c = half * (TC_BN / 2); c < (half + 1) * (TC_BN / 2) && !own_tile_empty; c += 16) {
       uint32_t hh[16], cr[16], ll[16];
       tmem_ld16(taddr + 0 * TC_BN + c, hh);
       tmem_ld16(taddr + 1 * TC_BN + c, cr);
       tmem_ld16(taddr + 2 * TC_BN + c, ll);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       int32_t dot[16];
-      bool any = false;
+      uint32_t cand = 0;  // bit j: column c + j of my row can reach the threshold
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         dot[j] = (int32_t)((((hh[j] << 7) + cr[j]) << 7) + ll[j]);  // wrapping i32, as dist.rs:147-151
         const int32_t tq = s_tq[c + j];
-        // tq = INT32_MIN or tr = INT32_MIN / 2 make the sum so negative that the pair is a candidate
-        any |= dot[j] >= (int32_t)((uint32_t)tr + (uint32_t)tq) || tq == INT32_MIN || tr == INT32_MIN / 2;
+        // tq = INT32_MIN or tr = INT32_MIN / 2 (bound off / degenerate norm) always qualify
+        const bool cj = dot[j] >= (int32_t)((uint32_t)tr + (uint32_t)tq) || tq == INT32_MIN || tr == INT32_MIN / 2;
+        cand |= (uint32_t)cj << j;
       }
-      if (__any_sync(0xffffffffu, any && row_live)) {
+      if (!row_live) cand = 0;
+      // exact f32 ANI + compacted append, one candidate per lane per round (candidates are rare:
+      // the number of rounds is the largest per-lane count, not 16)
+      while (__any_sync(0xffffffffu, cand != 0)) {
+        const bool have = cand != 0;
+        const int j = have ? __ffs(cand) - 1 : 0;
+        cand &= cand - 1;
+        int32_t d = dot[0];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const uint32_t lj = col0 + c + j;
-          hg::dist_emit(ep, row_live && lj < ep.n_qry, li, lj, dot[j]);
-        }
+        for (int jj = 1; jj < 16; ++jj) d = (jj == j) ? dot[jj] : d;
+        const uint32_t lj = col0 + c + j;
+        hg::dist_emit(ep, have && lj < ep.n_qry, li, lj, d);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into it or signal its barriers
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
@@ -247,7 +305,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_plane_map(CUtensorMap *map, const int8_t *planes, uint64_t rows2, uint32_t hv_d) {
+int make_plane_map(CUtensorMap *map, const int8_t *planes, uint64_t rows2, uint32_t hv_d, uint32_t box_rows) {
   static encode_tiled_fn fn = nullptr;
   if (!fn) {
     void *p = nullptr;
@@ -258,7 +316,7 @@ int make_plane_map(CUtensorMap *map, const int8_t *planes, uint64_t rows2, uint3
   }
   const cuuint64_t dims[2] = {hv_d, rows2};          // innermost first: K bytes, then rows of both planes
   const cuuint64_t strides[1] = {hv_d};              // bytes between rows
-  const cuuint32_t box[2] = {TC_BK, 128};
+  const cuuint32_t box[2] = {TC_BK, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)planes, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -291,31 +349,45 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
   void *p_q, *p_r = nullptr;
   if ((rc = hg_scratch(ctx, 9, 2 * qry_elems + 1024, &p_q))) return rc;
   if (!qry_covers_ref && (rc = hg_scratch(ctx, 8, 2 * ref_elems + 1024, &p_r))) return rc;
+  const uint32_t gx = (n_qry + TC_BN - 1) / TC_BN, gy_total = (n_ref + TC_BM - 1) / TC_BM;
+  // Stand-alone CTAs by default.  The 2 x 2 cluster + TMA multicast variant (HG_DIST_CLUSTER=2) halves
+  // the L2 reads but measured 10-15 % SLOWER on B200: the kernel is bound by bytes arriving per SM
+  // (~37 B/clk/SM), which multicast does not change.  Kept for the record and for larger-L2-pressure shapes.
+  int cl = 1;
+  if (const char *e = getenv("HG_DIST_CLUSTER")) cl = (atoi(e) == 2 && gx >= 2 && gy_total >= 2) ? 2 : 1;
+  const uint32_t box_rows = 128 / cl;
+
+  CUtensorMap tm_ref, tm_qry;
+  if ((rc = make_plane_map(&tm_qry, (const int8_t *)p_q, 2ull * n_qry, hv_d, box_rows))) return rc;
+  uint32_t ref_plane_rows = n_ref, ref_row_off = 0;
+  if (qry_covers_ref) {  // the ref rows are a window of the query planes
+    tm_ref = tm_qry;
+    ref_plane_rows = n_qry;
+    ref_row_off = (uint32_t)((d_ref - d_qry) / hv_d);
+  } else if ((rc = make_plane_map(&tm_ref, (const int8_t *)p_r, 2ull * n_ref, hv_d, box_rows))) {
+    return rc;
+  }
+
+  if (!ctx->tc_attr_set) {
+    HG_CUDA(cudaFuncSetAttribute(dist_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    ctx->tc_attr_set = 1;
+  }
+  // ---- GPU work starts here (stage timer 4..5 brackets exactly this) ----
   auto split = [&](const int16_t *src, uint64_t elems, void *dst) {
     uint64_t blocks = (elems / 8 + 255) / 256;
     if (blocks > (uint64_t)ctx->sm_count * 16) blocks = (uint64_t)ctx->sm_count * 16;
     split_limbs_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, elems, (int8_t *)dst);
     ctx->launches++;
   };
+
+  HG_PROF(ctx, 4);
   split(d_qry, qry_elems, p_q);
   if (!qry_covers_ref) split(d_ref, ref_elems, p_r);
   HG_CUDA(cudaGetLastError());
-
-  CUtensorMap tm_ref, tm_qry;
-  if ((rc = make_plane_map(&tm_qry, (const int8_t *)p_q, 2ull * n_qry, hv_d))) return rc;
-  uint32_t ref_plane_rows = n_ref, ref_row_off = 0;
-  if (qry_covers_ref) {  // the ref rows are a window of the query planes
-    tm_ref = tm_qry;
-    ref_plane_rows = n_qry;
-    ref_row_off = (uint32_t)((d_ref - d_qry) / hv_d);
-  } else if ((rc = make_plane_map(&tm_ref, (const int8_t *)p_r, 2ull * n_ref, hv_d))) {
-    return rc;
-  }
-
-  HG_CUDA(cudaFuncSetAttribute(dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  const uint32_t gx = (n_qry + TC_BN - 1) / TC_BN, gy_total = (n_ref + TC_BM - 1) / TC_BM;
-  for (uint32_t y0 = 0; y0 < gy_total; y0 += 65535) {
-    const uint32_t gy = gy_total - y0 < 65535 ? gy_total - y0 : 65535;
+  const uint32_t y_step = 65534;  // even, <= the gridDim.y limit
+  for (uint32_t y0 = 0; y0 < gy_total; y0 += y_step) {
+    const uint32_t gy = gy_total - y0 < y_step ? gy_total - y0 : y_step;
     hg::DistEpilogue ep;
     ep.ref_norm = d_ref_norm + (size_t)y0 * TC_BM;
     ep.qry_norm = d_qry_norm;
@@ -326,15 +398,31 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
     ep.ksize_f = (float)ksize;
     ep.ani_th = ani_th;
     ep.jmin = hg::dist_jmin(ani_th, ksize);
-  ep.cfrac = ep.jmin > 0.0f ? (float)((double)ep.jmin / (1.0 + (double)ep.jmin)) : 0.0f;
+    ep.cfrac = ep.jmin > 0.0f ? (float)((double)ep.jmin / (1.0 + (double)ep.jmin)) : 0.0f;
     ep.symmetric = symmetric;
     ep.hits = d_hits;
     ep.cap = cap;
     ep.n_hits = d_n_hits;
-    dist_tc_kernel<<<dim3(gx, gy), TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(tm_ref, tm_qry, ref_plane_rows,
-                                                                             ref_row_off + y0 * TC_BM, n_qry, hv_d, ep);
+    const uint32_t row_base = ref_row_off + y0 * TC_BM;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((gx + cl - 1) / cl * cl, (gy + cl - 1) / cl * cl, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = cl;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cl == 2)
+      HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc_kernel<2>, tm_ref, tm_qry, ref_plane_rows, row_base, n_qry, hv_d, ep));
+    else
+      HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc_kernel<1>, tm_ref, tm_qry, ref_plane_rows, row_base, n_qry, hv_d, ep));
     ctx->launches++;
   }
+  HG_PROF(ctx, 5);
   HG_CUDA(cudaGetLastError());
   return HG_OK;
 }

@@ -144,6 +144,7 @@ struct hg_ctx {
   cudaEvent_t ev[8];
   int ev_used;           // which stage boundaries were recorded in the last call
   // H2D pipeline of the host-pointer sketch entry
+  int tc_attr_set;
   cudaStream_t copy_stream;
   cudaEvent_t ev_copied[2], ev_done[2];
 };
