@@ -26,7 +26,8 @@ constexpr int KH_WARPS = KH_THREADS / 32;
 constexpr int KH_PPT = 32;                       // k-mer start positions per thread
 constexpr int KH_TILE = 32 * KH_PPT;             // start positions per WARP tile
 constexpr int KH_CHUNKS = (KH_TILE + 64) / 16;   // 16-base chunks staged per tile (halo + align)
-constexpr int KH_MIN_CTAS = 12;                  // 48 resident warps per SM (<= 40 registers)
+constexpr int KH_GROUP = 8;                      // positions hashed back to back before survivors are handled
+constexpr int KH_MIN_CTAS = 8;                   // 32 resident warps per SM at <= 64 registers (measured: occupancy beyond this does not help)
 
 __device__ __forceinline__ uint4 ld_stream16(const void *p) {
   uint4 r;
@@ -228,6 +229,11 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
     const uint32_t in32 = window8(nb0 + (K - 1) + 8 * o);  // the 8 incoming bases
     const uint32_t in32c = in32 ^ 0x77777777u;             // their complements
     const uint32_t kv8 = kv32 >> (8 * o);
+    // straight-line code for the whole group: the (rare) survivors are only flagged here and
+    // inserted after the group, so the scheduler can interleave the ALU-heavy rolling/expansion
+    // of one position with the multiply chains of its neighbours
+    uint64_t hs[KH_GROUP];
+    uint32_t hitmask = 0;
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
       // ---- roll the forward strand: drop the low nibble, append at nibble K-1 ----
@@ -279,7 +285,16 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
         w[m] = (uint64_t)lo | ((uint64_t)hi << 32);
       }
       const uint64_t h = hg::t1ha2_kmer<K>(w, seed);
-      if (h < threshold && ((kv8 >> jj) & 1u)) table_insert(table, gd.table_mask, h, count, status);
+      hs[jj % KH_GROUP] = h;
+      hitmask |= (uint32_t)(h < threshold) << jj;
+      if ((jj % KH_GROUP) == KH_GROUP - 1) {
+        const uint32_t gm = (hitmask & kv8) >> (jj + 1 - KH_GROUP);
+        if (gm & ((1u << KH_GROUP) - 1u)) {
+#pragma unroll
+          for (int e = 0; e < KH_GROUP; ++e)
+            if ((gm >> e) & 1u) table_insert(table, gd.table_mask, hs[e], count, status);
+        }
+      }
     }
   }
   }  // kv32 != 0
