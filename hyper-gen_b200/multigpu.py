@@ -120,3 +120,36 @@ def dist_sharded(compute, ref_hv, ref_norm, qry_hv, qry_norm, n_ref: int, n_qry:
         ref_hv, ref_norm = qry_hv, qry_norm
     local = compute(ref_hv[a:b], ref_norm[a:b], a, qry_hv, qry_norm) if b > a else np.zeros(0, HIT_DTYPE)
     return gather_hits(local, device)
+
+
+# ---------------------------------------------------------------------------------------------
+# file-level drivers (the multi-GPU form of sketch_cuda::sketch_cuda and dist::dist)
+# ---------------------------------------------------------------------------------------------
+def gather_objects(obj, dst: int = 0):
+    """Small python objects (FileSketch records) to rank `dst`."""
+    world = dist.get_world_size()
+    out = [None] * world if dist.get_rank() == dst else None
+    dist.gather_object(obj, out, dst=dst)
+    return out
+
+
+def sketch_files_distributed(files, sketch_fn, out_file: str | None = None):
+    """Every rank sketches its greedy (by file size) share of `files` with `sketch_fn(list_of_paths)
+    -> list[FileSketch]`; rank 0 reassembles the records in get_fasta_files order and writes the
+    sketch file.  No collective touches sequence data."""
+    import os
+    from . import fileio
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sizes = [os.path.getsize(f) for f in files]
+    mine = partition_greedy(sizes, world)[rank]
+    local = sketch_fn([files[i] for i in mine])
+    parts = gather_objects((mine, local))
+    if rank != 0:
+        return None
+    allsk = [None] * len(files)
+    for idx, sks in parts:
+        for i, s in zip(idx, sks):
+            allsk[i] = s
+    if out_file:
+        fileio.dump_sketch(allsk, out_file)
+    return allsk

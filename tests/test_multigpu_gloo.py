@@ -80,3 +80,49 @@ def test_dist_sharded_world2_gloo(symmetric, tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, symmetric, str(tmp_path)), nprocs=2, join=True)
     assert open(tmp_path / ("ok_%d" % int(symmetric))).read() == "1"
+
+
+def _sketch_worker(rank, world, port, d, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import hypergen_b200 as hg
+    from hypergen_b200 import multigpu as mg, fileio
+    import oracle as O
+
+    def sketch_fn(paths):  # the GPU call on a real run; the oracle here
+        out = []
+        for f in paths:
+            seq = fileio.read_merge_seq(f)
+            w = O.sketch_batch(seq, np.array([0, seq.size], np.uint64), scaled=200, hv_d=512, want_hv=False)
+            b = int(w["quant_bits"][0])
+            out.append(fileio.FileSketch(21, 200, True, 123, 512, b, int(w["norm2"][0]), f,
+                                         w["packed"][0, :b * 512 // 8].copy().view("<i2")))
+        return out
+
+    files = fileio.get_fasta_files(d)
+    res = mg.sketch_files_distributed(files, sketch_fn, os.path.join(out_dir, "db.sketch") if rank == 0 else None)
+    if rank == 0:
+        want = sketch_fn(files)
+        back = fileio.load_sketch(os.path.join(out_dir, "db.sketch"))
+        ok = len(back) == len(files) and all(a.file_str == b.file_str and a.hv_norm_2 == b.hv_norm_2 and
+                                             np.array_equal(a.hv, b.hv) for a, b in zip(back, want))
+        open(os.path.join(out_dir, "ok_sketch"), "w").write("1" if ok else "0")
+    else:
+        assert res is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sketch_files_distributed_world2_gloo(tmp_path):
+    from hypergen_b200 import synth
+    d = tmp_path / "g"
+    d.mkdir()
+    for g in range(7):
+        seq = synth.family_member(g, 20_000 + 7_000 * g).numpy()
+        with open(d / ("f%d.fna" % g), "wb") as f:
+            f.write(b">g%d\n" % g + bytes(seq) + b"\n")
+    port = _free_port()
+    mp.spawn(_sketch_worker, args=(2, port, str(d), str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "ok_sketch").read() == "1"
