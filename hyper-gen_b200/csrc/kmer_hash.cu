@@ -26,6 +26,7 @@ constexpr int KH_WARPS = KH_THREADS / 32;
 constexpr int KH_PPT = 32;                       // k-mer start positions per thread
 constexpr int KH_TILE = 32 * KH_PPT;             // start positions per WARP tile
 constexpr int KH_CHUNKS = (KH_TILE + 64) / 16;   // 16-base chunks staged per tile (halo + align)
+constexpr int KH_QCAP = 64;                      // per-warp queue of survivors, flushed once per tile
 constexpr int KH_GROUP = 8;                      // positions hashed back to back before survivors are handled
 constexpr int KH_MIN_CTAS = 8;                   // 32 resident warps per SM at <= 64 registers (measured: occupancy beyond this does not help)
 
@@ -106,10 +107,17 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
   // every warp owns a private staging area and runs on its own: no CTA-wide barrier anywhere
   __shared__ uint32_t s_nib_all[KH_WARPS][KH_CHUNKS * 2 + 8];    // 8 bases per word
   __shared__ uint32_t s_valid_all[KH_WARPS][KH_CHUNKS / 2 + 4];  // 16 bits per chunk
+  // survivors are queued here and inserted together at the end of the tile, so the round trip
+  // of the global atomicCAS is paid once per tile (all lanes in flight) instead of once per hit
+  __shared__ uint64_t s_queue_all[KH_WARPS][KH_QCAP];
+  __shared__ uint32_t s_qn_all[KH_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t *s_nib = s_nib_all[warp];
   uint32_t *s_valid = s_valid_all[warp];
   uint16_t *s_valid16 = reinterpret_cast<uint16_t *>(s_valid);
+  uint64_t *s_queue = s_queue_all[warp];
+  uint32_t *s_qn = &s_qn_all[warp];
+  if (lane == 0) *s_qn = 0;
 
   // One tile per warp, 8 consecutive tiles per CTA.  cta_genome[] (written by tile_map_kernel)
   // names the genome of the CTA's first tile; the warp walks the sorted first_tile column
@@ -292,12 +300,19 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
         if (gm & ((1u << KH_GROUP) - 1u)) {
 #pragma unroll
           for (int e = 0; e < KH_GROUP; ++e)
-            if ((gm >> e) & 1u) table_insert(table, gd.table_mask, hs[e], count, status);
+            if ((gm >> e) & 1u) {
+              const uint32_t pos = atomicAdd(s_qn, 1u);
+              if (pos < KH_QCAP) s_queue[pos] = hs[e];
+              else table_insert(table, gd.table_mask, hs[e], count, status);  // queue full (tiny `scaled`)
+            }
         }
       }
     }
   }
   }  // kv32 != 0
+  __syncwarp();
+  const uint32_t qn = min(*s_qn, (uint32_t)KH_QCAP);
+  for (uint32_t i = lane; i < qn; i += 32) table_insert(tables + gd.table_begin, gd.table_mask, s_queue[i], counts + g, status);
   }
 }
 
