@@ -39,7 +39,7 @@ GENOME_LEN = 5_000_000
 ALG_BYTES_PER_GENOME = GENOME_LEN + 8 * (GENOME_LEN // SCALED)
 # integer instructions the k-mer kernel executes per k-mer (ncu smsp__inst_executed /
 # k-mers, profiles/): used only for the auxiliary INT32 roofline
-KMER_INST_PER_KMER = float(os.environ.get("HG_KMER_INST_PER_KMER", "150"))
+KMER_INST_PER_KMER = float(os.environ.get("HG_KMER_INST_PER_KMER", "127"))
 
 
 def load_peaks():

@@ -138,3 +138,25 @@ def test_invalid_arguments_return_status(ctx, hg):
         with pytest.raises(hg.HyperGenError) as e:
             ctx.sketch_batch(seq, off, bad)
         assert e.value.code == hg.ffi.HG_E_INVALID
+
+
+def test_large_genome_and_many_small_ones(ctx, hg, oracle):
+    """One 60 Mbp genome (long N runs, lower-case islands) next to 300 tiny ones in a single batch:
+    exercises many tiles per genome, tables of different sizes and zero-tile genomes."""
+    from hypergen_b200 import synth
+    rng = np.random.default_rng(21)
+    big = synth.genome(0xB200 + 99, 60_000_000).numpy().copy()
+    for s in rng.integers(0, big.size - 200_000, 40):
+        big[s:s + int(rng.integers(1, 150_000))] = ord("N")
+    for s in rng.integers(0, big.size - 50_000, 60):
+        big[s:s + 40_000] |= 0x20
+    small = [random_dna(rng, int(rng.integers(0, 3000)), p_n=0.01) for _ in range(300)]
+    seq, off = _batch([big] + small + [big[:1_000_003]], lead=7)
+    p = hg.make_params()
+    got = ctx.sketch_batch(seq, off, p)
+    want = oracle.sketch_batch(seq, off)
+    assert np.array_equal(got["n_hashes"], want["n_hashes"]) and got["n_hashes"][0] > 30000
+    assert np.array_equal(got["hv"], want["hv"])
+    assert np.array_equal(got["norm2"], want["norm2"]) and np.array_equal(got["quant_bits"], want["quant_bits"])
+    h, hoff = ctx.kmer_hash(seq, off, p)
+    assert np.array_equal(h[: int(hoff[1])], oracle.kmer_hash_set(big))
