@@ -388,6 +388,14 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
     a, b = bounds[rank], bounds[rank + 1]
     n_pairs = nq * (nq - 1) // 2
 
+    # multi-GPU: one fused broadcast buffer (HVs + norms) and one fixed-size gather per step
+    if world > 1:
+        qbuf = torch.empty(nq * D * 2 + nq * 4, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            qbuf[: nq * D * 2] = hv.view(torch.uint8).view(-1)
+            qbuf[nq * D * 2:] = norm.view(torch.uint8).view(-1)
+        gather_cap = 1 << 16  # hits per rank carried by the one-shot gather (1 MiB per rank)
+
     def step():
         """broadcast queries -> local shard -> hits gathered on rank 0; returns device ms"""
         nonlocal hv, norm
@@ -396,15 +404,18 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
         with torch.cuda.stream(ext):  # collectives and kernels ordered on the context's stream
             e0.record()
             if world > 1:
-                hv, norm = multigpu.broadcast_queries(hv, norm, (nq, D), dev)
+                hv, norm = multigpu.broadcast_queries_fused(qbuf, nq, D)
             ctx.dist_dev(hv[a:b].data_ptr(), norm[a:b].data_ptr(), b - a, a, hv.data_ptr(), norm.data_ptr(), nq, 0, D, K,
                          85.0, True, path_sel[0], d_hits.data_ptr(), cap, d_cnt.data_ptr())
-            cnt = int(d_cnt.item())  # D2H of the local hit count
-            if cnt > cap:
-                raise RuntimeError("hit buffer too small: %d > %d" % (cnt, cap))
             if world > 1:
-                allh = multigpu.gather_hits(d_hits, dev, count=cnt)
+                allh, overflow = multigpu.gather_hits_fixed(d_hits, d_cnt, gather_cap)
+                if overflow:  # some shard produced more hits than the one-shot block carries
+                    cnt = int(d_cnt.item())
+                    allh = multigpu.gather_hits(d_hits, dev, count=min(cnt, cap))
             else:
+                cnt = int(d_cnt.item())  # D2H of the hit count
+                if cnt > cap:
+                    raise RuntimeError("hit buffer too small: %d > %d" % (cnt, cap))
                 hits_pin[: cnt * 16].copy_(d_hits[: cnt * 16], non_blocking=True)  # D2H of the hit list
                 torch.cuda.current_stream().synchronize()
                 allh = hits_pin[: cnt * 16].numpy().view(hg.ffi.HIT_DTYPE)

@@ -60,6 +60,15 @@ def pairs_in_rows(n: int, a: int, b: int) -> int:
     return f(b) - f(a)
 
 
+def broadcast_queries_fused(buf: torch.Tensor, n: int, d: int, src: int = 0):
+    """One broadcast for HVs + norms: `buf` is a uint8 tensor of n*d*2 + n*4 bytes (filled on `src`).
+    Returns (hv int16 [n, d], norm int32 [n]) views into it."""
+    dist.broadcast(buf, src=src)
+    hv = buf[: n * d * 2].view(torch.int16).view(n, d)
+    norm = buf[n * d * 2: n * d * 2 + n * 4].view(torch.int32)
+    return hv, norm
+
+
 def broadcast_queries(qry_hv: torch.Tensor | None, qry_norm: torch.Tensor | None, shape, device, src: int = 0):
     """Rank `src` owns the query HVs (n x D int16) and norms (n int32); everyone gets a copy."""
     rank = dist.get_rank()
@@ -101,6 +110,29 @@ def gather_hits(local_hits, device, dst: int = 0, count: int | None = None) -> n
     host = allbuf.cpu().numpy()
     parts = [np.frombuffer(host[r * mx * isz:(r * mx + counts[r]) * isz].tobytes(), dtype=HIT_DTYPE) for r in range(world)]
     return np.concatenate(parts) if parts else np.zeros(0, HIT_DTYPE)
+
+
+def gather_hits_fixed(local_hits: torch.Tensor, count_t: torch.Tensor, cap_per_rank: int, dst: int = 0):
+    """One-collective gather for the common (sparse) case: every rank contributes a fixed-size
+    record block [count:int64 | cap_per_rank x hg_hit] so that no host round trip is needed to size
+    the collective.  Returns (hits or None, overflowed: bool); on overflow (some rank had more than
+    cap_per_rank hits) the caller falls back to gather_hits().  `local_hits` is a uint8 device tensor,
+    `count_t` a 1-element int64 device tensor (the kernel's hit counter)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    isz = HIT_DTYPE.itemsize
+    block = 16 + cap_per_rank * isz
+    send = torch.empty(block, dtype=torch.uint8, device=local_hits.device)
+    send[:8] = count_t.view(torch.uint8)
+    send[16:] = local_hits[: cap_per_rank * isz]
+    recv = torch.empty(world * block, dtype=torch.uint8, device=local_hits.device)
+    dist.all_gather_into_tensor(recv, send)
+    counts = recv.view(world, block)[:, :8].contiguous().view(torch.int64).cpu().numpy().ravel()  # one small D2H
+    overflow = bool((counts > cap_per_rank).any())
+    if overflow or rank != dst:
+        return None, overflow
+    host = recv.cpu().numpy().reshape(world, block)
+    parts = [np.frombuffer(host[r, 16:16 + int(counts[r]) * isz].tobytes(), dtype=HIT_DTYPE) for r in range(world)]
+    return np.concatenate(parts), False
 
 
 def dist_sharded(compute, ref_hv, ref_norm, qry_hv, qry_norm, n_ref: int, n_qry: int, hv_d: int, symmetric: bool,

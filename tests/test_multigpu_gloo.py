@@ -126,3 +126,38 @@ def test_sketch_files_distributed_world2_gloo(tmp_path):
     port = _free_port()
     mp.spawn(_sketch_worker, args=(2, port, str(d), str(tmp_path)), nprocs=2, join=True)
     assert open(tmp_path / "ok_sketch").read() == "1"
+
+
+def _fixed_gather_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import hypergen_b200 as hg
+    from hypergen_b200 import multigpu as mg
+    ok = True
+    for n_local, cap in ((5 + 3 * rank, 16), (0, 4), (9 + rank, 8)):
+        h = np.zeros(max(n_local, cap), hg.ffi.HIT_DTYPE)
+        h["i"][:n_local] = 1000 * rank + np.arange(n_local)
+        h["j"][:n_local] = 7
+        raw = torch.from_numpy(np.frombuffer(h.tobytes(), dtype=np.uint8).copy())
+        got, overflow = mg.gather_hits_fixed(raw, torch.tensor([n_local], dtype=torch.int64), cap)
+        want_overflow = any((9 + r if cap == 8 else (5 + 3 * r if cap == 16 else 0)) > cap for r in range(world))
+        ok = ok and (overflow == want_overflow)
+        if rank == 0 and not overflow:
+            exp = np.concatenate([1000 * r + np.arange((5 + 3 * r) if cap == 16 else 0) for r in range(world)])
+            ok = ok and np.array_equal(np.sort(got["i"]), np.sort(exp.astype(np.uint32)))
+        if overflow:
+            full = mg.gather_hits(h[:n_local], "cpu")
+            if rank == 0:
+                ok = ok and full.size == sum(9 + r for r in range(world))
+    if rank == 0:
+        open(os.path.join(out_dir, "ok_fixed"), "w").write("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_hits_fixed_world2_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_fixed_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "ok_fixed").read() == "1"
