@@ -112,6 +112,17 @@ def gather_hits(local_hits, device, dst: int = 0, count: int | None = None) -> n
     return np.concatenate(parts) if parts else np.zeros(0, HIT_DTYPE)
 
 
+_PINNED = {}
+
+
+def _pinned(nbytes: int) -> torch.Tensor:
+    t = _PINNED.get("buf")
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        _PINNED["buf"] = t
+    return t[:nbytes]
+
+
 def gather_hits_fixed(local_hits: torch.Tensor, count_t: torch.Tensor, cap_per_rank: int, dst: int = 0):
     """One-collective gather for the common (sparse) case: every rank contributes a fixed-size
     record block [count:int64 | cap_per_rank x hg_hit] so that no host round trip is needed to size
@@ -126,12 +137,19 @@ def gather_hits_fixed(local_hits: torch.Tensor, count_t: torch.Tensor, cap_per_r
     send[16:] = local_hits[: cap_per_rank * isz]
     recv = torch.empty(world * block, dtype=torch.uint8, device=local_hits.device)
     dist.all_gather_into_tensor(recv, send)
-    counts = recv.view(world, block)[:, :8].contiguous().view(torch.int64).cpu().numpy().ravel()  # one small D2H
+    if rank == dst:  # the whole gathered buffer in one D2H into pinned memory (counts ride along)
+        host_t = _pinned(world * block)
+        host_t.copy_(recv, non_blocking=True)
+        if recv.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        host = host_t.numpy().reshape(world, block)
+        counts = host[:, :8].copy().view(np.int64).ravel()
+    else:
+        counts = recv.view(world, block)[:, :8].contiguous().view(torch.int64).cpu().numpy().ravel()
     overflow = bool((counts > cap_per_rank).any())
     if overflow or rank != dst:
         return None, overflow
-    host = recv.cpu().numpy().reshape(world, block)
-    parts = [np.frombuffer(host[r, 16:16 + int(counts[r]) * isz].tobytes(), dtype=HIT_DTYPE) for r in range(world)]
+    parts = [host[r, 16:16 + int(counts[r]) * isz].copy().view(HIT_DTYPE) for r in range(world)]
     return np.concatenate(parts), False
 
 
