@@ -356,7 +356,10 @@ def main():
 
     if rank == 0:
         print(json.dumps(line), flush=True)
+    torch.cuda.synchronize()
+    ctx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -394,7 +397,8 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
         if rank == 0:
             qbuf[: nq * D * 2] = hv.view(torch.uint8).view(-1)
             qbuf[nq * D * 2:] = norm.view(torch.uint8).view(-1)
-        gather_cap = 1 << 16  # hits per rank carried by the one-shot gather (1 MiB per rank)
+        gather_cap = 1 << 18  # hits per rank carried by the one-shot gather (4 MiB per rank)
+        gather_pin = torch.empty(cap * 16, dtype=torch.uint8, pin_memory=True)
 
     def step():
         """broadcast queries -> local shard -> hits gathered on rank 0; returns device ms"""
@@ -403,12 +407,19 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
         torch.cuda.synchronize()
         with torch.cuda.stream(ext):  # collectives and kernels ordered on the context's stream
             e0.record()
+            dbg = os.environ.get("HG_BENCH_DEBUG") and rank == 0
+            if dbg:
+                torch.cuda.synchronize(); tA = time.perf_counter()
             if world > 1:
                 hv, norm = multigpu.broadcast_queries_fused(qbuf, nq, D)
+            if dbg:
+                torch.cuda.synchronize(); tB = time.perf_counter()
             ctx.dist_dev(hv[a:b].data_ptr(), norm[a:b].data_ptr(), b - a, a, hv.data_ptr(), norm.data_ptr(), nq, 0, D, K,
                          85.0, True, path_sel[0], d_hits.data_ptr(), cap, d_cnt.data_ptr())
+            if dbg:
+                torch.cuda.synchronize(); ctx.sync(); tC = time.perf_counter()
             if world > 1:
-                allh, overflow = multigpu.gather_hits_fixed(d_hits, d_cnt, gather_cap)
+                allh, overflow = multigpu.gather_hits_fixed(d_hits, d_cnt, gather_cap, host_buf=gather_pin)
                 if overflow:  # some shard produced more hits than the one-shot block carries
                     cnt = int(d_cnt.item())
                     allh = multigpu.gather_hits(d_hits, dev, count=min(cnt, cap))
@@ -419,6 +430,9 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
                 hits_pin[: cnt * 16].copy_(d_hits[: cnt * 16], non_blocking=True)  # D2H of the hit list
                 torch.cuda.current_stream().synchronize()
                 allh = hits_pin[: cnt * 16].numpy().view(hg.ffi.HIT_DTYPE)
+            if dbg:
+                torch.cuda.synchronize(); tD = time.perf_counter()
+                print("[dist step] bcast %.3f ms, dist_dev %.3f ms, gather %.3f ms" % ((tB - tA) * 1e3, (tC - tB) * 1e3, (tD - tC) * 1e3), file=sys.stderr)
             e1.record()
         e1.synchronize()
         return e0.elapsed_time(e1), ctx.stage_ms()[3], (allh.size if allh is not None else 0)

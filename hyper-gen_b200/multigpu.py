@@ -112,23 +112,14 @@ def gather_hits(local_hits, device, dst: int = 0, count: int | None = None) -> n
     return np.concatenate(parts) if parts else np.zeros(0, HIT_DTYPE)
 
 
-_PINNED = {}
-
-
-def _pinned(nbytes: int) -> torch.Tensor:
-    t = _PINNED.get("buf")
-    if t is None or t.numel() < nbytes:
-        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
-        _PINNED["buf"] = t
-    return t[:nbytes]
-
-
-def gather_hits_fixed(local_hits: torch.Tensor, count_t: torch.Tensor, cap_per_rank: int, dst: int = 0):
+def gather_hits_fixed(local_hits: torch.Tensor, count_t: torch.Tensor, cap_per_rank: int, dst: int = 0,
+                      host_buf: torch.Tensor | None = None):
     """One-collective gather for the common (sparse) case: every rank contributes a fixed-size
     record block [count:int64 | cap_per_rank x hg_hit] so that no host round trip is needed to size
     the collective.  Returns (hits or None, overflowed: bool); on overflow (some rank had more than
     cap_per_rank hits) the caller falls back to gather_hits().  `local_hits` is a uint8 device tensor,
-    `count_t` a 1-element int64 device tensor (the kernel's hit counter)."""
+    `count_t` a 1-element int64 device tensor (the kernel's hit counter); `host_buf` an optional pinned
+    uint8 tensor of at least world * (16 + cap_per_rank * 16) bytes owned by the caller."""
     world, rank = dist.get_world_size(), dist.get_rank()
     isz = HIT_DTYPE.itemsize
     block = 16 + cap_per_rank * isz
@@ -137,20 +128,22 @@ def gather_hits_fixed(local_hits: torch.Tensor, count_t: torch.Tensor, cap_per_r
     send[16:] = local_hits[: cap_per_rank * isz]
     recv = torch.empty(world * block, dtype=torch.uint8, device=local_hits.device)
     dist.all_gather_into_tensor(recv, send)
-    if rank == dst:  # the whole gathered buffer in one D2H into pinned memory (counts ride along)
-        host_t = _pinned(world * block)
-        host_t.copy_(recv, non_blocking=True)
-        if recv.is_cuda:
-            torch.cuda.current_stream().synchronize()
-        host = host_t.numpy().reshape(world, block)
-        counts = host[:, :8].copy().view(np.int64).ravel()
-    else:
-        counts = recv.view(world, block)[:, :8].contiguous().view(torch.int64).cpu().numpy().ravel()
+    counts = recv.view(world, block)[:, :8].contiguous().view(torch.int64).cpu().numpy().ravel()  # 8 B per rank
     overflow = bool((counts > cap_per_rank).any())
     if overflow or rank != dst:
         return None, overflow
-    parts = [host[r, 16:16 + int(counts[r]) * isz].copy().view(HIT_DTYPE) for r in range(world)]
-    return np.concatenate(parts), False
+    total = int(counts.sum())
+    host_t = host_buf[: total * isz] if host_buf is not None and host_buf.numel() >= total * isz else \
+        torch.empty(total * isz, dtype=torch.uint8)
+    pos = 0
+    for r in range(world):  # only the used part of every rank's block crosses PCIe
+        nb = int(counts[r]) * isz
+        if nb:
+            host_t[pos:pos + nb].copy_(recv[r * block + 16: r * block + 16 + nb], non_blocking=True)
+            pos += nb
+    if recv.is_cuda:
+        torch.cuda.current_stream().synchronize()
+    return host_t.numpy()[: total * isz].view(HIT_DTYPE), False
 
 
 def dist_sharded(compute, ref_hv, ref_norm, qry_hv, qry_norm, n_ref: int, n_qry: int, hv_d: int, symmetric: bool,
