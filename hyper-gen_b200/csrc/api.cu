@@ -111,7 +111,7 @@ extern "C" int hg_int_peak(hg_ctx *c, int which, double *lane_ops_per_s) {
   HG_CUDA(cudaSetDevice(c->device));
   void *d_sink;
   int rc;
-  if ((rc = hg_scratch(c, 7, 256, &d_sink))) return rc;
+  if ((rc = hg_scratch(c, HG_S_MISC, 256, &d_sink))) return rc;
   const uint32_t blocks = (uint32_t)c->sm_count * 8, iters = 4096;
   if ((rc = hg_launch_int_peak(c, which, 64, (uint32_t *)d_sink, blocks))) return rc;  // warm-up
   cudaEvent_t e0, e1;
@@ -223,9 +223,9 @@ static int run_hash_stage(hg_ctx *c, const uint8_t *d_seq, const SketchPlan &pl,
                           uint32_t **d_counts_out) {
   void *d_desc, *d_tables, *d_counts, *h_desc;
   int rc;
-  if ((rc = hg_scratch(c, 1, sizeof(hg_genome_desc) * (n + 1), &d_desc))) return rc;
-  if ((rc = hg_scratch(c, 2, pl.total_slots * 8, &d_tables))) return rc;
-  if ((rc = hg_scratch(c, 3, sizeof(uint32_t) * n, &d_counts))) return rc;
+  if ((rc = hg_scratch(c, HG_S_DESC, sizeof(hg_genome_desc) * (n + 1), &d_desc))) return rc;
+  if ((rc = hg_scratch(c, HG_S_TABLES, pl.total_slots * 8, &d_tables))) return rc;
+  if ((rc = hg_scratch(c, HG_S_COUNTS, sizeof(uint32_t) * n, &d_counts))) return rc;
   if ((rc = hg_pinned(c, 0, sizeof(hg_genome_desc) * (n + 1), &h_desc))) return rc;
   memcpy(h_desc, pl.desc.data(), sizeof(hg_genome_desc) * (n + 1));
   c->ev_used = 0;
@@ -286,7 +286,7 @@ extern "C" int hg_encode_sets_dev(hg_ctx *c, const uint64_t *d_hashes, const uin
   }
   void *d_desc, *h_desc;
   int rc;
-  if ((rc = hg_scratch(c, 1, sizeof(hg_genome_desc) * n, &d_desc))) return rc;
+  if ((rc = hg_scratch(c, HG_S_DESC, sizeof(hg_genome_desc) * n, &d_desc))) return rc;
   if ((rc = hg_pinned(c, 0, sizeof(hg_genome_desc) * n, &h_desc))) return rc;
   memcpy(h_desc, desc.data(), sizeof(hg_genome_desc) * n);
   c->ev_used = 0;
@@ -309,10 +309,10 @@ extern "C" int hg_encode_sets(hg_ctx *c, const uint64_t *hashes, const uint64_t 
   HG_CUDA(cudaSetDevice(c->device));
   int rc;
   void *d_hashes, *d_hv = nullptr, *d_packed = nullptr, *d_small;
-  if ((rc = hg_scratch(c, 2, total * 8 + 64, &d_hashes))) return rc;
-  if (hv && (rc = hg_scratch(c, 4, (size_t)n * hv_d * 2, &d_hv))) return rc;
-  if (packed && (rc = hg_scratch(c, 5, (size_t)n * hv_d * 2, &d_packed))) return rc;
-  if ((rc = hg_scratch(c, 6, (size_t)n * 12, &d_small))) return rc;
+  if ((rc = hg_scratch(c, HG_S_TABLES, total * 8 + 64, &d_hashes))) return rc;
+  if (hv && (rc = hg_scratch(c, HG_S_HV, (size_t)n * hv_d * 2, &d_hv))) return rc;
+  if (packed && (rc = hg_scratch(c, HG_S_PACKED, (size_t)n * hv_d * 2, &d_packed))) return rc;
+  if ((rc = hg_scratch(c, HG_S_SMALL, (size_t)n * 12, &d_small))) return rc;
   uint8_t *d_bits = (uint8_t *)d_small + (size_t)n * 8;
   int32_t *d_norm = (int32_t *)d_small;
   HG_CUDA(cudaMemcpyAsync(d_hashes, hashes + hash_off[0], total * 8, cudaMemcpyHostToDevice, c->stream));
@@ -386,14 +386,14 @@ extern "C" int hg_sketch_batch(hg_ctx *c, const uint8_t *seq, const uint64_t *se
 
   // size every scratch buffer before anything is enqueued (growing one synchronises)
   void *d_seq, *d_desc, *d_tables, *d_counts, *d_hv = nullptr, *d_packed, *d_small, *d_map, *h_desc;
-  if ((rc = hg_scratch(c, 0, 2 * slot_bytes, &d_seq))) return rc;
-  if ((rc = hg_scratch(c, 1, sizeof(hg_genome_desc) * n_desc, &d_desc))) return rc;
-  if ((rc = hg_scratch(c, 2, max_slots * 8, &d_tables))) return rc;
-  if ((rc = hg_scratch(c, 3, sizeof(uint32_t) * n, &d_counts))) return rc;
-  if (hv && (rc = hg_scratch(c, 4, (size_t)n * D * 2, &d_hv))) return rc;
-  if ((rc = hg_scratch(c, 5, (size_t)n * D * 2, &d_packed))) return rc;
-  if ((rc = hg_scratch(c, 6, (size_t)n * 12, &d_small))) return rc;
-  if ((rc = hg_scratch(c, 7, (max_tiles / hg_kmer_tiles_per_cta() + 2) * 4 + 256, &d_map))) return rc;
+  if ((rc = hg_scratch(c, HG_S_SEQ, 2 * slot_bytes, &d_seq))) return rc;
+  if ((rc = hg_scratch(c, HG_S_DESC, sizeof(hg_genome_desc) * n_desc, &d_desc))) return rc;
+  if ((rc = hg_scratch(c, HG_S_TABLES, max_slots * 8, &d_tables))) return rc;
+  if ((rc = hg_scratch(c, HG_S_COUNTS, sizeof(uint32_t) * n, &d_counts))) return rc;
+  if (hv && (rc = hg_scratch(c, HG_S_HV, (size_t)n * D * 2, &d_hv))) return rc;
+  if ((rc = hg_scratch(c, HG_S_PACKED, (size_t)n * D * 2, &d_packed))) return rc;
+  if ((rc = hg_scratch(c, HG_S_SMALL, (size_t)n * 12, &d_small))) return rc;
+  if ((rc = hg_scratch(c, HG_S_MISC, (max_tiles / hg_kmer_tiles_per_cta() + 2) * 4 + 256, &d_map))) return rc;
   if ((rc = hg_pinned(c, 0, sizeof(hg_genome_desc) * n_desc, &h_desc))) return rc;
   uint8_t *d_bits = (uint8_t *)d_small + (size_t)n * 8;
   int32_t *d_norm = (int32_t *)d_small;
@@ -471,7 +471,7 @@ extern "C" int hg_kmer_hash(hg_ctx *c, const uint8_t *seq, const uint64_t *seg_o
   HG_CUDA(cudaSetDevice(c->device));
   const uint64_t lo = seg_off[0], hi = seg_off[n];
   void *d_seq;
-  if ((rc = hg_scratch(c, 0, hi - lo + 64, &d_seq))) return rc;
+  if ((rc = hg_scratch(c, HG_S_SEQ, hi - lo + 64, &d_seq))) return rc;
   const uint64_t shift = (uint64_t)((uintptr_t)(seq + lo) & 15);
   HG_CUDA(cudaMemcpyAsync((uint8_t *)d_seq + shift, seq + lo, hi - lo, cudaMemcpyHostToDevice, c->stream));
   std::vector<uint64_t> rel(n + 1);
@@ -518,9 +518,9 @@ extern "C" int hg_unpack(hg_ctx *c, const uint8_t *packed, uint64_t row_stride, 
   HG_CUDA(cudaSetDevice(c->device));
   int rc;
   void *d_p, *d_b, *d_h;
-  if ((rc = hg_scratch(c, 5, (size_t)n * row_stride, &d_p))) return rc;
-  if ((rc = hg_scratch(c, 6, n, &d_b))) return rc;
-  if ((rc = hg_scratch(c, 4, (size_t)n * hv_d * 2, &d_h))) return rc;
+  if ((rc = hg_scratch(c, HG_S_PACKED, (size_t)n * row_stride, &d_p))) return rc;
+  if ((rc = hg_scratch(c, HG_S_SMALL, n, &d_b))) return rc;
+  if ((rc = hg_scratch(c, HG_S_HV, (size_t)n * hv_d * 2, &d_h))) return rc;
   HG_CUDA(cudaMemcpyAsync(d_p, packed, (size_t)n * row_stride, cudaMemcpyHostToDevice, c->stream));
   HG_CUDA(cudaMemcpyAsync(d_b, bits, n, cudaMemcpyHostToDevice, c->stream));
   if ((rc = hg_unpack_dev(c, (const uint8_t *)d_p, row_stride, (const uint8_t *)d_b, n, hv_d, (int16_t *)d_h))) return rc;
@@ -554,7 +554,7 @@ extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref
     // both matrices (HBM-bound, ~0.1 ms per GB) and one 4-byte D2H
     void *d_max;
     int rc;
-    if ((rc = hg_scratch(c, 7, 256, &d_max))) return rc;
+    if ((rc = hg_scratch(c, HG_S_MISC, 256, &d_max))) return rc;
     int32_t m1 = 0, m2 = 0;
     if ((rc = hg_launch_absmax(c, d_ref, (uint64_t)n_ref * hv_d, (int32_t *)d_max))) return rc;
     HG_CUDA(cudaMemcpyAsync(&m1, d_max, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -616,10 +616,10 @@ extern "C" int hg_dist(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, u
   const bool same = (ref == qry && ref_norm == qry_norm && n_ref == n_qry);
   const size_t rb = (size_t)n_ref * hv_d * 2, qb = same ? 0 : (size_t)n_qry * hv_d * 2;
   void *d_mat, *d_norm, *d_hits, *d_cnt;
-  if ((rc = hg_scratch(c, 4, rb + qb + 512, &d_mat))) return rc;
-  if ((rc = hg_scratch(c, 6, ((size_t)n_ref + n_qry) * 4 + 256, &d_norm))) return rc;
-  if ((rc = hg_scratch(c, 5, cap * sizeof(hg_hit) + 256, &d_hits))) return rc;
-  if ((rc = hg_scratch(c, 3, 256, &d_cnt))) return rc;
+  if ((rc = hg_scratch(c, HG_S_HV, rb + qb + 512, &d_mat))) return rc;
+  if ((rc = hg_scratch(c, HG_S_SMALL, ((size_t)n_ref + n_qry) * 4 + 256, &d_norm))) return rc;
+  if ((rc = hg_scratch(c, HG_S_PACKED, cap * sizeof(hg_hit) + 256, &d_hits))) return rc;
+  if ((rc = hg_scratch(c, HG_S_COUNTS, 256, &d_cnt))) return rc;
   int16_t *d_ref = (int16_t *)d_mat;
   const size_t rb_al = (rb + 255) & ~(size_t)255;
   int16_t *d_qry = same ? d_ref : (int16_t *)((uint8_t *)d_mat + rb_al);

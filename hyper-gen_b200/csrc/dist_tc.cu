@@ -347,8 +347,8 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
   const bool qry_covers_ref = d_ref >= d_qry && d_ref + ref_elems <= d_qry + qry_elems &&
                               ((d_ref - d_qry) % hv_d) == 0;
   void *p_q, *p_r = nullptr;
-  if ((rc = hg_scratch(ctx, 9, 2 * qry_elems + 1024, &p_q))) return rc;
-  if (!qry_covers_ref && (rc = hg_scratch(ctx, 8, 2 * ref_elems + 1024, &p_r))) return rc;
+  if ((rc = hg_scratch(ctx, HG_S_QRY_LIMBS, 2 * qry_elems + 1024, &p_q))) return rc;
+  if (!qry_covers_ref && (rc = hg_scratch(ctx, HG_S_REF_LIMBS, 2 * ref_elems + 1024, &p_r))) return rc;
   const uint32_t gx = (n_qry + TC_BN - 1) / TC_BN, gy_total = (n_ref + TC_BM - 1) / TC_BM;
   // Stand-alone CTAs by default.  The 2 x 2 cluster + TMA multicast variant (HG_DIST_CLUSTER=2) halves
   // the L2 reads but measured 10-15 % SLOWER on B200: the kernel is bound by bytes arriving per SM

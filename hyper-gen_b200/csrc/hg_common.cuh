@@ -128,7 +128,7 @@ struct hg_ctx {
   cudaStream_t stream;
   unsigned long long launches;
   // grow-only device scratch
-  void *d_scratch[12];
+  void *d_scratch[12];        // indexed by hg_scratch_slot
   size_t d_scratch_bytes[12];
   // pinned host scratch
   void *h_pinned[4];
@@ -167,6 +167,21 @@ int hg_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     if (e__ != cudaSuccess) return hg_cuda_fail(e__, #call, __FILE__, __LINE__); \
   } while (0)
 
+// Grow-only device scratch slots.  A slot has one tenant per entry point; entry points of one
+// context never run concurrently (one stream), so slots may be shared between them.
+enum hg_scratch_slot {
+  HG_S_SEQ = 0,        // staged sequence bytes (two halves when the H2D pipeline is active)
+  HG_S_DESC = 1,       // hg_genome_desc[] (+ sentinels)
+  HG_S_TABLES = 2,     // per-genome hash tables / explicit hash sets
+  HG_S_COUNTS = 3,     // distinct-hash counters; dist: the hit counter of the host entry
+  HG_S_HV = 4,         // int16 HVs (sketch output staging; dist: both matrices of the host entry)
+  HG_S_PACKED = 5,     // packed sketches; dist: hit records of the host entry
+  HG_S_SMALL = 6,      // norms / bits / counts per sketch
+  HG_S_MISC = 7,       // CTA -> genome map, |hv| max, probe sink
+  HG_S_REF_LIMBS = 8,  // s8 limb planes of the ref matrix (dist_tc)
+  HG_S_QRY_LIMBS = 9,  // s8 limb planes of the query matrix (dist_tc)
+  HG_S_COUNT = 12
+};
 // scratch slot `slot` grown to at least `bytes` (contents not preserved)
 int hg_scratch(hg_ctx *ctx, int slot, size_t bytes, void **out);
 int hg_pinned(hg_ctx *ctx, int slot, size_t bytes, void **out);

@@ -331,7 +331,7 @@ int launch_kc(hg_ctx *ctx, uint32_t n_tiles, const uint8_t *d_seq, const hg_geno
               uint64_t threshold, uint64_t seed, uint64_t *d_tables, uint32_t *d_counts) {
   const uint32_t grid = (n_tiles + KH_WARPS - 1) / KH_WARPS;
   void *d_map;
-  int rc = hg_scratch(ctx, 7, (size_t)grid * 4 + 256, &d_map);
+  int rc = hg_scratch(ctx, HG_S_MISC, (size_t)grid * 4 + 256, &d_map);
   if (rc) return rc;
   tile_map_kernel<<<(n_genomes * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_desc, n_genomes, (uint32_t *)d_map);
   kmer_hash_kernel<K, CANON><<<grid, KH_THREADS, 0, ctx->stream>>>(d_seq, d_desc, n_genomes, n_tiles, threshold, seed,
