@@ -185,20 +185,32 @@ struct SketchPlan {
   uint32_t max_slots = 0;
 };
 
+static int make_plan_bl(const uint64_t *begin, const uint64_t *lens, uint32_t n, const hg_sketch_params *p, SketchPlan &pl);
+
 static int make_plan(const uint64_t *seg_off, uint32_t n, const hg_sketch_params *p, SketchPlan &pl) {
-  const uint32_t tile = hg_kmer_tile_positions();
-  pl.desc.resize(n + 1);  // + sentinel
-  uint64_t slots_total = 0, tiles_total = 0;
+  std::vector<uint64_t> lens(n);
   for (uint32_t g = 0; g < n; g++) {
     if (seg_off[g + 1] < seg_off[g]) { hg_set_error("seg_off not monotone at %u", g); return HG_E_INVALID; }
-    const uint64_t len = seg_off[g + 1] - seg_off[g];
+    lens[g] = seg_off[g + 1] - seg_off[g];
+  }
+  return make_plan_bl(seg_off, lens.data(), n, p, pl);
+}
+
+// genome g = bytes [begin[g], begin[g] + lens[g]) of the sequence buffer
+static int make_plan_bl(const uint64_t *begin, const uint64_t *lens, uint32_t n, const hg_sketch_params *p, SketchPlan &pl) {
+  const uint32_t tile = hg_kmer_tile_positions();
+  pl.desc.resize(n + 1);  // + sentinel
+  pl.max_slots = 0;
+  uint64_t slots_total = 0, tiles_total = 0;
+  for (uint32_t g = 0; g < n; g++) {
+    const uint64_t len = lens[g];
     const uint64_t n_kmers = len >= p->ksize ? len - p->ksize + 1 : 0;
     // open-addressing table at <= 50 % load for the expected FracMinHash sample size
     uint64_t want = 2 * (len / p->scaled + 1) + 32, slots = 64;
     while (slots < want) slots <<= 1;
     if (slots > (1ull << 31)) { hg_set_error("genome %u too large for one table", g); return HG_E_UNSUPPORTED; }
     hg_genome_desc &d = pl.desc[g];
-    d.seq_begin = seg_off[g];
+    d.seq_begin = begin[g];
     d.seq_len = len;
     d.table_begin = slots_total;
     d.table_mask = (uint32_t)(slots - 1);
@@ -493,6 +505,145 @@ extern "C" int hg_kmer_hash(hg_ctx *c, const uint8_t *seq, const uint64_t *seg_o
                               cudaMemcpyDeviceToHost, c->stream));
   HG_CUDA(cudaStreamSynchronize(c->stream));
   return HG_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// FASTA file bytes in (fastx_reader::read_merge_seq on the GPU)
+// ---------------------------------------------------------------------------------------
+uint32_t hg_fasta_block_bytes();
+int hg_launch_fasta_merge(hg_ctx *ctx, const uint8_t *d_raw, const uint64_t *d_file_off, const uint64_t *d_blk_off,
+                          uint32_t n_files, uint32_t max_blocks, void *d_sums, uint8_t *d_carry, uint64_t *d_out_off,
+                          uint8_t *d_merged, uint64_t *d_merged_len);
+
+struct FastaStage {
+  std::vector<uint64_t> dev_off;   // 16-byte aligned device offset of every file (+ end)
+  std::vector<uint64_t> merged_len;
+  uint8_t *d_merged = nullptr;
+};
+
+// H2D of the raw files (each at a 16-byte aligned offset), merge on the device, lengths back.
+static int fasta_stage(hg_ctx *c, const uint8_t *raw, const uint64_t *file_off, uint32_t n, FastaStage &st) {
+  const uint32_t B = hg_fasta_block_bytes();
+  st.dev_off.assign(n + 1, 0);
+  std::vector<uint64_t> blk_off(n + 1, 0);
+  uint64_t max_blocks = 0;
+  for (uint32_t f = 0; f < n; f++) {
+    if (file_off[f + 1] < file_off[f]) { hg_set_error("file_off not monotone at %u", f); return HG_E_INVALID; }
+    const uint64_t len = file_off[f + 1] - file_off[f];
+    st.dev_off[f + 1] = (st.dev_off[f] + len + 15) & ~15ull;
+    const uint64_t nb = (len + B - 1) / B;
+    blk_off[f + 1] = blk_off[f] + nb;
+    max_blocks = std::max(max_blocks, nb);
+  }
+  if (max_blocks > 0x7fffffffull) { hg_set_error("file too large"); return HG_E_UNSUPPORTED; }
+  const uint64_t total = st.dev_off[n], nblk = blk_off[n];
+  void *d_raw, *d_merged, *d_meta, *d_sums, *h_meta;
+  int rc;
+  // device layout of the small arrays: file_off (n+1) | blk_off (n+1) | merged_len (n) | out_off (nblk) | carry (nblk bytes)
+  const size_t meta_words = (size_t)(3 * n + 2) + nblk;
+  if ((rc = hg_scratch(c, HG_S_PACKED, total + 64, &d_raw))) return rc;      // raw bytes (free until the sketches are packed)
+  if ((rc = hg_scratch(c, HG_S_SEQ, total + 64, &d_merged))) return rc;      // merged sequences
+  if ((rc = hg_scratch(c, HG_S_MISC, meta_words * 8 + nblk + 256, &d_meta))) return rc;
+  if ((rc = hg_scratch(c, HG_S_TABLES, nblk * 16 + 256, &d_sums))) return rc;
+  if ((rc = hg_pinned(c, 1, (size_t)(2 * n + 2) * 8 + (size_t)n * 8, &h_meta))) return rc;
+  uint64_t *h_off = (uint64_t *)h_meta, *h_blk = h_off + (n + 1), *h_len = h_blk + (n + 1);
+  memcpy(h_off, st.dev_off.data(), (n + 1) * 8);
+  memcpy(h_blk, blk_off.data(), (n + 1) * 8);
+  uint64_t *d_off = (uint64_t *)d_meta, *d_blk = d_off + (n + 1), *d_len = d_blk + (n + 1), *d_out = d_len + n;
+  uint8_t *d_carry = (uint8_t *)(d_out + nblk);
+  HG_CUDA(cudaMemcpyAsync(d_off, h_off, (size_t)(2 * n + 2) * 8, cudaMemcpyHostToDevice, c->stream));
+  bool contiguous = true;
+  for (uint32_t f = 0; f <= n; f++) contiguous = contiguous && (st.dev_off[f] == file_off[f] - file_off[0]);
+  if (contiguous) {
+    if (total) HG_CUDA(cudaMemcpyAsync(d_raw, raw + file_off[0], file_off[n] - file_off[0], cudaMemcpyHostToDevice, c->stream));
+  } else {
+    for (uint32_t f = 0; f < n; f++)
+      if (file_off[f + 1] > file_off[f])
+        HG_CUDA(cudaMemcpyAsync((uint8_t *)d_raw + st.dev_off[f], raw + file_off[f], file_off[f + 1] - file_off[f],
+                                cudaMemcpyHostToDevice, c->stream));
+  }
+  // the kernels see every file as [dev_off[f], dev_off[f] + len): pass true lengths through a second offset array?
+  // dev_off[f+1] - dev_off[f] includes the alignment pad, so the true end is carried separately:
+  // pad bytes are overwritten with '\n' (ignored by the merge) to keep the kernels' interface to one offset array.
+  for (uint32_t f = 0; f < n; f++) {
+    const uint64_t len = file_off[f + 1] - file_off[f], pad = st.dev_off[f + 1] - st.dev_off[f] - len;
+    if (pad) HG_CUDA(cudaMemsetAsync((uint8_t *)d_raw + st.dev_off[f] + len, '\n', pad, c->stream));
+  }
+  if ((rc = hg_launch_fasta_merge(c, (const uint8_t *)d_raw, d_off, d_blk, n, (uint32_t)max_blocks, d_sums, d_carry, d_out,
+                                  (uint8_t *)d_merged, d_len)))
+    return rc;
+  HG_CUDA(cudaMemcpyAsync(h_len, d_len, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  HG_CUDA(cudaStreamSynchronize(c->stream));
+  st.merged_len.assign(h_len, h_len + n);
+  st.d_merged = (uint8_t *)d_merged;
+  return HG_OK;
+}
+
+extern "C" int hg_fasta_merge(hg_ctx *c, const uint8_t *raw, const uint64_t *file_off, uint32_t n, uint8_t *merged,
+                              uint64_t cap, uint64_t *merged_off) {
+  if (!c || !file_off || !merged_off) { hg_set_error("hg_fasta_merge: NULL argument"); return HG_E_INVALID; }
+  merged_off[0] = 0;
+  if (n == 0) return HG_OK;
+  if (!raw && file_off[n] > file_off[0]) { hg_set_error("hg_fasta_merge: raw is NULL"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(c->device));
+  FastaStage st;
+  int rc = fasta_stage(c, raw, file_off, n, st);
+  if (rc) return rc;
+  for (uint32_t f = 0; f < n; f++) merged_off[f + 1] = merged_off[f] + st.merged_len[f];
+  if (merged_off[n] > cap || (!merged && merged_off[n])) { hg_set_error("hg_fasta_merge: need room for %llu bytes", (unsigned long long)merged_off[n]); return HG_E_CAPACITY; }
+  for (uint32_t f = 0; f < n; f++)
+    if (st.merged_len[f])
+      HG_CUDA(cudaMemcpyAsync(merged + merged_off[f], st.d_merged + st.dev_off[f], st.merged_len[f], cudaMemcpyDeviceToHost, c->stream));
+  HG_CUDA(cudaStreamSynchronize(c->stream));
+  return HG_OK;
+}
+
+extern "C" int hg_sketch_fasta_batch(hg_ctx *c, const uint8_t *raw, const uint64_t *file_off, uint32_t n,
+                                     const hg_sketch_params *p, int16_t *hv, uint8_t *packed, uint8_t *quant_bits,
+                                     int32_t *norm2, uint32_t *n_hashes) {
+  if (!c || !file_off) { hg_set_error("hg_sketch_fasta_batch: NULL argument"); return HG_E_INVALID; }
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (n == 0) return HG_OK;
+  if (!raw && file_off[n] > file_off[0]) { hg_set_error("hg_sketch_fasta_batch: raw is NULL"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(c->device));
+  FastaStage st;
+  if ((rc = fasta_stage(c, raw, file_off, n, st))) return rc;
+  SketchPlan pl;
+  if ((rc = make_plan_bl(st.dev_off.data(), st.merged_len.data(), n, p, pl))) return rc;
+  const uint32_t D = p->hv_d;
+  void *d_desc, *d_tables, *d_counts, *d_hv = nullptr, *d_packed, *d_small, *d_map, *h_desc;
+  // (the raw bytes in HG_S_PACKED and the block summaries in HG_S_TABLES are dead by now)
+  if ((rc = hg_scratch(c, HG_S_DESC, sizeof(hg_genome_desc) * (n + 1), &d_desc))) return rc;
+  if ((rc = hg_scratch(c, HG_S_TABLES, pl.total_slots * 8, &d_tables))) return rc;
+  if ((rc = hg_scratch(c, HG_S_COUNTS, sizeof(uint32_t) * n, &d_counts))) return rc;
+  if (hv && (rc = hg_scratch(c, HG_S_HV, (size_t)n * D * 2, &d_hv))) return rc;
+  if ((rc = hg_scratch(c, HG_S_SMALL, (size_t)n * 12, &d_small))) return rc;
+  if ((rc = hg_pinned(c, 0, sizeof(hg_genome_desc) * (n + 1), &h_desc))) return rc;
+  // the CTA map shares HG_S_MISC with nothing that is still live; size it before the launch
+  if ((rc = hg_scratch(c, HG_S_MISC, ((size_t)pl.n_tiles / hg_kmer_tiles_per_cta() + 2) * 4 + 256, &d_map))) return rc;
+  uint8_t *d_bits = (uint8_t *)d_small + (size_t)n * 8;
+  int32_t *d_norm = (int32_t *)d_small;
+  uint32_t *d_nh = (uint32_t *)d_small + n;
+  memcpy(h_desc, pl.desc.data(), sizeof(hg_genome_desc) * (n + 1));
+  HG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(hg_genome_desc) * (n + 1), cudaMemcpyHostToDevice, c->stream));
+  HG_CUDA(cudaMemsetAsync(d_tables, 0xFF, pl.total_slots * 8, c->stream));
+  HG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n, c->stream));
+  HG_CUDA(cudaMemsetAsync(c->d_status, 0, 4 * sizeof(uint32_t), c->stream));
+  if ((rc = hg_launch_kmer_hash(c, st.d_merged, (const hg_genome_desc *)d_desc, n, pl.n_tiles, p, (uint64_t *)d_tables,
+                                (uint32_t *)d_counts)))
+    return rc;
+  // the raw bytes are dead after the merge: their slot now receives the packed sketches
+  if ((rc = hg_scratch(c, HG_S_PACKED, (size_t)n * D * 2, &d_packed))) return rc;
+  if ((rc = hg_launch_encode(c, (const hg_genome_desc *)d_desc, n, (const uint64_t *)d_tables, (const uint32_t *)d_counts, D,
+                             (int16_t *)d_hv, (uint8_t *)d_packed, d_bits, d_norm, d_nh)))
+    return rc;
+  if (hv) HG_CUDA(cudaMemcpyAsync(hv, d_hv, (size_t)n * D * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (packed) HG_CUDA(cudaMemcpyAsync(packed, d_packed, (size_t)n * D * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (quant_bits) HG_CUDA(cudaMemcpyAsync(quant_bits, d_bits, n, cudaMemcpyDeviceToHost, c->stream));
+  if (norm2) HG_CUDA(cudaMemcpyAsync(norm2, d_norm, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (n_hashes) HG_CUDA(cudaMemcpyAsync(n_hashes, d_nh, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  return hg_sketch_status(c);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@ HG_OK, HG_E_INVALID, HG_E_CUDA, HG_E_CAPACITY, HG_E_RANGE, HG_E_UNSUPPORTED = 0,
 EXPORTS = [
     "hg_init", "hg_destroy", "hg_sync", "hg_last_error", "hg_version", "hg_stream_handle", "hg_launch_count",
     "hg_set_profiling", "hg_stage_ms", "hg_int_peak", "hg_encode_sets", "hg_encode_sets_dev",
+    "hg_fasta_merge", "hg_sketch_fasta_batch",
     "hg_kmer_hash", "hg_sketch_batch", "hg_sketch_batch_dev", "hg_sketch_status", "hg_unpack", "hg_unpack_dev",
     "hg_dist", "hg_dist_dev", "hg_dist_last_path", "hg_dist_last_reason",
 ]
@@ -71,6 +72,8 @@ def load() -> C.CDLL:
     L.hg_int_peak.restype = i32; L.hg_int_peak.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.hg_encode_sets.restype = i32; L.hg_encode_sets.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp, vp]
     L.hg_encode_sets_dev.restype = i32; L.hg_encode_sets_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp, vp]
+    L.hg_fasta_merge.restype = i32; L.hg_fasta_merge.argtypes = [vp, vp, vp, u32, vp, u64, vp]
+    L.hg_sketch_fasta_batch.restype = i32; L.hg_sketch_fasta_batch.argtypes = [vp, vp, vp, u32, pp, vp, vp, vp, vp, vp]
     L.hg_kmer_hash.restype = i32; L.hg_kmer_hash.argtypes = [vp, vp, vp, u32, pp, vp, u64, vp]
     L.hg_sketch_batch.restype = i32; L.hg_sketch_batch.argtypes = [vp, vp, vp, u32, pp, vp, vp, vp, vp, vp]
     L.hg_sketch_batch_dev.restype = i32; L.hg_sketch_batch_dev.argtypes = [vp, vp, vp, u32, pp, vp, vp, vp, vp, vp]
@@ -216,6 +219,38 @@ class Context:
         off = np.ascontiguousarray(hash_off, np.uint64)
         _check(load().hg_encode_sets_dev(self._h, d_hashes, _ptr(off), off.size - 1, hv_d, d_hv, d_packed,
                                          d_quant_bits, d_norm2))
+
+    # -- raw FASTA in --
+    @staticmethod
+    def _concat_files(files):
+        off = np.zeros(len(files) + 1, np.uint64)
+        off[1:] = np.cumsum([len(f) for f in files])
+        raw = np.frombuffer(b"".join(bytes(f) for f in files), dtype=np.uint8) if int(off[-1]) else np.zeros(0, np.uint8)
+        return np.ascontiguousarray(raw), off
+
+    def fasta_merge(self, files):
+        """hg_fasta_merge: list of raw FASTA file contents (bytes) -> list of merged sequences (uint8 arrays)."""
+        raw, off = self._concat_files(files)
+        n = len(files)
+        merged = np.empty(max(int(off[-1]), 1), np.uint8)
+        moff = np.zeros(n + 1, np.uint64)
+        _check(load().hg_fasta_merge(self._h, _ptr(raw) if raw.size else None, _ptr(off), n, _ptr(merged), merged.size,
+                                     _ptr(moff)))
+        return [merged[int(moff[f]):int(moff[f + 1])].copy() for f in range(n)]
+
+    def sketch_fasta_batch(self, files, params: SketchParams, want_hv: bool = True):
+        """hg_sketch_fasta_batch: raw FASTA file contents in, sketches out (as sketch_batch)."""
+        raw, off = self._concat_files(files)
+        n = len(files)
+        D = int(params.hv_d)
+        hv = np.empty((n, D), np.int16) if want_hv else None
+        packed = np.empty((n, 2 * D), np.uint8)
+        qb = np.empty(n, np.uint8)
+        norm2 = np.empty(n, np.int32)
+        nh = np.empty(n, np.uint32)
+        _check(load().hg_sketch_fasta_batch(self._h, _ptr(raw) if raw.size else None, _ptr(off), n, C.byref(params),
+                                            _ptr(hv), _ptr(packed), _ptr(qb), _ptr(norm2), _ptr(nh)))
+        return dict(hv=hv, packed=packed, quant_bits=qb, norm2=norm2, n_hashes=nh)
 
     def sketch_status(self):
         _check(load().hg_sketch_status(self._h))

@@ -130,6 +130,12 @@ std::vector<types::FileSketch> load_sketch(const std::string &path) {
 
 namespace fastx_reader {
 
+std::vector<uint8_t> read_raw(const std::string &file_name) {
+  std::ifstream f(file_name, std::ios::binary);
+  if (!f) die("Opening .fna files failed: " + file_name);
+  return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+
 std::vector<uint8_t> read_merge_seq(const std::string &file_name) {
   std::ifstream f(file_name, std::ios::binary);
   if (!f) die("Opening .fna files failed: " + file_name);
@@ -170,13 +176,19 @@ void sketch_cuda(const types::SketchParams &params) {
   const size_t batch_files = 256;
   for (size_t b0 = 0; b0 < n_file; b0 += batch_files) {
     const size_t b1 = std::min(n_file, b0 + batch_files), m = b1 - b0;
-    // host FASTA reading in parallel (the reference's rayon par_iter over files)
+    // host file reading in parallel (the reference's rayon par_iter over files).  By default the raw
+    // file bytes go to the GPU, which does read_merge_seq's job itself (hg_sketch_fasta_batch);
+    // HG_HOST_PARSE=1 keeps the reference's host-side reader in the loop instead.
+    const bool host_parse = getenv("HG_HOST_PARSE") != nullptr;
     std::vector<std::vector<uint8_t>> seqs(m);
     {
       std::vector<std::thread> th;
       const int nt = std::max(1, std::min<int>(params.threads, (int)m));
       for (int t = 0; t < nt; t++)
-        th.emplace_back([&, t] { for (size_t i = (size_t)t; i < m; i += (size_t)nt) seqs[i] = fastx_reader::read_merge_seq(files[b0 + i]); });
+        th.emplace_back([&, t] {
+          for (size_t i = (size_t)t; i < m; i += (size_t)nt)
+            seqs[i] = host_parse ? fastx_reader::read_merge_seq(files[b0 + i]) : fastx_reader::read_raw(files[b0 + i]);
+        });
       for (auto &x : th) x.join();
     }
     std::vector<uint64_t> seg_off(m + 1, 0);
@@ -186,8 +198,12 @@ void sketch_cuda(const types::SketchParams &params) {
     std::vector<uint8_t> packed(m * 2 * D), bits(m);
     std::vector<int32_t> norm2(m);
     std::vector<uint32_t> nh(m);
-    check(hg_sketch_batch(ctx, seq.data(), seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
-                          norm2.data(), nh.data()), "hg_sketch_batch");
+    if (host_parse)
+      check(hg_sketch_batch(ctx, seq.data(), seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
+                            norm2.data(), nh.data()), "hg_sketch_batch");
+    else
+      check(hg_sketch_fasta_batch(ctx, seq.data(), seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
+                                  norm2.data(), nh.data()), "hg_sketch_fasta_batch");
     for (size_t i = 0; i < m; i++) {
       types::FileSketch &s = all[b0 + i];
       s.ksize = params.ksize; s.scaled = params.scaled; s.seed = params.seed; s.canonical = params.canonical;

@@ -134,6 +134,22 @@ HG_API int hg_encode_sets_dev(hg_ctx *ctx, const uint64_t *d_hashes, const uint6
                               uint32_t n_sets, uint32_t hv_d, int16_t *d_hv, uint8_t *d_packed,
                               uint8_t *d_quant_bits, int32_t *d_norm2);
 
+/* ---- FASTA file bytes in -------------------------------------------------------------- */
+
+/* fastx_reader::read_merge_seq (src/fastx_reader.rs:6-29) for a batch of files, on the GPU:
+ * file f = raw[file_off[f] .. file_off[f+1]) exactly as read from disk.  Every line starting
+ * with '>' becomes one 'N', every other line loses its trailing '\n' and one '\r' before it.
+ * merged_off (n_files + 1) receives the prefix offsets of the merged sequences in `merged`
+ * (capacity `cap`; HG_E_CAPACITY reports the need in merged_off[n_files]).  Stage hook. */
+HG_API int hg_fasta_merge(hg_ctx *ctx, const uint8_t *raw, const uint64_t *file_off, uint32_t n_files,
+                          uint8_t *merged, uint64_t cap, uint64_t *merged_off);
+
+/* hg_sketch_batch fed with raw FASTA files: the merge above, then the sketch pipeline, without
+ * the merged sequences ever visiting the host.  Outputs as hg_sketch_batch. */
+HG_API int hg_sketch_fasta_batch(hg_ctx *ctx, const uint8_t *raw, const uint64_t *file_off, uint32_t n_files,
+                                 const hg_sketch_params *p, int16_t *hv, uint8_t *packed,
+                                 uint8_t *quant_bits, int32_t *norm2, uint32_t *n_hashes);
+
 /* ---- sketch format ---------------------------------------------------------------- */
 
 /* decompress_hd_sketch (src/hd.rs:184-212) for n sketches on the GPU: packed rows of
