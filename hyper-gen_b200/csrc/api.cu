@@ -598,6 +598,10 @@ extern "C" int hg_fasta_merge(hg_ctx *c, const uint8_t *raw, const uint64_t *fil
   return HG_OK;
 }
 
+// Raw FASTA files in, sketches out.  Same ~64 MB chunk pipeline as hg_sketch_batch (copy stream +
+// double-buffered staging), with the merge kernels in front of the hash kernel.  Nothing comes back
+// to the host between the stages: tiles and tables are planned from the raw file sizes (an upper
+// bound of the merged lengths) and the hash kernel reads the true lengths the merge left in HBM.
 extern "C" int hg_sketch_fasta_batch(hg_ctx *c, const uint8_t *raw, const uint64_t *file_off, uint32_t n,
                                      const hg_sketch_params *p, int16_t *hv, uint8_t *packed, uint8_t *quant_bits,
                                      int32_t *norm2, uint32_t *n_hashes) {
@@ -607,37 +611,131 @@ extern "C" int hg_sketch_fasta_batch(hg_ctx *c, const uint8_t *raw, const uint64
   if (n == 0) return HG_OK;
   if (!raw && file_off[n] > file_off[0]) { hg_set_error("hg_sketch_fasta_batch: raw is NULL"); return HG_E_INVALID; }
   HG_CUDA(cudaSetDevice(c->device));
-  FastaStage st;
-  if ((rc = fasta_stage(c, raw, file_off, n, st))) return rc;
-  SketchPlan pl;
-  if ((rc = make_plan_bl(st.dev_off.data(), st.merged_len.data(), n, p, pl))) return rc;
-  const uint32_t D = p->hv_d;
-  void *d_desc, *d_tables, *d_counts, *d_hv = nullptr, *d_packed, *d_small, *d_map, *h_desc;
-  // (the raw bytes in HG_S_PACKED and the block summaries in HG_S_TABLES are dead by now)
-  if ((rc = hg_scratch(c, HG_S_DESC, sizeof(hg_genome_desc) * (n + 1), &d_desc))) return rc;
-  if ((rc = hg_scratch(c, HG_S_TABLES, pl.total_slots * 8, &d_tables))) return rc;
+  const uint32_t D = p->hv_d, B = hg_fasta_block_bytes();
+  const uint64_t chunk_bytes = hg_chunk_bytes();
+
+  struct Chunk {
+    uint32_t g0, g1;
+    std::vector<uint64_t> dev_off, blk_off;  // per file of the chunk (+ end): aligned offset in the slot, block prefix
+    uint64_t max_blocks = 0;
+    SketchPlan pl;
+  };
+  std::vector<Chunk> chunks;
+  for (uint32_t g = 0; g < n;) {
+    Chunk ch;
+    ch.g0 = g;
+    const uint64_t lo = file_off[g];
+    do {
+      if (file_off[g + 1] < file_off[g]) { hg_set_error("file_off not monotone at %u", g); return HG_E_INVALID; }
+      ++g;
+    } while (g < n && file_off[g + 1] - lo <= chunk_bytes);
+    ch.g1 = g;
+    const uint32_t m = ch.g1 - ch.g0;
+    ch.dev_off.assign(m + 1, 0);
+    ch.blk_off.assign(m + 1, 0);
+    std::vector<uint64_t> lens(m);
+    for (uint32_t t = 0; t < m; t++) {
+      lens[t] = file_off[ch.g0 + t + 1] - file_off[ch.g0 + t];
+      ch.dev_off[t + 1] = (ch.dev_off[t] + lens[t] + 15) & ~15ull;
+      const uint64_t nb = (lens[t] + B - 1) / B;
+      ch.blk_off[t + 1] = ch.blk_off[t] + nb;
+      ch.max_blocks = std::max(ch.max_blocks, nb);
+    }
+    if (ch.max_blocks > 0x7fffffffull) { hg_set_error("file too large"); return HG_E_UNSUPPORTED; }
+    if ((rc = make_plan_bl(ch.dev_off.data(), lens.data(), m, p, ch.pl))) return rc;  // upper bounds
+    chunks.push_back(std::move(ch));
+  }
+  uint64_t max_bytes = 0, max_slots = 0, max_tiles = 0, max_blk = 0;
+  uint32_t max_m = 0;
+  for (const Chunk &ch : chunks) {
+    max_bytes = std::max(max_bytes, ch.dev_off.back());
+    max_slots = std::max<uint64_t>(max_slots, ch.pl.total_slots);
+    max_tiles = std::max<uint64_t>(max_tiles, ch.pl.n_tiles);
+    max_blk = std::max(max_blk, ch.blk_off.back());
+    max_m = std::max(max_m, ch.g1 - ch.g0);
+  }
+  const uint64_t slot_bytes = (max_bytes + 64 + 255) & ~255ull;
+  const size_t n_desc = (size_t)n + chunks.size();
+  // per-chunk merge metadata in one buffer: file_off | blk_off | out_off | sums | carry
+  const size_t meta_bytes = ((size_t)(2 * (max_m + 1)) * 8 + max_blk * 8 + max_blk * 16 + max_blk + 256 + 15) & ~(size_t)15;
+  const size_t h_meta_per_chunk = (size_t)(2 * (max_m + 1)) * 8;
+
+  void *d_rawbuf, *d_merged, *d_meta, *d_desc, *d_tables, *d_counts, *d_hv = nullptr, *d_packed, *d_small, *d_map, *h_desc,
+      *h_meta;
+  if ((rc = hg_scratch(c, HG_S_REF_LIMBS, 2 * slot_bytes, &d_rawbuf))) return rc;  // raw files, double buffered
+  if ((rc = hg_scratch(c, HG_S_SEQ, slot_bytes, &d_merged))) return rc;
+  if ((rc = hg_scratch(c, HG_S_QRY_LIMBS, meta_bytes + (size_t)n * 8, &d_meta))) return rc;
+  if ((rc = hg_scratch(c, HG_S_DESC, sizeof(hg_genome_desc) * n_desc, &d_desc))) return rc;
+  if ((rc = hg_scratch(c, HG_S_TABLES, max_slots * 8, &d_tables))) return rc;
   if ((rc = hg_scratch(c, HG_S_COUNTS, sizeof(uint32_t) * n, &d_counts))) return rc;
   if (hv && (rc = hg_scratch(c, HG_S_HV, (size_t)n * D * 2, &d_hv))) return rc;
+  if ((rc = hg_scratch(c, HG_S_PACKED, (size_t)n * D * 2, &d_packed))) return rc;
   if ((rc = hg_scratch(c, HG_S_SMALL, (size_t)n * 12, &d_small))) return rc;
-  if ((rc = hg_pinned(c, 0, sizeof(hg_genome_desc) * (n + 1), &h_desc))) return rc;
-  // the CTA map shares HG_S_MISC with nothing that is still live; size it before the launch
-  if ((rc = hg_scratch(c, HG_S_MISC, ((size_t)pl.n_tiles / hg_kmer_tiles_per_cta() + 2) * 4 + 256, &d_map))) return rc;
+  if ((rc = hg_scratch(c, HG_S_MISC, (max_tiles / hg_kmer_tiles_per_cta() + 2) * 4 + 256, &d_map))) return rc;
+  if ((rc = hg_pinned(c, 0, sizeof(hg_genome_desc) * n_desc, &h_desc))) return rc;
+  if ((rc = hg_pinned(c, 1, h_meta_per_chunk * chunks.size(), &h_meta))) return rc;
   uint8_t *d_bits = (uint8_t *)d_small + (size_t)n * 8;
   int32_t *d_norm = (int32_t *)d_small;
   uint32_t *d_nh = (uint32_t *)d_small + n;
-  memcpy(h_desc, pl.desc.data(), sizeof(hg_genome_desc) * (n + 1));
-  HG_CUDA(cudaMemcpyAsync(d_desc, h_desc, sizeof(hg_genome_desc) * (n + 1), cudaMemcpyHostToDevice, c->stream));
-  HG_CUDA(cudaMemsetAsync(d_tables, 0xFF, pl.total_slots * 8, c->stream));
-  HG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n, c->stream));
+  uint64_t *d_len = (uint64_t *)((uint8_t *)d_meta + meta_bytes);  // true merged lengths, all files
+  uint64_t *dm_off = (uint64_t *)d_meta, *dm_blk = dm_off + (max_m + 1), *dm_out = dm_blk + (max_m + 1);
+  uint8_t *dm_sums = (uint8_t *)(dm_out + max_blk);
+  uint8_t *dm_carry = dm_sums + max_blk * 16;
+  if (!c->copy_stream) {
+    HG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      HG_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+      HG_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  c->ev_used = 0;
   HG_CUDA(cudaMemsetAsync(c->d_status, 0, 4 * sizeof(uint32_t), c->stream));
-  if ((rc = hg_launch_kmer_hash(c, st.d_merged, (const hg_genome_desc *)d_desc, n, pl.n_tiles, p, (uint64_t *)d_tables,
-                                (uint32_t *)d_counts)))
-    return rc;
-  // the raw bytes are dead after the merge: their slot now receives the packed sketches
-  if ((rc = hg_scratch(c, HG_S_PACKED, (size_t)n * D * 2, &d_packed))) return rc;
-  if ((rc = hg_launch_encode(c, (const hg_genome_desc *)d_desc, n, (const uint64_t *)d_tables, (const uint32_t *)d_counts, D,
-                             (int16_t *)d_hv, (uint8_t *)d_packed, d_bits, d_norm, d_nh)))
-    return rc;
+  HG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * n, c->stream));
+  HG_CUDA(cudaEventRecord(c->ev_done[0], c->stream));
+  HG_CUDA(cudaEventRecord(c->ev_done[1], c->stream));
+
+  size_t desc_pos = 0;
+  for (size_t ci = 0; ci < chunks.size(); ci++) {
+    const Chunk &ch = chunks[ci];
+    const int slot = (int)(ci & 1);
+    const uint32_t m = ch.g1 - ch.g0;
+    uint8_t *d_raw = (uint8_t *)d_rawbuf + slot * slot_bytes;
+    // ---- copy stream: every file of the chunk to its 16-byte aligned place in the raw slot ----
+    HG_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));
+    for (uint32_t t = 0; t < m; t++) {
+      const uint64_t len = file_off[ch.g0 + t + 1] - file_off[ch.g0 + t];
+      if (len) HG_CUDA(cudaMemcpyAsync(d_raw + ch.dev_off[t], raw + file_off[ch.g0 + t], len, cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    HG_CUDA(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+    // ---- compute stream ----
+    uint64_t *hm = (uint64_t *)((uint8_t *)h_meta + ci * h_meta_per_chunk);
+    memcpy(hm, ch.dev_off.data(), (m + 1) * 8);
+    memcpy(hm + (max_m + 1), ch.blk_off.data(), (m + 1) * 8);
+    HG_CUDA(cudaMemcpyAsync(dm_off, hm, h_meta_per_chunk, cudaMemcpyHostToDevice, c->stream));
+    hg_genome_desc *hd = (hg_genome_desc *)h_desc + desc_pos, *dd = (hg_genome_desc *)d_desc + desc_pos;
+    memcpy(hd, ch.pl.desc.data(), sizeof(hg_genome_desc) * (m + 1));
+    desc_pos += m + 1;
+    HG_CUDA(cudaMemcpyAsync(dd, hd, sizeof(hg_genome_desc) * (m + 1), cudaMemcpyHostToDevice, c->stream));
+    HG_CUDA(cudaMemsetAsync(d_tables, 0xFF, ch.pl.total_slots * 8, c->stream));
+    HG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+    for (uint32_t t = 0; t < m; t++) {  // alignment pads read as empty lines
+      const uint64_t len = file_off[ch.g0 + t + 1] - file_off[ch.g0 + t], pad = ch.dev_off[t + 1] - ch.dev_off[t] - len;
+      if (pad) HG_CUDA(cudaMemsetAsync(d_raw + ch.dev_off[t] + len, '\n', pad, c->stream));
+    }
+    if ((rc = hg_launch_fasta_merge(c, d_raw, dm_off, dm_blk, m, (uint32_t)ch.max_blocks, dm_sums, dm_carry, dm_out,
+                                    (uint8_t *)d_merged, d_len + ch.g0)))
+      return rc;
+    HG_CUDA(cudaEventRecord(c->ev_done[slot], c->stream));  // the raw slot may be overwritten now
+    c->d_actual_len = d_len + ch.g0;
+    rc = hg_launch_kmer_hash(c, (const uint8_t *)d_merged, dd, m, ch.pl.n_tiles, p, (uint64_t *)d_tables,
+                             (uint32_t *)d_counts + ch.g0);
+    c->d_actual_len = nullptr;
+    if (rc) return rc;
+    if ((rc = hg_launch_encode(c, dd, m, (const uint64_t *)d_tables, (const uint32_t *)d_counts + ch.g0, D,
+                               d_hv ? (int16_t *)d_hv + (size_t)ch.g0 * D : nullptr,
+                               (uint8_t *)d_packed + (size_t)ch.g0 * 2 * D, d_bits + ch.g0, d_norm + ch.g0, d_nh + ch.g0)))
+      return rc;
+  }
   if (hv) HG_CUDA(cudaMemcpyAsync(hv, d_hv, (size_t)n * D * 2, cudaMemcpyDeviceToHost, c->stream));
   if (packed) HG_CUDA(cudaMemcpyAsync(packed, d_packed, (size_t)n * D * 2, cudaMemcpyDeviceToHost, c->stream));
   if (quant_bits) HG_CUDA(cudaMemcpyAsync(quant_bits, d_bits, n, cudaMemcpyDeviceToHost, c->stream));

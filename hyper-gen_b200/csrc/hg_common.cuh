@@ -145,6 +145,7 @@ struct hg_ctx {
   int ev_used;           // which stage boundaries were recorded in the last call
   // H2D pipeline of the host-pointer sketch entry
   int tc_attr_set;
+  const uint64_t *d_actual_len;  // optional per-genome true lengths for the next k-mer launch (raw-FASTA path)
   cudaStream_t copy_stream;
   cudaEvent_t ev_copied[2], ev_done[2];
 };

@@ -100,7 +100,7 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
                  uint32_t n_genomes, uint32_t n_tiles, uint64_t threshold, uint64_t seed,
                  uint64_t *__restrict__ tables, uint32_t *__restrict__ counts,
                  uint32_t *__restrict__ status, uint32_t lut_lo, uint32_t lut_hi,
-                 const uint32_t *__restrict__ cta_genome) {
+                 const uint32_t *__restrict__ cta_genome, const uint64_t *__restrict__ actual_len) {
   constexpr int NW = (K + 7) / 8;          // nibble words == t1ha2 input words (8 bases each)
   constexpr int LASTN = K - 8 * (NW - 1);  // bases in the last word, 1..8
   constexpr uint32_t LASTMASK = LASTN == 8 ? 0xFFFFFFFFu : ((1u << (4 * LASTN)) - 1u);
@@ -127,7 +127,10 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
   uint32_t g = cta_genome[blockIdx.x];
   while (desc[g + 1].first_tile <= tile) ++g;  // warp-uniform, usually zero steps
   {
-  const hg_genome_desc gd = desc[g];
+  hg_genome_desc gd = desc[g];
+  // raw-FASTA path: the tiles were planned from an upper bound, the merge kernel wrote the real length
+  if (actual_len) gd.seq_len = min(gd.seq_len, actual_len[g]);
+  if ((uint64_t)(tile - gd.first_tile) * KH_TILE + K > gd.seq_len) return;  // no complete k-mer starts in this tile
   const uint64_t tile_base = (uint64_t)(tile - gd.first_tile) * KH_TILE;  // first start position
   uint64_t need_end = tile_base + KH_TILE + (K - 1);                      // bases [tile_base, need_end)
   if (need_end > gd.seq_len) need_end = gd.seq_len;
@@ -336,7 +339,7 @@ int launch_kc(hg_ctx *ctx, uint32_t n_tiles, const uint8_t *d_seq, const hg_geno
   tile_map_kernel<<<(n_genomes * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_desc, n_genomes, (uint32_t *)d_map);
   kmer_hash_kernel<K, CANON><<<grid, KH_THREADS, 0, ctx->stream>>>(d_seq, d_desc, n_genomes, n_tiles, threshold, seed,
                                                                    d_tables, d_counts, ctx->d_status, 0x00414700u,
-                                                                   0x00435400u, (const uint32_t *)d_map);
+                                                                   0x00435400u, (const uint32_t *)d_map, ctx->d_actual_len);
   ctx->launches += 2;
   HG_CUDA(cudaGetLastError());
   return HG_OK;

@@ -58,3 +58,30 @@ def test_sketch_from_raw_fasta_equals_sketch_from_merged(ctx, hg, oracle):
     for g in range(len(files)):
         nb = int(want["quant_bits"][g]) * 1024 // 8
         assert np.array_equal(got["packed"][g, :nb], want["packed"][g, :nb])
+
+
+def test_raw_fasta_chunk_pipeline(ctx, hg, oracle, monkeypatch):
+    """Several 1 MB chunks through the double-buffered copy/merge/hash/encode pipeline, with files
+    whose merged length is far below the raw size the tiles were planned from (long headers, a file
+    that is all header, a merged length below k)."""
+    from hypergen_b200 import synth
+    monkeypatch.setenv("HG_CHUNK_MB", "1")
+    rng = np.random.default_rng(77)
+    files = []
+    for g in range(14):
+        seq = synth.family_member(g + 90, 150_000 + 40_001 * (g % 5)).numpy()
+        files.append(_fasta(seq, width=70 + g, records=1 + g % 4))
+    files.insert(3, b">" + b"h" * 300_000 + b"\n" + bytes(random_dna(rng, 5000)) + b"\n")
+    files.insert(7, b">" + b"h" * 100_000)
+    files.insert(9, b">x\nACGTACGTAC\n")
+    files.insert(11, _fasta(random_dna(rng, 1_500_000, p_n=0.001)))       # a file larger than the chunk size
+    p = hg.make_params(scaled=200, hv_d=2048)
+    got = ctx.sketch_fasta_batch(files, p)
+    seqs = [oracle.read_merge_seq(f) for f in files]
+    off = np.cumsum([0] + [s.size for s in seqs]).astype(np.uint64)
+    want = oracle.sketch_batch(np.concatenate(seqs), off, scaled=200, hv_d=2048)
+    assert np.array_equal(got["n_hashes"], want["n_hashes"])
+    assert np.array_equal(got["hv"], want["hv"]) and np.array_equal(got["norm2"], want["norm2"])
+    assert np.array_equal(got["quant_bits"], want["quant_bits"])
+    again = ctx.sketch_fasta_batch(files, p)                                # scratch reuse across calls
+    assert np.array_equal(again["hv"], want["hv"])
