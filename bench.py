@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--dist-n", type=int, default=10000, help="sketches in the all-vs-all (config[2]: 10000)")
     ap.add_argument("--no-dist", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fasta", action="store_true", help="skip the raw-FASTA end-to-end leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -203,6 +204,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = multigpu.bind_to_gpu_numa(local_rank) if os.environ.get("HG_NUMA_BIND", "1") != "0" else {"bound": False}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -314,6 +316,53 @@ def main():
     # sanity: the e2e results equal the device-resident ones
     assert torch.equal(h_norm, d_norm.cpu()) and torch.equal(h_bits, d_bits.cpu())
 
+    # ---------------- the same, from raw FASTA file bytes (hg_sketch_fasta_batch) ----------------
+    # files = ">g\n" + 80-column lines; the library merges the records on the GPU (fastx_reader::read_merge_seq)
+    fasta = None
+    if not args.no_fasta:
+        hdr = torch.tensor(list(b">g\n"), dtype=torch.uint8, device=dev).expand(n, 3)
+        body = torch.cat([seq_dev.view(n, GENOME_LEN // 80, 80),
+                          torch.full((n, GENOME_LEN // 80, 1), 10, dtype=torch.uint8, device=dev)], dim=2).view(n, -1)
+        raw_dev = torch.cat([hdr, body], dim=1).contiguous()
+        file_len = raw_dev.shape[1]
+        raw_host = torch.empty(n * file_len, dtype=torch.uint8, pin_memory=True)
+        raw_host.copy_(raw_dev.view(-1))
+        del raw_dev, body, hdr
+        file_off = (np.arange(n + 1, dtype=np.uint64) * np.uint64(file_len))
+
+        def fasta_step():
+            rc = lib.hg_sketch_fasta_batch(ctx._h, raw_host.data_ptr(), file_off.ctypes.data, n, C.byref(params), None,
+                                           h_packed.data_ptr(), h_bits.data_ptr(), h_norm.data_ptr(), h_nh.data_ptr())
+            if rc != 0:
+                raise RuntimeError(lib.hg_last_error().decode())
+
+        for _ in range(2):
+            fasta_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fasta_step()
+        torch.cuda.synchronize()
+        fa_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        assert torch.equal(h_norm, d_norm.cpu()) and torch.equal(h_bits, d_bits.cpu())
+        fasta = {"value": world * n * e2e_steps / fa_s, "unit": "genomes/s", "ms_per_step": 1e3 * fa_s / e2e_steps,
+                 "h2d_bytes_per_step": int(n * file_len + (n + 1) * 8 + n * 40), "d2h_bytes_per_step": d2h,
+                 "h2d_gbs": world * n * file_len * e2e_steps / fa_s / 1e9,
+                 "input": "%d FASTA files of %d bytes (one record, 80-column lines) in pinned host memory; "
+                          "records merged on the GPU" % (n, file_len)}
+        del raw_host
+
+    # DRAM bytes of one kmer_hash launch, from the committed `ncu --set full` capture (bytes, per launch like `achieved`)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "kmer_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_per_launch"] * (n / tj["genomes_per_launch"])
+        traffic_src = tj["source"] + ("" if n == tj["genomes_per_launch"] else " (scaled per genome)")
+    except (OSError, KeyError, ValueError):
+        pass
+
     line = {
         "metric": "genomes sketched/sec (5 Mbp, k=21, D=4096)", "value": value, "unit": "genomes/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -324,11 +373,13 @@ def main():
         "e2e": {"value": e2e_value, "unit": "genomes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                 "h2d_gbs": world * h2d * e2e_steps / e2e_s / 1e9, "h2d_only_gbs_per_gpu": h2d_only_gbs,
-                "h2d_only_genomes_per_s_per_gpu": h2d_only_gbs * 1e9 / GENOME_LEN},
+                "h2d_only_genomes_per_s_per_gpu": h2d_only_gbs * 1e9 / GENOME_LEN, "from_fasta_files": fasta},
+        "numa": numa,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "kmer_hash_kernel<21,true>", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                     "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peaks["source"],
                      "alg_bytes_per_launch": n * ALG_BYTES_PER_GENOME, "ms_per_launch": kmer_ms,
                      "note": "bit-exact t1ha2 makes this kernel INT32-issue bound, not HBM bound (SURVEY.md 8d): see roofline_int32"},
         "stages_ms": {"staging_memset": stg_ms, "kmer_hash": kmer_ms, "encode_pack": enc_ms},
