@@ -851,9 +851,9 @@ extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref
 extern "C" int hg_dist_last_path(hg_ctx *c) { return c ? c->dist_path : 0; }
 extern "C" const char *hg_dist_last_reason(hg_ctx *c) { return c ? c->dist_reason : ""; }
 
-extern "C" int hg_dist(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uint32_t n_ref, const int16_t *qry,
-                       const int32_t *qry_norm, uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th,
-                       int symmetric, int path, hg_hit *hits, uint64_t cap, uint64_t *n_hits) {
+static int dist_host(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uint32_t n_ref, const int16_t *qry,
+                     const int32_t *qry_norm, uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
+                     int path, hg_hit *hits, uint64_t cap, uint64_t *n_hits, bool sorted, uint32_t *ani_milli) {
   if (!c || !n_hits) { hg_set_error("hg_dist: NULL argument"); return HG_E_INVALID; }
   *n_hits = 0;
   if ((n_ref && (!ref || !ref_norm)) || (n_qry && (!qry || !qry_norm)) || (cap && !hits)) {
@@ -891,8 +891,34 @@ extern "C" int hg_dist(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, u
     return HG_E_CAPACITY;
   }
   if (cnt) {
+    void *d_milli = nullptr;
+    if (sorted) {  // output stage on the device (src/utils.rs:262-269)
+      if (ani_milli && (rc = hg_scratch(c, HG_S_MISC, cnt * 4 + 256, &d_milli))) return rc;
+      if ((rc = hg_launch_sort_hits(c, (hg_hit *)d_hits, cnt, (uint32_t *)d_milli))) return rc;
+    }
     HG_CUDA(cudaMemcpyAsync(hits, d_hits, cnt * sizeof(hg_hit), cudaMemcpyDeviceToHost, c->stream));
-    HG_CUDA(cudaStreamSynchronize(c->stream));  // append order is unspecified: the output stage sorts
+    if (d_milli) HG_CUDA(cudaMemcpyAsync(ani_milli, d_milli, cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+    HG_CUDA(cudaStreamSynchronize(c->stream));  // unsorted: append order is unspecified
   }
   return HG_OK;
+}
+
+extern "C" int hg_dist(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uint32_t n_ref, const int16_t *qry,
+                       const int32_t *qry_norm, uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th,
+                       int symmetric, int path, hg_hit *hits, uint64_t cap, uint64_t *n_hits) {
+  return dist_host(c, ref, ref_norm, n_ref, qry, qry_norm, n_qry, hv_d, ksize, ani_th, symmetric, path, hits, cap, n_hits,
+                   false, nullptr);
+}
+
+extern "C" int hg_dist_sorted(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uint32_t n_ref, const int16_t *qry,
+                              const int32_t *qry_norm, uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th,
+                              int symmetric, int path, hg_hit *hits, uint32_t *ani_milli, uint64_t cap, uint64_t *n_hits) {
+  return dist_host(c, ref, ref_norm, n_ref, qry, qry_norm, n_qry, hv_d, ksize, ani_th, symmetric, path, hits, cap, n_hits,
+                   true, ani_milli);
+}
+
+extern "C" int hg_sort_hits_dev(hg_ctx *c, hg_hit *d_hits, uint64_t n, uint32_t *d_ani_milli) {
+  if (!c || (n && !d_hits)) { hg_set_error("hg_sort_hits_dev: NULL argument"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(c->device));
+  return hg_launch_sort_hits(c, d_hits, n, d_ani_milli);
 }

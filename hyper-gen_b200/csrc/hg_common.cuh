@@ -181,6 +181,8 @@ enum hg_scratch_slot {
   HG_S_MISC = 7,       // CTA -> genome map, |hv| max, probe sink
   HG_S_REF_LIMBS = 8,  // s8 limb planes of the ref matrix (dist_tc)
   HG_S_QRY_LIMBS = 9,  // s8 limb planes of the query matrix (dist_tc)
+  HG_S_SORT_TMP = 10,  // ping-pong buffer of the hit sort
+  HG_S_SORT_CNT = 11,  // digit counters of the hit sort
   HG_S_COUNT = 12
 };
 // scratch slot `slot` grown to at least `bytes` (contents not preserved)
@@ -220,4 +222,5 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
                       hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits);
 int hg_launch_int_peak(hg_ctx *ctx, int which, uint32_t iters, uint32_t *d_sink, uint32_t blocks);
 // max |hv| over a device matrix (decides the dist path); result in *d_out (int32)
+int hg_launch_sort_hits(hg_ctx *ctx, hg_hit *d_hits, uint64_t n, uint32_t *d_milli);
 int hg_launch_absmax(hg_ctx *ctx, const int16_t *d_hv, uint64_t n_elems, int32_t *d_out);

@@ -73,9 +73,10 @@ def dist(sd: SketchDist, ctx: Context | None = None, path: int = 0) -> str:
         else:
             qp, qb, qn = _stack_packed(qry)
             q_hv = ctx.unpack(qp, qb, hv_d)
-        hits = ctx.dist(r_hv, rn, q_hv, qn, ksize=ksize, ani_th=sd.ani_threshold, symmetric=if_sym, path=path)
-        order = reference_output_order(hits, len(ref), len(qry), if_sym)
-        text = fileio.format_ani_lines([s.file_str for s in ref], [s.file_str for s in qry], hits, order)
+        # dist + the output stage's sort on the GPU (hg_dist_sorted); `milli` is the `{:.3}` field in thousandths
+        hits, milli = ctx.dist(r_hv, rn, q_hv, qn, ksize=ksize, ani_th=sd.ani_threshold, symmetric=if_sym, path=path,
+                               sorted_output=True, want_milli=True)
+        text = fileio.format_ani_lines_milli([s.file_str for s in ref], [s.file_str for s in qry], hits, milli)
         if sd.out_file:
             with open(sd.out_file, "w") as f:
                 f.write(text)

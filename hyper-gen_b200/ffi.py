@@ -20,7 +20,7 @@ EXPORTS = [
     "hg_set_profiling", "hg_stage_ms", "hg_int_peak", "hg_encode_sets", "hg_encode_sets_dev",
     "hg_fasta_merge", "hg_sketch_fasta_batch",
     "hg_kmer_hash", "hg_sketch_batch", "hg_sketch_batch_dev", "hg_sketch_status", "hg_unpack", "hg_unpack_dev",
-    "hg_dist", "hg_dist_dev", "hg_dist_last_path", "hg_dist_last_reason",
+    "hg_dist", "hg_dist_dev", "hg_dist_last_path", "hg_dist_last_reason", "hg_sort_hits_dev", "hg_dist_sorted",
 ]
 
 
@@ -84,6 +84,9 @@ def load() -> C.CDLL:
     L.hg_dist.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, u32, C.c_float, i32, i32, vp, u64, C.POINTER(u64)]
     L.hg_dist_dev.restype = i32
     L.hg_dist_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp, u32, u32, u32, u32, C.c_float, i32, i32, vp, u64, vp]
+    L.hg_sort_hits_dev.restype = i32; L.hg_sort_hits_dev.argtypes = [vp, vp, u64, vp]
+    L.hg_dist_sorted.restype = i32
+    L.hg_dist_sorted.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, u32, C.c_float, i32, i32, vp, vp, u64, C.POINTER(u64)]
     L.hg_dist_last_path.restype = i32; L.hg_dist_last_path.argtypes = [vp]
     L.hg_dist_last_reason.restype = C.c_char_p; L.hg_dist_last_reason.argtypes = [vp]
     _lib = L
@@ -269,8 +272,10 @@ class Context:
 
     # -- stage 2 --
     def dist(self, ref_hv, ref_norm2, qry_hv, qry_norm2, ksize=21, ani_th=85.0, symmetric=False, path=0,
-             cap=None) -> np.ndarray:
-        """hg_dist with host buffers -> structured array of hits (i, j, dot, ani), unspecified order."""
+             cap=None, sorted_output=False, want_milli=False):
+        """hg_dist with host buffers -> structured array of hits (i, j, dot, ani), unspecified order.
+        sorted_output: hg_dist_sorted instead - the hits in the reference's output order (sorted on the
+        GPU); with want_milli also the ANI in thousandths as `{:.3}` rounds it -> (hits, milli)."""
         r = np.ascontiguousarray(ref_hv, np.int16)
         rn = np.ascontiguousarray(ref_norm2, np.int32)
         same = qry_hv is ref_hv
@@ -283,18 +288,29 @@ class Context:
         while True:
             hits = np.empty(cap, HIT_DTYPE)
             n_hits = C.c_uint64(0)
-            rc = load().hg_dist(self._h, _ptr(r), _ptr(rn), R, _ptr(q), _ptr(qn), Q, D, ksize, ani_th,
-                                int(symmetric), path, _ptr(hits), cap, C.byref(n_hits))
+            milli = np.empty(cap, np.uint32) if (sorted_output and want_milli) else None
+            if sorted_output:
+                rc = load().hg_dist_sorted(self._h, _ptr(r), _ptr(rn), R, _ptr(q), _ptr(qn), Q, D, ksize, ani_th,
+                                           int(symmetric), path, _ptr(hits), _ptr(milli), cap, C.byref(n_hits))
+            else:
+                rc = load().hg_dist(self._h, _ptr(r), _ptr(rn), R, _ptr(q), _ptr(qn), Q, D, ksize, ani_th,
+                                    int(symmetric), path, _ptr(hits), cap, C.byref(n_hits))
             if rc == HG_E_CAPACITY and n_hits.value > cap:
                 cap = int(n_hits.value)
                 continue
             _check(rc)
+            if milli is not None:
+                return hits[: n_hits.value].copy(), milli[: n_hits.value].copy()
             return hits[: n_hits.value].copy()
 
     def dist_dev(self, d_ref, d_ref_norm2, n_ref, i0, d_qry, d_qry_norm2, n_qry, j0, hv_d, ksize, ani_th,
                  symmetric, path, d_hits, cap, d_n_hits):
         _check(load().hg_dist_dev(self._h, d_ref, d_ref_norm2, n_ref, i0, d_qry, d_qry_norm2, n_qry, j0, hv_d, ksize,
                                   ani_th, int(symmetric), path, d_hits, cap, d_n_hits))
+
+    def sort_hits_dev(self, d_hits, n, d_ani_milli=None):
+        """hg_sort_hits_dev: device records to the reference's output order, in place."""
+        _check(load().hg_sort_hits_dev(self._h, d_hits, n, d_ani_milli))
 
     @property
     def dist_last_path(self) -> int:

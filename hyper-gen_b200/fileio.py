@@ -100,3 +100,9 @@ def format_ani_lines(ref_names, qry_names, hits, order) -> str:
     """`{ref}\\t{query}\\t{:.3}\\n` per reported pair, in `order` (utils.rs:274-281)."""
     return "".join("%s\t%s\t%.3f\n" % (ref_names[int(hits["i"][t])], qry_names[int(hits["j"][t])],
                                        float(hits["ani"][t])) for t in order)
+
+
+def format_ani_lines_milli(ref_names, qry_names, hits, milli) -> str:
+    """The same lines from hits already in output order and their ANI in thousandths (hg_dist_sorted)."""
+    return "".join("%s\t%s\t%d.%03d\n" % (ref_names[int(i)], qry_names[int(j)], m // 1000, m % 1000)
+                   for i, j, m in zip(hits["i"].tolist(), hits["j"].tolist(), milli.tolist()))

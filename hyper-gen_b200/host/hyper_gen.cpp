@@ -255,32 +255,29 @@ void dist(const types::SketchDist &sd) {
     qhv = qhv_store.data();
     qn = qs.norm.data();
   }
+  // dump_ani_file (utils.rs:262-285): stable ascending sort over the pair enumeration, reversed => ANI descending,
+  // ties in descending pair index.  hg_dist_sorted orders the hits on the GPU and also hands back the ANI in
+  // thousandths as `{:.3}` rounds it.
   uint64_t cap = 1 << 20, n_hits = 0;
   std::vector<hg_hit> hits;
+  std::vector<uint32_t> milli;
   for (;;) {
     hits.resize(cap);
-    const int rc = hg_dist(ctx, rhv.data(), rs.norm.data(), (uint32_t)R, qhv, qn, (uint32_t)Q, (uint32_t)D, ref[0].ksize,
-                           sd.ani_threshold, if_sym ? 1 : 0, 0, hits.data(), cap, &n_hits);
+    milli.resize(cap);
+    const int rc = hg_dist_sorted(ctx, rhv.data(), rs.norm.data(), (uint32_t)R, qhv, qn, (uint32_t)Q, (uint32_t)D,
+                                  ref[0].ksize, sd.ani_threshold, if_sym ? 1 : 0, 0, hits.data(), milli.data(), cap, &n_hits);
     if (rc == HG_E_CAPACITY && n_hits > cap) { cap = n_hits; continue; }
-    check(rc, "hg_dist");
+    check(rc, "hg_dist_sorted");
     break;
   }
   hits.resize(n_hits);
   hg_destroy(ctx);
-  // dump_ani_file (utils.rs:262-285): stable ascending sort over the pair enumeration, reversed
-  auto pair_index = [&](const hg_hit &h) -> uint64_t {
-    const uint64_t i = h.i, j = h.j;
-    return if_sym ? i * (Q - 1) - i * (i - 1) / 2 + (j - i - 1) : i * Q + j;
-  };
-  std::sort(hits.begin(), hits.end(), [&](const hg_hit &a, const hg_hit &b) {
-    if (a.ani != b.ani) return a.ani > b.ani;
-    return pair_index(a) > pair_index(b);
-  });
   std::string csv;
   char buf[64];
-  for (const auto &h : hits) {
+  for (size_t t = 0; t < hits.size(); t++) {
+    const hg_hit &h = hits[t];
     csv += ref[h.i].file_str; csv += '\t'; csv += qry[h.j].file_str;
-    snprintf(buf, sizeof(buf), "\t%.3f\n", (double)h.ani);
+    snprintf(buf, sizeof(buf), "\t%u.%03u\n", milli[t] / 1000u, milli[t] % 1000u);
     csv += buf;
   }
   std::ofstream f(sd.out_file, std::ios::binary);

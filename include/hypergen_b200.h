@@ -184,6 +184,23 @@ HG_API int hg_dist_dev(hg_ctx *ctx, const int16_t *d_ref_hv, const int32_t *d_re
                        int symmetric, int path, hg_hit *d_hits, uint64_t cap,
                        unsigned long long *d_n_hits);
 
+/* ---- output stage ------------------------------------------------------------------ */
+
+/* The order of utils::dump_ani_file (src/utils.rs:262-285): a stable ascending sort by ANI,
+ * reversed - i.e. ANI descending, equal ANIs in DESCENDING pair-enumeration index, which for
+ * both enumerations (src/dist.rs:243-265) is (i descending, j descending).  Sorts the n device
+ * records in place with an on-device radix sort.  If d_ani_milli is not NULL it also receives,
+ * per sorted record, the ANI in thousandths rounded exactly as the `{:.3}` of src/utils.rs:280
+ * prints it (so the host writes "%u.%03u"). */
+HG_API int hg_sort_hits_dev(hg_ctx *ctx, hg_hit *d_hits, uint64_t n, uint32_t *d_ani_milli);
+
+/* hg_dist followed by hg_sort_hits_dev: host pointers in, the hits in the reference's output
+ * order out (ani_milli may be NULL).  Same capacity contract as hg_dist. */
+HG_API int hg_dist_sorted(hg_ctx *ctx, const int16_t *ref_hv, const int32_t *ref_norm2, uint32_t n_ref,
+                          const int16_t *qry_hv, const int32_t *qry_norm2, uint32_t n_qry, uint32_t hv_d,
+                          uint32_t ksize, float ani_th, int symmetric, int path, hg_hit *hits,
+                          uint32_t *ani_milli, uint64_t cap, uint64_t *n_hits);
+
 /* Which path the last hg_dist / hg_dist_dev took (1 SIMT, 2 tensor) and why. */
 HG_API int hg_dist_last_path(hg_ctx *ctx);
 HG_API const char *hg_dist_last_reason(hg_ctx *ctx);
