@@ -12,11 +12,17 @@
 // is accumulated as three s32 accumulators (the two cross products share one), each < 2^31
 // for D <= 32768.  The recombination wraps in i32 exactly like the reference's i32 sum.
 //
-// One CTA per 128 x 128 output tile, 10 warps: warp 0 issues TMA loads of the four 128 x 128 B
-// operand tiles (128B-swizzled, K-major) through a 3-stage mbarrier ring, one thread of warp 1
-// issues the tcgen05.mma stream and commits stage releases, warps 2-9 drain the three TMEM
-// accumulators with tcgen05.ld, apply a division-free bound and run the shared exact epilogue
+// Default kernel (dist_tc2_kernel): persistent CTA PAIRS (cluster 2 x 1, tcgen05 cta_group::2), one pair
+// per TPC, each walking 256 x 128 output tiles.  Per k-block a CTA TMA-loads its own 128 ref rows and
+// only HALF of the query tile (64 rows) - 48 KB instead of 64 KB for the same MMA work - because the
+// pair's MMA reads the query half of both CTAs; the kernel is bound by operand bytes arriving per SM
+// (L2 -> SM, ~37 B/clk/SM measured), so this is where the time goes.  10 warps per CTA: warp 0 issues
+// TMA (128B-swizzled, K-major boxes) through a 4-stage mbarrier ring and runs ahead into the next
+// tile while the epilogue drains, one thread of the leader CTA's warp 1 issues the tcgen05.mma stream
+// (M = 256) and multicasts the stage releases to both CTAs, warps 2-9 of each CTA drain their three
+// TMEM accumulators with tcgen05.ld, apply a division-free bound and run the shared exact epilogue
 // (dist_common.cuh) only where a pair can reach the threshold.
+// Fallback (HG_DIST_KERNEL=1): dist_tc_kernel, one stand-alone CTA per 128 x 128 tile.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -31,7 +37,8 @@ constexpr int TC_TILE_BYTES = 128 * TC_BK;            // one operand tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;     // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_EPI_WARPS = 8;                      // two per TMEM lane quarter, half the columns each
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*col bounds*/;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*col bounds*/ +
+                              8 * 256 * 8 /*candidate lists: TC_EPI_WARPS x TC_LIST_CAP x 8 B*/;
 constexpr uint32_t TC_TMEM_COLS = 512;
 
 // instruction descriptor, kind::i8: D = s32, A = B = signed 8-bit, both K-major, M = 128, N = 128
@@ -52,46 +59,57 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes, uint32_t on) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %2, 0;\n\t"
+      "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar),
+      "r"(bytes), "r"(on)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
-                                               uint16_t cta_mask) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, uint32_t on) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
-      "l"(map), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1)
+      "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %5, 0;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(on)
       : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(cta_mask)
-               : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // smem matrix descriptor: K-major, 128B swizzle, 8-row atoms 1024 B apart (SBO), version 1
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// Low word: start address >> 4 (14 bits) | LBO field = 1; high word: SBO = 1024 >> 4, version 1 (bit 46),
+// layout 2 = SWIZZLE_128B (bits 61-63).  Shared addresses are < 2^18, so the low word of (addr + off) is
+// desc_lo(addr) + (off >> 4): the issue loop adds compile-time constants instead of re-encoding.
+constexpr uint32_t TC_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+// The single-thread instructions (tcgen05.mma / commit, TMA) are issued from WARP-UNIFORM code with the
+// issuing lane selected by a predicate (`on` is 1 in exactly one lane, from elect_one()).  Inside an
+// `if (lane == 0)` branch ptxas cannot keep the descriptors in uniform registers and wraps every MMA in
+// an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~10 extra dependent instructions), which left the
+// issuing thread, not the tensor pipe, as the bottleneck (~126 clk per 64-clk MMA).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t on;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(on));
+  return on;
 }
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate, uint32_t on) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(TC_IDESC), "r"(accumulate)
+      "setp.ne.b32 e, %5, 0;\n\t"
+      "mov.b64 da, {%1, %6};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(TC_IDESC), "r"(accumulate), "r"(on), "r"(TC_DESC_HI)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %1, 0;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
+      "r"(on)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -101,30 +119,103 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
 }
 
-// CL = 1: stand-alone CTAs.  CL = 2: 2 x 2 thread-block clusters — the two CTAs of a cluster row
-// share their A (ref) tile and the two of a cluster column their B (query) tile; each CTA loads
-// half of each shared tile and TMA-multicasts it to its peer, halving the L2 -> SM operand
-// traffic that bounds this kernel.
-template <int CL>
+// ---- epilogue pieces shared by both kernels ---------------------------------------------------
+// Cheap per-element test first: ani >= ani_th implies dot >= cfrac * (norm_r + norm_q)
+// (dist_common.cuh), split into a per-row and a per-column integer so that an element costs
+// two shift-adds, one add and one compare.  Only lanes that pass run the exact f32 ANI sequence
+// and the compacted append.
+
+// per-column bound of query column lj (INT32_MIN = always take the exact path)
+__device__ __forceinline__ int32_t tc_col_bound(const hg::DistEpilogue &ep, uint32_t lj) {
+  if (!(ep.cfrac > 0.0f) || lj >= ep.n_qry) return INT32_MIN;
+  const int32_t nq = ep.qry_norm[lj];
+  return nq > 0 ? __float2int_rd(ep.cfrac * __int2float_rz(nq)) - 1 : INT32_MIN;
+}
+__device__ __forceinline__ int32_t tc_row_bound(const hg::DistEpilogue &ep, uint32_t li) {
+  if (!(ep.cfrac > 0.0f) || li >= ep.n_ref) return INT32_MIN / 2;
+  const int32_t nr = ep.ref_norm[li];
+  return nr > 0 ? __float2int_rd(ep.cfrac * __int2float_rz(nr)) - 1 : INT32_MIN / 2;
+}
+
+// Candidates are not evaluated while the accumulators are being drained: each epilogue warp parks
+// them (row, column, exact dot) in its own shared-memory list and runs the exact f32 ANI + append
+// (dist_common.cuh) over the list afterwards, 32 candidates per round.  In the persistent kernel
+// that second phase starts after TMEM has been handed back, so it overlaps the next tile's MMAs;
+// it also balances the lanes (hits cluster on a few rows of the diagonal tiles).
+constexpr int TC_LIST_CAP = 256;  // candidates per warp list (8 B each); a full list is evaluated in place
+
+__device__ __forceinline__ void tc_process(const hg::DistEpilogue &ep, const uint2 *list, uint32_t n, uint32_t row0, uint32_t col0) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t e = lane; e < ((n + 31u) & ~31u); e += 32) {
+    const bool live = e < n;
+    const uint2 c = live ? list[e] : make_uint2(0u, 0u);
+    const uint32_t li = row0 + (c.x >> 8), lj = col0 + (c.x & 255u);
+    hg::dist_emit(ep, live && li < ep.n_ref && lj < ep.n_qry, li, lj, (int32_t)c.y);
+  }
+  __syncwarp();
+}
+
+// One epilogue warp drains columns [c_begin, c_end) of its 32 TMEM lanes (three accumulators at
+// column offsets 0, BN, 2 BN from taddr): row `rowl` of the tile per lane, query columns col0 + c.
+// Appends the candidates to list[0..n_list); returns the new n_list.
+__device__ __forceinline__ uint32_t tc_drain(const hg::DistEpilogue &ep, uint32_t taddr, int c_begin, int c_end,
+                                             const int32_t *s_tq, int32_t tr, bool row_live, uint32_t rowl, uint32_t row0,
+                                             uint32_t col0, uint2 *list, uint32_t n_list) {
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; c += 16) {
+    uint32_t hh[16], cr[16], ll[16];
+    tmem_ld16(taddr + 0 * TC_BN + c, hh);
+    tmem_ld16(taddr + 1 * TC_BN + c, cr);
+    tmem_ld16(taddr + 2 * TC_BN + c, ll);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    int32_t dot[16];
+    uint32_t cand = 0;  // bit j: column c + j of my row can reach the threshold
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      dot[j] = (int32_t)((((hh[j] << 7) + cr[j]) << 7) + ll[j]);  // wrapping i32, as dist.rs:147-151
+      const int32_t tq = s_tq[c + j];
+      // tq = INT32_MIN or tr = INT32_MIN / 2 (bound off / degenerate norm) always qualify
+      const bool cj = dot[j] >= (int32_t)((uint32_t)tr + (uint32_t)tq) || tq == INT32_MIN || tr == INT32_MIN / 2;
+      cand |= (uint32_t)cj << j;
+    }
+    if (!row_live) cand = 0;
+    if (!__any_sync(0xffffffffu, cand != 0)) continue;  // the common case
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // 8 columns at a time: at most 256 candidates, always fits an empty list
+      const uint32_t m = (cand >> (8 * h)) & 255u;
+      const uint32_t cnt = __popc(m);
+      uint32_t inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += y;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+      if (total == 0) continue;
+      if (n_list + total > TC_LIST_CAP) {  // evaluate what is parked (slow path: TMEM stays held)
+        tc_process(ep, list, n_list, row0, col0);
+        n_list = 0;
+      }
+      uint32_t pos = n_list + inc - cnt;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if ((m >> j) & 1u) list[pos++] = make_uint2((rowl << 8) | (uint32_t)(c + 8 * h + j), (uint32_t)dot[8 * h + j]);
+      n_list += total;
+      __syncwarp();
+    }
+  }
+  return n_list;
+}
+
+// ---- fallback kernel: one stand-alone CTA per 128 x 128 tile ----------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_qry,
                uint32_t ref_plane_rows, uint32_t ref_row_base, uint32_t qry_plane_rows, uint32_t hv_d,
                hg::DistEpilogue ep) {
   const uint32_t row0 = blockIdx.y * TC_BM, col0 = blockIdx.x * TC_BN;
-  // symmetric: a tile (cluster of tiles) whose largest global j is not above its smallest global
-  // i is empty.  The test is uniform over a cluster, so whole clusters leave together.
-  {
-    const uint32_t crow0 = (blockIdx.y / CL) * CL * TC_BM, ccol_end = (blockIdx.x / CL + 1) * CL * TC_BN;
-    if (ep.symmetric && (uint64_t)ep.j0 + ccol_end - 1 <= (uint64_t)ep.i0 + crow0) return;
-  }
-  const bool own_tile_empty = ep.symmetric && (uint64_t)ep.j0 + col0 + TC_BN - 1 <= (uint64_t)ep.i0 + row0;
-  // position inside the cluster: cx along N (blockIdx.x), cy along M (blockIdx.y); rank = cx + CL * cy
-  const uint32_t cx = CL == 1 ? 0u : (blockIdx.x % CL), cy = CL == 1 ? 0u : (blockIdx.y % CL);
-  const uint32_t crank = cx + CL * cy;
-  const uint16_t mask_a = CL == 1 ? 1 : (uint16_t)(((1u << CL) - 1u) << (CL * cy));               // same cluster row
-  const uint16_t mask_b = CL == 1 ? 1 : (uint16_t)((1u << cx) | (1u << (cx + CL)));               // same cluster column
-  const uint16_t mask_e = (uint16_t)(mask_a | mask_b);  // everyone that writes into my stages
-  (void)crank;
+  // symmetric: a tile whose largest global j is not above its smallest global i is empty
+  if (ep.symmetric && (uint64_t)ep.j0 + col0 + TC_BN - 1 <= (uint64_t)ep.i0 + row0) return;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle wants 1024 B alignment
@@ -137,8 +228,7 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    // a stage is released when my own MMAs and those of every CTA I multicast into have read it
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL == 1 ? 1 : 2 * CL - 1); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -150,134 +240,314 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // every peer's barriers are initialised before anyone signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t num_kb = hv_d / TC_BK;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer (whole warp in step, one elected lane issues) =====
+    {
+      const uint32_t on = elect_one();
       for (uint32_t kb = 0; kb < num_kb; ++kb) {
         const int s = kb % TC_STAGES;
         const uint32_t ph = (kb / TC_STAGES) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), TC_STAGE_BYTES);
+        mbar_expect_tx(full_bar(s), TC_STAGE_BYTES, on);
         const uint32_t st = base + s * TC_STAGE_BYTES;
         const int k0 = (int)(kb * TC_BK);
-        if (CL == 1) {
-          tma_load_2d(st + 0 * TC_TILE_BYTES, &tm_ref, full_bar(s), k0, (int)(ref_row_base + row0));  // ref hi limbs
-          tma_load_2d(st + 1 * TC_TILE_BYTES, &tm_ref, full_bar(s), k0, (int)(ref_plane_rows + ref_row_base + row0));  // ref lo
-          tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_qry, full_bar(s), k0, (int)col0);                    // qry hi limbs
-          tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_qry, full_bar(s), k0, (int)(qry_plane_rows + col0));  // qry lo limbs
-        } else {
-          // my 1/CL slice of the row-shared A tile and of the column-shared B tile, multicast
-          constexpr int HR = 128 / CL;                     // rows per slice
-          constexpr int HB = HR * TC_BK;                   // bytes per slice
-          const int ar = (int)(ref_row_base + row0 + cx * HR), br = (int)(col0 + cy * HR);
-          tma_load_2d_mc(st + 0 * TC_TILE_BYTES + cx * HB, &tm_ref, full_bar(s), k0, ar, mask_a);
-          tma_load_2d_mc(st + 1 * TC_TILE_BYTES + cx * HB, &tm_ref, full_bar(s), k0, (int)ref_plane_rows + ar, mask_a);
-          tma_load_2d_mc(st + 2 * TC_TILE_BYTES + cy * HB, &tm_qry, full_bar(s), k0, br, mask_b);
-          tma_load_2d_mc(st + 3 * TC_TILE_BYTES + cy * HB, &tm_qry, full_bar(s), k0, (int)qry_plane_rows + br, mask_b);
-        }
+        tma_load_2d(st + 0 * TC_TILE_BYTES, &tm_ref, full_bar(s), k0, (int)(ref_row_base + row0), on);  // ref hi limbs
+        tma_load_2d(st + 1 * TC_TILE_BYTES, &tm_ref, full_bar(s), k0, (int)(ref_plane_rows + ref_row_base + row0), on);  // ref lo
+        tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_qry, full_bar(s), k0, (int)col0, on);                    // qry hi limbs
+        tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_qry, full_bar(s), k0, (int)(qry_plane_rows + col0), on);  // qry lo limbs
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (a single thread drives the tensor core) =====
-    if (lane == 0) {
-      for (uint32_t kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (kb / TC_STAGES) & 1u;
-        mbar_wait(full_bar(s), ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = base + s * TC_STAGE_BYTES;
+    // ===== MMA issuer (one elected thread drives the tensor core; the warp stays converged) =====
+    {
+      const uint32_t on = elect_one();
+      const uint32_t d0 = umma_desc_lo(base);
+      // the stage ring is walked with a compile-time stage index so that every descriptor is d0 + constant
+      for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += TC_STAGES) {
+        const uint32_t ph = (kb0 / TC_STAGES) & 1u;
 #pragma unroll
-        for (int ks = 0; ks < TC_BK / 32; ++ks) {  // one MMA covers K = 32 int8
-          const uint64_t a_hi = umma_desc(st + 0 * TC_TILE_BYTES + 32 * ks), a_lo = umma_desc(st + 1 * TC_TILE_BYTES + 32 * ks);
-          const uint64_t b_hi = umma_desc(st + 2 * TC_TILE_BYTES + 32 * ks), b_lo = umma_desc(st + 3 * TC_TILE_BYTES + 32 * ks);
-          const uint32_t acc = (kb | (uint32_t)ks) != 0u;
-          umma_i8(tmem_base + 0 * TC_BN, a_hi, b_hi, acc);  // Hr.Hq
-          umma_i8(tmem_base + 1 * TC_BN, a_hi, b_lo, acc);  // Hr.Lq
-          umma_i8(tmem_base + 1 * TC_BN, a_lo, b_hi, 1u);   //   + Lr.Hq
-          umma_i8(tmem_base + 2 * TC_BN, a_lo, b_lo, acc);  // Lr.Lq
+        for (int s = 0; s < TC_STAGES; ++s) {
+          if (kb0 + s < num_kb) {
+            mbar_wait(full_bar(s), ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 32; ++ks) {  // one MMA covers K = 32 int8
+              const uint32_t off = (uint32_t)(s * TC_STAGE_BYTES + 32 * ks) >> 4;
+              const uint32_t a_hi = d0 + off, a_lo = a_hi + (TC_TILE_BYTES >> 4);
+              const uint32_t b_hi = a_hi + (2 * TC_TILE_BYTES >> 4), b_lo = a_hi + (3 * TC_TILE_BYTES >> 4);
+              const uint32_t acc = (kb0 | (uint32_t)s | (uint32_t)ks) != 0u;
+              umma_i8(tmem_base + 0 * TC_BN, a_hi, b_hi, acc, on);  // Hr.Hq
+              umma_i8(tmem_base + 1 * TC_BN, a_hi, b_lo, acc, on);  // Hr.Lq
+              umma_i8(tmem_base + 1 * TC_BN, a_lo, b_hi, 1u, on);   //   + Lr.Hq
+              umma_i8(tmem_base + 2 * TC_BN, a_lo, b_lo, acc, on);  // Lr.Lq
+            }
+            umma_commit(empty_bar(s), on);  // the stage is free once these MMAs have read it
+          }
         }
-        if (CL == 1) umma_commit(empty_bar(s));  // the stage is free once these MMAs have read it
-        else umma_commit_mc(empty_bar(s), mask_e);
       }
-      umma_commit(accum_bar);       // all accumulators final
+      umma_commit(accum_bar, on);       // all accumulators final
     }
   } else {
     // ===== epilogue: TMEM -> registers -> exact i32 dot -> bound test -> (rare) ANI + append =====
-    // Cheap per-element test first: ani >= ani_th implies dot >= cfrac * (norm_r + norm_q)
-    // (dist_common.cuh), split into a per-row and a per-column integer so that an element
-    // costs two shift-adds, one add and one compare.  Only 16-column chunks in which some
-    // lane passes run the exact f32 ANI sequence and the compacted append.
     const int ew = warp - 2;                 // 0..7
     const uint32_t q = warp & 3;             // TMEM lane quarter this warp may read
     const int half = (ew >> 2);              // which 64 columns this warp drains
     int32_t *s_tq = reinterpret_cast<int32_t *>(aligned + TC_STAGES * TC_STAGE_BYTES + 256);
-    const bool use_bound = ep.cfrac > 0.0f;
     {  // per-column bounds, one column per epilogue thread of the first four warps
       const int t = threadIdx.x - 64;
-      if (t < TC_BN) {
-        const uint32_t lj = col0 + t;
-        int32_t v = INT32_MIN;  // out-of-range / degenerate columns always go to the exact path
-        if (use_bound && lj < ep.n_qry) {
-          const int32_t nq = ep.qry_norm[lj];
-          if (nq > 0) v = __float2int_rd(ep.cfrac * __int2float_rz(nq)) - 1;
-        }
-        s_tq[t] = v;
-      }
+      if (t < TC_BN) s_tq[t] = tc_col_bound(ep, col0 + t);
     }
     asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");  // epilogue warps only
     const uint32_t li = row0 + q * 32 + lane;
-    const bool row_live = li < ep.n_ref;
-    int32_t tr = INT32_MIN / 2;
-    if (use_bound && row_live) {
-      const int32_t nr = ep.ref_norm[li];
-      if (nr > 0) tr = __float2int_rd(ep.cfrac * __int2float_rz(nr)) - 1;
-    }
+    const int32_t tr = tc_row_bound(ep, li);
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t taddr = tmem_base + ((q * 32u) << 16);
-#pragma unroll 1
-    for (int c = half * (TC_BN / 2); c < (half + 1) * (TC_BN / 2) && !own_tile_empty; c += 16) {
-      uint32_t hh[16], cr[16], ll[16];
-      tmem_ld16(taddr + 0 * TC_BN + c, hh);
-      tmem_ld16(taddr + 1 * TC_BN + c, cr);
-      tmem_ld16(taddr + 2 * TC_BN + c, ll);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      int32_t dot[16];
-      uint32_t cand = 0;  // bit j: column c + j of my row can reach the threshold
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        dot[j] = (int32_t)((((hh[j] << 7) + cr[j]) << 7) + ll[j]);  // wrapping i32, as dist.rs:147-151
-        const int32_t tq = s_tq[c + j];
-        // tq = INT32_MIN or tr = INT32_MIN / 2 (bound off / degenerate norm) always qualify
-        const bool cj = dot[j] >= (int32_t)((uint32_t)tr + (uint32_t)tq) || tq == INT32_MIN || tr == INT32_MIN / 2;
-        cand |= (uint32_t)cj << j;
-      }
-      if (!row_live) cand = 0;
-      // exact f32 ANI + compacted append, one candidate per lane per round (candidates are rare:
-      // the number of rounds is the largest per-lane count, not 16)
-      while (__any_sync(0xffffffffu, cand != 0)) {
-        const bool have = cand != 0;
-        const int j = have ? __ffs(cand) - 1 : 0;
-        cand &= cand - 1;
-        int32_t d = dot[0];
-#pragma unroll
-        for (int jj = 1; jj < 16; ++jj) d = (jj == j) ? dot[jj] : d;
-        const uint32_t lj = col0 + c + j;
-        hg::dist_emit(ep, have && lj < ep.n_qry, li, lj, d);
-      }
-    }
+    uint2 *list = reinterpret_cast<uint2 *>(aligned + TC_STAGES * TC_STAGE_BYTES + 256 + 512) + ew * TC_LIST_CAP;
+    const uint32_t n_list = tc_drain(ep, tmem_base + ((q * 32u) << 16), half * (TC_BN / 2), (half + 1) * (TC_BN / 2), s_tq, tr,
+                                     li < ep.n_ref, q * 32 + lane, row0, col0, list, 0u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_process(ep, list, n_list, row0, col0);
   }
   __syncthreads();
-  if (CL > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into it or signal its barriers
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ---- default kernel: persistent CTA pairs, cta_group::2, 256 x 128 tiles ----------------------
+constexpr int T2_STAGES = 4;
+constexpr int T2_A_BYTES = 128 * TC_BK;               // my 128 ref rows, one limb plane
+constexpr int T2_B_BYTES = 64 * TC_BK;                // my half of the 128 query rows, one limb plane
+constexpr int T2_STAGE_BYTES = 2 * T2_A_BYTES + 2 * T2_B_BYTES;  // 48 KB
+constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*col bounds x 2*/ +
+                              8 * 256 * 8 /*candidate lists*/;
+// instruction descriptor as TC_IDESC with M = 256 (the pair's rows)
+constexpr uint32_t T2_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+// TMA load whose completion bytes go to an mbarrier of either CTA of the pair (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1,
+                                                 uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %5, 0;\n\t"
+      "@e cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 e, %5, 0;\n\t"
+      "mov.b64 da, {%1, %6};\n\t"
+      "mov.b64 db, {%2, %6};\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(T2_IDESC), "r"(accumulate), "r"(on), "r"(TC_DESC_HI)
+      : "memory");
+}
+// arrive on the barrier at this offset in both CTAs once the pair's MMAs issued so far are done
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint32_t on) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\tsetp.ne.b32 e, %2, 0;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(bar),
+      "h"((uint16_t)3), "r"(on)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
+// The pair's walk over the non-empty 256 x 128 tiles, row-block major.  Symmetric: tile (R, C) is
+// empty when its largest global j is not above its smallest global i, which leaves columns
+// C >= cmin(R) in row-block R.
+struct PairTiles {
+  uint32_t gx, gy2, R, C;
+  int64_t delta;  // i0 - j0
+  int sym;
+  __device__ uint32_t cmin(uint32_t r) const {
+    if (!sym) return 0;
+    const int64_t v = delta + 256ll * (int64_t)r + 1;
+    if (v <= 0) return 0;
+    const uint64_t c = (uint64_t)v / 128u;
+    return c > gx ? gx : (uint32_t)c;
+  }
+  __device__ void init(const hg::DistEpilogue &ep) {
+    gx = (ep.n_qry + TC_BN - 1) / TC_BN;
+    gy2 = (ep.n_ref + 255) / 256;
+    delta = (int64_t)ep.i0 - (int64_t)ep.j0;
+    sym = ep.symmetric;
+    R = 0;
+    C = cmin(0);
+  }
+  __device__ bool advance(uint32_t k) {  // k non-empty tiles forward; false past the end
+    while (R < gy2) {
+      const uint32_t avail = gx - C;
+      if (k < avail) { C += k; return true; }
+      k -= avail;
+      ++R;
+      C = cmin(R);
+    }
+    return false;
+  }
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_qry,
+                uint32_t ref_plane_rows, uint32_t ref_row_base, uint32_t qry_plane_rows, uint32_t hv_d,
+                hg::DistEpilogue ep) {
+  uint32_t rank;  // 0 = leader (issues the MMAs, owns the full / tmem-empty barriers), 1 = peer
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *aligned = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_base = base + T2_STAGES * T2_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                  // used in the leader only
+  auto empty_bar = [&](int s) { return bar_base + 8u * (T2_STAGES + s); };   // one per CTA, signalled by multicast commit
+  const uint32_t accum_bar = bar_base + 8u * (2 * T2_STAGES);                // one per CTA, multicast commit
+  const uint32_t tmem_empty_bar = bar_base + 8u * (2 * T2_STAGES + 1);       // leader only: both epilogues drained
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aligned + T2_STAGES * T2_STAGE_BYTES + 8 * (2 * T2_STAGES + 2));
+  int32_t *s_tq_all = reinterpret_cast<int32_t *>(aligned + T2_STAGES * T2_STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    mbar_init(tmem_empty_bar, 2 * TC_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // the same warp in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)),
+                 "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t num_kb = hv_d / TC_BK;
+
+  PairTiles tiles;
+  tiles.init(ep);
+  bool valid = tiles.advance(pair);
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; completion bytes go to the LEADER's full barrier) =====
+    {
+      const uint32_t on = elect_one();
+      uint32_t it = 0;
+      for (; valid; valid = tiles.advance(n_pairs)) {
+        const uint32_t row0 = tiles.R * 256u + rank * 128u, colh = tiles.C * TC_BN + rank * 64u;
+        for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % T2_STAGES;
+          const uint32_t ph = (it / T2_STAGES) & 1u;
+          mbar_wait_cluster(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), 2 * T2_STAGE_BYTES, rank == 0 ? on : 0u);  // the leader expects its bytes and the peer's
+          const uint32_t fb = mapa_u32(full_bar(s), 0);
+          const uint32_t st = base + s * T2_STAGE_BYTES;
+          const int k0 = (int)(kb * TC_BK);
+          tma_load_2d_pair(st, &tm_ref, fb, k0, (int)(ref_row_base + row0), on);                                  // ref hi
+          tma_load_2d_pair(st + T2_A_BYTES, &tm_ref, fb, k0, (int)(ref_plane_rows + ref_row_base + row0), on);    // ref lo
+          tma_load_2d_pair(st + 2 * T2_A_BYTES, &tm_qry, fb, k0, (int)colh, on);                                  // qry hi, my half
+          tma_load_2d_pair(st + 2 * T2_A_BYTES + T2_B_BYTES, &tm_qry, fb, k0, (int)(qry_plane_rows + colh), on);  // qry lo
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
+    if (rank == 0) {
+      const uint32_t on = elect_one();
+      const uint32_t d0 = umma_desc_lo(base);
+      uint32_t it = 0, tile_n = 0;  // it: full trips around the stage ring
+      for (; valid; valid = tiles.advance(n_pairs), ++tile_n) {
+        if (tile_n) {  // both epilogues have drained the previous tile's accumulators
+          mbar_wait_cluster(tmem_empty_bar, (tile_n - 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        // num_kb is a multiple of T2_STAGES (host-checked), so every tile starts at stage 0 and the ring is
+        // walked with a compile-time stage index: every descriptor is d0 + constant
+        for (uint32_t kb0 = 0; kb0 < num_kb; kb0 += T2_STAGES, ++it) {
+          const uint32_t ph = it & 1u;
+#pragma unroll
+          for (int s = 0; s < T2_STAGES; ++s) {
+            mbar_wait(full_bar(s), ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 32; ++ks) {
+              const uint32_t off = (uint32_t)(s * T2_STAGE_BYTES + 32 * ks) >> 4;
+              const uint32_t a_hi = d0 + off, a_lo = a_hi + (T2_A_BYTES >> 4);
+              const uint32_t b_hi = a_hi + (2 * T2_A_BYTES >> 4), b_lo = a_hi + ((2 * T2_A_BYTES + T2_B_BYTES) >> 4);
+              const uint32_t acc = (kb0 | (uint32_t)s | (uint32_t)ks) != 0u;
+              umma_i8_pair(tmem_base + 0 * TC_BN, a_hi, b_hi, acc, on);  // Hr.Hq
+              umma_i8_pair(tmem_base + 1 * TC_BN, a_hi, b_lo, acc, on);  // Hr.Lq
+              umma_i8_pair(tmem_base + 1 * TC_BN, a_lo, b_hi, 1u, on);   //   + Lr.Hq
+              umma_i8_pair(tmem_base + 2 * TC_BN, a_lo, b_lo, acc, on);  // Lr.Lq
+            }
+            umma_commit_pair(empty_bar(s), on);  // the stage is free in both CTAs once these MMAs have read it
+          }
+        }
+        umma_commit_pair(accum_bar, on);       // accumulators final: wake both epilogues
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs, each its own 128 rows) =====
+    const int ew = warp - 2;
+    const uint32_t q = warp & 3;
+    const int half = (ew >> 2);
+    const uint32_t te = mapa_u32(tmem_empty_bar, 0);
+    uint2 *list = reinterpret_cast<uint2 *>(aligned + T2_STAGES * T2_STAGE_BYTES + 256 + 1024) + ew * TC_LIST_CAP;
+    uint32_t tile_n = 0;
+    for (; valid; valid = tiles.advance(n_pairs), ++tile_n) {
+      const uint32_t row0 = tiles.R * 256u + rank * 128u, col0 = tiles.C * TC_BN;
+      int32_t *s_tq = s_tq_all + (tile_n & 1u) * TC_BN;  // double buffered: one barrier per tile is enough
+      {
+        const int t = threadIdx.x - 64;
+        if (t < TC_BN) s_tq[t] = tc_col_bound(ep, col0 + t);
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
+      const uint32_t li = row0 + q * 32 + lane;
+      const int32_t tr = tc_row_bound(ep, li);
+      // my 128 x 128 part of the tile may be empty (below the diagonal, or past the last ref row)
+      const bool mine_empty = row0 >= ep.n_ref || (ep.symmetric && (uint64_t)ep.j0 + col0 + TC_BN - 1 <= (uint64_t)ep.i0 + row0);
+      mbar_wait_cluster(accum_bar, tile_n & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t n_list = 0;
+      if (!mine_empty)
+        n_list = tc_drain(ep, tmem_base + ((q * 32u) << 16), half * (TC_BN / 2), (half + 1) * (TC_BN / 2), s_tq, tr,
+                          li < ep.n_ref, q * 32 + lane, row0, col0, list, 0u);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(te);  // this warp's TMEM reads are done: the next tile's MMAs may start
+      tc_process(ep, list, n_list, row0, col0);  // exact ANI + append, under the next tile's mainloop
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves while the peer may still read its smem or signal its barriers
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
   }
 }
 
@@ -350,27 +620,27 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
   if ((rc = hg_scratch(ctx, HG_S_QRY_LIMBS, 2 * qry_elems + 1024, &p_q))) return rc;
   if (!qry_covers_ref && (rc = hg_scratch(ctx, HG_S_REF_LIMBS, 2 * ref_elems + 1024, &p_r))) return rc;
   const uint32_t gx = (n_qry + TC_BN - 1) / TC_BN, gy_total = (n_ref + TC_BM - 1) / TC_BM;
-  // Stand-alone CTAs by default.  The 2 x 2 cluster + TMA multicast variant (HG_DIST_CLUSTER=2) halves
-  // the L2 reads but measured 10-15 % SLOWER on B200: the kernel is bound by bytes arriving per SM
-  // (~37 B/clk/SM), which multicast does not change.  Kept for the record and for larger-L2-pressure shapes.
-  int cl = 1;
-  if (const char *e = getenv("HG_DIST_CLUSTER")) cl = (atoi(e) == 2 && gx >= 2 && gy_total >= 2) ? 2 : 1;
-  const uint32_t box_rows = 128 / cl;
+  // HG_DIST_KERNEL=1 selects the stand-alone-CTA fallback; default is the persistent CTA-pair kernel
+  int pair_kernel = 1;
+  if (const char *e = getenv("HG_DIST_KERNEL")) pair_kernel = atoi(e) == 1 ? 0 : 1;
+  if (hv_d % (TC_BK * T2_STAGES) != 0) pair_kernel = 0;  // the pair kernel walks whole trips of its 4-stage ring
 
   CUtensorMap tm_ref, tm_qry;
-  if ((rc = make_plane_map(&tm_qry, (const int8_t *)p_q, 2ull * n_qry, hv_d, box_rows))) return rc;
+  if ((rc = make_plane_map(&tm_qry, (const int8_t *)p_q, 2ull * n_qry, hv_d, pair_kernel ? 64 : 128))) return rc;
   uint32_t ref_plane_rows = n_ref, ref_row_off = 0;
+  const int8_t *ref_planes = (const int8_t *)p_r;
+  uint64_t ref_rows2 = 2ull * n_ref;
   if (qry_covers_ref) {  // the ref rows are a window of the query planes
-    tm_ref = tm_qry;
+    ref_planes = (const int8_t *)p_q;
+    ref_rows2 = 2ull * n_qry;
     ref_plane_rows = n_qry;
     ref_row_off = (uint32_t)((d_ref - d_qry) / hv_d);
-  } else if ((rc = make_plane_map(&tm_ref, (const int8_t *)p_r, 2ull * n_ref, hv_d, box_rows))) {
-    return rc;
   }
+  if ((rc = make_plane_map(&tm_ref, ref_planes, ref_rows2, hv_d, 128))) return rc;
 
   if (!ctx->tc_attr_set) {
-    HG_CUDA(cudaFuncSetAttribute(dist_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    HG_CUDA(cudaFuncSetAttribute(dist_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
     ctx->tc_attr_set = 1;
   }
   // ---- GPU work starts here (stage timer 4..5 brackets exactly this) ----
@@ -385,9 +655,7 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
   split(d_qry, qry_elems, p_q);
   if (!qry_covers_ref) split(d_ref, ref_elems, p_r);
   HG_CUDA(cudaGetLastError());
-  const uint32_t y_step = 65534;  // even, <= the gridDim.y limit
-  for (uint32_t y0 = 0; y0 < gy_total; y0 += y_step) {
-    const uint32_t gy = gy_total - y0 < y_step ? gy_total - y0 : y_step;
+  auto make_ep = [&](uint32_t y0) {
     hg::DistEpilogue ep;
     ep.ref_norm = d_ref_norm + (size_t)y0 * TC_BM;
     ep.qry_norm = d_qry_norm;
@@ -403,24 +671,37 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
     ep.hits = d_hits;
     ep.cap = cap;
     ep.n_hits = d_n_hits;
-    const uint32_t row_base = ref_row_off + y0 * TC_BM;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((gx + cl - 1) / cl * cl, (gy + cl - 1) / cl * cl, 1);
-    cfg.blockDim = dim3(TC_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = TC_SMEM_BYTES;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cl;
-    attr[0].val.clusterDim.y = cl;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (cl == 2)
-      HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc_kernel<2>, tm_ref, tm_qry, ref_plane_rows, row_base, n_qry, hv_d, ep));
-    else
-      HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc_kernel<1>, tm_ref, tm_qry, ref_plane_rows, row_base, n_qry, hv_d, ep));
+    return ep;
+  };
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.stream = ctx->stream;
+  if (pair_kernel) {
+    // one CTA pair per TPC, each walking the 256 x 128 tiles with stride n_pairs
+    const uint64_t tiles = (uint64_t)gx * ((n_ref + 255) / 256);
+    const uint32_t n_pairs = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)std::max(ctx->sm_count / 2, 1));
+    cfg.gridDim = dim3(2 * n_pairs, 1, 1);
+    cfg.dynamicSmemBytes = T2_SMEM_BYTES;
+    attr[0].val.clusterDim.x = 2;
+    HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel, tm_ref, tm_qry, ref_plane_rows, ref_row_off, n_qry, hv_d, make_ep(0)));
     ctx->launches++;
+  } else {
+    const uint32_t y_step = 65534;  // <= the gridDim.y limit
+    for (uint32_t y0 = 0; y0 < gy_total; y0 += y_step) {
+      const uint32_t gy = gy_total - y0 < y_step ? gy_total - y0 : y_step;
+      cfg.gridDim = dim3(gx, gy, 1);
+      cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+      attr[0].val.clusterDim.x = 1;
+      HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc_kernel, tm_ref, tm_qry, ref_plane_rows, ref_row_off + y0 * TC_BM, n_qry, hv_d,
+                                 make_ep(y0)));
+      ctx->launches++;
+    }
   }
   HG_PROF(ctx, 5);
   HG_CUDA(cudaGetLastError());
