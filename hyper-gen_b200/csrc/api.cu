@@ -851,36 +851,16 @@ extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref
 extern "C" int hg_dist_last_path(hg_ctx *c) { return c ? c->dist_path : 0; }
 extern "C" const char *hg_dist_last_reason(hg_ctx *c) { return c ? c->dist_reason : ""; }
 
-static int dist_host(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uint32_t n_ref, const int16_t *qry,
-                     const int32_t *qry_norm, uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
-                     int path, hg_hit *hits, uint64_t cap, uint64_t *n_hits, bool sorted, uint32_t *ani_milli) {
-  if (!c || !n_hits) { hg_set_error("hg_dist: NULL argument"); return HG_E_INVALID; }
-  *n_hits = 0;
-  if ((n_ref && (!ref || !ref_norm)) || (n_qry && (!qry || !qry_norm)) || (cap && !hits)) {
-    hg_set_error("hg_dist: NULL argument"); return HG_E_INVALID;
-  }
-  if (n_ref == 0 || n_qry == 0) return HG_OK;
-  HG_CUDA(cudaSetDevice(c->device));
+// shared tail of the host-pointer dist entries: matrices already on the device
+static int dist_finish(hg_ctx *c, const int16_t *d_ref, const int32_t *d_rn, uint32_t n_ref, const int16_t *d_qry,
+                       const int32_t *d_qn, uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path,
+                       hg_hit *hits, uint64_t cap, uint64_t *n_hits, bool sorted, uint32_t *ani_milli) {
   int rc;
-  const bool same = (ref == qry && ref_norm == qry_norm && n_ref == n_qry);
-  const size_t rb = (size_t)n_ref * hv_d * 2, qb = same ? 0 : (size_t)n_qry * hv_d * 2;
-  void *d_mat, *d_norm, *d_hits, *d_cnt;
-  if ((rc = hg_scratch(c, HG_S_HV, rb + qb + 512, &d_mat))) return rc;
-  if ((rc = hg_scratch(c, HG_S_SMALL, ((size_t)n_ref + n_qry) * 4 + 256, &d_norm))) return rc;
+  void *d_hits, *d_cnt;
   if ((rc = hg_scratch(c, HG_S_PACKED, cap * sizeof(hg_hit) + 256, &d_hits))) return rc;
   if ((rc = hg_scratch(c, HG_S_COUNTS, 256, &d_cnt))) return rc;
-  int16_t *d_ref = (int16_t *)d_mat;
-  const size_t rb_al = (rb + 255) & ~(size_t)255;
-  int16_t *d_qry = same ? d_ref : (int16_t *)((uint8_t *)d_mat + rb_al);
-  int32_t *d_rn = (int32_t *)d_norm, *d_qn = same ? d_rn : d_rn + n_ref;
-  HG_CUDA(cudaMemcpyAsync(d_ref, ref, rb, cudaMemcpyHostToDevice, c->stream));
-  HG_CUDA(cudaMemcpyAsync(d_rn, ref_norm, (size_t)n_ref * 4, cudaMemcpyHostToDevice, c->stream));
-  if (!same) {
-    HG_CUDA(cudaMemcpyAsync(d_qry, qry, qb, cudaMemcpyHostToDevice, c->stream));
-    HG_CUDA(cudaMemcpyAsync(d_qn, qry_norm, (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));
-  }
-  rc = hg_dist_dev(c, d_ref, d_rn, n_ref, 0, d_qry, d_qn, n_qry, 0, hv_d, ksize, ani_th, symmetric, path,
-                   (hg_hit *)d_hits, cap, (unsigned long long *)d_cnt);
+  rc = hg_dist_dev(c, d_ref, d_rn, n_ref, 0, d_qry, d_qn, n_qry, 0, hv_d, ksize, ani_th, symmetric, path, (hg_hit *)d_hits, cap,
+                   (unsigned long long *)d_cnt);
   if (rc) return rc;
   unsigned long long cnt = 0;
   HG_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
@@ -901,6 +881,99 @@ static int dist_host(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uin
     HG_CUDA(cudaStreamSynchronize(c->stream));  // unsorted: append order is unspecified
   }
   return HG_OK;
+}
+
+static int dist_host(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uint32_t n_ref, const int16_t *qry,
+                     const int32_t *qry_norm, uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
+                     int path, hg_hit *hits, uint64_t cap, uint64_t *n_hits, bool sorted, uint32_t *ani_milli) {
+  if (!c || !n_hits) { hg_set_error("hg_dist: NULL argument"); return HG_E_INVALID; }
+  *n_hits = 0;
+  if ((n_ref && (!ref || !ref_norm)) || (n_qry && (!qry || !qry_norm)) || (cap && !hits)) {
+    hg_set_error("hg_dist: NULL argument"); return HG_E_INVALID;
+  }
+  if (n_ref == 0 || n_qry == 0) return HG_OK;
+  HG_CUDA(cudaSetDevice(c->device));
+  int rc;
+  const bool same = (ref == qry && ref_norm == qry_norm && n_ref == n_qry);
+  const size_t rb = (size_t)n_ref * hv_d * 2, qb = same ? 0 : (size_t)n_qry * hv_d * 2;
+  void *d_mat, *d_norm;
+  if ((rc = hg_scratch(c, HG_S_HV, rb + qb + 512, &d_mat))) return rc;
+  if ((rc = hg_scratch(c, HG_S_SMALL, ((size_t)n_ref + n_qry) * 4 + 256, &d_norm))) return rc;
+  int16_t *d_ref = (int16_t *)d_mat;
+  const size_t rb_al = (rb + 255) & ~(size_t)255;
+  int16_t *d_qry = same ? d_ref : (int16_t *)((uint8_t *)d_mat + rb_al);
+  int32_t *d_rn = (int32_t *)d_norm, *d_qn = same ? d_rn : d_rn + n_ref;
+  HG_CUDA(cudaMemcpyAsync(d_ref, ref, rb, cudaMemcpyHostToDevice, c->stream));
+  HG_CUDA(cudaMemcpyAsync(d_rn, ref_norm, (size_t)n_ref * 4, cudaMemcpyHostToDevice, c->stream));
+  if (!same) {
+    HG_CUDA(cudaMemcpyAsync(d_qry, qry, qb, cudaMemcpyHostToDevice, c->stream));
+    HG_CUDA(cudaMemcpyAsync(d_qn, qry_norm, (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));
+  }
+  return dist_finish(c, d_ref, d_rn, n_ref, d_qry, d_qn, n_qry, hv_d, ksize, ani_th, symmetric, path, hits, cap, n_hits, sorted,
+                     ani_milli);
+}
+
+// `dist` straight from what the sketch file holds (FileSketch.hv bit-packed + hv_quant_bits + hv_norm_2,
+// src/types.rs:224-235): only the packed bytes cross PCIe (b/16 of the i16 matrix), decompress_file_sketch
+// (src/hd.rs:171-232) runs on the device, then the dist kernel and, if asked, the output-stage sort.
+extern "C" int hg_dist_packed(hg_ctx *c, const uint8_t *ref_packed, uint64_t ref_stride, const uint8_t *ref_bits,
+                              const int32_t *ref_norm, uint32_t n_ref, const uint8_t *qry_packed, uint64_t qry_stride,
+                              const uint8_t *qry_bits, const int32_t *qry_norm, uint32_t n_qry, uint32_t hv_d, uint32_t ksize,
+                              float ani_th, int symmetric, int path, int sorted, hg_hit *hits, uint32_t *ani_milli, uint64_t cap,
+                              uint64_t *n_hits) {
+  if (!c || !n_hits) { hg_set_error("hg_dist_packed: NULL argument"); return HG_E_INVALID; }
+  *n_hits = 0;
+  if ((n_ref && (!ref_packed || !ref_bits || !ref_norm)) || (n_qry && (!qry_packed || !qry_bits || !qry_norm)) || (cap && !hits)) {
+    hg_set_error("hg_dist_packed: NULL argument"); return HG_E_INVALID;
+  }
+  if (hv_d == 0 || hv_d % 256 != 0 || ref_stride % 4 != 0 || qry_stride % 4 != 0) {
+    hg_set_error("hg_dist_packed: hv_d %% 256 or row stride %% 4"); return HG_E_INVALID;
+  }
+  if (n_ref == 0 || n_qry == 0) return HG_OK;
+  const bool same = (ref_packed == qry_packed && ref_bits == qry_bits && ref_norm == qry_norm && n_ref == n_qry);
+  uint32_t rmax = 0, qmax = 0;
+  for (uint32_t g = 0; g < n_ref; g++) {
+    if (ref_bits[g] < 1 || ref_bits[g] > 16) { hg_set_error("hg_dist_packed: ref sketch %u has hv_quant_bits %u", g, (unsigned)ref_bits[g]); return HG_E_INVALID; }
+    rmax = std::max<uint32_t>(rmax, ref_bits[g]);
+  }
+  for (uint32_t g = 0; g < n_qry && !same; g++) {
+    if (qry_bits[g] < 1 || qry_bits[g] > 16) { hg_set_error("hg_dist_packed: query sketch %u has hv_quant_bits %u", g, (unsigned)qry_bits[g]); return HG_E_INVALID; }
+    qmax = std::max<uint32_t>(qmax, qry_bits[g]);
+  }
+  const size_t rw = (size_t)rmax * hv_d / 8, qw = (size_t)qmax * hv_d / 8;  // bytes of a row that can be live
+  if (rw > ref_stride || (!same && qw > qry_stride)) { hg_set_error("hg_dist_packed: row stride below hv_quant_bits * hv_d / 8"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(c->device));
+  int rc;
+  const size_t rb = (size_t)n_ref * hv_d * 2, qb = same ? 0 : (size_t)n_qry * hv_d * 2;
+  const size_t rb_al = (rb + 255) & ~(size_t)255;
+  const size_t rp = ((size_t)n_ref * rw + 255) & ~(size_t)255, qp = same ? 0 : (size_t)n_qry * qw;
+  void *d_mat, *d_small, *d_pk;
+  if ((rc = hg_scratch(c, HG_S_HV, rb + qb + 512, &d_mat))) return rc;
+  if ((rc = hg_scratch(c, HG_S_SMALL, ((size_t)n_ref + n_qry) * 5 + 512, &d_small))) return rc;
+  if ((rc = hg_scratch(c, HG_S_TABLES, rp + qp + 256, &d_pk))) return rc;
+  int16_t *d_ref = (int16_t *)d_mat, *d_qry = same ? d_ref : (int16_t *)((uint8_t *)d_mat + rb_al);
+  int32_t *d_rn = (int32_t *)d_small, *d_qn = same ? d_rn : d_rn + n_ref;
+  uint8_t *d_rbits = (uint8_t *)d_small + ((size_t)n_ref + n_qry) * 4, *d_qbits = same ? d_rbits : d_rbits + n_ref;
+  uint8_t *d_rp = (uint8_t *)d_pk, *d_qp = d_rp + rp;
+  HG_CUDA(cudaMemcpy2DAsync(d_rp, rw, ref_packed, ref_stride, rw, n_ref, cudaMemcpyHostToDevice, c->stream));
+  HG_CUDA(cudaMemcpyAsync(d_rbits, ref_bits, n_ref, cudaMemcpyHostToDevice, c->stream));
+  HG_CUDA(cudaMemcpyAsync(d_rn, ref_norm, (size_t)n_ref * 4, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = hg_launch_unpack(c, d_rp, rw, d_rbits, n_ref, hv_d, d_ref))) return rc;
+  if (!same) {
+    HG_CUDA(cudaMemcpy2DAsync(d_qp, qw, qry_packed, qry_stride, qw, n_qry, cudaMemcpyHostToDevice, c->stream));
+    HG_CUDA(cudaMemcpyAsync(d_qbits, qry_bits, n_qry, cudaMemcpyHostToDevice, c->stream));
+    HG_CUDA(cudaMemcpyAsync(d_qn, qry_norm, (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = hg_launch_unpack(c, d_qp, qw, d_qbits, n_qry, hv_d, d_qry))) return rc;
+  }
+  // b-bit two's-complement values are below 2^(b-1): with b <= 13 every element fits the int8 limb split,
+  // so the auto path needs no |hv| scan
+  if (path == 0 && std::max(rmax, qmax) <= 13 && (uint64_t)n_ref * n_qry >= 128ull * 128ull) path = 2;
+  rc = dist_finish(c, d_ref, d_rn, n_ref, d_qry, d_qn, n_qry, hv_d, ksize, ani_th, symmetric, path, hits, cap, n_hits, sorted != 0,
+                   ani_milli);
+  if (path == 2 && c->dist_path == 2)
+    snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor: hv_quant_bits <= %u fits two s8 limbs; tcgen05 kind::i8",
+             std::max(rmax, qmax));
+  return rc;
 }
 
 extern "C" int hg_dist(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uint32_t n_ref, const int16_t *qry,

@@ -12,7 +12,7 @@
 // like the value.  A first kernel ORs (key ^ key[0]) over all records; byte positions where every
 // record agrees are skipped (for 10 000 sketches and ani_th = 85 that leaves 7 of 12 passes).
 // Each pass: per-block digit counts -> exclusive scan (digit-major, then block) -> stable scatter.
-// In the scatter every warp owns a contiguous 512-record run of the block's chunk and walks it in order,
+// In the scatter every warp owns a contiguous run (128 or 512 records) of the block's chunk and walks it in order,
 // ranking equal digits inside a 32-record round with match_any, so no block barrier sits in the loop.
 //
 // Also here: the `{:.3}` field of the TSV as an integer (thousandths), see ani_milli_kernel.
@@ -22,10 +22,9 @@ namespace {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ROUNDS = 16;                              // 32-record rounds per warp
-constexpr int RS_WARP_ITEMS = 32 * RS_ROUNDS;              // 512
-constexpr int RS_CHUNK = RS_WARPS * RS_WARP_ITEMS;         // 4096 records per block
 constexpr int RS_PASSES = 12;
+// ROUNDS = 32-record rounds per warp: a block owns 256 * ROUNDS records (4096 for large inputs, 1024 when
+// the input is small enough that more, shorter blocks fill the SMs better)
 
 // byte `pass` of the key, least significant first: j (0-3), i (4-7), ani bits (8-11); complemented
 __device__ __forceinline__ uint32_t rs_digit(const uint4 &h, int pass) {
@@ -54,8 +53,10 @@ __global__ void rs_diff_kernel(const uint4 *__restrict__ hits, uint64_t n, uint3
 }
 
 // counts[d * n_blocks + b] = records of block b's chunk with digit d
+template <int ROUNDS>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_count_kernel(const uint4 *__restrict__ hits, uint64_t n, int pass, uint32_t n_blocks, uint32_t *__restrict__ counts) {
+  constexpr int RS_CHUNK = RS_THREADS * ROUNDS;
   __shared__ uint32_t s_cnt[256];
   s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -106,9 +107,11 @@ __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *__restrict__ co
 }
 
 // stable scatter of block b's chunk to the scanned offsets
+template <int RS_ROUNDS>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint64_t n, int pass, uint32_t n_blocks,
                   const uint32_t *__restrict__ offsets) {
+  constexpr int RS_WARP_ITEMS = 32 * RS_ROUNDS, RS_CHUNK = RS_WARPS * RS_WARP_ITEMS;
   __shared__ uint32_t s_base[RS_WARPS][256];  // next output slot per (warp, digit)
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int w = 0; w < RS_WARPS; ++w) s_base[w][threadIdx.x] = 0;
@@ -166,7 +169,9 @@ int hg_launch_sort_hits(hg_ctx *ctx, hg_hit *d_hits, uint64_t n, uint32_t *d_mil
   if (n == 0) return HG_OK;
   if (n > 0xffffffffull) { hg_set_error("hg_sort_hits: more than 2^32 - 1 records"); return HG_E_UNSUPPORTED; }
   int rc;
-  const uint32_t n_blocks = (uint32_t)((n + RS_CHUNK - 1) / RS_CHUNK);
+  const int rounds = n <= (1u << 20) ? 4 : 16;
+  const uint32_t chunk = (uint32_t)RS_THREADS * rounds;
+  const uint32_t n_blocks = (uint32_t)((n + chunk - 1) / chunk);
   void *d_tmp, *d_cnt;
   if (n > 1) {
     if ((rc = hg_scratch(ctx, HG_S_SORT_TMP, n * sizeof(hg_hit), &d_tmp))) return rc;
@@ -182,9 +187,13 @@ int hg_launch_sort_hits(hg_ctx *ctx, hg_hit *d_hits, uint64_t n, uint32_t *d_mil
     uint4 *src = (uint4 *)d_hits, *dst = (uint4 *)d_tmp;
     for (int pass = 0; pass < RS_PASSES; ++pass) {
       if (((diff[pass >> 2] >> ((pass & 3) * 8)) & 255u) == 0) continue;  // every record has the same byte here
-      rs_count_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(src, n, pass, n_blocks, (uint32_t *)d_cnt);
+      if (rounds == 4) rs_count_kernel<4><<<n_blocks, RS_THREADS, 0, ctx->stream>>>(src, n, pass, n_blocks, (uint32_t *)d_cnt);
+      else rs_count_kernel<16><<<n_blocks, RS_THREADS, 0, ctx->stream>>>(src, n, pass, n_blocks, (uint32_t *)d_cnt);
       rs_scan_kernel<<<1, 1024, 0, ctx->stream>>>((uint32_t *)d_cnt, (uint64_t)256 * n_blocks);
-      rs_scatter_kernel<<<n_blocks, RS_THREADS, 0, ctx->stream>>>(src, dst, n, pass, n_blocks, (const uint32_t *)d_cnt);
+      if (rounds == 4)
+        rs_scatter_kernel<4><<<n_blocks, RS_THREADS, 0, ctx->stream>>>(src, dst, n, pass, n_blocks, (const uint32_t *)d_cnt);
+      else
+        rs_scatter_kernel<16><<<n_blocks, RS_THREADS, 0, ctx->stream>>>(src, dst, n, pass, n_blocks, (const uint32_t *)d_cnt);
       ctx->launches += 3;
       std::swap(src, dst);
     }

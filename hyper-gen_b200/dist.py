@@ -66,16 +66,12 @@ def dist(sd: SketchDist, ctx: Context | None = None, path: int = 0) -> str:
         if ref[0].hv_d != qry[0].hv_d:
             raise ValueError("Ref and query sketches use different HV dimensions!")  # dist.rs:36-39
         hv_d, ksize = ref[0].hv_d, ref[0].ksize
+        # packed rows as the sketch file holds them -> GPU: decompress (hd.rs:171-232), dist, and the output
+        # stage's sort all on the device (hg_dist_packed); `milli` is the `{:.3}` field in thousandths
         rp, rb, rn = _stack_packed(ref)
-        r_hv = ctx.unpack(rp, rb, hv_d)  # hd::decompress_file_sketch on the GPU
-        if if_sym:
-            q_hv, qn = r_hv, rn
-        else:
-            qp, qb, qn = _stack_packed(qry)
-            q_hv = ctx.unpack(qp, qb, hv_d)
-        # dist + the output stage's sort on the GPU (hg_dist_sorted); `milli` is the `{:.3}` field in thousandths
-        hits, milli = ctx.dist(r_hv, rn, q_hv, qn, ksize=ksize, ani_th=sd.ani_threshold, symmetric=if_sym, path=path,
-                               sorted_output=True, want_milli=True)
+        qp, qb, qn = (rp, rb, rn) if if_sym else _stack_packed(qry)
+        hits, milli = ctx.dist_packed(rp, rb, rn, qp, qb, qn, hv_d, ksize=ksize, ani_th=sd.ani_threshold,
+                                      symmetric=if_sym, path=path, sorted_output=True)
         text = fileio.format_ani_lines_milli([s.file_str for s in ref], [s.file_str for s in qry], hits, milli)
         if sd.out_file:
             with open(sd.out_file, "w") as f:

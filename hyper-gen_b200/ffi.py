@@ -20,7 +20,7 @@ EXPORTS = [
     "hg_set_profiling", "hg_stage_ms", "hg_int_peak", "hg_encode_sets", "hg_encode_sets_dev",
     "hg_fasta_merge", "hg_sketch_fasta_batch",
     "hg_kmer_hash", "hg_sketch_batch", "hg_sketch_batch_dev", "hg_sketch_status", "hg_unpack", "hg_unpack_dev",
-    "hg_dist", "hg_dist_dev", "hg_dist_last_path", "hg_dist_last_reason", "hg_sort_hits_dev", "hg_dist_sorted",
+    "hg_dist", "hg_dist_dev", "hg_dist_last_path", "hg_dist_last_reason", "hg_sort_hits_dev", "hg_dist_sorted", "hg_dist_packed",
 ]
 
 
@@ -87,6 +87,9 @@ def load() -> C.CDLL:
     L.hg_sort_hits_dev.restype = i32; L.hg_sort_hits_dev.argtypes = [vp, vp, u64, vp]
     L.hg_dist_sorted.restype = i32
     L.hg_dist_sorted.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, u32, C.c_float, i32, i32, vp, vp, u64, C.POINTER(u64)]
+    L.hg_dist_packed.restype = i32
+    L.hg_dist_packed.argtypes = [vp, vp, u64, vp, vp, u32, vp, u64, vp, vp, u32, u32, u32, C.c_float, i32, i32, i32, vp, vp,
+                                 u64, C.POINTER(u64)]
     L.hg_dist_last_path.restype = i32; L.hg_dist_last_path.argtypes = [vp]
     L.hg_dist_last_reason.restype = C.c_char_p; L.hg_dist_last_reason.argtypes = [vp]
     _lib = L
@@ -307,6 +310,33 @@ class Context:
                  symmetric, path, d_hits, cap, d_n_hits):
         _check(load().hg_dist_dev(self._h, d_ref, d_ref_norm2, n_ref, i0, d_qry, d_qry_norm2, n_qry, j0, hv_d, ksize,
                                   ani_th, int(symmetric), path, d_hits, cap, d_n_hits))
+
+    def dist_packed(self, ref_packed, ref_bits, ref_norm2, qry_packed, qry_bits, qry_norm2, hv_d, ksize=21, ani_th=85.0,
+                    symmetric=False, path=0, sorted_output=True, cap=None):
+        """hg_dist_packed: packed sketch rows (n x stride uint8) + quant bits + norms -> (hits, ani_milli)."""
+        rp = np.ascontiguousarray(ref_packed, np.uint8)
+        rb = np.ascontiguousarray(ref_bits, np.uint8)
+        rn = np.ascontiguousarray(ref_norm2, np.int32)
+        same = qry_packed is ref_packed
+        qp = rp if same else np.ascontiguousarray(qry_packed, np.uint8)
+        qb = rb if same else np.ascontiguousarray(qry_bits, np.uint8)
+        qn = rn if same else np.ascontiguousarray(qry_norm2, np.int32)
+        R, Q = rp.shape[0], qp.shape[0]
+        if cap is None:
+            cap = max(1024, R * Q // 64)
+        while True:
+            hits = np.empty(cap, HIT_DTYPE)
+            milli = np.empty(cap, np.uint32)
+            n_hits = C.c_uint64(0)
+            rc = load().hg_dist_packed(self._h, _ptr(rp), rp.strides[0] if R else 0, _ptr(rb), _ptr(rn), R, _ptr(qp),
+                                       qp.strides[0] if Q else 0, _ptr(qb), _ptr(qn), Q, hv_d, ksize, ani_th,
+                                       int(symmetric), path, int(sorted_output), _ptr(hits), _ptr(milli), cap,
+                                       C.byref(n_hits))
+            if rc == HG_E_CAPACITY and n_hits.value > cap:
+                cap = int(n_hits.value)
+                continue
+            _check(rc)
+            return hits[: n_hits.value].copy(), milli[: n_hits.value].copy()
 
     def sort_hits_dev(self, d_hits, n, d_ani_milli=None):
         """hg_sort_hits_dev: device records to the reference's output order, in place."""

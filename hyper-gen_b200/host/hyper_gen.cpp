@@ -242,32 +242,22 @@ void dist(const types::SketchDist &sd) {
   const size_t D = ref[0].hv_d, R = ref.size(), Q = qry.size();
   hg_ctx *ctx = nullptr;
   check(hg_init(0, &ctx), "hg_init");
-  Stacked rs = stack(ref, D);
-  std::vector<int16_t> rhv(R * D), qhv_store;
-  check(hg_unpack(ctx, rs.packed.data(), 2 * D, rs.bits.data(), (uint32_t)R, (uint32_t)D, rhv.data()), "hg_unpack");
-  const int16_t *qhv = rhv.data();
-  const int32_t *qn = rs.norm.data();
-  Stacked qs;
-  if (!if_sym) {
-    qs = stack(qry, D);
-    qhv_store.resize(Q * D);
-    check(hg_unpack(ctx, qs.packed.data(), 2 * D, qs.bits.data(), (uint32_t)Q, (uint32_t)D, qhv_store.data()), "hg_unpack");
-    qhv = qhv_store.data();
-    qn = qs.norm.data();
-  }
-  // dump_ani_file (utils.rs:262-285): stable ascending sort over the pair enumeration, reversed => ANI descending,
-  // ties in descending pair index.  hg_dist_sorted orders the hits on the GPU and also hands back the ANI in
-  // thousandths as `{:.3}` rounds it.
+  // The packed rows go to the GPU as they sit in the sketch file; decompress_file_sketch (hd.rs:171-232),
+  // compute_hv_ani (dist.rs:231-294) and the sort of dump_ani_file (utils.rs:262-269) all run there.
+  Stacked rs = stack(ref, D), qs;
+  if (!if_sym) qs = stack(qry, D);
+  const Stacked &q = if_sym ? rs : qs;
   uint64_t cap = 1 << 20, n_hits = 0;
   std::vector<hg_hit> hits;
-  std::vector<uint32_t> milli;
+  std::vector<uint32_t> milli;  // ANI in thousandths, rounded as `{:.3}` rounds it
   for (;;) {
     hits.resize(cap);
     milli.resize(cap);
-    const int rc = hg_dist_sorted(ctx, rhv.data(), rs.norm.data(), (uint32_t)R, qhv, qn, (uint32_t)Q, (uint32_t)D,
-                                  ref[0].ksize, sd.ani_threshold, if_sym ? 1 : 0, 0, hits.data(), milli.data(), cap, &n_hits);
+    const int rc = hg_dist_packed(ctx, rs.packed.data(), 2 * D, rs.bits.data(), rs.norm.data(), (uint32_t)R, q.packed.data(),
+                                  2 * D, q.bits.data(), q.norm.data(), (uint32_t)Q, (uint32_t)D, ref[0].ksize,
+                                  sd.ani_threshold, if_sym ? 1 : 0, 0, 1, hits.data(), milli.data(), cap, &n_hits);
     if (rc == HG_E_CAPACITY && n_hits > cap) { cap = n_hits; continue; }
-    check(rc, "hg_dist_sorted");
+    check(rc, "hg_dist_packed");
     break;
   }
   hits.resize(n_hits);

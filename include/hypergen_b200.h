@@ -201,6 +201,18 @@ HG_API int hg_dist_sorted(hg_ctx *ctx, const int16_t *ref_hv, const int32_t *ref
                           uint32_t ksize, float ani_th, int symmetric, int path, hg_hit *hits,
                           uint32_t *ani_milli, uint64_t cap, uint64_t *n_hits);
 
+/* `dist` straight from the sketch-file payload: bit-packed rows (FileSketch.hv as bytes,
+ * src/types.rs:224-235; row g holds quant_bits[g] * hv_d / 8 live bytes, rows `*_stride` bytes
+ * apart), hv_quant_bits and hv_norm_2.  Only the live bytes cross PCIe; decompress_file_sketch
+ * (src/hd.rs:171-232) runs on the device in front of the dist kernel.  sorted != 0: the hits
+ * come back in dump_ani_file's order as from hg_dist_sorted (ani_milli may be NULL); otherwise
+ * as from hg_dist.  Pass the same pointers for ref and query for the symmetric all-vs-all. */
+HG_API int hg_dist_packed(hg_ctx *ctx, const uint8_t *ref_packed, uint64_t ref_stride, const uint8_t *ref_quant_bits,
+                          const int32_t *ref_norm2, uint32_t n_ref, const uint8_t *qry_packed,
+                          uint64_t qry_stride, const uint8_t *qry_quant_bits, const int32_t *qry_norm2,
+                          uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path,
+                          int sorted, hg_hit *hits, uint32_t *ani_milli, uint64_t cap, uint64_t *n_hits);
+
 /* Which path the last hg_dist / hg_dist_dev took (1 SIMT, 2 tensor) and why. */
 HG_API int hg_dist_last_path(hg_ctx *ctx);
 HG_API const char *hg_dist_last_reason(hg_ctx *ctx);

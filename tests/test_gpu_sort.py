@@ -77,3 +77,62 @@ def test_dist_sorted_is_dist_plus_reference_order(ctx, hg, oracle):
             assert np.array_equal(hits["ani"].view(np.uint32), ani[want].view(np.uint32))
             assert np.array_equal(hits["dot"], dot[want])
             assert milli.tolist() == [int(("%.3f" % float(a)).replace(".", "")) for a in hits["ani"]]
+
+
+def _pack_bits(hv, b):
+    """BitPacker8x at an explicit width b (hd.rs:139-153): lane l = idx % 8 carries the stream
+    sum(u[8 r + l] << (b r)); its 32-bit word j sits at byte 32 j + 4 l of the block's 32 b bytes."""
+    u = (hv.astype(np.int64) + (1 << (b - 1))).astype(np.uint64)
+    out = np.zeros(b * hv.size // 8, np.uint8)
+    for blk in range(hv.size // 256):
+        ub = u[blk * 256:(blk + 1) * 256]
+        o = out[blk * 32 * b:(blk + 1) * 32 * b].view(np.uint32).reshape(b, 8)
+        for l in range(8):
+            stream = 0
+            for r in range(32):
+                stream |= int(ub[8 * r + l]) << (b * r)
+            for j in range(b):
+                o[j, l] = (stream >> (32 * j)) & 0xFFFFFFFF
+    return out
+
+
+def test_dist_packed_equals_unpack_then_dist(ctx, hg, oracle):
+    """hg_dist_packed (sketch-file payload in, sorted hits out) == oracle decompress + dist + order;
+    mixed hv_quant_bits per row, different strides for ref and query, symmetric and not."""
+    from hypergen_b200 import synth, dist as hdist
+    D = 1024
+    seq, off = synth.family_batch(140, 120_000, first=500)
+    sk = oracle.sketch_batch(seq.numpy(), off, scaled=150, hv_d=D)
+    hv, norm, bits, packed = sk["hv"].copy(), sk["norm2"].copy(), sk["quant_bits"].copy(), sk["packed"]
+    # re-pack a few rows at a wider bit width than needed (legal in the file format) to mix widths
+    for g in (3, 77, 139):
+        bits[g] = min(int(bits[g]) + 2, 13)
+    rows = [_pack_bits(hv[g], int(bits[g])) for g in range(140)]
+    b0, p0 = oracle.compress_hd_sketch(hv[0])                   # pins the test's packer to the oracle's
+    assert b0 == int(bits[0]) and np.array_equal(rows[0], p0)
+    rp = np.zeros((140, 2 * D), np.uint8)
+    for g, r in enumerate(rows):
+        rp[g, :r.size] = r
+    qsel = np.arange(20, 90)
+    qp = np.zeros((qsel.size, 2 * D + 64), np.uint8)           # another stride
+    qp[:, :2 * D] = rp[qsel]
+    for sym in (True, False):
+        if sym:
+            args = (rp, bits, norm, rp, bits, norm)
+            qh, qn = hv, norm
+        else:
+            args = (rp, bits, norm, qp, bits[qsel].copy(), norm[qsel].copy())
+            qh, qn = hv[qsel], norm[qsel]
+        ani, dot = oracle.dist_all(hv, norm, qh, qn, symmetric=sym)
+        for th in (85.0, 0.0):
+            hits, milli = ctx.dist_packed(*args, D, ani_th=th, symmetric=sym)
+            want = oracle.ani_output_order(ani, th)
+            idx = hdist.pair_index(hits["i"].astype(np.int64), hits["j"].astype(np.int64), qh.shape[0], sym)
+            assert np.array_equal(idx, want), (sym, th)
+            assert np.array_equal(hits["ani"].view(np.uint32), ani[want].view(np.uint32))
+            assert np.array_equal(hits["dot"], dot[want])
+            assert milli.tolist() == [int(("%.3f" % float(a)).replace(".", "")) for a in hits["ani"]]
+        if sym:   # 140 x 140 fills a tensor tile and every width is <= 13 bits: tensor path without the |hv| scan
+            assert ctx.dist_last_path == 2 and "hv_quant_bits" in ctx.dist_last_reason
+        else:     # 140 x 70 pairs do not fill one 128 x 128 tile: exact SIMT path
+            assert ctx.dist_last_path == 1
