@@ -119,6 +119,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
 }
 
+// tcgen05.ld writes its destination registers asynchronously until tcgen05.wait::ld.  This empty volatile asm
+// is ordered after the wait (volatile asms keep their order) and "redefines" the registers, so no use of the
+// loaded values can be scheduled ahead of the wait.
+__device__ __forceinline__ void tmem_ld_fence(uint32_t (&v)[16]) {
+  asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                    "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+}
+
 // ---- epilogue pieces shared by both kernels ---------------------------------------------------
 // Cheap per-element test first: ani >= ani_th implies dot >= cfrac * (norm_r + norm_q)
 // (dist_common.cuh), split into a per-row and a per-column integer so that an element costs
@@ -162,13 +170,25 @@ __device__ __forceinline__ uint32_t tc_drain(const hg::DistEpilogue &ep, uint32_
                                              const int32_t *s_tq, int32_t tr, bool row_live, uint32_t rowl, uint32_t row0,
                                              uint32_t col0, uint2 *list, uint32_t n_list) {
   const uint32_t lane = threadIdx.x & 31;
+  // software pipelined: the loads of chunk c + 16 are in flight while chunk c is tested
+  uint32_t nh[16], nc[16], nl[16];
+  tmem_ld16(taddr + 0 * TC_BN + c_begin, nh);
+  tmem_ld16(taddr + 1 * TC_BN + c_begin, nc);
+  tmem_ld16(taddr + 2 * TC_BN + c_begin, nl);
 #pragma unroll 1
   for (int c = c_begin; c < c_end; c += 16) {
     uint32_t hh[16], cr[16], ll[16];
-    tmem_ld16(taddr + 0 * TC_BN + c, hh);
-    tmem_ld16(taddr + 1 * TC_BN + c, cr);
-    tmem_ld16(taddr + 2 * TC_BN + c, ll);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    tmem_ld_fence(nh);
+    tmem_ld_fence(nc);
+    tmem_ld_fence(nl);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { hh[j] = nh[j]; cr[j] = nc[j]; ll[j] = nl[j]; }
+    if (c + 16 < c_end) {
+      tmem_ld16(taddr + 0 * TC_BN + c + 16, nh);
+      tmem_ld16(taddr + 1 * TC_BN + c + 16, nc);
+      tmem_ld16(taddr + 2 * TC_BN + c + 16, nl);
+    }
     int32_t dot[16];
     uint32_t cand = 0;  // bit j: column c + j of my row can reach the threshold
 #pragma unroll

@@ -23,8 +23,7 @@ namespace {
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_PASSES = 12;
-// ROUNDS = 32-record rounds per warp: a block owns 256 * ROUNDS records (4096 for large inputs, 1024 when
-// the input is small enough that more, shorter blocks fill the SMs better)
+// ROUNDS = 32-record rounds per warp: a block owns 256 * ROUNDS records (4096; 1024 for very small inputs)
 
 // byte `pass` of the key, least significant first: j (0-3), i (4-7), ani bits (8-11); complemented
 __device__ __forceinline__ uint32_t rs_digit(const uint4 &h, int pass) {
@@ -169,7 +168,7 @@ int hg_launch_sort_hits(hg_ctx *ctx, hg_hit *d_hits, uint64_t n, uint32_t *d_mil
   if (n == 0) return HG_OK;
   if (n > 0xffffffffull) { hg_set_error("hg_sort_hits: more than 2^32 - 1 records"); return HG_E_UNSUPPORTED; }
   int rc;
-  const int rounds = n <= (1u << 20) ? 4 : 16;
+  const int rounds = n <= (1u << 15) ? 4 : 16;  // measured: at 185 k records the longer single-block scan of 1 KiB blocks costs more than it wins
   const uint32_t chunk = (uint32_t)RS_THREADS * rounds;
   const uint32_t n_blocks = (uint32_t)((n + chunk - 1) / chunk);
   void *d_tmp, *d_cnt;
