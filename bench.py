@@ -165,7 +165,25 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "genomes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """Keep stdout for the one JSON line: everything else that writes to fd 1 from here on (NCCL's
+    version banner, library chatter) goes to stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 def main():
@@ -191,6 +209,7 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
 
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -406,7 +425,7 @@ def main():
         line["cpu_baseline"] = None
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        _emit(line)
     torch.cuda.synchronize()
     ctx.close()
     if world > 1:
