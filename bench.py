@@ -508,8 +508,8 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
         return e0.elapsed_time(e1), ctx.stage_ms()[3], (allh.size if allh is not None else 0)
 
     ctx.set_profiling(True)
-    # first call: path 0 = auto (scans max |hv| to decide tensor vs SIMT and records why); a caller
-    # that knows FileSketch.hv_quant_bits <= 13 passes the path directly, as the timed steps do
+    # first call: path 0 = auto (single-plane tensor kernel if the rows are narrow, else two-limb tensor
+    # kernel, else SIMT; records why); the timed steps pass the chosen path directly
     path_sel = [0]
     step()
     path_sel[0], path_reason = ctx.dist_last_path, ctx.dist_last_reason
@@ -535,10 +535,13 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
     }
     alg_ops = 2.0 * D * n_pairs
     int8_peak = 2.0 * peaks["bf16_tflops"]  # kind::i8 runs at twice the bf16 MMA rate
+    mac_mult = 1.0 if path_sel[0] == 3 else 4.0  # MMAs executed per algorithmic MAC
+    note = ("algorithmic 2*D ops per pair; peak = 2 x measured bf16 (kind::i8 runs at twice the bf16 MMA rate); "
+            + ("single s8 plane (x = 2a + s): executed MACs = algorithmic MACs; kernel_ms includes the i16 -> s8 pre-pass and its host sync"
+               if path_sel[0] == 3 else "the two-limb split executes 4x these MACs, so frac tops out at 0.25"))
     out["roofline"] = {"bound": "tensor", "achieved": alg_ops / (kms * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s",
-                       "frac": alg_ops / (kms * 1e-3) / 1e12 / int8_peak,
-                       "note": "algorithmic 2*D ops per pair; peak = 2 x measured bf16 (kind::i8 runs at twice the bf16 MMA rate); the two-limb split executes 4x these MACs, so frac tops out at 0.25",
-                       "executed_frac": 4.0 * alg_ops / (kms * 1e-3) / 1e12 / int8_peak}
+                       "frac": alg_ops / (kms * 1e-3) / 1e12 / int8_peak, "note": note,
+                       "executed_frac": mac_mult * alg_ops / (kms * 1e-3) / 1e12 / int8_peak}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # CPU port of dist::compute_hv_ani (dist.rs:231-294) on a bounded sample of the same sketches
         import oracle as O

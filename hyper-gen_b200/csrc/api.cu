@@ -66,7 +66,7 @@ extern "C" void hg_destroy(hg_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (int i = 0; i < 12; i++) if (c->d_scratch[i]) cudaFree(c->d_scratch[i]);
+  for (int i = 0; i < HG_S_COUNT; i++) if (c->d_scratch[i]) cudaFree(c->d_scratch[i]);
   for (int i = 0; i < 4; i++) if (c->h_pinned[i]) cudaFreeHost(c->h_pinned[i]);
   if (c->d_status) cudaFree(c->d_status);
   for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -792,45 +792,68 @@ extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref
     hg_set_error("hg_dist_dev: NULL argument"); return HG_E_INVALID;
   }
   if (hv_d == 0 || hv_d % 256 != 0) { hg_set_error("hg_dist_dev: hv_d %u must be a multiple of 256", hv_d); return HG_E_INVALID; }
-  if (path < 0 || path > 2) { hg_set_error("hg_dist_dev: path %d", path); return HG_E_INVALID; }
+  if (path < 0 || path > 3) { hg_set_error("hg_dist_dev: path %d", path); return HG_E_INVALID; }
   HG_CUDA(cudaSetDevice(c->device));
   HG_CUDA(cudaMemsetAsync(d_n_hits, 0, sizeof(unsigned long long), c->stream));
   if (n_ref == 0 || n_qry == 0) return HG_OK;
+  c->ev_used &= ~(3 << 4);
+  int rc;
 
+  // ---- choose: 3 = single-plane tensor kernel, 2 = two-limb tensor kernel, 1 = SIMT ----
   int use = path;
-  if (use == 0) {
-    // tensor path only when every element fits the int8 limb split; this costs one read of
-    // both matrices (HBM-bound, ~0.1 ms per GB) and one 4-byte D2H
-    void *d_max;
-    int rc;
-    if ((rc = hg_scratch(c, HG_S_MISC, 256, &d_max))) return rc;
-    int32_t m1 = 0, m2 = 0;
-    if ((rc = hg_launch_absmax(c, d_ref, (uint64_t)n_ref * hv_d, (int32_t *)d_max))) return rc;
-    HG_CUDA(cudaMemcpyAsync(&m1, d_max, 4, cudaMemcpyDeviceToHost, c->stream));
-    HG_CUDA(cudaStreamSynchronize(c->stream));
-    if (d_qry != d_ref) {
-      if ((rc = hg_launch_absmax(c, d_qry, (uint64_t)n_qry * hv_d, (int32_t *)d_max))) return rc;
-      HG_CUDA(cudaMemcpyAsync(&m2, d_max, 4, cudaMemcpyDeviceToHost, c->stream));
-      HG_CUDA(cudaStreamSynchronize(c->stream));
+  int32_t absmax = -1;  // max |hv| once some scan has produced it
+  if (path == 0 && (uint64_t)n_ref * n_qry < 128ull * 128ull) {
+    use = 1;
+    snprintf(c->dist_reason, sizeof(c->dist_reason), "SIMT: %u x %u pairs do not fill one 128x128 tensor tile", n_ref, n_qry);
+  } else if (path == 0 || path == 3) {
+    // the narrow path's own pre-pass (one read of both matrices) tells whether the rows fit one s8 plane
+    uint64_t outliers = 0;
+    rc = hg_launch_dist_narrow(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th, symmetric,
+                               d_hits, cap, d_n_hits, &absmax, &outliers);
+    if (rc == HG_OK) {
+      c->dist_path = 3;
+      if (path == 3)
+        snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor-narrow: forced by caller");
+      else
+        snprintf(c->dist_reason, sizeof(c->dist_reason),
+                 "tensor-narrow: rows fit one s8 plane as x = 2a + s (max |hv| = %d, %llu outlier elements corrected per candidate); "
+                 "tcgen05 kind::i8, one MMA per K step", absmax, (unsigned long long)outliers);
+      return HG_OK;
     }
-    const int32_t m = m1 > m2 ? m1 : m2;
-    if (m > HG_TC_MAX_ABS) {
+    if (rc != HG_E_UNSUPPORTED || path == 3) return rc;
+    use = 0;  // declined: two-limb tensor kernel if every |hv| fits 13 bits, else SIMT
+  }
+  if (use == 0) {
+    char why[96];
+    snprintf(why, sizeof(why), "%s", hg_last_error());
+    if (absmax < 0) {  // the narrow path declined before its scan: one read of both matrices and one 4-byte D2H each
+      void *d_max;
+      if ((rc = hg_scratch(c, HG_S_MISC, 256, &d_max))) return rc;
+      int32_t m1 = 0, m2 = 0;
+      if ((rc = hg_launch_absmax(c, d_ref, (uint64_t)n_ref * hv_d, (int32_t *)d_max))) return rc;
+      HG_CUDA(cudaMemcpyAsync(&m1, d_max, 4, cudaMemcpyDeviceToHost, c->stream));
+      HG_CUDA(cudaStreamSynchronize(c->stream));
+      if (d_qry != d_ref) {
+        if ((rc = hg_launch_absmax(c, d_qry, (uint64_t)n_qry * hv_d, (int32_t *)d_max))) return rc;
+        HG_CUDA(cudaMemcpyAsync(&m2, d_max, 4, cudaMemcpyDeviceToHost, c->stream));
+        HG_CUDA(cudaStreamSynchronize(c->stream));
+      }
+      absmax = m1 > m2 ? m1 : m2;
+    }
+    if (absmax > HG_TC_MAX_ABS) {
       use = 1;
       snprintf(c->dist_reason, sizeof(c->dist_reason),
-               "SIMT: max |hv| = %d exceeds the 13-bit budget (%d) of the int8 limb split", m, HG_TC_MAX_ABS);
-    } else if ((uint64_t)n_ref * n_qry < 128ull * 128ull) {
-      use = 1;
-      snprintf(c->dist_reason, sizeof(c->dist_reason), "SIMT: %u x %u pairs do not fill one 128x128 tensor tile", n_ref, n_qry);
+               "SIMT: max |hv| = %d exceeds the 13-bit budget (%d) of the int8 limb split", absmax, HG_TC_MAX_ABS);
     } else {
       use = 2;
-      snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor: max |hv| = %d fits two s8 limbs; tcgen05 kind::i8", m);
+      snprintf(c->dist_reason, sizeof(c->dist_reason),
+               "tensor: max |hv| = %d fits two s8 limbs, tcgen05 kind::i8 (one s8 plane declined: %.80s)", absmax, why);
     }
-  } else {
+  } else if (path != 0) {
     snprintf(c->dist_reason, sizeof(c->dist_reason), "%s: forced by caller", use == 1 ? "SIMT" : "tensor");
   }
   c->dist_path = use;
-  c->ev_used &= ~(3 << 4);
-  int rc2;
+  int rc2 = HG_OK;
   if (use == 2) {
     rc2 = hg_launch_dist_tc(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th,
                             symmetric, d_hits, cap, d_n_hits);
@@ -965,15 +988,19 @@ extern "C" int hg_dist_packed(hg_ctx *c, const uint8_t *ref_packed, uint64_t ref
     HG_CUDA(cudaMemcpyAsync(d_qn, qry_norm, (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));
     if ((rc = hg_launch_unpack(c, d_qp, qw, d_qbits, n_qry, hv_d, d_qry))) return rc;
   }
-  // b-bit two's-complement values are below 2^(b-1): with b <= 13 every element fits the int8 limb split,
-  // so the auto path needs no |hv| scan
-  if (path == 0 && std::max(rmax, qmax) <= 13 && (uint64_t)n_ref * n_qry >= 128ull * 128ull) path = 2;
-  rc = dist_finish(c, d_ref, d_rn, n_ref, d_qry, d_qn, n_qry, hv_d, ksize, ani_th, symmetric, path, hits, cap, n_hits, sorted != 0,
-                   ani_milli);
-  if (path == 2 && c->dist_path == 2)
-    snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor: hv_quant_bits <= %u fits two s8 limbs; tcgen05 kind::i8",
-             std::max(rmax, qmax));
-  return rc;
+  // b-bit two's-complement values are below 2^(b-1): with b > 10 no row can fit the single s8 plane
+  // (x = 2a + s spans 510), and with b <= 13 every element fits the int8 limb split, so that case needs no scan
+  if (path == 0 && std::max(rmax, qmax) > 10 && std::max(rmax, qmax) <= 13 && (uint64_t)n_ref * n_qry >= 128ull * 128ull) {
+    path = 2;
+    rc = dist_finish(c, d_ref, d_rn, n_ref, d_qry, d_qn, n_qry, hv_d, ksize, ani_th, symmetric, path, hits, cap, n_hits, sorted != 0,
+                     ani_milli);
+    if (c->dist_path == 2)
+      snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor: hv_quant_bits <= %u fits two s8 limbs; tcgen05 kind::i8",
+               std::max(rmax, qmax));
+    return rc;
+  }
+  return dist_finish(c, d_ref, d_rn, n_ref, d_qry, d_qn, n_qry, hv_d, ksize, ani_th, symmetric, path, hits, cap, n_hits, sorted != 0,
+                     ani_milli);
 }
 
 extern "C" int hg_dist(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uint32_t n_ref, const int16_t *qry,

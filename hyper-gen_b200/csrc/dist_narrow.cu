@@ -1,0 +1,664 @@
+// dist_narrow.cu — single-plane tensor dist path: one tcgen05 kind::i8 MMA per K step instead of the
+// four of the two-limb split (dist_tc.cu), still bit-exact.
+//
+// Replaces the pair loop of dist::compute_hv_ani + compute_pairwise_ani (reference
+// src/dist.rs:139-161,231-294) when the sketch rows are "narrow".  A sketch HV produced by
+// hd::encode_hash_hd* (src/hd.rs:15-112) is hv[d] = 2 * count[d] - n: every element of a row has the
+// parity of n, and at the BASELINE configs with D = 4096 / scaled = 1500 the elements span about
+// +-240 (hv_quant_bits = 9).  So with a per-row centre s (same parity)
+//        x[d] = 2 a[d] + s,   a[d] in [-128, 127]          (one s8 plane, no limb split)
+// and for a ref row x (centre s_r) and a query row y = 2 b + s_q
+//        x . y = 4 (a . b) + s_q * sum(x~) + s_r * 2 sum(b)           (wrapping i32, like dist.rs:147-151)
+// i.e. ONE s8 GEMM plus per-row / per-column constants applied in the epilogue.
+//
+// Rows that do not fit exactly (an element outside [s - 256, s + 254], or of the other parity) keep
+// the clamped value x~ = 2 a + s in the plane and list their residuals eps[d] = x[d] - x~[d] as
+// sparse "outlier" entries.  Since x . y = x~ . y~ + sum_d eps_x[d] y[d] + sum_d eps_y[d] x~[d], the
+// kernel loosens the candidate bound of such a row by the largest value the correction can take and
+// adds the exact correction for the (few) candidates before the exact ANI sequence.  The path is
+// taken only while the outlier lists stay small (a budget per row on average); otherwise the caller
+// falls back to the two-limb kernel (|hv| <= 8127) or the SIMT kernel, both exact as well.
+//
+// Kernel: persistent CTA pairs (cluster 2 x 1, tcgen05 cta_group::2, M = 256, N = 256, K = 32), one
+// pair per TPC, 256 x 256 output tiles.  Per 128-deep K block a CTA TMA-loads its own 128 ref rows
+// and its half (128 rows) of the query tile: 32 KB per stage, 6-stage mbarrier ring.  The s32
+// accumulator (256 TMEM columns) is double buffered, so the epilogue of tile t (tcgen05.ld, the
+// constants above, division-free ANI bound, candidate list, exact ANI + append) runs entirely under
+// the MMAs of tile t + 1.  Operand bytes per MMA clock are twice those of the two-limb kernel
+// (L2 -> SM is the limit), hence the 256-wide tile.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "dist_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+using namespace hgtc;
+
+constexpr int N1_BN = 256;                              // tile columns (the pair's N); rows: 256 (128 per CTA)
+constexpr int N1_STAGES = 6;
+constexpr int N1_A_BYTES = 128 * TC_BK;                 // my 128 ref rows
+constexpr int N1_B_BYTES = 128 * TC_BK;                 // my half of the 256 query rows
+constexpr int N1_STAGE_BYTES = N1_A_BYTES + N1_B_BYTES; // 32 KB
+constexpr int N1_EPI_WARPS = 8;                         // two per TMEM lane quarter, half the columns each
+constexpr int N1_THREADS = 64 + 32 * N1_EPI_WARPS;
+constexpr int N1_LIST_CAP = 256;                        // candidates per warp list (8 B each)
+constexpr int N1_COL_WORDS = 3 * N1_BN;                 // per tile: bound, centre, 2 sum(b) of every column
+constexpr int N1_SMEM_BYTES = N1_STAGES * N1_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+                              2 * N1_COL_WORDS * 4 /*column constants, double buffered*/ + N1_EPI_WARPS * N1_LIST_CAP * 8;
+constexpr uint32_t N1_TMEM_COLS = 512;                  // two accumulator buffers of 256 columns
+// instruction descriptor, kind::i8: D = s32, A = B = signed 8-bit, both K-major, M = 256 (pair), N = 256
+constexpr uint32_t N1_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((N1_BN >> 3) << 17) | ((256u >> 4) << 24);
+
+constexpr int32_t ROW_ALWAYS = INT32_MIN / 2;  // row bound: every column is a candidate
+constexpr int32_t COL_ALWAYS = INT32_MIN;      // column bound: every row is a candidate
+constexpr int32_t COL_NEVER = INT32_MAX;       // column past the last query
+
+struct NarrowSide {  // per-row constants of one matrix, already offset to the first row of the launch
+  const int32_t *s;         // centre
+  const int32_t *a2;        // 2 * sum_d a[d]
+  const uint32_t *e;        // sum_d |eps[d]|  (0: the row is exactly 2 a + s)
+  const uint32_t *out_off;  // first outlier entry
+  const uint32_t *out_cnt;
+};
+struct NarrowArgs {
+  NarrowSide r, q;
+  const uint32_t *r_out, *q_out;  // outlier entries: (d << 16) | (eps & 0xffff)
+  const int8_t *r_plane;          // s8 plane of the ref rows (first row of the launch)
+  const int16_t *q_hv;            // the query matrix itself
+  uint32_t hv_d;
+  uint32_t q_absmax;              // max |y[d]| over the query matrix
+  uint32_t r_tmax;                // max |x~[d]| over the ref matrix (<= |s| + 256)
+};
+
+// ---- i16 rows -> s8 plane + per-row constants + outlier lists ---------------------------------
+struct PrepOut {
+  int8_t *plane;
+  int32_t *s, *a2;
+  uint32_t *e, *out_off, *out_cnt;
+  uint32_t *entries;
+  uint32_t cap;     // entries available
+  uint32_t *stats;  // [0] max |x|, [1] max (|s| + 256), [2] entry cursor, [3] overflow flag
+};
+
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int PREP_THREADS = 256;
+
+__global__ void __launch_bounds__(PREP_THREADS)
+narrow_prep_kernel(const int16_t *__restrict__ hv, uint32_t n_rows, uint32_t hv_d, PrepOut o) {
+  __shared__ int sh_lo[8], sh_hi[8];
+  __shared__ uint32_t sh_a[8], sh_e[8], sh_c[8];
+  __shared__ uint32_t sh_base;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t nv = hv_d / 8;  // uint4 loads per row
+  for (uint32_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(hv + (size_t)row * hv_d);
+    // pass 1: range and sum of the row
+    int lo = 32767, hi = -32768, sum_x = 0;
+    uint32_t n_odd = 0;
+    for (uint32_t i = tid; i < nv; i += PREP_THREADS) {
+      const uint4 v = src[i];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int x = (int)(int16_t)(w[e >> 1] >> (16 * (e & 1)));
+        lo = min(lo, x);
+        hi = max(hi, x);
+        sum_x += x;  // |sum| <= 32768 * 32768: fits
+        n_odd += (uint32_t)x & 1u;
+      }
+    }
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    sum_x = (int)warp_sum((uint32_t)sum_x);
+    n_odd = warp_sum(n_odd);
+    __syncthreads();  // the previous row's shared values are no longer needed
+    if (lane == 0) { sh_lo[warp] = lo; sh_hi[warp] = hi; sh_a[warp] = (uint32_t)sum_x; sh_c[warp] = n_odd; }
+    __syncthreads();
+    lo = sh_lo[0];
+    hi = sh_hi[0];
+    sum_x = (int)sh_a[0];
+    n_odd = sh_c[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { lo = min(lo, sh_lo[w]); hi = max(hi, sh_hi[w]); sum_x += (int)sh_a[w]; n_odd += sh_c[w]; }
+    __syncthreads();  // sh_a / sh_c are reused for the plane sums below
+    // centre with the parity of the row (hv = 2 count - n: one parity per row; the majority speaks for it):
+    // the middle of the range when the whole row fits [s - 256, s + 254], else the mean (a few far
+    // elements become outliers instead of dragging the window away from everything else)
+    const int par = 2 * n_odd > hv_d ? 1 : 0;
+    int mid = (lo + hi + 2) >> 1;
+    if (hi - lo > 510) {
+      const int half = (int)(hv_d / 2);
+      mid = sum_x >= 0 ? (sum_x + half) / (int)hv_d : -((-sum_x + half) / (int)hv_d);
+    }
+    const int s = mid - ((mid - par) & 1);
+    // pass 2 (the row is in L1/L2): plane, sum a, residuals
+    uint32_t sum_a = 0, sum_e = 0, cnt = 0, bad = 0;
+    uint2 *dst = reinterpret_cast<uint2 *>(o.plane + (size_t)row * hv_d);
+    for (uint32_t i = tid; i < nv; i += PREP_THREADS) {
+      const uint4 v = src[i];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t pk[2] = {0, 0};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int x = (int)(int16_t)(w[e >> 1] >> (16 * (e & 1)));
+        const int t = x - s;
+        const int a = max(-128, min(127, t >> 1));
+        const int eps = t - 2 * a;
+        sum_a += (uint32_t)a;
+        if (eps != 0) { ++cnt; sum_e += (uint32_t)abs(eps); }
+        if (eps < -32768 || eps > 32767) bad = 1;  // does not fit an outlier entry (needs |x - s| > 32000): decline
+        pk[e >> 2] |= (uint32_t)(a & 0xFF) << (8 * (e & 3));
+      }
+      dst[i] = make_uint2(pk[0], pk[1]);
+    }
+    // block totals + exclusive prefix of the outlier counts
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= (uint32_t)d) inc += y;
+    }
+    const uint32_t wa = warp_sum(sum_a), we = warp_sum(sum_e);
+    if (bad) atomicExch(&o.stats[3], 1u);
+    if (lane == 31) sh_c[warp] = inc;
+    if (lane == 0) { sh_a[warp] = wa; sh_e[warp] = we; }
+    __syncthreads();
+    uint32_t tot_a = 0, tot_e = 0, tot_c = 0, before = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      tot_a += sh_a[w];
+      tot_e += sh_e[w];
+      if ((uint32_t)w < warp) before += sh_c[w];
+      tot_c += sh_c[w];
+    }
+    if (tid == 0) {
+      uint32_t base = 0, kept = tot_c;
+      if (tot_c) {
+        base = atomicAdd(&o.stats[2], tot_c);
+        if (base > o.cap || tot_c > o.cap - base) { atomicExch(&o.stats[3], 1u); kept = 0; }
+      }
+      sh_base = kept ? base : 0xFFFFFFFFu;
+      o.s[row] = s;
+      o.a2[row] = (int32_t)(2u * tot_a);
+      o.e[row] = tot_e;
+      o.out_off[row] = base;
+      o.out_cnt[row] = kept;
+      atomicMax(&o.stats[0], (uint32_t)max(abs(lo), abs(hi)));
+      atomicMax(&o.stats[1], (uint32_t)abs(s) + 256u);
+    }
+    if (tot_c == 0) continue;  // uniform over the block
+    __syncthreads();
+    const uint32_t base = sh_base;
+    if (base == 0xFFFFFFFFu) continue;
+    // pass 3 (rows with outliers only): write the entries, thread by thread in scan order
+    uint32_t pos = base + before + inc - cnt;
+    for (uint32_t i = tid; i < nv; i += PREP_THREADS) {
+      const uint4 v = src[i];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int x = (int)(int16_t)(w[e >> 1] >> (16 * (e & 1)));
+        const int t = x - s;
+        const int a = max(-128, min(127, t >> 1));
+        const int eps = t - 2 * a;
+        if (eps != 0) o.entries[pos++] = ((8u * i + (uint32_t)e) << 16) | ((uint32_t)eps & 0xFFFFu);
+      }
+    }
+  }
+}
+
+// ---- tile walk: non-empty 256 x 256 tiles, row-block major ------------------------------------
+struct N1Tiles {
+  uint32_t gx, gy, R, C;
+  int64_t delta;  // i0 - j0
+  int sym;
+  __device__ uint32_t cmin(uint32_t r) const {  // symmetric: tiles whose largest j is not above their smallest i are empty
+    if (!sym) return 0;
+    const int64_t v = delta + 256ll * (int64_t)r + 1;
+    if (v <= 0) return 0;
+    const uint64_t c = (uint64_t)v / (uint32_t)N1_BN;
+    return c > gx ? gx : (uint32_t)c;
+  }
+  __device__ void init(const hg::DistEpilogue &ep) {
+    gx = (ep.n_qry + N1_BN - 1) / N1_BN;
+    gy = (ep.n_ref + 255) / 256;
+    delta = (int64_t)ep.i0 - (int64_t)ep.j0;
+    sym = ep.symmetric;
+    R = 0;
+    C = cmin(0);
+  }
+  __device__ bool advance(uint32_t k) {
+    while (R < gy) {
+      const uint32_t avail = gx - C;
+      if (k < avail) { C += k; return true; }
+      k -= avail;
+      ++R;
+      C = cmin(R);
+    }
+    return false;
+  }
+};
+
+// bound of a row / column lowered by the largest correction its outliers can contribute
+__device__ __forceinline__ int32_t n1_loosen(int32_t t, uint32_t e, uint32_t m, int32_t always) {
+  if (t == always || e == 0) return t;
+  const uint64_t M = (uint64_t)e * m;
+  if (M > (1ull << 29)) return always;
+  return (int32_t)((int64_t)t - (int64_t)M);  // t >= -1, so this stays far above both sentinels
+}
+
+// exact i32 correction of candidate (li, lj): sum eps_r[d] y[d] + sum eps_q[d] x~[d]
+__device__ __noinline__ int32_t n1_correction(const NarrowArgs &na, uint32_t li, uint32_t lj, uint32_t er, uint32_t eq) {
+  uint32_t c = 0;
+  if (er) {
+    const uint32_t off = na.r.out_off[li], cnt = na.r.out_cnt[li];
+    const int16_t *y = na.q_hv + (size_t)lj * na.hv_d;
+    for (uint32_t t = 0; t < cnt; ++t) {
+      const uint32_t w = na.r_out[off + t];
+      c += (uint32_t)((int32_t)(int16_t)(w & 0xFFFFu) * (int32_t)y[w >> 16]);
+    }
+  }
+  if (eq) {
+    const uint32_t off = na.q.out_off[lj], cnt = na.q.out_cnt[lj];
+    const int8_t *a = na.r_plane + (size_t)li * na.hv_d;
+    const int32_t s = na.r.s[li];
+    for (uint32_t t = 0; t < cnt; ++t) {
+      const uint32_t w = na.q_out[off + t];
+      c += (uint32_t)((int32_t)(int16_t)(w & 0xFFFFu) * (2 * (int32_t)a[w >> 16] + s));
+    }
+  }
+  return (int32_t)c;
+}
+
+__device__ __forceinline__ void n1_process(const hg::DistEpilogue &ep, const NarrowArgs &na, const uint2 *list, uint32_t n,
+                                           uint32_t row0, uint32_t col0) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t e = lane; e < ((n + 31u) & ~31u); e += 32) {
+    const bool live0 = e < n;
+    const uint2 c = live0 ? list[e] : make_uint2(0u, 0u);
+    const uint32_t li = row0 + (c.x >> 8), lj = col0 + (c.x & 255u);
+    const bool live = live0 && li < ep.n_ref && lj < ep.n_qry;
+    int32_t dot = (int32_t)c.y;
+    if (live) {
+      const uint32_t er = na.r.e[li], eq = na.q.e[lj];
+      if (er | eq) dot = (int32_t)((uint32_t)dot + (uint32_t)n1_correction(na, li, lj, er, eq));
+    }
+    hg::dist_emit(ep, live, li, lj, dot);
+  }
+  __syncwarp();
+}
+
+// One epilogue warp drains columns [c_begin, c_end) of its 32 TMEM lanes: row `rowl` of the CTA's
+// 128 rows per lane.  x~ . y~ = 4 acc + s_q * X_r + s_r * T_q with X_r = sum x~ of my row and, per
+// column, the centre s_q and T_q = 2 sum(b).  Candidates (rowl, column, x~ . y~) go to `list`.
+__device__ __forceinline__ uint32_t n1_drain(const hg::DistEpilogue &ep, const NarrowArgs &na, uint32_t taddr, int c_begin,
+                                             int c_end, const int32_t *s_col, int32_t tr, int32_t sr, int32_t xr, bool row_live,
+                                             uint32_t rowl, uint32_t row0, uint32_t col0, uint2 *list, uint32_t n_list) {
+  const uint32_t lane = threadIdx.x & 31;
+  const bool row_always = tr == ROW_ALWAYS;
+  uint32_t nx[16];
+  tmem_ld16(taddr + c_begin, nx);
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; c += 16) {
+    uint32_t ac[16];
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    tmem_ld_fence(nx);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ac[j] = nx[j];
+    if (c + 16 < c_end) tmem_ld16(taddr + c + 16, nx);
+    int32_t dot[16];
+    uint32_t cand = 0;
+#pragma unroll
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      const int4 tq4 = *reinterpret_cast<const int4 *>(s_col + c + j4);
+      const int4 sq4 = *reinterpret_cast<const int4 *>(s_col + N1_BN + c + j4);
+      const int4 tt4 = *reinterpret_cast<const int4 *>(s_col + 2 * N1_BN + c + j4);
+      const int32_t tq[4] = {tq4.x, tq4.y, tq4.z, tq4.w}, sq[4] = {sq4.x, sq4.y, sq4.z, sq4.w}, tt[4] = {tt4.x, tt4.y, tt4.z, tt4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j4 + u;
+        dot[j] = (int32_t)(4u * ac[j] + (uint32_t)sq[u] * (uint32_t)xr + (uint32_t)sr * (uint32_t)tt[u]);  // wrapping i32
+        const bool cj = (dot[j] >= (int32_t)((uint32_t)tr + (uint32_t)tq[u]) || tq[u] == COL_ALWAYS || row_always) && tq[u] != COL_NEVER;
+        cand |= (uint32_t)cj << j;
+      }
+    }
+    if (!row_live) cand = 0;
+    if (!__any_sync(0xffffffffu, cand != 0)) continue;  // the common case
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // 8 columns at a time: at most 256 candidates, always fits an empty list
+      const uint32_t m = (cand >> (8 * h)) & 255u;
+      const uint32_t cnt = __popc(m);
+      uint32_t inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += y;
+      }
+      const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+      if (total == 0) continue;
+      if (n_list + total > N1_LIST_CAP) {  // evaluate what is parked (slow path: the accumulator stays held)
+        n1_process(ep, na, list, n_list, row0, col0);
+        n_list = 0;
+      }
+      uint32_t pos = n_list + inc - cnt;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if ((m >> j) & 1u) list[pos++] = make_uint2((rowl << 8) | (uint32_t)(c + 8 * h + j), (uint32_t)dot[8 * h + j]);
+      n_list += total;
+      __syncwarp();
+    }
+  }
+  return n_list;
+}
+
+__global__ void __launch_bounds__(N1_THREADS, 1)
+dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_qry, uint32_t ref_row_base,
+               hg::DistEpilogue ep, NarrowArgs na) {
+  uint32_t rank;  // 0 = leader (issues the MMAs, owns the full / tmem-empty barriers), 1 = peer
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle wants 1024 B alignment
+  uint8_t *aligned = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_base = base + N1_STAGES * N1_STAGE_BYTES;
+  auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };                       // used in the leader only
+  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (N1_STAGES + s); };        // one per CTA, multicast commit
+  auto accum_bar = [&](uint32_t b) { return bar_base + 8u * (2 * N1_STAGES + b); };    // one per CTA and buffer, multicast commit
+  auto tmem_empty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * N1_STAGES + 2 + b); };  // leader only: both epilogues drained
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aligned + N1_STAGES * N1_STAGE_BYTES + 8 * (2 * N1_STAGES + 4));
+  int32_t *s_col_all = reinterpret_cast<int32_t *>(aligned + N1_STAGES * N1_STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < N1_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(accum_bar(b), 1); mbar_init(tmem_empty_bar(b), 2 * N1_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // the same warp in both CTAs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)),
+                 "r"(N1_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anyone signals them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t num_kb = na.hv_d / TC_BK;
+
+  N1Tiles tiles;
+  tiles.init(ep);
+  bool valid = tiles.advance(pair);
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; completion bytes go to the LEADER's full barrier) =====
+    const uint32_t on = elect_one();
+    uint32_t s = 0, ph = 0;
+    for (; valid; valid = tiles.advance(n_pairs)) {
+      const uint32_t row0 = tiles.R * 256u + rank * 128u, colh = tiles.C * N1_BN + rank * 128u;
+      for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        mbar_wait_cluster(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), 2 * N1_STAGE_BYTES, rank == 0 ? on : 0u);  // the leader expects its bytes and the peer's
+        const uint32_t fb = mapa_u32(full_bar(s), 0);
+        const uint32_t st = base + s * N1_STAGE_BYTES;
+        const int k0 = (int)(kb * TC_BK);
+        tma_load_2d_pair(st, &tm_ref, fb, k0, (int)(ref_row_base + row0), on);  // my 128 ref rows
+        tma_load_2d_pair(st + N1_A_BYTES, &tm_qry, fb, k0, (int)colh, on);      // my half of the query rows
+        if (++s == N1_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
+    if (rank == 0) {
+      const uint32_t on = elect_one();
+      const uint32_t d0 = umma_desc_lo(base);
+      uint32_t s = 0, ph = 0, tile_n = 0;
+      for (; valid; valid = tiles.advance(n_pairs), ++tile_n) {
+        const uint32_t b = tile_n & 1u;
+        // both epilogues have drained this buffer's previous tile (passes at once for tiles 0 and 1)
+        mbar_wait_cluster(tmem_empty_bar(b), ((tile_n >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + b * N1_BN;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = d0 + s * (uint32_t)(N1_STAGE_BYTES >> 4);
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 32; ++ks)  // one MMA covers K = 32 int8
+            umma_i8_pair(tacc, a0 + (uint32_t)((32 * ks) >> 4), a0 + (uint32_t)((N1_A_BYTES + 32 * ks) >> 4), N1_IDESC,
+                         (kb | (uint32_t)ks) != 0u, on);
+          umma_commit_pair(empty_bar(s), on);  // the stage is free in both CTAs once these MMAs have read it
+          if (++s == N1_STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma_commit_pair(accum_bar(b), on);  // accumulator final: wake both epilogues
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs, each its own 128 rows) =====
+    const int ew = warp - 2;
+    const uint32_t q = warp & 3;  // TMEM lane quarter this warp may read
+    const int half = (ew >> 2);   // which 128 columns this warp drains
+    uint2 *list = reinterpret_cast<uint2 *>(aligned + N1_STAGES * N1_STAGE_BYTES + 256 + 2 * N1_COL_WORDS * 4) + ew * N1_LIST_CAP;
+    uint32_t tile_n = 0;
+    for (; valid; valid = tiles.advance(n_pairs), ++tile_n) {
+      const uint32_t b = tile_n & 1u;
+      const uint32_t row0 = tiles.R * 256u + rank * 128u, col0 = tiles.C * N1_BN;
+      int32_t *s_col = s_col_all + b * N1_COL_WORDS;  // double buffered: one barrier per tile is enough
+      {
+        const uint32_t t = threadIdx.x - 64, lj = col0 + t;  // one column per epilogue thread
+        int32_t tq = COL_NEVER, sq = 0, tt = 0;
+        if (lj < ep.n_qry) {
+          tq = COL_ALWAYS;
+          if (ep.cfrac > 0.0f) {
+            const int32_t nq = ep.qry_norm[lj];
+            if (nq > 0) tq = n1_loosen(__float2int_rd(ep.cfrac * __int2float_rz(nq)) - 1, na.q.e[lj], na.r_tmax, COL_ALWAYS);
+          }
+          sq = na.q.s[lj];
+          tt = na.q.a2[lj];
+        }
+        s_col[t] = tq;
+        s_col[N1_BN + t] = sq;
+        s_col[2 * N1_BN + t] = tt;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * N1_EPI_WARPS) : "memory");  // epilogue warps only
+      const uint32_t rowl = q * 32 + lane, li = row0 + rowl;
+      int32_t tr = ROW_ALWAYS, sr = 0, xr = 0;
+      if (li < ep.n_ref) {
+        if (ep.cfrac > 0.0f) {
+          const int32_t nr = ep.ref_norm[li];
+          if (nr > 0) tr = n1_loosen(__float2int_rd(ep.cfrac * __int2float_rz(nr)) - 1, na.r.e[li], na.q_absmax, ROW_ALWAYS);
+        }
+        sr = na.r.s[li];
+        xr = (int32_t)((uint32_t)na.r.a2[li] + na.hv_d * (uint32_t)sr);  // sum x~ = 2 sum a + D s
+      }
+      // my 128 x 256 part of the tile may be empty (below the diagonal, or past the last ref row)
+      const bool mine_empty = row0 >= ep.n_ref || (ep.symmetric && (uint64_t)ep.j0 + col0 + N1_BN - 1 <= (uint64_t)ep.i0 + row0);
+      mbar_wait_cluster(accum_bar(b), (tile_n >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t n_list = 0;
+      if (!mine_empty)
+        n_list = n1_drain(ep, na, tmem_base + ((q * 32u) << 16) + b * N1_BN, half * (N1_BN / 2), (half + 1) * (N1_BN / 2), s_col, tr,
+                          sr, xr, li < ep.n_ref, rowl, row0, col0, list, 0u);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(b), 0));  // this warp's TMEM reads of buffer b are done
+      n1_process(ep, na, list, n_list, row0, col0);                        // exact ANI + append, under the next tiles' MMAs
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves while the peer may still read its smem or signal its barriers
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(N1_TMEM_COLS) : "memory");
+  }
+}
+
+struct PrepBuffers {  // one matrix: plane + constants + entries, carved out of two scratch slots
+  int8_t *plane;
+  PrepOut out;
+  uint32_t h_stats[4];
+};
+
+size_t meta_bytes(uint32_t n_rows, uint32_t cap) { return ((size_t)n_rows * 5 + cap + 4) * 4 + 256; }
+
+void carve(PrepBuffers &pb, void *plane, void *meta, uint32_t n_rows, uint32_t cap) {
+  pb.plane = (int8_t *)plane;
+  uint32_t *m = (uint32_t *)meta;
+  pb.out.plane = pb.plane;
+  pb.out.stats = m;  // 4 words, zeroed before the launch
+  pb.out.s = (int32_t *)(m + 4);
+  pb.out.a2 = (int32_t *)(m + 4 + (size_t)n_rows);
+  pb.out.e = m + 4 + 2 * (size_t)n_rows;
+  pb.out.out_off = m + 4 + 3 * (size_t)n_rows;
+  pb.out.out_cnt = m + 4 + 4 * (size_t)n_rows;
+  pb.out.entries = m + 4 + 5 * (size_t)n_rows;
+  pb.out.cap = cap;
+}
+
+}  // namespace
+
+// Returns HG_OK when the narrow kernel was launched; HG_E_UNSUPPORTED when it declines (shape, or the rows need
+// more outlier entries than the budget) — *absmax_out then holds max |hv| if the scan ran, else -1.
+int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref, uint32_t i0,
+                          const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry, uint32_t j0, uint32_t hv_d,
+                          uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
+                          unsigned long long *d_n_hits, int32_t *absmax_out, uint64_t *outliers_out) {
+  if (absmax_out) *absmax_out = -1;
+  if (outliers_out) *outliers_out = 0;
+  if (n_ref == 0 || n_qry == 0) return HG_OK;
+  if (hv_d % TC_BK != 0 || hv_d > 32768) {
+    hg_set_error("narrow tensor path needs hv_d %% 128 == 0 and hv_d <= 32768, got %u", hv_d);
+    return HG_E_UNSUPPORTED;
+  }
+  if (((uintptr_t)d_ref | (uintptr_t)d_qry) & 15) {
+    hg_set_error("narrow tensor path needs 16-byte aligned HV matrices");
+    return HG_E_UNSUPPORTED;
+  }
+  int rc;
+  const uint64_t ref_elems = (uint64_t)n_ref * hv_d, qry_elems = (uint64_t)n_qry * hv_d;
+  // the query block may alias the ref block (all-vs-all) or contain it (row shard of the same matrix)
+  const bool qry_covers_ref = d_ref >= d_qry && d_ref + ref_elems <= d_qry + qry_elems && ((d_ref - d_qry) % hv_d) == 0;
+  // outlier budget: entries per row on average (HG_NARROW_BUDGET overrides; tests use it to force the correction path)
+  uint32_t per_row = 4;
+  if (const char *e = getenv("HG_NARROW_BUDGET")) per_row = (uint32_t)std::max(0, atoi(e));
+  const uint64_t cap_q64 = (uint64_t)n_qry * per_row + 1024, cap_r64 = (uint64_t)n_ref * per_row + 1024;
+  if (cap_q64 > 0x7FFFFFFFull || cap_r64 > 0x7FFFFFFFull) { hg_set_error("narrow tensor path: outlier budget too large"); return HG_E_UNSUPPORTED; }
+  const uint32_t cap_q = (uint32_t)cap_q64, cap_r = (uint32_t)cap_r64;
+
+  PrepBuffers pq, pr;
+  void *p_plane_q, *p_plane_r = nullptr, *p_meta;
+  const size_t mq = (meta_bytes(n_qry, cap_q) + 255) & ~(size_t)255, mr = qry_covers_ref ? 0 : meta_bytes(n_ref, cap_r);
+  if ((rc = hg_scratch(ctx, HG_S_QRY_LIMBS, qry_elems + 1024, &p_plane_q))) return rc;
+  if (!qry_covers_ref && (rc = hg_scratch(ctx, HG_S_REF_LIMBS, ref_elems + 1024, &p_plane_r))) return rc;
+  if ((rc = hg_scratch(ctx, HG_S_NARROW_META, mq + mr, &p_meta))) return rc;
+  carve(pq, p_plane_q, p_meta, n_qry, cap_q);
+  if (!qry_covers_ref) carve(pr, p_plane_r, (uint8_t *)p_meta + mq, n_ref, cap_r);
+
+  if (!ctx->n1_attr_set) {
+    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
+    ctx->n1_attr_set = 1;
+  }
+  // ---- GPU work starts here ----
+  HG_PROF(ctx, 4);
+  auto prep = [&](const int16_t *src, uint32_t rows, PrepBuffers &pb) -> int {
+    HG_CUDA(cudaMemsetAsync(pb.out.stats, 0, 16, ctx->stream));
+    const uint32_t blocks = std::min<uint32_t>(rows, (uint32_t)ctx->sm_count * 8);
+    narrow_prep_kernel<<<blocks, PREP_THREADS, 0, ctx->stream>>>(src, rows, hv_d, pb.out);
+    ctx->launches++;
+    HG_CUDA(cudaMemcpyAsync(pb.h_stats, pb.out.stats, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    return HG_OK;
+  };
+  if ((rc = prep(d_qry, n_qry, pq))) return rc;
+  if (!qry_covers_ref && (rc = prep(d_ref, n_ref, pr))) return rc;
+  HG_CUDA(cudaGetLastError());
+  HG_CUDA(cudaStreamSynchronize(ctx->stream));  // the outlier count decides whether this path is taken
+  const uint32_t *sq = pq.h_stats, *sr = qry_covers_ref ? pq.h_stats : pr.h_stats;
+  if (absmax_out) *absmax_out = (int32_t)std::max(sq[0], sr[0]);
+  if (outliers_out) *outliers_out = (uint64_t)sq[2] + (qry_covers_ref ? 0 : sr[2]);
+  if (sq[3] || sr[3]) {
+    hg_set_error("rows are not narrow: more than %u outlier entries per row on average (x = 2a + s, a in s8)", per_row);
+    return HG_E_UNSUPPORTED;
+  }
+
+  CUtensorMap tm_ref, tm_qry;
+  if ((rc = make_plane_map(&tm_qry, pq.plane, n_qry, hv_d, 128))) return rc;
+  uint32_t ref_row_off = 0;
+  NarrowArgs na;
+  na.q = {pq.out.s, pq.out.a2, pq.out.e, pq.out.out_off, pq.out.out_cnt};
+  na.q_out = pq.out.entries;
+  na.q_hv = d_qry;
+  na.hv_d = hv_d;
+  na.q_absmax = sq[0];
+  na.r_tmax = sr[1];
+  if (qry_covers_ref) {  // the ref rows are a window of the query plane
+    ref_row_off = (uint32_t)((d_ref - d_qry) / hv_d);
+    tm_ref = tm_qry;
+    na.r = {pq.out.s + ref_row_off, pq.out.a2 + ref_row_off, pq.out.e + ref_row_off, pq.out.out_off + ref_row_off,
+            pq.out.out_cnt + ref_row_off};
+    na.r_out = pq.out.entries;
+    na.r_plane = pq.plane + (size_t)ref_row_off * hv_d;
+  } else {
+    if ((rc = make_plane_map(&tm_ref, pr.plane, n_ref, hv_d, 128))) return rc;
+    na.r = {pr.out.s, pr.out.a2, pr.out.e, pr.out.out_off, pr.out.out_cnt};
+    na.r_out = pr.out.entries;
+    na.r_plane = pr.plane;
+  }
+
+  hg::DistEpilogue ep;
+  ep.ref_norm = d_ref_norm;
+  ep.qry_norm = d_qry_norm;
+  ep.n_ref = n_ref;
+  ep.n_qry = n_qry;
+  ep.i0 = i0;
+  ep.j0 = j0;
+  ep.ksize_f = (float)ksize;
+  ep.ani_th = ani_th;
+  ep.jmin = hg::dist_jmin(ani_th, ksize);
+  ep.cfrac = ep.jmin > 0.0f ? (float)((double)ep.jmin / (1.0 + (double)ep.jmin)) : 0.0f;
+  ep.symmetric = symmetric;
+  ep.hits = d_hits;
+  ep.cap = cap;
+  ep.n_hits = d_n_hits;
+
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.blockDim = dim3(N1_THREADS, 1, 1);
+  cfg.stream = ctx->stream;
+  // one CTA pair per TPC, each walking the 256 x 256 tiles with stride n_pairs
+  const uint64_t tiles = (uint64_t)((n_qry + N1_BN - 1) / N1_BN) * ((n_ref + 255) / 256);
+  const uint32_t n_pairs = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)std::max(ctx->sm_count / 2, 1));
+  cfg.gridDim = dim3(2 * n_pairs, 1, 1);
+  cfg.dynamicSmemBytes = N1_SMEM_BYTES;
+  HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel, tm_ref, tm_qry, ref_row_off, ep, na));
+  ctx->launches++;
+  HG_PROF(ctx, 5);
+  HG_CUDA(cudaGetLastError());
+  return HG_OK;
+}

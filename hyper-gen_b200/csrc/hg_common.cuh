@@ -128,8 +128,8 @@ struct hg_ctx {
   cudaStream_t stream;
   unsigned long long launches;
   // grow-only device scratch
-  void *d_scratch[12];        // indexed by hg_scratch_slot
-  size_t d_scratch_bytes[12];
+  void *d_scratch[13];        // indexed by hg_scratch_slot
+  size_t d_scratch_bytes[13];
   // pinned host scratch
   void *h_pinned[4];
   size_t h_pinned_bytes[4];
@@ -145,6 +145,7 @@ struct hg_ctx {
   int ev_used;           // which stage boundaries were recorded in the last call
   // H2D pipeline of the host-pointer sketch entry
   int tc_attr_set;
+  int n1_attr_set;
   const uint64_t *d_actual_len;  // optional per-genome true lengths for the next k-mer launch (raw-FASTA path)
   cudaStream_t copy_stream;
   cudaEvent_t ev_copied[2], ev_done[2];
@@ -183,7 +184,8 @@ enum hg_scratch_slot {
   HG_S_QRY_LIMBS = 9,  // s8 limb planes of the query matrix (dist_tc)
   HG_S_SORT_TMP = 10,  // ping-pong buffer of the hit sort
   HG_S_SORT_CNT = 11,  // digit counters of the hit sort
-  HG_S_COUNT = 12
+  HG_S_NARROW_META = 12,  // per-row constants + outlier lists of the single-plane dist path (dist_narrow)
+  HG_S_COUNT = 13
 };
 // scratch slot `slot` grown to at least `bytes` (contents not preserved)
 int hg_scratch(hg_ctx *ctx, int slot, size_t bytes, void **out);
@@ -220,6 +222,12 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
                       uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
                       uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
                       hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits);
+// single s8 plane (x = 2a + s) + sparse outlier corrections; HG_E_UNSUPPORTED when the rows are not narrow
+int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref,
+                          uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
+                          uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
+                          hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits, int32_t *absmax_out,
+                          uint64_t *outliers_out);
 int hg_launch_int_peak(hg_ctx *ctx, int which, uint32_t iters, uint32_t *d_sink, uint32_t blocks);
 // max |hv| over a device matrix (decides the dist path); result in *d_out (int32)
 int hg_launch_sort_hits(hg_ctx *ctx, hg_hit *d_hits, uint64_t n, uint32_t *d_milli);

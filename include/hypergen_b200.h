@@ -167,8 +167,14 @@ HG_API int hg_unpack_dev(hg_ctx *ctx, const uint8_t *d_packed, uint64_t row_stri
  * of src/dist.rs:153-160, and is reported iff ani >= ani_th.  The order of the hits is
  * unspecified (the reference sorts by ANI when it writes its output, src/utils.rs:262-269).
  * If more than `cap` pairs pass, returns HG_E_CAPACITY with *n_hits = need.
- *   path: 0 = auto (tcgen05 int8 limb path when every |hv| fits 13 bits, else SIMT),
- *         1 = force SIMT (CUDA-core) path, 2 = force tensor path. */
+ *   path: 0 = auto: the single-plane tcgen05 int8 kernel when the rows are narrow (sketch rows are
+ *             hv = 2 count - n, one parity per row; x = 2a + s with a in s8 when the row spans
+ *             <= 510 — every hv_quant_bits = 9 sketch — plus sparse exact corrections for the odd
+ *             element outside), else the two-limb tcgen05 int8 kernel when every |hv| fits 13
+ *             bits, else SIMT; fewer than 128 x 128 pairs go to SIMT directly,
+ *         1 = force SIMT (CUDA-core) path, 2 = force the two-limb tensor path,
+ *         3 = force the single-plane tensor path (HG_E_UNSUPPORTED if the rows are not narrow).
+ *   Every path is exact: identical i32 dots and f32 ANI bits. */
 HG_API int hg_dist(hg_ctx *ctx, const int16_t *ref_hv, const int32_t *ref_norm2, uint32_t n_ref,
                    const int16_t *qry_hv, const int32_t *qry_norm2, uint32_t n_qry, uint32_t hv_d,
                    uint32_t ksize, float ani_th, int symmetric, int path, hg_hit *hits, uint64_t cap,
@@ -213,7 +219,7 @@ HG_API int hg_dist_packed(hg_ctx *ctx, const uint8_t *ref_packed, uint64_t ref_s
                           uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path,
                           int sorted, hg_hit *hits, uint32_t *ani_milli, uint64_t cap, uint64_t *n_hits);
 
-/* Which path the last hg_dist / hg_dist_dev took (1 SIMT, 2 tensor) and why. */
+/* Which path the last hg_dist / hg_dist_dev took (1 SIMT, 2 two-limb tensor, 3 single-plane tensor) and why. */
 HG_API int hg_dist_last_path(hg_ctx *ctx);
 HG_API const char *hg_dist_last_reason(hg_ctx *ctx);
 

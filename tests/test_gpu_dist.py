@@ -9,7 +9,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-PATHS = [1, 2]  # 1 = SIMT, 2 = tcgen05 tensor path
+PATHS = [1, 2, 3]  # 1 = SIMT, 2 = tcgen05 two-limb tensor path, 3 = tcgen05 single-plane (narrow) tensor path
 
 
 def _sketches(oracle, n, length=150_000, hv_d=4096, scaled=1500, first=0):
@@ -85,8 +85,11 @@ def test_headline_shape_D4096_and_D8192(ctx, hg, oracle, path):
 
 
 @pytest.mark.parametrize("path", PATHS)
-def test_degenerate_inputs(ctx, hg, oracle, path):
+def test_degenerate_inputs(ctx, hg, oracle, path, monkeypatch):
     """zero vectors (0/0 -> NaN -> 0), negative dots (ln of a negative -> NaN -> 0), identical HVs (100)."""
+    # random parity and a 600-wide range: for the single-plane path every other element is an outlier;
+    # with the budget lifted it must still be exact (all of it through the sparse corrections)
+    monkeypatch.setenv("HG_NARROW_BUDGET", "2048")
     rng = np.random.default_rng(5)
     D = 1024
     hv = rng.integers(-300, 300, (130, D)).astype(np.int16)
@@ -133,3 +136,121 @@ def test_golden_small_pipeline(ctx, hg):
     assert np.array_equal(idx[order], z["order"])
     assert np.array_equal(hits["ani"][order].view(np.uint32), z["ani"][z["order"]].view(np.uint32))
     assert np.array_equal(hits["dot"][order], z["dot"][z["order"]])
+
+
+# ---- single-plane (narrow) tensor path: x = 2a + s in one s8 plane + sparse outlier corrections ----
+
+def _narrow_rows(rng, n, D, spread=110):
+    """rows shaped like sketch HVs (hv = 2 count - n: one parity per row, centred near 0)"""
+    par = rng.integers(0, 2, (n, 1))
+    return (2 * np.clip(np.rint(rng.normal(0, spread / 3, (n, D))), -spread, spread).astype(np.int64) + par).astype(np.int16)
+
+
+def _norms(oracle, hv):
+    return np.array([oracle.hv_l2_norm_sq(v) for v in hv], np.int32)
+
+
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_narrow_many_tiles_exact(ctx, hg, oracle, symmetric):
+    """several 256 x 256 tiles per CTA pair (TMEM double buffering, stage ring across tiles, ragged edges)"""
+    rng = np.random.default_rng(31)
+    D = 512
+    hv = _narrow_rows(rng, 700, D)
+    hv[5] = hv[400]          # a 100 % pair far from the diagonal
+    hv[650] = hv[12]
+    norm = _norms(oracle, hv)
+    if symmetric:
+        r, rn, q, qn = hv, norm, hv, norm
+    else:
+        r, rn, q, qn = hv[:300], norm[:300], hv[100:], norm[100:]
+    ani, dot = oracle.dist_all(r, rn, q, qn, symmetric=symmetric)
+    hits = ctx.dist(r, rn, q, qn, ani_th=0.0, symmetric=symmetric, path=3, cap=ani.size + 16)
+    assert ctx.dist_last_path == 3
+    idx = _as_pairs(hits, r.shape[0], q.shape[0], symmetric)
+    assert np.array_equal(np.sort(idx), np.arange(ani.size))
+    assert np.array_equal(hits["dot"], dot[idx])
+    assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32))
+
+
+@pytest.mark.parametrize("ani_th", [0.0, 85.0])
+def test_narrow_outlier_corrections(ctx, hg, oracle, ani_th):
+    """rows with a few elements outside the s8 plane (range and parity outliers, both sides): the kernel
+    loosens their bound and corrects each candidate exactly"""
+    hv, norm = _sketches(oracle, 300, length=120_000, hv_d=1024, scaled=300)
+    hv = hv.copy()
+    rng = np.random.default_rng(7)
+    rows = rng.choice(300, 40, replace=False)
+    for t, r in enumerate(rows):
+        d = rng.choice(1024, 1 + t % 5, replace=False)
+        if t % 3 == 0:
+            hv[r, d] += np.int16(1)                                   # wrong parity
+        elif t % 3 == 1:
+            hv[r, d] = (hv[r, d] + rng.choice([-700, 600, 1400], d.size)).astype(np.int16)   # far outside the plane
+        else:
+            hv[r, d] = np.int16(8001)                                # odd and far
+    norm = _norms(oracle, hv)
+    for symmetric in (True, False):
+        if symmetric:
+            r_, rn, q_, qn = hv, norm, hv, norm
+        else:
+            r_, rn, q_, qn = hv[:130], norm[:130], hv[90:], norm[90:]
+        ani, dot = oracle.dist_all(r_, rn, q_, qn, symmetric=symmetric)
+        hits = ctx.dist(r_, rn, q_, qn, ani_th=ani_th, symmetric=symmetric, path=0, cap=ani.size + 16)
+        assert ctx.dist_last_path == 3 and "narrow" in ctx.dist_last_reason, ctx.dist_last_reason
+        idx = _as_pairs(hits, r_.shape[0], q_.shape[0], symmetric)
+        want = np.nonzero(ani >= np.float32(ani_th))[0]
+        assert np.array_equal(np.sort(idx), want)
+        assert np.array_equal(hits["dot"], dot[idx])
+        assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32))
+
+
+def test_auto_path_narrow_for_sketches_and_two_limb_for_wide_rows(ctx, hg, oracle):
+    hv, norm = _sketches(oracle, 140, length=200_000)
+    ani, dot = oracle.dist_all(hv, norm, hv, norm, symmetric=True)
+    hits = ctx.dist(hv, norm, hv, norm, ani_th=85.0, symmetric=True, path=0)
+    assert ctx.dist_last_path == 3, ctx.dist_last_reason
+    assert np.array_equal(np.sort(_as_pairs(hits, 140, 140, True)), np.nonzero(ani >= np.float32(85.0))[0])
+    # rows as wide as scaled=500 / D=8192 sketches (sigma 100): far too many elements outside one s8 plane
+    rng = np.random.default_rng(3)
+    wide = (2 * rng.binomial(10000, 0.5, (140, 1024)) - 10000).astype(np.int16)
+    wn = _norms(oracle, wide)
+    ani, dot = oracle.dist_all(wide, wn, wide, wn, symmetric=True)
+    hits = ctx.dist(wide, wn, wide, wn, ani_th=0.0, symmetric=True, path=0, cap=ani.size)
+    assert ctx.dist_last_path == 2 and "declined" in ctx.dist_last_reason, ctx.dist_last_reason
+    idx = _as_pairs(hits, 140, 140, True)
+    assert np.array_equal(hits["dot"], dot[idx])
+    assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32))
+    with pytest.raises(hg.HyperGenError) as ei:
+        ctx.dist(wide, wn, wide, wn, ani_th=0.0, symmetric=True, path=3, cap=ani.size)
+    assert ei.value.code == hg.ffi.HG_E_UNSUPPORTED
+
+
+def test_narrow_row_shard_offsets(ctx, hg, oracle):
+    """hg_dist_dev on a row shard of the query matrix (i0 > 0, symmetric filter on global indices) - the
+    multi-GPU dist step - through the single-plane path"""
+    import torch
+    rng = np.random.default_rng(11)
+    D, n = 512, 600
+    hv = _narrow_rows(rng, n, D)
+    hv[37, [3, 99]] = [901, -777]  # one outlier row inside the shard
+    norm = _norms(oracle, hv)
+    ani, dot = oracle.dist_all(hv, norm, hv, norm, symmetric=True)
+    d_hv = torch.from_numpy(hv).cuda()
+    d_n = torch.from_numpy(norm).cuda()
+    i0, rows = 256 + 17, 300
+    cap = rows * n
+    d_hits = torch.empty(cap * 16, dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.dist_dev(d_hv.data_ptr() + i0 * D * 2, d_n.data_ptr() + i0 * 4, rows, i0, d_hv.data_ptr(), d_n.data_ptr(), n, 0, D, 21,
+                 0.0, True, 3, d_hits.data_ptr(), cap, d_cnt.data_ptr())
+    ctx.sync()
+    cnt = int(d_cnt.item())
+    hits = np.frombuffer(d_hits.cpu().numpy().tobytes(), dtype=hg.ffi.HIT_DTYPE)[:cnt]
+    idx = _as_pairs(hits, n, n, True)
+    ii, jj = np.meshgrid(np.arange(i0, i0 + rows), np.arange(n), indexing="ij")
+    keep = jj > ii
+    want = np.sort(ii[keep] * (n - 1) - ii[keep] * (ii[keep] - 1) // 2 + (jj[keep] - ii[keep] - 1))
+    assert np.array_equal(np.sort(idx), want)
+    assert np.array_equal(hits["dot"], dot[idx])
+    assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32))
