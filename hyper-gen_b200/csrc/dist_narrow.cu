@@ -70,8 +70,8 @@ struct NarrowArgs {
   const int8_t *r_plane;          // s8 plane of the ref rows (first row of the launch)
   const int16_t *q_hv;            // the query matrix itself
   uint32_t hv_d;
-  uint32_t q_absmax;              // max |y[d]| over the query matrix
-  uint32_t r_tmax;                // max |x~[d]| over the ref matrix (<= |s| + 256)
+  // written by the pre-pass: [0] max |x|, [1] max (|s| + 256) >= max |x~|, [2] entries used, [3] declined
+  const uint32_t *q_stats, *r_stats;
 };
 
 // ---- i16 rows -> s8 plane + per-row constants + outlier lists ---------------------------------
@@ -100,128 +100,129 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
   return v;
 }
 
-constexpr int PREP_THREADS = 256;
+constexpr int PREP_THREADS = 256;  // 8 warps, one row per warp
 
+// the 8 int16 of one 16-byte load
+__device__ __forceinline__ void unpack8(const uint4 &v, int (&x)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[e] = (int)(int16_t)(w[e >> 1] >> (16 * (e & 1)));
+}
+
+// One warp per row, no block-level synchronisation: pass 1 (range, sum, parity) streams the row with
+// eight 16-byte loads in flight per lane; pass 2 re-reads it (L1/L2) and writes the plane; rows with
+// outliers (rare) take a third pass that writes their entries.
 __global__ void __launch_bounds__(PREP_THREADS)
 narrow_prep_kernel(const int16_t *__restrict__ hv, uint32_t n_rows, uint32_t hv_d, PrepOut o) {
-  __shared__ int sh_lo[8], sh_hi[8];
-  __shared__ uint32_t sh_a[8], sh_e[8], sh_c[8];
-  __shared__ uint32_t sh_base;
-  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t nv = hv_d / 8;  // uint4 loads per row
-  for (uint32_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(hv + (size_t)row * hv_d);
-    // pass 1: range and sum of the row
-    int lo = 32767, hi = -32768, sum_x = 0;
-    uint32_t n_odd = 0;
-    for (uint32_t i = tid; i < nv; i += PREP_THREADS) {
-      const uint4 v = src[i];
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t row = blockIdx.x * (PREP_THREADS / 32) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const uint32_t nt = hv_d / 256;  // 16-byte loads per lane (hv_d is a multiple of 256)
+  const uint4 *src = reinterpret_cast<const uint4 *>(hv + (size_t)row * hv_d) + lane;
+  // pass 1: range, sum and parity count of the row
+  int lo = 32767, hi = -32768, sum_x = 0;
+  uint32_t n_odd = 0;
+  for (uint32_t t0 = 0; t0 < nt; t0 += 8) {
+    uint4 v[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int x = (int)(int16_t)(w[e >> 1] >> (16 * (e & 1)));
-        lo = min(lo, x);
-        hi = max(hi, x);
-        sum_x += x;  // |sum| <= 32768 * 32768: fits
-        n_odd += (uint32_t)x & 1u;
+    for (int u = 0; u < 8; ++u)
+      if (t0 + u < nt) v[u] = __ldg(src + 32 * (t0 + u));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (t0 + u < nt) {
+        int x[8];
+        unpack8(v[u], x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          lo = min(lo, x[e]);
+          hi = max(hi, x[e]);
+          sum_x += x[e];  // |sum| <= 32768 * 32768: fits
+          n_odd += (uint32_t)x[e] & 1u;
+        }
       }
     }
-    lo = warp_min(lo);
-    hi = warp_max(hi);
-    sum_x = (int)warp_sum((uint32_t)sum_x);
-    n_odd = warp_sum(n_odd);
-    __syncthreads();  // the previous row's shared values are no longer needed
-    if (lane == 0) { sh_lo[warp] = lo; sh_hi[warp] = hi; sh_a[warp] = (uint32_t)sum_x; sh_c[warp] = n_odd; }
-    __syncthreads();
-    lo = sh_lo[0];
-    hi = sh_hi[0];
-    sum_x = (int)sh_a[0];
-    n_odd = sh_c[0];
+  }
+  lo = warp_min(lo);
+  hi = warp_max(hi);
+  sum_x = (int)warp_sum((uint32_t)sum_x);
+  n_odd = warp_sum(n_odd);
+  // centre with the parity of the row (hv = 2 count - n: one parity per row; the majority speaks for it):
+  // the middle of the range when the whole row fits [s - 256, s + 254], else the mean (a few far
+  // elements become outliers instead of dragging the window away from everything else)
+  const int par = 2 * n_odd > hv_d ? 1 : 0;
+  int mid = (lo + hi + 2) >> 1;
+  if (hi - lo > 510) {
+    const int half = (int)(hv_d / 2);
+    mid = sum_x >= 0 ? (sum_x + half) / (int)hv_d : -((-sum_x + half) / (int)hv_d);
+  }
+  const int s = mid - ((mid - par) & 1);
+  // pass 2: plane, sum a, residuals
+  uint32_t sum_a = 0, sum_e = 0, cnt = 0, bad = 0;
+  uint2 *dst = reinterpret_cast<uint2 *>(o.plane + (size_t)row * hv_d) + lane;
+  for (uint32_t t0 = 0; t0 < nt; t0 += 8) {
+    uint4 v[8];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) { lo = min(lo, sh_lo[w]); hi = max(hi, sh_hi[w]); sum_x += (int)sh_a[w]; n_odd += sh_c[w]; }
-    __syncthreads();  // sh_a / sh_c are reused for the plane sums below
-    // centre with the parity of the row (hv = 2 count - n: one parity per row; the majority speaks for it):
-    // the middle of the range when the whole row fits [s - 256, s + 254], else the mean (a few far
-    // elements become outliers instead of dragging the window away from everything else)
-    const int par = 2 * n_odd > hv_d ? 1 : 0;
-    int mid = (lo + hi + 2) >> 1;
-    if (hi - lo > 510) {
-      const int half = (int)(hv_d / 2);
-      mid = sum_x >= 0 ? (sum_x + half) / (int)hv_d : -((-sum_x + half) / (int)hv_d);
-    }
-    const int s = mid - ((mid - par) & 1);
-    // pass 2 (the row is in L1/L2): plane, sum a, residuals
-    uint32_t sum_a = 0, sum_e = 0, cnt = 0, bad = 0;
-    uint2 *dst = reinterpret_cast<uint2 *>(o.plane + (size_t)row * hv_d);
-    for (uint32_t i = tid; i < nv; i += PREP_THREADS) {
-      const uint4 v = src[i];
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      uint32_t pk[2] = {0, 0};
+    for (int u = 0; u < 8; ++u)
+      if (t0 + u < nt) v[u] = __ldg(src + 32 * (t0 + u));
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int x = (int)(int16_t)(w[e >> 1] >> (16 * (e & 1)));
-        const int t = x - s;
-        const int a = max(-128, min(127, t >> 1));
-        const int eps = t - 2 * a;
-        sum_a += (uint32_t)a;
-        if (eps != 0) { ++cnt; sum_e += (uint32_t)abs(eps); }
-        if (eps < -32768 || eps > 32767) bad = 1;  // does not fit an outlier entry (needs |x - s| > 32000): decline
-        pk[e >> 2] |= (uint32_t)(a & 0xFF) << (8 * (e & 3));
+    for (int u = 0; u < 8; ++u) {
+      if (t0 + u < nt) {
+        int x[8];
+        unpack8(v[u], x);
+        uint32_t pk[2] = {0, 0};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int t = x[e] - s;
+          const int a = max(-128, min(127, t >> 1));
+          const int eps = t - 2 * a;
+          sum_a += (uint32_t)a;
+          if (eps != 0) { ++cnt; sum_e += (uint32_t)abs(eps); }
+          if (eps < -32768 || eps > 32767) bad = 1;  // does not fit an outlier entry (needs |x - s| > 32000): decline
+          pk[e >> 2] |= (uint32_t)(a & 0xFF) << (8 * (e & 3));
+        }
+        dst[32 * (t0 + u)] = make_uint2(pk[0], pk[1]);
       }
-      dst[i] = make_uint2(pk[0], pk[1]);
     }
-    // block totals + exclusive prefix of the outlier counts
-    uint32_t inc = cnt;
+  }
+  // warp totals + exclusive prefix of the outlier counts
+  uint32_t inc = cnt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= (uint32_t)d) inc += y;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= (uint32_t)d) inc += y;
+  }
+  const uint32_t tot_c = __shfl_sync(0xffffffffu, inc, 31);
+  const uint32_t tot_a = warp_sum(sum_a), tot_e = warp_sum(sum_e);
+  if (__any_sync(0xffffffffu, bad != 0) && lane == 0) atomicExch(&o.stats[3], 1u);
+  uint32_t base = 0, kept = tot_c;
+  if (lane == 0) {
+    if (tot_c) {
+      base = atomicAdd(&o.stats[2], tot_c);
+      if (base > o.cap || tot_c > o.cap - base) { atomicExch(&o.stats[3], 1u); kept = 0; }
     }
-    const uint32_t wa = warp_sum(sum_a), we = warp_sum(sum_e);
-    if (bad) atomicExch(&o.stats[3], 1u);
-    if (lane == 31) sh_c[warp] = inc;
-    if (lane == 0) { sh_a[warp] = wa; sh_e[warp] = we; }
-    __syncthreads();
-    uint32_t tot_a = 0, tot_e = 0, tot_c = 0, before = 0;
+    o.s[row] = s;
+    o.a2[row] = (int32_t)(2u * tot_a);
+    o.e[row] = tot_e;
+    o.out_off[row] = base;
+    o.out_cnt[row] = kept;
+    const uint32_t am = (uint32_t)max(abs(lo), abs(hi)), tm = (uint32_t)abs(s) + 256u;
+    if (am > *(volatile uint32_t *)&o.stats[0]) atomicMax(&o.stats[0], am);
+    if (tm > *(volatile uint32_t *)&o.stats[1]) atomicMax(&o.stats[1], tm);
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  kept = __shfl_sync(0xffffffffu, kept, 0);
+  if (kept == 0) return;
+  // pass 3 (rows with outliers only): write the entries, lane by lane in scan order
+  uint32_t pos = base + inc - cnt;
+  for (uint32_t t = 0; t < nt; ++t) {
+    int x[8];
+    unpack8(__ldg(src + 32 * t), x);
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      tot_a += sh_a[w];
-      tot_e += sh_e[w];
-      if ((uint32_t)w < warp) before += sh_c[w];
-      tot_c += sh_c[w];
-    }
-    if (tid == 0) {
-      uint32_t base = 0, kept = tot_c;
-      if (tot_c) {
-        base = atomicAdd(&o.stats[2], tot_c);
-        if (base > o.cap || tot_c > o.cap - base) { atomicExch(&o.stats[3], 1u); kept = 0; }
-      }
-      sh_base = kept ? base : 0xFFFFFFFFu;
-      o.s[row] = s;
-      o.a2[row] = (int32_t)(2u * tot_a);
-      o.e[row] = tot_e;
-      o.out_off[row] = base;
-      o.out_cnt[row] = kept;
-      atomicMax(&o.stats[0], (uint32_t)max(abs(lo), abs(hi)));
-      atomicMax(&o.stats[1], (uint32_t)abs(s) + 256u);
-    }
-    if (tot_c == 0) continue;  // uniform over the block
-    __syncthreads();
-    const uint32_t base = sh_base;
-    if (base == 0xFFFFFFFFu) continue;
-    // pass 3 (rows with outliers only): write the entries, thread by thread in scan order
-    uint32_t pos = base + before + inc - cnt;
-    for (uint32_t i = tid; i < nv; i += PREP_THREADS) {
-      const uint4 v = src[i];
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int x = (int)(int16_t)(w[e >> 1] >> (16 * (e & 1)));
-        const int t = x - s;
-        const int a = max(-128, min(127, t >> 1));
-        const int eps = t - 2 * a;
-        if (eps != 0) o.entries[pos++] = ((8u * i + (uint32_t)e) << 16) | ((uint32_t)eps & 0xFFFFu);
-      }
+    for (int e = 0; e < 8; ++e) {
+      const int tt = x[e] - s;
+      const int a = max(-128, min(127, tt >> 1));
+      const int eps = tt - 2 * a;
+      if (eps != 0) o.entries[pos++] = ((8u * (lane + 32 * t) + (uint32_t)e) << 16) | ((uint32_t)eps & 0xFFFFu);
     }
   }
 }
@@ -373,6 +374,10 @@ __device__ __forceinline__ uint32_t n1_drain(const hg::DistEpilogue &ep, const N
 __global__ void __launch_bounds__(N1_THREADS, 1)
 dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_qry, uint32_t ref_row_base,
                hg::DistEpilogue ep, NarrowArgs na) {
+  // the pre-pass ran on this stream just before: if it found the rows not narrow (outlier budget exceeded)
+  // nothing is computed here and the host, which reads the same flag after this launch, takes another path
+  if (na.q_stats[3] | na.r_stats[3]) return;
+  const uint32_t q_absmax = na.q_stats[0], r_tmax = na.r_stats[1];
   uint32_t rank;  // 0 = leader (issues the MMAs, owns the full / tmem-empty barriers), 1 = peer
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
@@ -472,7 +477,7 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
           tq = COL_ALWAYS;
           if (ep.cfrac > 0.0f) {
             const int32_t nq = ep.qry_norm[lj];
-            if (nq > 0) tq = n1_loosen(__float2int_rd(ep.cfrac * __int2float_rz(nq)) - 1, na.q.e[lj], na.r_tmax, COL_ALWAYS);
+            if (nq > 0) tq = n1_loosen(__float2int_rd(ep.cfrac * __int2float_rz(nq)) - 1, na.q.e[lj], r_tmax, COL_ALWAYS);
           }
           sq = na.q.s[lj];
           tt = na.q.a2[lj];
@@ -487,7 +492,7 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
       if (li < ep.n_ref) {
         if (ep.cfrac > 0.0f) {
           const int32_t nr = ep.ref_norm[li];
-          if (nr > 0) tr = n1_loosen(__float2int_rd(ep.cfrac * __int2float_rz(nr)) - 1, na.r.e[li], na.q_absmax, ROW_ALWAYS);
+          if (nr > 0) tr = n1_loosen(__float2int_rd(ep.cfrac * __int2float_rz(nr)) - 1, na.r.e[li], q_absmax, ROW_ALWAYS);
         }
         sr = na.r.s[li];
         xr = (int32_t)((uint32_t)na.r.a2[li] + na.hv_d * (uint32_t)sr);  // sum x~ = 2 sum a + D s
@@ -583,23 +588,14 @@ int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_re
   HG_PROF(ctx, 4);
   auto prep = [&](const int16_t *src, uint32_t rows, PrepBuffers &pb) -> int {
     HG_CUDA(cudaMemsetAsync(pb.out.stats, 0, 16, ctx->stream));
-    const uint32_t blocks = std::min<uint32_t>(rows, (uint32_t)ctx->sm_count * 8);
+    const uint32_t blocks = (rows + PREP_THREADS / 32 - 1) / (PREP_THREADS / 32);
     narrow_prep_kernel<<<blocks, PREP_THREADS, 0, ctx->stream>>>(src, rows, hv_d, pb.out);
     ctx->launches++;
-    HG_CUDA(cudaMemcpyAsync(pb.h_stats, pb.out.stats, 16, cudaMemcpyDeviceToHost, ctx->stream));
     return HG_OK;
   };
   if ((rc = prep(d_qry, n_qry, pq))) return rc;
   if (!qry_covers_ref && (rc = prep(d_ref, n_ref, pr))) return rc;
   HG_CUDA(cudaGetLastError());
-  HG_CUDA(cudaStreamSynchronize(ctx->stream));  // the outlier count decides whether this path is taken
-  const uint32_t *sq = pq.h_stats, *sr = qry_covers_ref ? pq.h_stats : pr.h_stats;
-  if (absmax_out) *absmax_out = (int32_t)std::max(sq[0], sr[0]);
-  if (outliers_out) *outliers_out = (uint64_t)sq[2] + (qry_covers_ref ? 0 : sr[2]);
-  if (sq[3] || sr[3]) {
-    hg_set_error("rows are not narrow: more than %u outlier entries per row on average (x = 2a + s, a in s8)", per_row);
-    return HG_E_UNSUPPORTED;
-  }
 
   CUtensorMap tm_ref, tm_qry;
   if ((rc = make_plane_map(&tm_qry, pq.plane, n_qry, hv_d, 128))) return rc;
@@ -609,8 +605,8 @@ int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_re
   na.q_out = pq.out.entries;
   na.q_hv = d_qry;
   na.hv_d = hv_d;
-  na.q_absmax = sq[0];
-  na.r_tmax = sr[1];
+  na.q_stats = pq.out.stats;
+  na.r_stats = qry_covers_ref ? pq.out.stats : pr.out.stats;
   if (qry_covers_ref) {  // the ref rows are a window of the query plane
     ref_row_off = (uint32_t)((d_ref - d_qry) / hv_d);
     tm_ref = tm_qry;
@@ -660,5 +656,17 @@ int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_re
   ctx->launches++;
   HG_PROF(ctx, 5);
   HG_CUDA(cudaGetLastError());
+  // The kernel itself honours the pre-pass's verdict (it does nothing when the rows are not narrow), so the
+  // host learns it only now, with no bubble between pre-pass and kernel.
+  HG_CUDA(cudaMemcpyAsync(pq.h_stats, pq.out.stats, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!qry_covers_ref) HG_CUDA(cudaMemcpyAsync(pr.h_stats, pr.out.stats, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  HG_CUDA(cudaStreamSynchronize(ctx->stream));
+  const uint32_t *sq = pq.h_stats, *sr = qry_covers_ref ? pq.h_stats : pr.h_stats;
+  if (absmax_out) *absmax_out = (int32_t)std::max(sq[0], sr[0]);
+  if (outliers_out) *outliers_out = (uint64_t)sq[2] + (qry_covers_ref ? 0 : sr[2]);
+  if (sq[3] || sr[3]) {
+    hg_set_error("rows are not narrow: more than %u outlier entries per row on average (x = 2a + s, a in s8)", per_row);
+    return HG_E_UNSUPPORTED;
+  }
   return HG_OK;
 }

@@ -210,9 +210,9 @@ def test_auto_path_narrow_for_sketches_and_two_limb_for_wide_rows(ctx, hg, oracl
     hits = ctx.dist(hv, norm, hv, norm, ani_th=85.0, symmetric=True, path=0)
     assert ctx.dist_last_path == 3, ctx.dist_last_reason
     assert np.array_equal(np.sort(_as_pairs(hits, 140, 140, True)), np.nonzero(ani >= np.float32(85.0))[0])
-    # rows as wide as scaled=500 / D=8192 sketches (sigma 100): far too many elements outside one s8 plane
+    # rows twice as wide as scaled=500 / D=8192 sketches (sigma 200): a fifth of the elements lie outside one s8 plane
     rng = np.random.default_rng(3)
-    wide = (2 * rng.binomial(10000, 0.5, (140, 1024)) - 10000).astype(np.int16)
+    wide = (2 * rng.binomial(40000, 0.5, (140, 1024)) - 40000).astype(np.int16)
     wn = _norms(oracle, wide)
     ani, dot = oracle.dist_all(wide, wn, wide, wn, symmetric=True)
     hits = ctx.dist(wide, wn, wide, wn, ani_th=0.0, symmetric=True, path=0, cap=ani.size)

@@ -132,7 +132,7 @@ def test_dist_packed_equals_unpack_then_dist(ctx, hg, oracle):
             assert np.array_equal(hits["ani"].view(np.uint32), ani[want].view(np.uint32))
             assert np.array_equal(hits["dot"], dot[want])
             assert milli.tolist() == [int(("%.3f" % float(a)).replace(".", "")) for a in hits["ani"]]
-        if sym:   # 140 x 140 fills a tensor tile and every width is <= 13 bits: tensor path without the |hv| scan
-            assert ctx.dist_last_path == 2 and "hv_quant_bits" in ctx.dist_last_reason
+        if sym:   # 140 x 140 fills a tensor tile and the rows are narrow: single-plane tensor path
+            assert ctx.dist_last_path == 3 and "narrow" in ctx.dist_last_reason, ctx.dist_last_reason
         else:     # 140 x 70 pairs do not fill one 128 x 128 tile: exact SIMT path
             assert ctx.dist_last_path == 1
