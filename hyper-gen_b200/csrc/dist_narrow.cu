@@ -102,46 +102,51 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 
 constexpr int PREP_THREADS = 256;  // 8 warps, one row per warp
 
-// the 8 int16 of one 16-byte load
-__device__ __forceinline__ void unpack8(const uint4 &v, int (&x)[8]) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int e = 0; e < 8; ++e) x[e] = (int)(int16_t)(w[e >> 1] >> (16 * (e & 1)));
-}
-
-// One warp per row, no block-level synchronisation: pass 1 (range, sum, parity) streams the row with
-// eight 16-byte loads in flight per lane; pass 2 re-reads it (L1/L2) and writes the plane; rows with
-// outliers (rare) take a third pass that writes their entries.
+// One warp per row, no block-level synchronisation, two int16 per instruction (VIMNMX.S16x2, VIADD.16x2,
+// IDP.2A).  NT > 0: the row's NT 16-byte loads per lane stay in registers between the passes (hv_d = 256 NT);
+// NT = 0: any hv_d, pass 2 re-reads the row (L1/L2).  Pass 1: range, sum, parity count.  Pass 2: plane,
+// 2 sum(a), residual statistics.  Pass 3, rows with outliers only: their entries.
+template <int NT>
 __global__ void __launch_bounds__(PREP_THREADS)
 narrow_prep_kernel(const int16_t *__restrict__ hv, uint32_t n_rows, uint32_t hv_d, PrepOut o) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t row = blockIdx.x * (PREP_THREADS / 32) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
-  const uint32_t nt = hv_d / 256;  // 16-byte loads per lane (hv_d is a multiple of 256)
+  const uint32_t nt = NT ? (uint32_t)NT : hv_d / 256;  // 16-byte loads per lane (hv_d is a multiple of 256)
   const uint4 *src = reinterpret_cast<const uint4 *>(hv + (size_t)row * hv_d) + lane;
-  // pass 1: range, sum and parity count of the row
-  int lo = 32767, hi = -32768, sum_x = 0;
-  uint32_t n_odd = 0;
-  for (uint32_t t0 = 0; t0 < nt; t0 += 8) {
-    uint4 v[8];
+  constexpr int KEEP = NT ? NT : 1;
+  uint4 keep[KEEP];
+  // pass 1
+  uint32_t lo2 = 0x7FFF7FFFu, hi2 = 0x80008000u, n_odd = 0;
+  int sum_x = 0;
+  auto pass1 = [&](const uint4 &v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (t0 + u < nt) v[u] = __ldg(src + 32 * (t0 + u));
+    for (int j = 0; j < 4; ++j) {
+      lo2 = __vmins2(lo2, w[j]);
+      hi2 = __vmaxs2(hi2, w[j]);
+      sum_x = __dp2a_lo((int)w[j], 0x0101, sum_x);  // both halves; |sum| <= 32768 * 32768 fits
+      n_odd += __popc(w[j] & 0x00010001u);
+    }
+  };
+  if (NT) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (t0 + u < nt) {
-        int x[8];
-        unpack8(v[u], x);
+    for (int t = 0; t < KEEP; ++t) keep[t] = __ldg(src + 32 * t);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          lo = min(lo, x[e]);
-          hi = max(hi, x[e]);
-          sum_x += x[e];  // |sum| <= 32768 * 32768: fits
-          n_odd += (uint32_t)x[e] & 1u;
-        }
-      }
+    for (int t = 0; t < KEEP; ++t) pass1(keep[t]);
+  } else {
+    for (uint32_t t0 = 0; t0 < nt; t0 += 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (t0 + u < nt) v[u] = __ldg(src + 32 * (t0 + u));
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (t0 + u < nt) pass1(v[u]);
     }
   }
+  int lo = min((int)(int16_t)(lo2 & 0xFFFFu), (int)(int16_t)(lo2 >> 16));
+  int hi = max((int)(int16_t)(hi2 & 0xFFFFu), (int)(int16_t)(hi2 >> 16));
   lo = warp_min(lo);
   hi = warp_max(hi);
   sum_x = (int)warp_sum((uint32_t)sum_x);
@@ -156,32 +161,46 @@ narrow_prep_kernel(const int16_t *__restrict__ hv, uint32_t n_rows, uint32_t hv_
     mid = sum_x >= 0 ? (sum_x + half) / (int)hv_d : -((-sum_x + half) / (int)hv_d);
   }
   const int s = mid - ((mid - par) & 1);
-  // pass 2: plane, sum a, residuals
-  uint32_t sum_a = 0, sum_e = 0, cnt = 0, bad = 0;
+  // x - s must fit 16 bits for the packed arithmetic and the outlier entries; such rows (|x - s| > 32000)
+  // make the whole path decline
+  const bool bad = hi - s > 32000 || s - lo > 32000;
+  // pass 2
+  const uint32_t ns2 = (uint32_t)(-s & 0xFFFF) * 0x00010001u;  // -s in both halves
+  uint32_t cnt = 0, sum_e = 0;
+  int sum_2a = 0;
   uint2 *dst = reinterpret_cast<uint2 *>(o.plane + (size_t)row * hv_d) + lane;
-  for (uint32_t t0 = 0; t0 < nt; t0 += 8) {
-    uint4 v[8];
+  auto pass2 = [&](const uint4 &v, uint2 *out) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t r[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (t0 + u < nt) v[u] = __ldg(src + 32 * (t0 + u));
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t t2 = __vadd2(w[j], ns2);                                     // x - s
+      const uint32_t tc = __vmaxs2(__vmins2(t2, 0x00FE00FEu), 0xFF00FF00u);      // clamped to [-256, 254]
+      const uint32_t te = tc & 0xFFFEFFFEu;                                       // 2 a  (a = floor(tc / 2))
+      sum_2a = __dp2a_lo((int)te, 0x0101, sum_2a);
+      r[j] = tc >> 1;                                                             // a: byte 0 (low half), byte 2 (high half)
+      if (t2 != te) {                                                             // rare: a residual in this pair
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (t0 + u < nt) {
-        int x[8];
-        unpack8(v[u], x);
-        uint32_t pk[2] = {0, 0};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int t = x[e] - s;
-          const int a = max(-128, min(127, t >> 1));
-          const int eps = t - 2 * a;
-          sum_a += (uint32_t)a;
+        for (int h = 0; h < 2; ++h) {
+          const int eps = (int)(int16_t)(t2 >> (16 * h)) - (int)(int16_t)(te >> (16 * h));
           if (eps != 0) { ++cnt; sum_e += (uint32_t)abs(eps); }
-          if (eps < -32768 || eps > 32767) bad = 1;  // does not fit an outlier entry (needs |x - s| > 32000): decline
-          pk[e >> 2] |= (uint32_t)(a & 0xFF) << (8 * (e & 3));
         }
-        dst[32 * (t0 + u)] = make_uint2(pk[0], pk[1]);
       }
+    }
+    *out = make_uint2(__byte_perm(r[0], r[1], 0x6420), __byte_perm(r[2], r[3], 0x6420));
+  };
+  if (NT) {
+#pragma unroll
+    for (int t = 0; t < KEEP; ++t) pass2(keep[t], dst + 32 * t);
+  } else {
+    for (uint32_t t0 = 0; t0 < nt; t0 += 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (t0 + u < nt) v[u] = __ldg(src + 32 * (t0 + u));
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (t0 + u < nt) pass2(v[u], dst + 32 * (t0 + u));
     }
   }
   // warp totals + exclusive prefix of the outlier counts
@@ -192,16 +211,16 @@ narrow_prep_kernel(const int16_t *__restrict__ hv, uint32_t n_rows, uint32_t hv_
     if (lane >= (uint32_t)d) inc += y;
   }
   const uint32_t tot_c = __shfl_sync(0xffffffffu, inc, 31);
-  const uint32_t tot_a = warp_sum(sum_a), tot_e = warp_sum(sum_e);
-  if (__any_sync(0xffffffffu, bad != 0) && lane == 0) atomicExch(&o.stats[3], 1u);
+  const uint32_t tot_2a = warp_sum((uint32_t)sum_2a), tot_e = warp_sum(sum_e);
   uint32_t base = 0, kept = tot_c;
   if (lane == 0) {
-    if (tot_c) {
+    if (bad) { atomicExch(&o.stats[3], 1u); kept = 0; }
+    if (kept) {
       base = atomicAdd(&o.stats[2], tot_c);
       if (base > o.cap || tot_c > o.cap - base) { atomicExch(&o.stats[3], 1u); kept = 0; }
     }
     o.s[row] = s;
-    o.a2[row] = (int32_t)(2u * tot_a);
+    o.a2[row] = (int32_t)tot_2a;
     o.e[row] = tot_e;
     o.out_off[row] = base;
     o.out_cnt[row] = kept;
@@ -215,11 +234,11 @@ narrow_prep_kernel(const int16_t *__restrict__ hv, uint32_t n_rows, uint32_t hv_
   // pass 3 (rows with outliers only): write the entries, lane by lane in scan order
   uint32_t pos = base + inc - cnt;
   for (uint32_t t = 0; t < nt; ++t) {
-    int x[8];
-    unpack8(__ldg(src + 32 * t), x);
+    const uint4 v = __ldg(src + 32 * t);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int tt = x[e] - s;
+      const int tt = (int)(int16_t)(w[e >> 1] >> (16 * (e & 1))) - s;
       const int a = max(-128, min(127, tt >> 1));
       const int eps = tt - 2 * a;
       if (eps != 0) o.entries[pos++] = ((8u * (lane + 32 * t) + (uint32_t)e) << 16) | ((uint32_t)eps & 0xFFFFu);
@@ -589,7 +608,10 @@ int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_re
   auto prep = [&](const int16_t *src, uint32_t rows, PrepBuffers &pb) -> int {
     HG_CUDA(cudaMemsetAsync(pb.out.stats, 0, 16, ctx->stream));
     const uint32_t blocks = (rows + PREP_THREADS / 32 - 1) / (PREP_THREADS / 32);
-    narrow_prep_kernel<<<blocks, PREP_THREADS, 0, ctx->stream>>>(src, rows, hv_d, pb.out);
+    if (hv_d == 4096) narrow_prep_kernel<16><<<blocks, PREP_THREADS, 0, ctx->stream>>>(src, rows, hv_d, pb.out);
+    else if (hv_d == 2048) narrow_prep_kernel<8><<<blocks, PREP_THREADS, 0, ctx->stream>>>(src, rows, hv_d, pb.out);
+    else if (hv_d == 1024) narrow_prep_kernel<4><<<blocks, PREP_THREADS, 0, ctx->stream>>>(src, rows, hv_d, pb.out);
+    else narrow_prep_kernel<0><<<blocks, PREP_THREADS, 0, ctx->stream>>>(src, rows, hv_d, pb.out);
     ctx->launches++;
     return HG_OK;
   };
