@@ -42,10 +42,13 @@ __device__ __forceinline__ uint32_t seg_c1(uint32_t x) { return (x >> 14) & 0x3F
 __device__ __forceinline__ uint32_t seg_has(uint32_t x) { return (x >> 28) & 1u; }
 __device__ __forceinline__ uint32_t seg_hdr(uint32_t x) { return (x >> 29) & 1u; }
 __device__ __forceinline__ uint32_t seg_compose(uint32_t a, uint32_t b) {  // a, then b
-  const uint32_t after0 = seg_has(a) ? seg_hdr(a) : 0u, after1 = seg_has(a) ? seg_hdr(a) : 1u;  // state after a
-  const uint32_t c0 = seg_c0(a) + (after0 ? seg_c1(b) : seg_c0(b));
-  const uint32_t c1 = seg_c1(a) + (after1 ? seg_c1(b) : seg_c0(b));
-  return seg_make(c0, c1, seg_has(a) | seg_has(b), seg_has(b) ? seg_hdr(b) : seg_hdr(a));
+  // With a line start in a, b starts in the state a hands on whatever a started in: both counts of a grow by
+  // the same count of b.  Without one, b inherits a's incoming state: the counts add field by field.
+  const uint32_t cb = b & 0x0FFFFFFFu;
+  const uint32_t pick = (a >> 29) & 1u ? (cb >> 14) : (cb & 0x3FFFu);
+  const uint32_t add = (a >> 28) & 1u ? pick * 0x4001u : cb;
+  const uint32_t flags = (b >> 28) & 1u ? (b & 0x30000000u) : (a & 0x30000000u);
+  return ((a & 0x0FFFFFFFu) + add) | flags;
 }
 
 // what one thread learns about its 16 bytes (bit i = byte i)
@@ -77,24 +80,39 @@ __device__ __forceinline__ bool any_eq16(const uint32_t (&w)[4], uint32_t c4) { 
 
 // The thread's 16 bytes come in with one 16-byte load when the file is 16-byte aligned in the
 // buffer (the host entry stages files that way), else with byte loads; the byte before and the byte
-// after come from the neighbouring lanes (one extra byte load at the warp edges).
-__device__ __forceinline__ Lane classify(const uint8_t *__restrict__ f, uint64_t len, uint64_t p0) {
-  Lane L;
-  L.w[0] = L.w[1] = L.w[2] = L.w[3] = 0x0A0A0A0Au;  // bytes past the end read as '\n'
+// after come from the neighbouring lanes (one extra byte load at the warp edges).  Loading is
+// separate from classifying so that the next block's bytes are in flight while this one is worked on.
+struct Raw {
+  uint32_t w[4];
+  uint32_t edge;  // lane 0: the byte before the warp's bytes; lane 31: the byte after them
+};
+__device__ __forceinline__ Raw load_raw(const uint8_t *__restrict__ f, uint64_t len, uint64_t p0) {
+  Raw r;
+  r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0x0A0A0A0Au;  // bytes past the end read as '\n'
+  r.edge = (uint32_t)'\n';                          // '\n' before the first byte of the file and after the last
   if (p0 + FA_BPT <= len && (((uintptr_t)(f + p0)) & 15) == 0) {
-    const uint4 v = *reinterpret_cast<const uint4 *>(f + p0);
-    L.w[0] = v.x; L.w[1] = v.y; L.w[2] = v.z; L.w[3] = v.w;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(f + p0));
+    r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
   } else {
 #pragma unroll
     for (int i = 0; i < FA_BPT; ++i)
-      if (p0 + i < len) L.w[i >> 2] = (L.w[i >> 2] & ~(0xFFu << (8 * (i & 3)))) | ((uint32_t)f[p0 + i] << (8 * (i & 3)));
+      if (p0 + i < len) r.w[i >> 2] = (r.w[i >> 2] & ~(0xFFu << (8 * (i & 3)))) | ((uint32_t)f[p0 + i] << (8 * (i & 3)));
   }
   const int lane = threadIdx.x & 31;
-  // previous byte ('\n' before the first byte of the file) and next byte ('\n' after the last)
+  if (lane == 0 && p0 != 0 && p0 <= len) r.edge = (uint32_t)f[p0 - 1];
+  if (lane == 31 && p0 + FA_BPT < len) r.edge = (uint32_t)f[p0 + FA_BPT];
+  return r;
+}
+
+__device__ __forceinline__ Lane classify(const Raw &r, uint64_t len, uint64_t p0) {
+  Lane L;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) L.w[j] = r.w[j];
+  const int lane = threadIdx.x & 31;
   uint32_t prev = __shfl_up_sync(0xffffffffu, L.w[3] >> 24, 1);
   uint32_t next = __shfl_down_sync(0xffffffffu, L.w[0] & 0xFFu, 1);
-  if (lane == 0) prev = (p0 == 0 || p0 > len) ? (uint32_t)'\n' : (uint32_t)f[p0 - 1];
-  if (lane == 31) next = (p0 + FA_BPT < len) ? (uint32_t)f[p0 + FA_BPT] : (uint32_t)'\n';
+  if (lane == 0) prev = r.edge;
+  if (lane == 31) next = r.edge;
   const uint32_t valid = p0 + FA_BPT <= len ? 0xFFFFu : (p0 < len ? ((1u << (uint32_t)(len - p0)) - 1u) : 0u);
   const uint32_t nl = eq16(L.w, 0x0A0A0A0Au);
   L.ls = ((nl << 1) | (prev == '\n' ? 1u : 0u)) & valid;
@@ -133,7 +151,7 @@ __device__ __forceinline__ uint32_t lane_seg(const Lane &L, uint32_t &m0) {
 
 // inclusive scan of the runs over the CTA; returns this thread's EXCLUSIVE prefix, `total` = the whole block
 __device__ __forceinline__ uint32_t block_seg_scan(uint32_t mine, uint32_t &total) {
-  __shared__ uint32_t s_w[FA_THREADS / 32];
+  __shared__ uint32_t s_w[FA_THREADS / 32 + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t x = mine;
 #pragma unroll
@@ -141,41 +159,61 @@ __device__ __forceinline__ uint32_t block_seg_scan(uint32_t mine, uint32_t &tota
     const uint32_t pv = __shfl_up_sync(0xffffffffu, x, o);
     if (lane >= o) x = seg_compose(pv, x);
   }
-  if (lane == 31) s_w[warp] = x;
+  if (lane == 31) s_w[warp + 1] = x;
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of the 8 warp totals: s_w[w] = everything before warp w, s_w[8] = the block
+    uint32_t y = (lane >= 1 && lane <= FA_THREADS / 32) ? s_w[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < FA_THREADS / 32; o <<= 1) {
+      const uint32_t pv = __shfl_up_sync(0xffffffffu, y, o);
+      if (lane >= o) y = seg_compose(pv, y);
+    }
+    if (lane <= FA_THREADS / 32) s_w[lane] = y;
+  }
   __syncthreads();
   uint32_t ex = __shfl_up_sync(0xffffffffu, x, 1);
   if (lane == 0) ex = 0;  // the identity run
-  uint32_t before = 0, all = 0;
-#pragma unroll
-  for (int w = 0; w < FA_THREADS / 32; ++w) {
-    if (w == warp) before = all;
-    all = seg_compose(all, s_w[w]);
-  }
-  total = all;
-  return seg_compose(before, ex);
+  total = s_w[FA_THREADS / 32];
+  const uint32_t out = seg_compose(s_w[warp], ex);
+  __syncthreads();  // s_w may be rewritten by the next call
+  return out;
 }
+
+// A CTA walks FA_NB consecutive 4 KB blocks of one file with the next block's loads in flight.
+constexpr int FA_NB = 1;  // measured: more blocks per CTA do not help, the kernels are instruction-bound, not latency-bound
 
 __global__ void __launch_bounds__(FA_THREADS)
 fasta_scan_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ file_off, const uint64_t *__restrict__ blk_off,
                   BlockSum *__restrict__ sums) {
   const uint32_t f = blockIdx.y;
   const uint64_t len = file_off[f + 1] - file_off[f];
-  const uint64_t b0 = (uint64_t)blockIdx.x * FA_BLOCK;
-  if (b0 >= len) return;
-  const Lane L = classify(raw + file_off[f], len, b0 + (uint64_t)threadIdx.x * FA_BPT);
-  uint32_t m0, total;
-  (void)block_seg_scan(lane_seg(L, m0), total);
-  if (threadIdx.x == 0) {
-    BlockSum s;
-    s.c0 = seg_c0(total);
-    s.c1 = seg_c1(total);
-    s.has_ls = seg_has(total);
-    s.last_hdr = seg_hdr(total);
-    sums[blk_off[f] + blockIdx.x] = s;
+  const uint64_t nb = (len + FA_BLOCK - 1) / FA_BLOCK;
+  uint64_t blk = (uint64_t)blockIdx.x * FA_NB;
+  if (blk >= nb) return;
+  const uint64_t blk_end = blk + FA_NB < nb ? blk + FA_NB : nb;
+  const uint8_t *fp = raw + file_off[f];
+  Raw cur = load_raw(fp, len, blk * FA_BLOCK + (uint64_t)threadIdx.x * FA_BPT);
+  for (; blk < blk_end; ++blk) {
+    const uint64_t p0 = blk * FA_BLOCK + (uint64_t)threadIdx.x * FA_BPT;
+    Raw nxt = cur;
+    if (blk + 1 < blk_end) nxt = load_raw(fp, len, p0 + FA_BLOCK);
+    const Lane L = classify(cur, len, p0);
+    uint32_t m0, total;
+    (void)block_seg_scan(lane_seg(L, m0), total);
+    if (threadIdx.x == 0) {
+      BlockSum s;
+      s.c0 = seg_c0(total);
+      s.c1 = seg_c1(total);
+      s.has_ls = seg_has(total);
+      s.last_hdr = seg_hdr(total);
+      sums[blk_off[f] + blk] = s;
+    }
+    cur = nxt;
   }
 }
 
-// one warp per file: sequential chain over the file's block summaries, 32 at a time
+// one warp per file: the block summaries compose like the runs inside a block, so 32 of them are chained
+// with a five-step warp scan (carry-in state and output offset of every block, merged length of the file)
 __global__ void fasta_chain_kernel(const uint64_t *__restrict__ file_off, const uint64_t *__restrict__ blk_off,
                                    uint32_t n_files, const BlockSum *__restrict__ sums, uint8_t *__restrict__ carry,
                                    uint64_t *__restrict__ out_off, uint64_t *__restrict__ merged_len) {
@@ -186,19 +224,34 @@ __global__ void fasta_chain_kernel(const uint64_t *__restrict__ file_off, const 
   uint64_t off = 0;
   for (uint64_t base = 0; base < nb; base += 32) {
     const uint64_t b = base + lane;
-    BlockSum s = {0, 0, 0, 0};
+    BlockSum s = {0, 0, 0, 0};  // the identity run
     if (b < nb) s = sums[blk_off[f] + b];
-    // walk the 32 summaries in order (state is a 1-bit recurrence; cheap enough serially via shuffles)
-    for (int l = 0; l < 32 && base + l < nb; ++l) {
-      const uint32_t c0 = __shfl_sync(0xffffffffu, s.c0, l), c1 = __shfl_sync(0xffffffffu, s.c1, l);
-      const uint32_t hl = __shfl_sync(0xffffffffu, s.has_ls, l), lh = __shfl_sync(0xffffffffu, s.last_hdr, l);
-      if (lane == l) {
-        carry[blk_off[f] + b] = (uint8_t)state;
-        out_off[blk_off[f] + b] = off;
+    // inclusive scan over the 32 summaries: (c0, c1, has, hdr) of blocks base .. base + lane
+    uint32_t c0 = s.c0, c1 = s.c1, has = s.has_ls, hdr = s.last_hdr;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t p0 = __shfl_up_sync(0xffffffffu, c0, o), p1 = __shfl_up_sync(0xffffffffu, c1, o);
+      const uint32_t ph = __shfl_up_sync(0xffffffffu, has, o), pd = __shfl_up_sync(0xffffffffu, hdr, o);
+      if (lane >= (uint32_t)o) {  // (p) then (mine)
+        const uint32_t after0 = ph ? pd : 0u, after1 = ph ? pd : 1u;
+        const uint32_t n0 = p0 + (after0 ? c1 : c0), n1 = p1 + (after1 ? c1 : c0);
+        c0 = n0; c1 = n1;
+        hdr = has ? hdr : pd;
+        has |= ph;
       }
-      off += state ? c1 : c0;
-      if (hl) state = lh;
     }
+    // exclusive values of my block = inclusive values of the previous lane, applied to the carried (state, off)
+    uint32_t e0 = __shfl_up_sync(0xffffffffu, c0, 1), e1 = __shfl_up_sync(0xffffffffu, c1, 1);
+    uint32_t eh = __shfl_up_sync(0xffffffffu, has, 1), ed = __shfl_up_sync(0xffffffffu, hdr, 1);
+    if (lane == 0) { e0 = 0; e1 = 0; eh = 0; ed = 0; }
+    if (b < nb) {
+      carry[blk_off[f] + b] = (uint8_t)(eh ? ed : state);
+      out_off[blk_off[f] + b] = off + (state ? e1 : e0);
+    }
+    const uint32_t t0 = __shfl_sync(0xffffffffu, c0, 31), t1 = __shfl_sync(0xffffffffu, c1, 31);
+    const uint32_t th = __shfl_sync(0xffffffffu, has, 31), td = __shfl_sync(0xffffffffu, hdr, 31);
+    off += state ? t1 : t0;
+    if (th) state = td;
   }
   if (lane == 0) merged_len[f] = off;
 }
@@ -212,37 +265,57 @@ fasta_emit_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ 
   __shared__ __align__(16) uint8_t s_out[FA_BLOCK + 32];
   const uint32_t f = blockIdx.y;
   const uint64_t len = file_off[f + 1] - file_off[f];
-  const uint64_t b0 = (uint64_t)blockIdx.x * FA_BLOCK;
-  if (b0 >= len) return;
-  const uint64_t p0 = b0 + (uint64_t)threadIdx.x * FA_BPT;
-  const Lane L = classify(raw + file_off[f], len, p0);
-  const bool carry_in = carry[blk_off[f] + blockIdx.x] != 0;
-  uint32_t m0, total;
-  const uint32_t ex = block_seg_scan(lane_seg(L, m0), total);
-  bool oh;
-  const uint32_t m = emit_mask(L, seg_has(ex) ? (seg_hdr(ex) != 0) : carry_in, oh);
-  uint8_t *dst = merged + file_off[f] + out_off[blk_off[f] + blockIdx.x];
-  const uint32_t al = (uint32_t)((uintptr_t)dst & 15);  // staged at the destination's phase
-  uint32_t k = al + (carry_in ? seg_c1(ex) : seg_c0(ex));
-  if (m == 0xFFFFu && L.hdr_start == 0 && (k & 3u) == 0) {  // every byte kept, word-aligned target
-#pragma unroll
-    for (int j = 0; j < 4; ++j) *reinterpret_cast<uint32_t *>(s_out + k + 4 * j) = L.w[j];
-  } else {
-#pragma unroll
-    for (int i = 0; i < FA_BPT; ++i)
-      if ((m >> i) & 1u) s_out[k++] = ((L.hdr_start >> i) & 1u) ? (uint8_t)'N' : (uint8_t)(L.w[i >> 2] >> (8 * (i & 3)));
-  }
-  __syncthreads();
-  const uint32_t n_out = carry_in ? seg_c1(total) : seg_c0(total);
-  const uint32_t end = al + n_out;  // staged bytes are s_out[al, end)
-  uint8_t *dst0 = dst - al;         // 16-byte aligned
-  for (uint32_t c = threadIdx.x; 16 * c < end; c += FA_THREADS) {
-    const uint32_t lo = 16 * c, hi = lo + 16;
-    if (lo >= al && hi <= end) {
-      *reinterpret_cast<uint4 *>(dst0 + lo) = *reinterpret_cast<const uint4 *>(s_out + lo);
-    } else {
-      for (uint32_t q = (lo > al ? lo : al); q < (hi < end ? hi : end); ++q) dst0[q] = s_out[q];
+  const uint64_t nb = (len + FA_BLOCK - 1) / FA_BLOCK;
+  uint64_t blk = (uint64_t)blockIdx.x * FA_NB;
+  if (blk >= nb) return;
+  const uint64_t blk_end = blk + FA_NB < nb ? blk + FA_NB : nb;
+  const uint8_t *fp = raw + file_off[f];
+  Raw cur = load_raw(fp, len, blk * FA_BLOCK + (uint64_t)threadIdx.x * FA_BPT);
+  uint32_t cur_carry = carry[blk_off[f] + blk];
+  uint64_t cur_off = out_off[blk_off[f] + blk];
+  for (; blk < blk_end; ++blk) {
+    const uint64_t p0 = blk * FA_BLOCK + (uint64_t)threadIdx.x * FA_BPT;
+    Raw nxt = cur;
+    uint32_t nxt_carry = 0;
+    uint64_t nxt_off = 0;
+    if (blk + 1 < blk_end) {
+      nxt = load_raw(fp, len, p0 + FA_BLOCK);
+      nxt_carry = carry[blk_off[f] + blk + 1];
+      nxt_off = out_off[blk_off[f] + blk + 1];
     }
+    const Lane L = classify(cur, len, p0);
+    const bool carry_in = cur_carry != 0;
+    uint32_t m0, total;
+    const uint32_t ex = block_seg_scan(lane_seg(L, m0), total);
+    bool oh;
+    const uint32_t m = emit_mask(L, seg_has(ex) ? (seg_hdr(ex) != 0) : carry_in, oh);
+    uint8_t *dst = merged + file_off[f] + cur_off;
+    const uint32_t al = (uint32_t)((uintptr_t)dst & 15);  // staged at the destination's phase
+    uint32_t k = al + (carry_in ? seg_c1(ex) : seg_c0(ex));
+    if (m == 0xFFFFu && L.hdr_start == 0 && (k & 3u) == 0) {  // every byte kept, word-aligned target
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint32_t *>(s_out + k + 4 * j) = L.w[j];
+    } else {
+#pragma unroll
+      for (int i = 0; i < FA_BPT; ++i)
+        if ((m >> i) & 1u) s_out[k++] = ((L.hdr_start >> i) & 1u) ? (uint8_t)'N' : (uint8_t)(L.w[i >> 2] >> (8 * (i & 3)));
+    }
+    __syncthreads();
+    const uint32_t n_out = carry_in ? seg_c1(total) : seg_c0(total);
+    const uint32_t end = al + n_out;  // staged bytes are s_out[al, end)
+    uint8_t *dst0 = dst - al;         // 16-byte aligned
+    for (uint32_t c = threadIdx.x; 16 * c < end; c += FA_THREADS) {
+      const uint32_t lo = 16 * c, hi = lo + 16;
+      if (lo >= al && hi <= end) {
+        *reinterpret_cast<uint4 *>(dst0 + lo) = *reinterpret_cast<const uint4 *>(s_out + lo);
+      } else {
+        for (uint32_t q = (lo > al ? lo : al); q < (hi < end ? hi : end); ++q) dst0[q] = s_out[q];
+      }
+    }
+    __syncthreads();  // s_out is refilled by the next block
+    cur = nxt;
+    cur_carry = nxt_carry;
+    cur_off = nxt_off;
   }
 }
 
@@ -258,7 +331,7 @@ int hg_launch_fasta_merge(hg_ctx *ctx, const uint8_t *d_raw, const uint64_t *d_f
   for (uint32_t f0 = 0; f0 < n_files; f0 += 65535) {
     const uint32_t nf = n_files - f0 < 65535 ? n_files - f0 : 65535;
     if (max_blocks)
-      fasta_scan_kernel<<<dim3(max_blocks, nf), FA_THREADS, 0, ctx->stream>>>(d_raw, d_file_off + f0, d_blk_off + f0,
+      fasta_scan_kernel<<<dim3((max_blocks + FA_NB - 1) / FA_NB, nf), FA_THREADS, 0, ctx->stream>>>(d_raw, d_file_off + f0, d_blk_off + f0,
                                                                              (BlockSum *)d_sums);
     ctx->launches++;
   }
@@ -269,7 +342,7 @@ int hg_launch_fasta_merge(hg_ctx *ctx, const uint8_t *d_raw, const uint64_t *d_f
   for (uint32_t f0 = 0; f0 < n_files; f0 += 65535) {
     const uint32_t nf = n_files - f0 < 65535 ? n_files - f0 : 65535;
     if (max_blocks)
-      fasta_emit_kernel<<<dim3(max_blocks, nf), FA_THREADS, 0, ctx->stream>>>(d_raw, d_file_off + f0, d_blk_off + f0,
+      fasta_emit_kernel<<<dim3((max_blocks + FA_NB - 1) / FA_NB, nf), FA_THREADS, 0, ctx->stream>>>(d_raw, d_file_off + f0, d_blk_off + f0,
                                                                              d_carry, d_out_off, d_merged);
     ctx->launches++;
   }
