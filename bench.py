@@ -534,9 +534,9 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
         "path": path_sel[0], "path_reason": path_reason,
     }
     alg_ops = 2.0 * D * n_pairs
-    int8_peak = 2.0 * peaks["bf16_tflops"]  # kind::i8 runs at twice the bf16 MMA rate
+    int8_peak = 2.0 * peaks["bf16_tflops"] * world  # kind::i8 runs at twice the bf16 MMA rate; all ranks' tensor pipes
     mac_mult = 1.0 if path_sel[0] == 3 else 4.0  # MMAs executed per algorithmic MAC
-    note = ("algorithmic 2*D ops per pair; peak = 2 x measured bf16 (kind::i8 runs at twice the bf16 MMA rate); "
+    note = ("algorithmic 2*D ops per pair; peak = n_gpus x 2 x measured bf16 (kind::i8 runs at twice the bf16 MMA rate); "
             + ("single s8 plane (x = 2a + s): executed MACs = algorithmic MACs; kernel_ms includes the i16 -> s8 pre-pass and its host sync"
                if path_sel[0] == 3 else "the two-limb split executes 4x these MACs, so frac tops out at 0.25"))
     out["roofline"] = {"bound": "tensor", "achieved": alg_ops / (kms * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s",

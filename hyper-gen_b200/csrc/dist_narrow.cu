@@ -38,16 +38,23 @@ namespace {
 
 using namespace hgtc;
 
-constexpr int N1_BN = 256;                              // tile columns (the pair's N); rows: 256 (128 per CTA)
-constexpr int N1_STAGES = 6;
-constexpr int N1_A_BYTES = 128 * TC_BK;                 // my 128 ref rows
+constexpr int N1_BN = 256;                              // tile columns (the pair's N)
+constexpr int N1_A_BYTES = 128 * TC_BK;                 // 128 of my ref rows
 constexpr int N1_B_BYTES = 128 * TC_BK;                 // my half of the 256 query rows
-constexpr int N1_STAGE_BYTES = N1_A_BYTES + N1_B_BYTES; // 32 KB
+// NACC = accumulators (256 TMEM columns each) per tile.  NACC = 1: 256 x 256 pair tiles, the accumulator double
+// buffered (epilogue fully hidden), 32 KB per stage.  NACC = 2: 512 x 256 pair tiles - two A tiles per CTA share
+// one B stage, 25 % fewer operand bytes per MAC (what the kernel is bound by) - at the price of a single-buffered
+// accumulator pair, i.e. an exposed epilogue; 48 KB per stage.
+template <int NACC> struct N1Cfg {
+  static constexpr int STAGES = NACC == 1 ? 6 : 4;
+  static constexpr int STAGE_BYTES = NACC * N1_A_BYTES + N1_B_BYTES;
+  static constexpr int TILE_ROWS = 256 * NACC;
+};
 constexpr int N1_EPI_WARPS = 8;                         // two per TMEM lane quarter, half the columns each
 constexpr int N1_THREADS = 64 + 32 * N1_EPI_WARPS;
 constexpr int N1_LIST_CAP = 256;                        // candidates per warp list (8 B each)
 constexpr int N1_COL_WORDS = 3 * N1_BN;                 // per tile: bound, centre, 2 sum(b) of every column
-constexpr int N1_SMEM_BYTES = N1_STAGES * N1_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ +
+constexpr int N1_SMEM_BYTES = 6 * (N1_A_BYTES + N1_B_BYTES) /* == 4 * (2 A + B) */ + 1024 /*align slack*/ + 256 /*barriers*/ +
                               2 * N1_COL_WORDS * 4 /*column constants, double buffered*/ + N1_EPI_WARPS * N1_LIST_CAP * 8;
 constexpr uint32_t N1_TMEM_COLS = 512;                  // two accumulator buffers of 256 columns
 // instruction descriptor, kind::i8: D = s32, A = B = signed 8-bit, both K-major, M = 256 (pair), N = 256
@@ -246,21 +253,22 @@ narrow_prep_kernel(const int16_t *__restrict__ hv, uint32_t n_rows, uint32_t hv_
   }
 }
 
-// ---- tile walk: non-empty 256 x 256 tiles, row-block major ------------------------------------
+// ---- tile walk: non-empty (256 NACC) x 256 tiles, row-block major ------------------------------------
 struct N1Tiles {
-  uint32_t gx, gy, R, C;
+  uint32_t gx, gy, R, C, tile_rows;
   int64_t delta;  // i0 - j0
   int sym;
   __device__ uint32_t cmin(uint32_t r) const {  // symmetric: tiles whose largest j is not above their smallest i are empty
     if (!sym) return 0;
-    const int64_t v = delta + 256ll * (int64_t)r + 1;
+    const int64_t v = delta + (int64_t)tile_rows * (int64_t)r + 1;
     if (v <= 0) return 0;
     const uint64_t c = (uint64_t)v / (uint32_t)N1_BN;
     return c > gx ? gx : (uint32_t)c;
   }
-  __device__ void init(const hg::DistEpilogue &ep) {
+  __device__ void init(const hg::DistEpilogue &ep, uint32_t rows_per_tile) {
+    tile_rows = rows_per_tile;
     gx = (ep.n_qry + N1_BN - 1) / N1_BN;
-    gy = (ep.n_ref + 255) / 256;
+    gy = (ep.n_ref + tile_rows - 1) / tile_rows;
     delta = (int64_t)ep.i0 - (int64_t)ep.j0;
     sym = ep.symmetric;
     R = 0;
@@ -390,9 +398,14 @@ __device__ __forceinline__ uint32_t n1_drain(const hg::DistEpilogue &ep, const N
   return n_list;
 }
 
+template <int NACC>
 __global__ void __launch_bounds__(N1_THREADS, 1)
 dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_qry, uint32_t ref_row_base,
                hg::DistEpilogue ep, NarrowArgs na) {
+  using Cfg = N1Cfg<NACC>;
+  constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr uint32_t TILE_ROWS = Cfg::TILE_ROWS;
+  constexpr uint32_t NBUF = NACC == 1 ? 2 : 1;  // accumulator sets in TMEM
   // the pre-pass ran on this stream just before: if it found the rows not narrow (outlier budget exceeded)
   // nothing is computed here and the host, which reads the same flag after this launch, takes another path
   if (na.q_stats[3] | na.r_stats[3]) return;
@@ -404,17 +417,17 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle wants 1024 B alignment
   uint8_t *aligned = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar_base = base + N1_STAGES * N1_STAGE_BYTES;
+  const uint32_t bar_base = base + STAGES * STAGE_BYTES;
   auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };                       // used in the leader only
-  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (N1_STAGES + s); };        // one per CTA, multicast commit
-  auto accum_bar = [&](uint32_t b) { return bar_base + 8u * (2 * N1_STAGES + b); };    // one per CTA and buffer, multicast commit
-  auto tmem_empty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * N1_STAGES + 2 + b); };  // leader only: both epilogues drained
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aligned + N1_STAGES * N1_STAGE_BYTES + 8 * (2 * N1_STAGES + 4));
-  int32_t *s_col_all = reinterpret_cast<int32_t *>(aligned + N1_STAGES * N1_STAGE_BYTES + 256);
+  auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (STAGES + s); };           // one per CTA, multicast commit
+  auto accum_bar = [&](uint32_t b) { return bar_base + 8u * (2 * STAGES + b); };       // one per CTA and buffer, multicast commit
+  auto tmem_empty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * STAGES + 2 + b); };  // leader only: both epilogues drained
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aligned + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  int32_t *s_col_all = reinterpret_cast<int32_t *>(aligned + STAGES * STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < N1_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(accum_bar(b), 1); mbar_init(tmem_empty_bar(b), 2 * N1_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -432,7 +445,7 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
   const uint32_t num_kb = na.hv_d / TC_BK;
 
   N1Tiles tiles;
-  tiles.init(ep);
+  tiles.init(ep, TILE_ROWS);
   bool valid = tiles.advance(pair);
 
   if (warp == 0) {
@@ -440,16 +453,18 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
     const uint32_t on = elect_one();
     uint32_t s = 0, ph = 0;
     for (; valid; valid = tiles.advance(n_pairs)) {
-      const uint32_t row0 = tiles.R * 256u + rank * 128u, colh = tiles.C * N1_BN + rank * 128u;
+      const uint32_t row0 = tiles.R * TILE_ROWS + rank * 128u, colh = tiles.C * N1_BN + rank * 128u;
       for (uint32_t kb = 0; kb < num_kb; ++kb) {
         mbar_wait_cluster(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), 2 * N1_STAGE_BYTES, rank == 0 ? on : 0u);  // the leader expects its bytes and the peer's
+        mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES, rank == 0 ? on : 0u);  // the leader expects its bytes and the peer's
         const uint32_t fb = mapa_u32(full_bar(s), 0);
-        const uint32_t st = base + s * N1_STAGE_BYTES;
+        const uint32_t st = base + s * STAGE_BYTES;
         const int k0 = (int)(kb * TC_BK);
-        tma_load_2d_pair(st, &tm_ref, fb, k0, (int)(ref_row_base + row0), on);  // my 128 ref rows
-        tma_load_2d_pair(st + N1_A_BYTES, &tm_qry, fb, k0, (int)colh, on);      // my half of the query rows
-        if (++s == N1_STAGES) { s = 0; ph ^= 1u; }
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)  // 128 of my ref rows per accumulator (accumulator a: tile rows 256 a .. 256 a + 255)
+          tma_load_2d_pair(st + a * N1_A_BYTES, &tm_ref, fb, k0, (int)(ref_row_base + row0 + 256u * a), on);
+        tma_load_2d_pair(st + NACC * N1_A_BYTES, &tm_qry, fb, k0, (int)colh, on);  // my half of the query rows
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -459,36 +474,39 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
       const uint32_t d0 = umma_desc_lo(base);
       uint32_t s = 0, ph = 0, tile_n = 0;
       for (; valid; valid = tiles.advance(n_pairs), ++tile_n) {
-        const uint32_t b = tile_n & 1u;
-        // both epilogues have drained this buffer's previous tile (passes at once for tiles 0 and 1)
-        mbar_wait_cluster(tmem_empty_bar(b), ((tile_n >> 1) & 1u) ^ 1u);
+        const uint32_t b = tile_n % NBUF, use = tile_n / NBUF;
+        // both epilogues have drained this buffer's previous tile (passes at once for its first use)
+        mbar_wait_cluster(tmem_empty_bar(b), (use & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem_base + b * N1_BN;
+        const uint32_t tacc = tmem_base + (NACC == 1 ? b * N1_BN : 0u);
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(s), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a0 = d0 + s * (uint32_t)(N1_STAGE_BYTES >> 4);
+          const uint32_t a0 = d0 + s * (uint32_t)(STAGE_BYTES >> 4);
 #pragma unroll
-          for (int ks = 0; ks < TC_BK / 32; ++ks)  // one MMA covers K = 32 int8
-            umma_i8_pair(tacc, a0 + (uint32_t)((32 * ks) >> 4), a0 + (uint32_t)((N1_A_BYTES + 32 * ks) >> 4), N1_IDESC,
-                         (kb | (uint32_t)ks) != 0u, on);
+          for (int ks = 0; ks < TC_BK / 32; ++ks) {  // one MMA covers K = 32 int8
+#pragma unroll
+            for (int a = 0; a < NACC; ++a)
+              umma_i8_pair(tacc + a * N1_BN, a0 + (uint32_t)((a * N1_A_BYTES + 32 * ks) >> 4),
+                           a0 + (uint32_t)((NACC * N1_A_BYTES + 32 * ks) >> 4), N1_IDESC, (kb | (uint32_t)ks) != 0u, on);
+          }
           umma_commit_pair(empty_bar(s), on);  // the stage is free in both CTAs once these MMAs have read it
-          if (++s == N1_STAGES) { s = 0; ph ^= 1u; }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        umma_commit_pair(accum_bar(b), on);  // accumulator final: wake both epilogues
+        umma_commit_pair(accum_bar(b), on);  // accumulators final: wake both epilogues
       }
     }
   } else {
-    // ===== epilogue (both CTAs, each its own 128 rows) =====
+    // ===== epilogue (both CTAs, each its own 128 rows of every accumulator) =====
     const int ew = warp - 2;
     const uint32_t q = warp & 3;  // TMEM lane quarter this warp may read
     const int half = (ew >> 2);   // which 128 columns this warp drains
-    uint2 *list = reinterpret_cast<uint2 *>(aligned + N1_STAGES * N1_STAGE_BYTES + 256 + 2 * N1_COL_WORDS * 4) + ew * N1_LIST_CAP;
+    uint2 *list = reinterpret_cast<uint2 *>(aligned + STAGES * STAGE_BYTES + 256 + 2 * N1_COL_WORDS * 4) + ew * N1_LIST_CAP;
     uint32_t tile_n = 0;
     for (; valid; valid = tiles.advance(n_pairs), ++tile_n) {
-      const uint32_t b = tile_n & 1u;
-      const uint32_t row0 = tiles.R * 256u + rank * 128u, col0 = tiles.C * N1_BN;
-      int32_t *s_col = s_col_all + b * N1_COL_WORDS;  // double buffered: one barrier per tile is enough
+      const uint32_t b = tile_n % NBUF, use = tile_n / NBUF;
+      const uint32_t row0 = tiles.R * TILE_ROWS + rank * 128u, col0 = tiles.C * N1_BN;
+      int32_t *s_col = s_col_all + (tile_n & 1u) * N1_COL_WORDS;  // double buffered: one barrier per tile is enough
       {
         const uint32_t t = threadIdx.x - 64, lj = col0 + t;  // one column per epilogue thread
         int32_t tq = COL_NEVER, sq = 0, tt = 0;
@@ -506,24 +524,36 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
         s_col[2 * N1_BN + t] = tt;
       }
       asm volatile("bar.sync 1, %0;" ::"r"(32 * N1_EPI_WARPS) : "memory");  // epilogue warps only
-      const uint32_t rowl = q * 32 + lane, li = row0 + rowl;
-      int32_t tr = ROW_ALWAYS, sr = 0, xr = 0;
-      if (li < ep.n_ref) {
-        if (ep.cfrac > 0.0f) {
-          const int32_t nr = ep.ref_norm[li];
-          if (nr > 0) tr = n1_loosen(__float2int_rd(ep.cfrac * __int2float_rz(nr)) - 1, na.r.e[li], q_absmax, ROW_ALWAYS);
+      // row constants of my row in every accumulator
+      int32_t tr[NACC], sr[NACC], xr[NACC];
+      bool live[NACC];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) {
+        const uint32_t li = row0 + 256u * a + q * 32 + lane;
+        tr[a] = ROW_ALWAYS; sr[a] = 0; xr[a] = 0;
+        live[a] = li < ep.n_ref;
+        if (live[a]) {
+          if (ep.cfrac > 0.0f) {
+            const int32_t nr = ep.ref_norm[li];
+            if (nr > 0) tr[a] = n1_loosen(__float2int_rd(ep.cfrac * __int2float_rz(nr)) - 1, na.r.e[li], q_absmax, ROW_ALWAYS);
+          }
+          sr[a] = na.r.s[li];
+          xr[a] = (int32_t)((uint32_t)na.r.a2[li] + na.hv_d * (uint32_t)sr[a]);  // sum x~ = 2 sum a + D s
         }
-        sr = na.r.s[li];
-        xr = (int32_t)((uint32_t)na.r.a2[li] + na.hv_d * (uint32_t)sr);  // sum x~ = 2 sum a + D s
       }
-      // my 128 x 256 part of the tile may be empty (below the diagonal, or past the last ref row)
-      const bool mine_empty = row0 >= ep.n_ref || (ep.symmetric && (uint64_t)ep.j0 + col0 + N1_BN - 1 <= (uint64_t)ep.i0 + row0);
-      mbar_wait_cluster(accum_bar(b), (tile_n >> 1) & 1u);
+      mbar_wait_cluster(accum_bar(b), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t n_list = 0;
-      if (!mine_empty)
-        n_list = n1_drain(ep, na, tmem_base + ((q * 32u) << 16) + b * N1_BN, half * (N1_BN / 2), (half + 1) * (N1_BN / 2), s_col, tr,
-                          sr, xr, li < ep.n_ref, rowl, row0, col0, list, 0u);
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) {
+        const uint32_t rowa = row0 + 256u * a;
+        // my 128 x 256 part of this accumulator may be empty (below the diagonal, or past the last ref row)
+        const bool mine_empty = rowa >= ep.n_ref || (ep.symmetric && (uint64_t)ep.j0 + col0 + N1_BN - 1 <= (uint64_t)ep.i0 + rowa);
+        if (!mine_empty)
+          n_list = n1_drain(ep, na, tmem_base + ((q * 32u) << 16) + (NACC == 1 ? b * N1_BN : a * N1_BN), half * (N1_BN / 2),
+                            (half + 1) * (N1_BN / 2), s_col, tr[a], sr[a], xr[a], live[a], 256u * a + q * 32 + lane, row0, col0,
+                            list, n_list);
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(b), 0));  // this warp's TMEM reads of buffer b are done
@@ -600,7 +630,8 @@ int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_re
   if (!qry_covers_ref) carve(pr, p_plane_r, (uint8_t *)p_meta + mq, n_ref, cap_r);
 
   if (!ctx->n1_attr_set) {
-    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
     ctx->n1_attr_set = 1;
   }
   // ---- GPU work starts here ----
@@ -669,12 +700,18 @@ int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_re
   cfg.numAttrs = 1;
   cfg.blockDim = dim3(N1_THREADS, 1, 1);
   cfg.stream = ctx->stream;
-  // one CTA pair per TPC, each walking the 256 x 256 tiles with stride n_pairs
-  const uint64_t tiles = (uint64_t)((n_qry + N1_BN - 1) / N1_BN) * ((n_ref + 255) / 256);
+  // one CTA pair per TPC, each walking its tiles with stride n_pairs.  512-row tiles (two accumulators, fewer
+  // operand bytes per MAC) when there are enough of them to keep every pair busy for several tiles; HG_NARROW_NACC
+  // overrides (1 or 2).
+  int nacc = n_ref >= 2048 ? 2 : 1;
+  if (const char *e = getenv("HG_NARROW_NACC")) nacc = atoi(e) == 2 ? 2 : 1;
+  const uint32_t tile_rows = 256u * nacc;
+  const uint64_t tiles = (uint64_t)((n_qry + N1_BN - 1) / N1_BN) * ((n_ref + tile_rows - 1) / tile_rows);
   const uint32_t n_pairs = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)std::max(ctx->sm_count / 2, 1));
   cfg.gridDim = dim3(2 * n_pairs, 1, 1);
   cfg.dynamicSmemBytes = N1_SMEM_BYTES;
-  HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel, tm_ref, tm_qry, ref_row_off, ep, na));
+  if (nacc == 2) HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<2>, tm_ref, tm_qry, ref_row_off, ep, na));
+  else HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<1>, tm_ref, tm_qry, ref_row_off, ep, na));
   ctx->launches++;
   HG_PROF(ctx, 5);
   HG_CUDA(cudaGetLastError());

@@ -150,9 +150,12 @@ def _norms(oracle, hv):
     return np.array([oracle.hv_l2_norm_sq(v) for v in hv], np.int32)
 
 
+@pytest.mark.parametrize("nacc", [1, 2])
 @pytest.mark.parametrize("symmetric", [False, True])
-def test_narrow_many_tiles_exact(ctx, hg, oracle, symmetric):
-    """several 256 x 256 tiles per CTA pair (TMEM double buffering, stage ring across tiles, ragged edges)"""
+def test_narrow_many_tiles_exact(ctx, hg, oracle, symmetric, nacc, monkeypatch):
+    """several tiles per CTA pair (stage ring across tiles, ragged edges): 256 x 256 tiles with the TMEM
+    accumulator double buffered (nacc 1) and 512 x 256 tiles with two accumulators (nacc 2)"""
+    monkeypatch.setenv("HG_NARROW_NACC", str(nacc))
     rng = np.random.default_rng(31)
     D = 512
     hv = _narrow_rows(rng, 700, D)
@@ -172,10 +175,12 @@ def test_narrow_many_tiles_exact(ctx, hg, oracle, symmetric):
     assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32))
 
 
+@pytest.mark.parametrize("nacc", [1, 2])
 @pytest.mark.parametrize("ani_th", [0.0, 85.0])
-def test_narrow_outlier_corrections(ctx, hg, oracle, ani_th):
+def test_narrow_outlier_corrections(ctx, hg, oracle, ani_th, nacc, monkeypatch):
     """rows with a few elements outside the s8 plane (range and parity outliers, both sides): the kernel
     loosens their bound and corrects each candidate exactly"""
+    monkeypatch.setenv("HG_NARROW_NACC", str(nacc))
     hv, norm = _sketches(oracle, 300, length=120_000, hv_d=1024, scaled=300)
     hv = hv.copy()
     rng = np.random.default_rng(7)
@@ -225,12 +230,14 @@ def test_auto_path_narrow_for_sketches_and_two_limb_for_wide_rows(ctx, hg, oracl
     assert ei.value.code == hg.ffi.HG_E_UNSUPPORTED
 
 
-def test_narrow_row_shard_offsets(ctx, hg, oracle):
+@pytest.mark.parametrize("nacc", [1, 2])
+def test_narrow_row_shard_offsets(ctx, hg, oracle, nacc, monkeypatch):
     """hg_dist_dev on a row shard of the query matrix (i0 > 0, symmetric filter on global indices) - the
     multi-GPU dist step - through the single-plane path"""
     import torch
+    monkeypatch.setenv("HG_NARROW_NACC", str(nacc))
     rng = np.random.default_rng(11)
-    D, n = 512, 600
+    D, n = 2048, 600
     hv = _narrow_rows(rng, n, D)
     hv[37, [3, 99]] = [901, -777]  # one outlier row inside the shard
     norm = _norms(oracle, hv)
