@@ -41,10 +41,10 @@ using namespace hgtc;
 constexpr int N1_BN = 256;                              // tile columns (the pair's N)
 constexpr int N1_A_BYTES = 128 * TC_BK;                 // 128 of my ref rows
 constexpr int N1_B_BYTES = 128 * TC_BK;                 // my half of the 256 query rows
-// NACC = accumulators (256 TMEM columns each) per tile.  NACC = 1: 256 x 256 pair tiles, the accumulator double
-// buffered (epilogue fully hidden), 32 KB per stage.  NACC = 2: 512 x 256 pair tiles - two A tiles per CTA share
-// one B stage, 25 % fewer operand bytes per MAC (what the kernel is bound by) - at the price of a single-buffered
-// accumulator pair, i.e. an exposed epilogue; 48 KB per stage.
+// NACC = accumulators (256 TMEM columns each) per tile.  NACC = 1 (default): 256 x 256 pair tiles, the accumulator
+// double buffered (epilogue fully hidden), 32 KB per stage.  NACC = 2: 512 x 256 pair tiles - two A tiles per CTA
+// share one B stage, 25 % fewer operand bytes per MAC - at the price of a single-buffered accumulator pair, i.e. an
+// exposed epilogue; 48 KB per stage.  Measured slower (see the launcher), kept selectable.
 template <int NACC> struct N1Cfg {
   static constexpr int STAGES = NACC == 1 ? 6 : 4;
   static constexpr int STAGE_BYTES = NACC * N1_A_BYTES + N1_B_BYTES;
@@ -700,10 +700,10 @@ int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_re
   cfg.numAttrs = 1;
   cfg.blockDim = dim3(N1_THREADS, 1, 1);
   cfg.stream = ctx->stream;
-  // one CTA pair per TPC, each walking its tiles with stride n_pairs.  512-row tiles (two accumulators, fewer
-  // operand bytes per MAC) when there are enough of them to keep every pair busy for several tiles; HG_NARROW_NACC
-  // overrides (1 or 2).
-  int nacc = n_ref >= 2048 ? 2 : 1;
+  // one CTA pair per TPC, each walking its tiles with stride n_pairs.  256-row tiles by default: the 512-row
+  // variant (two accumulators, 25 % fewer operand bytes per MAC, exposed epilogue) measured 13 % slower on
+  // config 3 (0.239 vs 0.212 ms) and 5 % slower on config 4; HG_NARROW_NACC=2 selects it.
+  int nacc = 1;
   if (const char *e = getenv("HG_NARROW_NACC")) nacc = atoi(e) == 2 ? 2 : 1;
   const uint32_t tile_rows = 256u * nacc;
   const uint64_t tiles = (uint64_t)((n_qry + N1_BN - 1) / N1_BN) * ((n_ref + tile_rows - 1) / tile_rows);
