@@ -516,12 +516,12 @@ int hg_launch_fasta_merge(hg_ctx *ctx, const uint8_t *d_raw, const uint64_t *d_f
                           uint8_t *d_merged, uint64_t *d_merged_len);
 
 struct FastaStage {
-  std::vector<uint64_t> dev_off;   // 16-byte aligned device offset of every file (+ end)
+  std::vector<uint64_t> dev_off;   // device offset of every file (+ end)
   std::vector<uint64_t> merged_len;
   uint8_t *d_merged = nullptr;
 };
 
-// H2D of the raw files (each at a 16-byte aligned offset), merge on the device, lengths back.
+// H2D of the raw files (one copy, files back to back), merge on the device, lengths back.
 static int fasta_stage(hg_ctx *c, const uint8_t *raw, const uint64_t *file_off, uint32_t n, FastaStage &st) {
   const uint32_t B = hg_fasta_block_bytes();
   st.dev_off.assign(n + 1, 0);
@@ -530,7 +530,7 @@ static int fasta_stage(hg_ctx *c, const uint8_t *raw, const uint64_t *file_off, 
   for (uint32_t f = 0; f < n; f++) {
     if (file_off[f + 1] < file_off[f]) { hg_set_error("file_off not monotone at %u", f); return HG_E_INVALID; }
     const uint64_t len = file_off[f + 1] - file_off[f];
-    st.dev_off[f + 1] = (st.dev_off[f] + len + 15) & ~15ull;
+    st.dev_off[f + 1] = st.dev_off[f] + len;  // files back to back, as in the host buffer: one copy (the kernels take any byte phase)
     const uint64_t nb = (len + B - 1) / B;
     blk_off[f + 1] = blk_off[f] + nb;
     max_blocks = std::max(max_blocks, nb);
@@ -552,23 +552,7 @@ static int fasta_stage(hg_ctx *c, const uint8_t *raw, const uint64_t *file_off, 
   uint64_t *d_off = (uint64_t *)d_meta, *d_blk = d_off + (n + 1), *d_len = d_blk + (n + 1), *d_out = d_len + n;
   uint8_t *d_carry = (uint8_t *)(d_out + nblk);
   HG_CUDA(cudaMemcpyAsync(d_off, h_off, (size_t)(2 * n + 2) * 8, cudaMemcpyHostToDevice, c->stream));
-  bool contiguous = true;
-  for (uint32_t f = 0; f <= n; f++) contiguous = contiguous && (st.dev_off[f] == file_off[f] - file_off[0]);
-  if (contiguous) {
-    if (total) HG_CUDA(cudaMemcpyAsync(d_raw, raw + file_off[0], file_off[n] - file_off[0], cudaMemcpyHostToDevice, c->stream));
-  } else {
-    for (uint32_t f = 0; f < n; f++)
-      if (file_off[f + 1] > file_off[f])
-        HG_CUDA(cudaMemcpyAsync((uint8_t *)d_raw + st.dev_off[f], raw + file_off[f], file_off[f + 1] - file_off[f],
-                                cudaMemcpyHostToDevice, c->stream));
-  }
-  // the kernels see every file as [dev_off[f], dev_off[f] + len): pass true lengths through a second offset array?
-  // dev_off[f+1] - dev_off[f] includes the alignment pad, so the true end is carried separately:
-  // pad bytes are overwritten with '\n' (ignored by the merge) to keep the kernels' interface to one offset array.
-  for (uint32_t f = 0; f < n; f++) {
-    const uint64_t len = file_off[f + 1] - file_off[f], pad = st.dev_off[f + 1] - st.dev_off[f] - len;
-    if (pad) HG_CUDA(cudaMemsetAsync((uint8_t *)d_raw + st.dev_off[f] + len, '\n', pad, c->stream));
-  }
+  if (total) HG_CUDA(cudaMemcpyAsync(d_raw, raw + file_off[0], total, cudaMemcpyHostToDevice, c->stream));
   if ((rc = hg_launch_fasta_merge(c, (const uint8_t *)d_raw, d_off, d_blk, n, (uint32_t)max_blocks, d_sums, d_carry, d_out,
                                   (uint8_t *)d_merged, d_len)))
     return rc;
@@ -616,7 +600,7 @@ extern "C" int hg_sketch_fasta_batch(hg_ctx *c, const uint8_t *raw, const uint64
 
   struct Chunk {
     uint32_t g0, g1;
-    std::vector<uint64_t> dev_off, blk_off;  // per file of the chunk (+ end): aligned offset in the slot, block prefix
+    std::vector<uint64_t> dev_off, blk_off;  // per file of the chunk (+ end): offset in the slot, block prefix
     uint64_t max_blocks = 0;
     SketchPlan pl;
   };
@@ -636,7 +620,7 @@ extern "C" int hg_sketch_fasta_batch(hg_ctx *c, const uint8_t *raw, const uint64
     std::vector<uint64_t> lens(m);
     for (uint32_t t = 0; t < m; t++) {
       lens[t] = file_off[ch.g0 + t + 1] - file_off[ch.g0 + t];
-      ch.dev_off[t + 1] = (ch.dev_off[t] + lens[t] + 15) & ~15ull;
+      ch.dev_off[t + 1] = ch.dev_off[t] + lens[t];  // back to back, as in the host buffer
       const uint64_t nb = (lens[t] + B - 1) / B;
       ch.blk_off[t + 1] = ch.blk_off[t] + nb;
       ch.max_blocks = std::max(ch.max_blocks, nb);
@@ -700,12 +684,9 @@ extern "C" int hg_sketch_fasta_batch(hg_ctx *c, const uint8_t *raw, const uint64
     const int slot = (int)(ci & 1);
     const uint32_t m = ch.g1 - ch.g0;
     uint8_t *d_raw = (uint8_t *)d_rawbuf + slot * slot_bytes;
-    // ---- copy stream: every file of the chunk to its 16-byte aligned place in the raw slot ----
+    // ---- copy stream: the chunk's files in one copy (per-file copies cost ~6 us each of PCIe idle time) ----
     HG_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_done[slot], 0));
-    for (uint32_t t = 0; t < m; t++) {
-      const uint64_t len = file_off[ch.g0 + t + 1] - file_off[ch.g0 + t];
-      if (len) HG_CUDA(cudaMemcpyAsync(d_raw + ch.dev_off[t], raw + file_off[ch.g0 + t], len, cudaMemcpyHostToDevice, c->copy_stream));
-    }
+    if (ch.dev_off[m]) HG_CUDA(cudaMemcpyAsync(d_raw, raw + file_off[ch.g0], ch.dev_off[m], cudaMemcpyHostToDevice, c->copy_stream));
     HG_CUDA(cudaEventRecord(c->ev_copied[slot], c->copy_stream));
     // ---- compute stream ----
     uint64_t *hm = (uint64_t *)((uint8_t *)h_meta + ci * h_meta_per_chunk);
@@ -718,10 +699,6 @@ extern "C" int hg_sketch_fasta_batch(hg_ctx *c, const uint8_t *raw, const uint64
     HG_CUDA(cudaMemcpyAsync(dd, hd, sizeof(hg_genome_desc) * (m + 1), cudaMemcpyHostToDevice, c->stream));
     HG_CUDA(cudaMemsetAsync(d_tables, 0xFF, ch.pl.total_slots * 8, c->stream));
     HG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
-    for (uint32_t t = 0; t < m; t++) {  // alignment pads read as empty lines
-      const uint64_t len = file_off[ch.g0 + t + 1] - file_off[ch.g0 + t], pad = ch.dev_off[t + 1] - ch.dev_off[t] - len;
-      if (pad) HG_CUDA(cudaMemsetAsync(d_raw + ch.dev_off[t] + len, '\n', pad, c->stream));
-    }
     if ((rc = hg_launch_fasta_merge(c, d_raw, dm_off, dm_blk, m, (uint32_t)ch.max_blocks, dm_sums, dm_carry, dm_out,
                                     (uint8_t *)d_merged, d_len + ch.g0)))
       return rc;

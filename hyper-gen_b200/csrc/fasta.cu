@@ -78,25 +78,46 @@ __device__ __forceinline__ bool any_eq16(const uint32_t (&w)[4], uint32_t c4) { 
   return (z & 0x80808080u) != 0;
 }
 
-// The thread's 16 bytes come in with one 16-byte load when the file is 16-byte aligned in the
-// buffer (the host entry stages files that way), else with byte loads; the byte before and the byte
-// after come from the neighbouring lanes (one extra byte load at the warp edges).  Loading is
-// separate from classifying so that the next block's bytes are in flight while this one is worked on.
+// The byte before and the byte after a thread's 16 come from the neighbouring lanes (one extra byte load at
+// the warp edges).  Loading is separate from classifying (a CTA may walk several blocks, FA_NB).
 struct Raw {
   uint32_t w[4];
   uint32_t edge;  // lane 0: the byte before the warp's bytes; lane 31: the byte after them
 };
+// Files sit back to back in the buffer, so a file starts at any byte phase: the 16 bytes are cut out of
+// two aligned 16-byte loads with funnel shifts (the phase is the same for every thread of a file, so
+// the word-shift switch is warp-uniform).  Reads up to 15 bytes before f + p0 (never before the buffer:
+// it starts 16-byte aligned) and up to 31 past it (the buffer has that slack).
 __device__ __forceinline__ Raw load_raw(const uint8_t *__restrict__ f, uint64_t len, uint64_t p0) {
   Raw r;
   r.w[0] = r.w[1] = r.w[2] = r.w[3] = 0x0A0A0A0Au;  // bytes past the end read as '\n'
   r.edge = (uint32_t)'\n';                          // '\n' before the first byte of the file and after the last
-  if (p0 + FA_BPT <= len && (((uintptr_t)(f + p0)) & 15) == 0) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(f + p0));
-    r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
-  } else {
+  if (p0 < len) {
+    const uintptr_t addr = (uintptr_t)(f + p0);
+    const uint32_t mis = (uint32_t)(addr & 15);
+    const uint4 *a = reinterpret_cast<const uint4 *>(addr - mis);
+    const uint32_t n_valid = len - p0 < FA_BPT ? (uint32_t)(len - p0) : FA_BPT;
+    const uint4 v0 = __ldg(a);
+    uint4 v1 = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+    if (mis + n_valid > 16) v1 = __ldg(a + 1);
+    const uint32_t bs = (mis & 3u) * 8u;
+    uint32_t y[5];
+    switch (mis >> 2) {
+      case 0: y[0] = v0.x; y[1] = v0.y; y[2] = v0.z; y[3] = v0.w; y[4] = v1.x; break;
+      case 1: y[0] = v0.y; y[1] = v0.z; y[2] = v0.w; y[3] = v1.x; y[4] = v1.y; break;
+      case 2: y[0] = v0.z; y[1] = v0.w; y[2] = v1.x; y[3] = v1.y; y[4] = v1.z; break;
+      default: y[0] = v0.w; y[1] = v1.x; y[2] = v1.y; y[3] = v1.z; y[4] = v1.w; break;
+    }
 #pragma unroll
-    for (int i = 0; i < FA_BPT; ++i)
-      if (p0 + i < len) r.w[i >> 2] = (r.w[i >> 2] & ~(0xFFu << (8 * (i & 3)))) | ((uint32_t)f[p0 + i] << (8 * (i & 3)));
+    for (int j = 0; j < 4; ++j) r.w[j] = __funnelshift_r(y[j], y[j + 1], bs);
+    if (n_valid < FA_BPT) {  // the file's last thread: what follows belongs to the next file
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int keep = (int)n_valid - 4 * j;  // bytes of word j inside the file
+        if (keep <= 0) r.w[j] = 0x0A0A0A0Au;
+        else if (keep < 4) r.w[j] = (r.w[j] & ((1u << (8 * keep)) - 1u)) | (0x0A0A0A0Au & ~((1u << (8 * keep)) - 1u));
+      }
+    }
   }
   const int lane = threadIdx.x & 31;
   if (lane == 0 && p0 != 0 && p0 <= len) r.edge = (uint32_t)f[p0 - 1];
