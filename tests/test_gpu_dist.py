@@ -261,3 +261,18 @@ def test_narrow_row_shard_offsets(ctx, hg, oracle, nacc, monkeypatch):
     assert np.array_equal(np.sort(idx), want)
     assert np.array_equal(hits["dot"], dot[idx])
     assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32))
+
+
+@pytest.mark.parametrize("hv_d", [256, 2048])
+def test_narrow_short_and_mid_k(ctx, hg, oracle, hv_d):
+    """hv_d = 256 is two K blocks, fewer than the 6-stage ring; 2048 is sixteen"""
+    rng = np.random.default_rng(hv_d)
+    hv = _narrow_rows(rng, 330, hv_d)
+    hv[7] = hv[300]
+    norm = _norms(oracle, hv)
+    ani, dot = oracle.dist_all(hv, norm, hv, norm, symmetric=True)
+    hits = ctx.dist(hv, norm, hv, norm, ani_th=0.0, symmetric=True, path=3, cap=ani.size + 16)
+    idx = _as_pairs(hits, 330, 330, True)
+    assert np.array_equal(np.sort(idx), np.arange(ani.size))
+    assert np.array_equal(hits["dot"], dot[idx])
+    assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32))
