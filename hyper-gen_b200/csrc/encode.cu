@@ -201,23 +201,57 @@ encode_kernel(const hg_genome_desc *__restrict__ desc, const uint64_t *__restric
   }
 }
 
-// decompress_hd_sketch (hd.rs:184-212): one thread per value.
-__global__ void unpack_kernel(const uint8_t *__restrict__ packed, uint64_t row_stride,
-                              const uint8_t *__restrict__ bits, uint32_t n, uint32_t hv_d,
-                              int16_t *__restrict__ hv) {
+// decompress_hd_sketch (hd.rs:184-212).  BitPacker8x keeps value 8r + l of a 256-value block at bit b*r of lane
+// stream l, and word j of stream l at word 8j + l of the block: the 8 values of one "row" r sit at the same bit
+// offset of 8 adjacent words.  One thread per row: two (or, when the field straddles a word, four) 16-byte loads,
+// 8 funnel shifts, one 16-byte store of 8 int16.
+__global__ void __launch_bounds__(256)
+unpack_kernel(const uint8_t *__restrict__ packed, uint64_t row_stride, const uint8_t *__restrict__ bits, uint32_t n,
+              uint32_t hv_d, int16_t *__restrict__ hv) {
   const uint32_t g = blockIdx.y;
   const uint32_t b = bits[g];
   const uint32_t *row = reinterpret_cast<const uint32_t *>(packed + (size_t)g * row_stride);
   const uint32_t umask = b >= 16 ? 0xFFFFu : ((1u << b) - 1u);
-  const int offset = 1 << (b - 1);
-  for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < hv_d; d += gridDim.x * blockDim.x) {
-    const uint32_t blk = d >> 8, within = d & 255, l = within & 7, r = within >> 3;
+  const uint32_t offset = 1u << (b - 1);
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < hv_d / 8; t += gridDim.x * blockDim.x) {
+    const uint32_t blk = t >> 5, r = t & 31;
     const uint32_t bit = b * r, j = bit >> 5, sh = bit & 31;
-    const uint32_t *wb = row + blk * 8 * b + l;
-    const uint32_t w0 = wb[8 * j];
-    const uint32_t w1 = (j + 1 < b) ? wb[8 * (j + 1)] : 0u;
-    const uint32_t u = __funnelshift_r(w0, w1, sh) & umask;
-    hv[(size_t)g * hv_d + d] = (int16_t)(uint16_t)(u - (uint32_t)offset);
+    const uint4 *wb = reinterpret_cast<const uint4 *>(row + blk * 8 * b + 8 * j);  // row_stride % 4 == 0, rows 16-byte aligned when it is % 16
+    uint32_t lo[8], hi[8];
+    if ((((uintptr_t)wb) & 15) == 0) {
+      const uint4 a0 = wb[0], a1 = wb[1];
+      lo[0] = a0.x; lo[1] = a0.y; lo[2] = a0.z; lo[3] = a0.w; lo[4] = a1.x; lo[5] = a1.y; lo[6] = a1.z; lo[7] = a1.w;
+    } else {
+      const uint32_t *w = reinterpret_cast<const uint32_t *>(wb);
+#pragma unroll
+      for (int l = 0; l < 8; ++l) lo[l] = w[l];
+    }
+#pragma unroll
+    for (int l = 0; l < 8; ++l) hi[l] = 0;
+    if (sh + b > 32) {  // the field continues in the next word of every lane stream (then j + 1 < b)
+      if ((((uintptr_t)wb) & 15) == 0) {
+        const uint4 a0 = wb[2], a1 = wb[3];
+        hi[0] = a0.x; hi[1] = a0.y; hi[2] = a0.z; hi[3] = a0.w; hi[4] = a1.x; hi[5] = a1.y; hi[6] = a1.z; hi[7] = a1.w;
+      } else {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(wb) + 8;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) hi[l] = w[l];
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int l = 0; l < 8; l += 2) {
+      const uint32_t u0 = (__funnelshift_r(lo[l], hi[l], sh) & umask) - offset;
+      const uint32_t u1 = (__funnelshift_r(lo[l + 1], hi[l + 1], sh) & umask) - offset;
+      o[l >> 1] = (u0 & 0xFFFFu) | (u1 << 16);
+    }
+    int16_t *dst = hv + (size_t)g * hv_d + 8 * (size_t)t;
+    if ((((uintptr_t)dst) & 15) == 0) {
+      *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {  // caller-provided matrix at an odd address
+#pragma unroll
+      for (int l = 0; l < 8; ++l) dst[l] = (int16_t)(uint16_t)(o[l >> 1] >> (16 * (l & 1)));
+    }
   }
 }
 
@@ -275,7 +309,7 @@ int hg_launch_encode(hg_ctx *ctx, const hg_genome_desc *d_desc, uint32_t n_genom
 int hg_launch_unpack(hg_ctx *ctx, const uint8_t *d_packed, uint64_t row_stride, const uint8_t *d_quant_bits,
                      uint32_t n, uint32_t hv_d, int16_t *d_hv) {
   if (n == 0) return HG_OK;
-  dim3 grid((hv_d + 255) / 256 < 8 ? (hv_d + 255) / 256 : 8, n);
+  dim3 grid((hv_d / 8 + 255) / 256 < 8 ? (hv_d / 8 + 255) / 256 : 8, n);
   // gridDim.y is limited to 65535
   for (uint32_t g0 = 0; g0 < n; g0 += 65535) {
     const uint32_t cnt = n - g0 < 65535 ? n - g0 : 65535;

@@ -69,39 +69,41 @@ rs_count_kernel(const uint4 *__restrict__ hits, uint64_t n, int pass, uint32_t n
   counts[(uint64_t)threadIdx.x * n_blocks + blockIdx.x] = s_cnt[threadIdx.x];
 }
 
-// in-place exclusive scan of `len` counters by one block (len = 256 * n_blocks; small next to the records)
+// in-place exclusive scan of `len` counters by one block (len = 256 * n_blocks; small next to the records):
+// every thread owns a contiguous run, so there is one block-wide scan (two barriers) whatever the length
 __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t *__restrict__ counts, uint64_t len) {
   __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint64_t base = 0; base < len; base += 1024) {
-    const uint64_t t = base + threadIdx.x;
-    const uint32_t v = t < len ? counts[t] : 0u;
-    uint32_t x = v;
+  const uint64_t items = (len + 1023) / 1024;
+  const uint64_t b = (uint64_t)threadIdx.x * items;
+  const uint64_t e = b + items < len ? b + items : len;
+  uint32_t sum = 0;
+#pragma unroll 4
+  for (uint64_t i = b; i < e; ++i) sum += counts[i];
+  uint32_t x = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (uint32_t)o) x += y;
+  }
+  if (lane == 31) s_warp[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t w = s_warp[lane];
+    uint32_t ws = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if (lane >= (uint32_t)o) x += y;
+      const uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
+      if (lane >= (uint32_t)o) ws += y;
     }
-    if (lane == 31) s_warp[warp] = x;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = s_warp[lane], ws = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
-        if (lane >= (uint32_t)o) ws += y;
-      }
-      s_warp[lane] = ws - w;  // exclusive over warps
-    }
-    __syncthreads();
-    const uint32_t carry = s_carry;
-    if (t < len) counts[t] = carry + s_warp[warp] + x - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + x;
-    __syncthreads();
+    s_warp[lane] = ws - w;  // exclusive over warps
+  }
+  __syncthreads();
+  uint32_t run = s_warp[warp] + x - sum;
+  for (uint64_t i = b; i < e; ++i) {
+    const uint32_t v = counts[i];
+    counts[i] = run;
+    run += v;
   }
 }
 
