@@ -183,7 +183,9 @@ HG_API int hg_dist(hg_ctx *ctx, const int16_t *ref_hv, const int32_t *ref_norm2,
 /* Device-resident variant: HVs/norms/hits in HBM, hit order unspecified (atomic append),
  * *d_n_hits counts every passing pair even beyond cap.  (i, j) are offset by i0 / j0 so a
  * row shard of a larger ref matrix reports global indices; with `symmetric` the filter is
- * global_j > global_i.  Asynchronous on the context stream. */
+ * global_j > global_i.  Work is enqueued on the context stream; paths 1 and 2 return without waiting
+ * for it, paths 0 and 3 wait once at the end (the host reads the single-plane pre-pass's verdict
+ * there, after the kernel has been enqueued behind it, so the GPU never idles on that read). */
 HG_API int hg_dist_dev(hg_ctx *ctx, const int16_t *d_ref_hv, const int32_t *d_ref_norm2, uint32_t n_ref,
                        uint32_t i0, const int16_t *d_qry_hv, const int32_t *d_qry_norm2,
                        uint32_t n_qry, uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th,

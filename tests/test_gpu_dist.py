@@ -276,3 +276,35 @@ def test_narrow_short_and_mid_k(ctx, hg, oracle, hv_d):
     assert np.array_equal(np.sort(idx), np.arange(ani.size))
     assert np.array_equal(hits["dot"], dot[idx])
     assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32))
+
+
+def test_narrow_random_sweep(ctx, hg, oracle):
+    """random shapes, thresholds, symmetric or not, outliers sprinkled on both sides: auto path == oracle"""
+    rng = np.random.default_rng(2026)
+    for trial in range(8):
+        D = int(rng.choice([256, 512, 1024, 2048]))
+        R, Q = int(rng.integers(130, 700)), int(rng.integers(130, 700))
+        sym = bool(trial % 2)
+        th = float(rng.choice([0.0, 80.0, 95.0]))
+        q = _narrow_rows(rng, Q, D, spread=int(rng.integers(40, 125)))
+        for _ in range(int(rng.integers(0, 6))):            # a few near-duplicates so that thresholds > 0 keep something
+            a, b = rng.integers(0, Q, 2)
+            q[a] = q[b]
+            q[a, rng.integers(0, D, 8)] += np.int16(2)
+        for _ in range(int(rng.integers(0, 12))):           # outliers: far values and parity flips
+            q[rng.integers(0, Q), rng.integers(0, D)] += np.int16(rng.choice([1, -1, 700, -900, 3001]))
+        if sym:
+            r, R = q, Q
+        else:
+            r = np.concatenate([q[: min(R, Q) // 2], _narrow_rows(rng, R - min(R, Q) // 2, D)])
+            r[rng.integers(0, R), rng.integers(0, D)] = np.int16(-2500)
+        rn = _norms(oracle, r)
+        qn = rn if sym else _norms(oracle, q)
+        ani, dot = oracle.dist_all(r, rn, q, qn, symmetric=sym)
+        hits = ctx.dist(r, rn, q, qn, ani_th=th, symmetric=sym, path=0, cap=ani.size + 16)
+        assert ctx.dist_last_path == 3, (trial, ctx.dist_last_reason)
+        idx = _as_pairs(hits, R, Q, sym)
+        want = np.nonzero(ani >= np.float32(th))[0]
+        assert np.array_equal(np.sort(idx), want), (trial, D, R, Q, sym, th)
+        assert np.array_equal(hits["dot"], dot[idx]), trial
+        assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32)), trial
