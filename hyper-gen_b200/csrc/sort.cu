@@ -16,7 +16,14 @@
 // ranking equal digits inside a 32-record round with match_any, so no block barrier sits in the loop.
 //
 // Also here: the `{:.3}` field of the TSV as an integer (thousandths), see ani_milli_kernel.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cstdlib>
+
 #include "hg_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -155,6 +162,133 @@ rs_scatter_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, uint64_
   }
 }
 
+// ---- the whole sort as ONE cooperative kernel (small and medium inputs) -------------------------
+// The multi-kernel path above spends its time in launch gaps: at 185 k records every one of its 22 kernels is a
+// 10-15 us affair on 46 blocks.  Here every block keeps its positional chunk of 256 * ROUNDS records in registers,
+// and the passes are separated by grid-wide barriers instead of kernel boundaries: which key bytes are live
+// (rs_diff), per pass the block histograms -> barrier -> every block derives its own scatter offsets from the
+// count matrix (no single-block scan) -> stable scatter -> barrier -> reload the chunk.  The last phase copies
+// back if the records ended in the ping-pong buffer and writes the `{:.3}` thousandths.  Data written by other
+// blocks is read with ld.global.cg: L1 may still hold the lines of an earlier pass.
+template <int ROUNDS>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_fused_kernel(uint4 *__restrict__ a, uint4 *__restrict__ b, uint64_t n, uint32_t *__restrict__ counts,
+                uint32_t *__restrict__ diff, uint32_t *__restrict__ milli) {
+  constexpr int WARP_ITEMS = 32 * ROUNDS, CHUNK = RS_WARPS * WARP_ITEMS;
+  __shared__ uint32_t s_base[RS_WARPS][256];  // per (warp, digit): count, then next output slot
+  __shared__ uint32_t s_scan[RS_WARPS];
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_blocks = gridDim.x;
+  const uint64_t wbase = (uint64_t)blockIdx.x * CHUNK + (uint64_t)warp * WARP_ITEMS;
+  uint4 rec[ROUNDS];
+  // which key bytes differ anywhere
+  {
+    const uint4 h0 = __ldcg(a);
+    uint32_t dj = 0, di = 0, da = 0;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const uint64_t t = wbase + (uint64_t)r * 32 + lane;
+      if (t < n) {
+        rec[r] = __ldcg(a + t);
+        dj |= rec[r].y ^ h0.y;
+        di |= rec[r].x ^ h0.x;
+        da |= rec[r].w ^ h0.w;
+      }
+    }
+    dj = __reduce_or_sync(0xffffffffu, dj);
+    di = __reduce_or_sync(0xffffffffu, di);
+    da = __reduce_or_sync(0xffffffffu, da);
+    if (lane == 0) {
+      if (dj) atomicOr(diff + 0, dj);
+      if (di) atomicOr(diff + 1, di);
+      if (da) atomicOr(diff + 2, da);
+    }
+  }
+  grid.sync();
+  const uint32_t dmask[3] = {__ldcg(diff + 0), __ldcg(diff + 1), __ldcg(diff + 2)};
+  uint4 *src = a, *dst = b;
+  for (int pass = 0; pass < RS_PASSES; ++pass) {
+    if (((dmask[pass >> 2] >> ((pass & 3) * 8)) & 255u) == 0) continue;  // every record has the same byte here (grid-uniform)
+    // per-warp digit histograms of my chunk
+    for (int w = 0; w < RS_WARPS; ++w) s_base[w][threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const uint64_t t = wbase + (uint64_t)r * 32 + lane;
+      if (t < n) atomicAdd(&s_base[warp][rs_digit(rec[r], pass)], 1u);
+    }
+    __syncthreads();
+    {
+      uint32_t c = 0;
+#pragma unroll
+      for (int w = 0; w < RS_WARPS; ++w) c += s_base[w][threadIdx.x];
+      counts[(uint64_t)threadIdx.x * n_blocks + blockIdx.x] = c;  // digit-major, like the multi-kernel path
+    }
+    grid.sync();
+    // my scatter offsets: everything with a smaller digit + my digit in the blocks before me
+    uint32_t tot = 0, pre = 0;
+    {
+      const uint32_t *row = counts + (uint64_t)threadIdx.x * n_blocks;
+      for (uint32_t bb = 0; bb < n_blocks; ++bb) {
+        const uint32_t c = __ldcg(row + bb);
+        pre += bb < blockIdx.x ? c : 0u;
+        tot += c;
+      }
+    }
+    uint32_t x = tot;  // exclusive scan of tot over the 256 digits (thread = digit)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) s_scan[warp] = x;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) before += (uint32_t)w < warp ? s_scan[w] : 0u;
+    {
+      uint32_t run = before + x - tot + pre;  // first slot of (my block, digit threadIdx.x); then warp by warp
+#pragma unroll
+      for (int w = 0; w < RS_WARPS; ++w) {
+        const uint32_t c = s_base[w][threadIdx.x];
+        s_base[w][threadIdx.x] = run;
+        run += c;
+      }
+    }
+    __syncthreads();
+    // stable scatter: every warp walks its run in order, equal digits of a round ranked with match_any
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const uint64_t t = wbase + (uint64_t)r * 32 + lane;
+      const bool live = t < n;
+      const uint32_t d = live ? rs_digit(rec[r], pass) : 256u + lane;  // dead lanes match nobody
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t ahead = __popc(peers & ((1u << lane) - 1u));
+      uint32_t slot = 0;
+      if (live) slot = s_base[warp][d] + ahead;
+      __syncwarp();
+      if (live && ahead == 0) s_base[warp][d] += (uint32_t)__popc(peers);
+      __syncwarp();
+      if (live) dst[slot] = rec[r];
+    }
+    grid.sync();
+    { uint4 *tmp = src; src = dst; dst = tmp; }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {  // my positional chunk of the new order
+      const uint64_t t = wbase + (uint64_t)r * 32 + lane;
+      if (t < n) rec[r] = __ldcg(src + t);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint64_t t = wbase + (uint64_t)r * 32 + lane;
+    if (t < n) {
+      if (src != a) a[t] = rec[r];
+      if (milli) milli[t] = (uint32_t)__double2ll_rn((double)__uint_as_float(rec[r].w) * 1000.0);  // see ani_milli_kernel
+    }
+  }
+}
+
 // thousandths of the ANI, rounded as `{:.3}` rounds: ani * 1000 is exact in binary64 (24-bit x 10-bit
 // significands), so rint() - round half to even - is the correctly rounded decimal
 __global__ void ani_milli_kernel(const uint4 *__restrict__ hits, uint64_t n, uint32_t *__restrict__ milli) {
@@ -175,6 +309,30 @@ int hg_launch_sort_hits(hg_ctx *ctx, hg_hit *d_hits, uint64_t n, uint32_t *d_mil
   const uint32_t n_blocks = (uint32_t)((n + chunk - 1) / chunk);
   void *d_tmp, *d_cnt;
   if (n > 1) {
+    // small and medium inputs: the whole sort (and the thousandths) as one cooperative kernel
+    if (!getenv("HG_SORT_MULTI")) {
+      for (int fr : {4, 16}) {
+        const uint32_t fchunk = (uint32_t)RS_THREADS * fr;
+        const uint64_t fblocks = (n + fchunk - 1) / fchunk;
+        int per_sm = 0;
+        if (fr == 4) HG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rs_fused_kernel<4>, RS_THREADS, 0));
+        else HG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rs_fused_kernel<16>, RS_THREADS, 0));
+        if (fblocks > (uint64_t)per_sm * ctx->sm_count) continue;  // all blocks must be resident for the grid barriers
+        if ((rc = hg_scratch(ctx, HG_S_SORT_TMP, n * sizeof(hg_hit), &d_tmp))) return rc;
+        if ((rc = hg_scratch(ctx, HG_S_SORT_CNT, (size_t)256 * fblocks * 4 + 256, &d_cnt))) return rc;
+        uint32_t *d_diff = (uint32_t *)d_cnt + (size_t)256 * fblocks;
+        HG_CUDA(cudaMemsetAsync(d_diff, 0, 16, ctx->stream));
+        uint4 *pa = (uint4 *)d_hits, *pb = (uint4 *)d_tmp;
+        uint64_t nn = n;
+        uint32_t *pc = (uint32_t *)d_cnt, *pm = d_milli;
+        void *args[] = {&pa, &pb, &nn, &pc, &d_diff, &pm};
+        if (fr == 4) HG_CUDA(cudaLaunchCooperativeKernel((void *)rs_fused_kernel<4>, dim3((unsigned)fblocks), dim3(RS_THREADS), args, 0, ctx->stream));
+        else HG_CUDA(cudaLaunchCooperativeKernel((void *)rs_fused_kernel<16>, dim3((unsigned)fblocks), dim3(RS_THREADS), args, 0, ctx->stream));
+        ctx->launches++;
+        HG_CUDA(cudaGetLastError());
+        return HG_OK;
+      }
+    }
     if ((rc = hg_scratch(ctx, HG_S_SORT_TMP, n * sizeof(hg_hit), &d_tmp))) return rc;
     if ((rc = hg_scratch(ctx, HG_S_SORT_CNT, (size_t)256 * n_blocks * 4 + 256, &d_cnt))) return rc;
     uint32_t *d_diff = (uint32_t *)d_cnt;  // first 3 words, read back before the counters are used

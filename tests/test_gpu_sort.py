@@ -21,8 +21,15 @@ def _sort_on_gpu(ctx, hits, want_milli=True):
 
 @pytest.mark.parametrize("n,R,Q,levels", [(0, 10, 10, 4), (1, 10, 10, 4), (2, 3, 3, 1), (37, 9, 9, 3), (5000, 300, 300, 50),
                                           (4096, 70000, 5, 7), (4097, 100, 70000, 4097), (300_000, 2000, 2000, 1000),
-                                          (1_100_000, 1500, 1500, 3)])
-def test_sort_matches_reference_order(ctx, hg, oracle, n, R, Q, levels):
+                                          (520_000, 1500, 1500, 77), (1_100_000, 1500, 1500, 3)])
+@pytest.mark.parametrize("multi", [False, True])
+def test_sort_matches_reference_order(ctx, hg, oracle, n, R, Q, levels, multi, monkeypatch):
+    """multi=False: one cooperative kernel up to ~600 k records (4 or 16 rounds per warp), the multi-kernel
+    path beyond; multi=True: the multi-kernel path at every size"""
+    if multi:
+        if n > 300_000:
+            pytest.skip("already the multi-kernel path (or covered at 300 k)")
+        monkeypatch.setenv("HG_SORT_MULTI", "1")
     rng = np.random.default_rng(n + levels)
     # full R x Q enumeration; a few distinct ANI levels so that ties dominate
     pair = rng.choice(R * Q, size=n, replace=False) if n else np.zeros(0, np.int64)
