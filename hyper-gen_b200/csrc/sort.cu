@@ -222,15 +222,16 @@ rs_fused_kernel(uint4 *__restrict__ a, uint4 *__restrict__ b, uint64_t n, uint32
       uint32_t c = 0;
 #pragma unroll
       for (int w = 0; w < RS_WARPS; ++w) c += s_base[w][threadIdx.x];
-      counts[(uint64_t)threadIdx.x * n_blocks + blockIdx.x] = c;  // digit-major, like the multi-kernel path
+      counts[(uint64_t)blockIdx.x * 256 + threadIdx.x] = c;  // block-major: the reads below are coalesced
     }
     grid.sync();
     // my scatter offsets: everything with a smaller digit + my digit in the blocks before me
     uint32_t tot = 0, pre = 0;
     {
-      const uint32_t *row = counts + (uint64_t)threadIdx.x * n_blocks;
+      const uint32_t *col = counts + threadIdx.x;
+#pragma unroll 8
       for (uint32_t bb = 0; bb < n_blocks; ++bb) {
-        const uint32_t c = __ldcg(row + bb);
+        const uint32_t c = __ldcg(col + (uint64_t)bb * 256);
         pre += bb < blockIdx.x ? c : 0u;
         tot += c;
       }
@@ -311,7 +312,12 @@ int hg_launch_sort_hits(hg_ctx *ctx, hg_hit *d_hits, uint64_t n, uint32_t *d_mil
   if (n > 1) {
     // small and medium inputs: the whole sort (and the thousandths) as one cooperative kernel
     if (!getenv("HG_SORT_MULTI")) {
+      // few blocks matter more than short blocks (measured at 185 k records: 46 blocks of 4096 sort in 0.17 ms,
+      // 181 blocks of 1024 in 0.48 ms, the multi-kernel path in 0.26 ms): 16 rounds per warp unless the input is tiny
+      int only = n <= (1u << 14) ? 4 : 16;
+      if (const char *e = getenv("HG_SORT_ROUNDS")) only = atoi(e);
       for (int fr : {4, 16}) {
+        if (fr != only) continue;
         const uint32_t fchunk = (uint32_t)RS_THREADS * fr;
         const uint64_t fblocks = (n + fchunk - 1) / fchunk;
         int per_sm = 0;
