@@ -453,8 +453,8 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
     else:
         hv = norm = None
     cap = 4_000_000
-    d_hits = torch.empty(cap * 16, dtype=torch.uint8, device=dev)
-    d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    # counter and hit array live in one buffer laid out as the multi-GPU gather sends it (no staging copy)
+    hit_blk, d_cnt, d_hits = multigpu.hit_block(cap, dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     hits_pin = torch.empty(cap * 16, dtype=torch.uint8, pin_memory=True)
     bounds = multigpu.triangle_rows(nq, world, align=128)
@@ -469,6 +469,7 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
             qbuf[nq * D * 2:] = norm.view(torch.uint8).view(-1)
         gather_cap = 1 << 18  # hits per rank carried by the one-shot gather (4 MiB per rank)
         gather_pin = torch.empty(cap * 16, dtype=torch.uint8, pin_memory=True)
+        gather_recv = torch.empty(world * (16 + gather_cap * 16), dtype=torch.uint8, device=dev)
 
     def step():
         """broadcast queries -> local shard -> hits gathered on rank 0; returns device ms"""
@@ -489,7 +490,8 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
             if dbg:
                 torch.cuda.synchronize(); ctx.sync(); tC = time.perf_counter()
             if world > 1:
-                allh, overflow = multigpu.gather_hits_fixed(d_hits, d_cnt, gather_cap, host_buf=gather_pin)
+                allh, overflow = multigpu.gather_hits_fixed(None, None, gather_cap, host_buf=gather_pin, block=hit_blk,
+                                                            recv=gather_recv)
                 if overflow:  # some shard produced more hits than the one-shot block carries
                     cnt = int(d_cnt.item())
                     allh = multigpu.gather_hits(d_hits, dev, count=min(cnt, cap))

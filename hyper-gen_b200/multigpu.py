@@ -143,23 +143,37 @@ def gather_hits(local_hits, device, dst: int = 0, count: int | None = None) -> n
     return np.concatenate(parts) if parts else np.zeros(0, HIT_DTYPE)
 
 
-def gather_hits_fixed(local_hits: torch.Tensor, count_t: torch.Tensor, cap_per_rank: int, dst: int = 0,
-                      host_buf: torch.Tensor | None = None):
+def hit_block(cap_per_rank: int, device) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """One device buffer laid out as the gather sends it: [count:int64 | pad | cap_per_rank x hg_hit].
+    Returns (block, count view (1 x int64), hits view (uint8)): point the dist kernel's counter and hit array at the
+    views and gather_hits_fixed(block=...) sends the block as it is - no staging copy."""
+    block = torch.zeros(16 + cap_per_rank * HIT_DTYPE.itemsize, dtype=torch.uint8, device=device)
+    return block, block[:8].view(torch.int64), block[16:]
+
+
+def gather_hits_fixed(local_hits: torch.Tensor | None, count_t: torch.Tensor | None, cap_per_rank: int, dst: int = 0,
+                      host_buf: torch.Tensor | None = None, block: torch.Tensor | None = None,
+                      recv: torch.Tensor | None = None):
     """One-collective gather for the common (sparse) case: every rank contributes a fixed-size
     record block [count:int64 | cap_per_rank x hg_hit] so that no host round trip is needed to size
     the collective.  Returns (hits or None, overflowed: bool); on overflow (some rank had more than
     cap_per_rank hits) the caller falls back to gather_hits().  `local_hits` is a uint8 device tensor,
-    `count_t` a 1-element int64 device tensor (the kernel's hit counter); `host_buf` an optional pinned
-    uint8 tensor of at least world * (16 + cap_per_rank * 16) bytes owned by the caller."""
+    `count_t` a 1-element int64 device tensor (the kernel's hit counter) - or pass `block` from hit_block(),
+    which already is the record block; `recv` an optional reusable device buffer of world * block bytes;
+    `host_buf` an optional pinned uint8 tensor of at least world * cap_per_rank * 16 bytes owned by the caller."""
     world, rank = dist.get_world_size(), dist.get_rank()
     isz = HIT_DTYPE.itemsize
-    block = 16 + cap_per_rank * isz
-    send = torch.empty(block, dtype=torch.uint8, device=local_hits.device)
-    send[:8] = count_t.view(torch.uint8)
-    send[16:] = local_hits[: cap_per_rank * isz]
-    recv = torch.empty(world * block, dtype=torch.uint8, device=local_hits.device)
+    nbytes = 16 + cap_per_rank * isz
+    if block is None:
+        block = torch.empty(nbytes, dtype=torch.uint8, device=local_hits.device)
+        block[:8] = count_t.view(torch.uint8)
+        block[16:] = local_hits[: cap_per_rank * isz]
+    send = block[:nbytes]
+    if recv is None or recv.numel() < world * nbytes:
+        recv = torch.empty(world * nbytes, dtype=torch.uint8, device=send.device)
+    recv = recv[: world * nbytes]
     dist.all_gather_into_tensor(recv, send)
-    counts = recv.view(world, block)[:, :8].contiguous().view(torch.int64).cpu().numpy().ravel()  # 8 B per rank
+    counts = recv.view(world, nbytes)[:, :8].contiguous().view(torch.int64).cpu().numpy().ravel()  # 8 B per rank
     overflow = bool((counts > cap_per_rank).any())
     if overflow or rank != dst:
         return None, overflow
@@ -170,7 +184,7 @@ def gather_hits_fixed(local_hits: torch.Tensor, count_t: torch.Tensor, cap_per_r
     for r in range(world):  # only the used part of every rank's block crosses PCIe
         nb = int(counts[r]) * isz
         if nb:
-            host_t[pos:pos + nb].copy_(recv[r * block + 16: r * block + 16 + nb], non_blocking=True)
+            host_t[pos:pos + nb].copy_(recv[r * nbytes + 16: r * nbytes + 16 + nb], non_blocking=True)
             pos += nb
     if recv.is_cuda:
         torch.cuda.current_stream().synchronize()

@@ -142,6 +142,12 @@ def _fixed_gather_worker(rank, world, port, out_dir):
         h["j"][:n_local] = 7
         raw = torch.from_numpy(np.frombuffer(h.tobytes(), dtype=np.uint8).copy())
         got, overflow = mg.gather_hits_fixed(raw, torch.tensor([n_local], dtype=torch.int64), cap)
+        # the same through a hit_block (counter + hits in the layout the gather sends: no staging copy)
+        blk, cnt_v, hits_v = mg.hit_block(cap, "cpu")
+        cnt_v[0] = n_local
+        hits_v[: min(n_local, cap) * 16] = raw[: min(n_local, cap) * 16]
+        got2, overflow2 = mg.gather_hits_fixed(None, None, cap, block=blk, recv=torch.empty(world * (16 + cap * 16), dtype=torch.uint8))
+        ok = ok and overflow2 == overflow and ((got is None) == (got2 is None)) and (got is None or np.array_equal(got, got2))
         want_overflow = any((9 + r if cap == 8 else (5 + 3 * r if cap == 16 else 0)) > cap for r in range(world))
         ok = ok and (overflow == want_overflow)
         if rank == 0 and not overflow:
