@@ -760,10 +760,12 @@ extern "C" int hg_unpack(hg_ctx *c, const uint8_t *packed, uint64_t row_stride, 
 // ---------------------------------------------------------------------------------------
 static const int32_t HG_TC_MAX_ABS = 8127;  // |x| <= 8127 splits into two s8 limbs (x = 128 h + l)
 
-extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref, uint32_t i0,
-                           const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry, uint32_t j0,
-                           uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path, hg_hit *d_hits,
-                           uint64_t cap, unsigned long long *d_n_hits) {
+// allow_narrow = false: the single-plane path has already been tried (and declined) on these matrices, absmax is
+// max |hv| from its pre-pass
+static int dist_dev_impl(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref, uint32_t i0,
+                         const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry, uint32_t j0,
+                         uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path, hg_hit *d_hits,
+                         uint64_t cap, unsigned long long *d_n_hits, bool allow_narrow, int32_t absmax) {
   if (!c || !d_n_hits) { hg_set_error("hg_dist_dev: NULL argument"); return HG_E_INVALID; }
   if ((n_ref && (!d_ref || !d_ref_norm)) || (n_qry && (!d_qry || !d_qry_norm)) || (cap && !d_hits)) {
     hg_set_error("hg_dist_dev: NULL argument"); return HG_E_INVALID;
@@ -777,11 +779,15 @@ extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref
   int rc;
 
   // ---- choose: 3 = single-plane tensor kernel, 2 = two-limb tensor kernel, 1 = SIMT ----
-  int use = path;
-  int32_t absmax = -1;  // max |hv| once some scan has produced it
+  int use = path;  // absmax: max |hv| once some scan has produced it (-1: not yet)
   if (path == 0 && (uint64_t)n_ref * n_qry < 128ull * 128ull) {
     use = 1;
     snprintf(c->dist_reason, sizeof(c->dist_reason), "SIMT: %u x %u pairs do not fill one 128x128 tensor tile", n_ref, n_qry);
+  } else if (!allow_narrow && (path == 0 || path == 3)) {
+    if (path == 3) { hg_set_error("rows are not narrow (single-plane path declined)"); return HG_E_UNSUPPORTED; }
+    snprintf(c->dist_reason, sizeof(c->dist_reason), "rows are not narrow");
+    hg_set_error("rows are not narrow");
+    use = 0;
   } else if (path == 0 || path == 3) {
     // the narrow path's own pre-pass (one read of both matrices) tells whether the rows fit one s8 plane
     uint64_t outliers = 0;
@@ -848,20 +854,21 @@ extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref
   return rc2;
 }
 
+extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref, uint32_t i0,
+                           const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry, uint32_t j0,
+                           uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path, hg_hit *d_hits,
+                           uint64_t cap, unsigned long long *d_n_hits) {
+  return dist_dev_impl(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th, symmetric, path, d_hits,
+                       cap, d_n_hits, true, -1);
+}
+
 extern "C" int hg_dist_last_path(hg_ctx *c) { return c ? c->dist_path : 0; }
 extern "C" const char *hg_dist_last_reason(hg_ctx *c) { return c ? c->dist_reason : ""; }
 
-// shared tail of the host-pointer dist entries: matrices already on the device
-static int dist_finish(hg_ctx *c, const int16_t *d_ref, const int32_t *d_rn, uint32_t n_ref, const int16_t *d_qry,
-                       const int32_t *d_qn, uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path,
-                       hg_hit *hits, uint64_t cap, uint64_t *n_hits, bool sorted, uint32_t *ani_milli) {
+// shared tail of the host-pointer dist entries: hit count back, output-stage sort if asked, hits back
+static int dist_tail(hg_ctx *c, void *d_hits, void *d_cnt, hg_hit *hits, uint64_t cap, uint64_t *n_hits, bool sorted,
+                     uint32_t *ani_milli) {
   int rc;
-  void *d_hits, *d_cnt;
-  if ((rc = hg_scratch(c, HG_S_PACKED, cap * sizeof(hg_hit) + 256, &d_hits))) return rc;
-  if ((rc = hg_scratch(c, HG_S_COUNTS, 256, &d_cnt))) return rc;
-  rc = hg_dist_dev(c, d_ref, d_rn, n_ref, 0, d_qry, d_qn, n_qry, 0, hv_d, ksize, ani_th, symmetric, path, (hg_hit *)d_hits, cap,
-                   (unsigned long long *)d_cnt);
-  if (rc) return rc;
   unsigned long long cnt = 0;
   HG_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, c->stream));
   HG_CUDA(cudaStreamSynchronize(c->stream));
@@ -881,6 +888,167 @@ static int dist_finish(hg_ctx *c, const int16_t *d_ref, const int32_t *d_rn, uin
     HG_CUDA(cudaStreamSynchronize(c->stream));  // unsorted: append order is unspecified
   }
   return HG_OK;
+}
+
+static int dist_out_buffers(hg_ctx *c, uint64_t cap, void **d_hits, void **d_cnt) {
+  int rc;
+  if ((rc = hg_scratch(c, HG_S_PACKED, cap * sizeof(hg_hit) + 256, d_hits))) return rc;
+  return hg_scratch(c, HG_S_COUNTS, 256, d_cnt);
+}
+
+// matrices already on the device: dist kernel (auto / forced path) + tail
+static int dist_finish(hg_ctx *c, const int16_t *d_ref, const int32_t *d_rn, uint32_t n_ref, const int16_t *d_qry,
+                       const int32_t *d_qn, uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path,
+                       hg_hit *hits, uint64_t cap, uint64_t *n_hits, bool sorted, uint32_t *ani_milli, bool allow_narrow = true,
+                       int32_t absmax = -1) {
+  int rc;
+  void *d_hits, *d_cnt;
+  if ((rc = dist_out_buffers(c, cap, &d_hits, &d_cnt))) return rc;
+  rc = dist_dev_impl(c, d_ref, d_rn, n_ref, 0, d_qry, d_qn, n_qry, 0, hv_d, ksize, ani_th, symmetric, path, (hg_hit *)d_hits, cap,
+                     (unsigned long long *)d_cnt, allow_narrow, absmax);
+  if (rc) return rc;
+  return dist_tail(c, d_hits, d_cnt, hits, cap, n_hits, sorted, ani_milli);
+}
+
+// ---- host matrices streamed in row chunks: H2D of chunk c + 1 under unpack / pre-pass / dist kernel of chunk c ----
+struct HostRows {
+  const uint8_t *base;  // first row on the host
+  uint64_t stride;      // bytes between host rows
+  uint64_t width;       // bytes of a row that travel (int16 rows: 2 hv_d; packed rows: max hv_quant_bits * hv_d / 8)
+  const uint8_t *bits;  // packed rows: hv_quant_bits per row (host); int16 rows: NULL
+  const int32_t *norm;  // host
+  uint32_t n;
+  uint8_t *d_stage;     // packed rows: where they land (width apart); int16 rows: the matrix itself
+  uint8_t *d_bits;      // packed rows
+  int16_t *d_hv;
+  int32_t *d_norm;
+};
+
+static bool dist_stream_eligible(int path, bool same, int symmetric, uint32_t n_ref, uint32_t n_qry, uint32_t hv_d,
+                                 const void *d_a, const void *d_b) {
+  if (const char *e = getenv("HG_DIST_STREAM")) if (atoi(e) == 0) return false;
+  if (path != 0 && path != 3) return false;
+  if ((uint64_t)n_ref * n_qry < 128ull * 128ull && path == 0) return false;  // SIMT territory
+  if (same && !symmetric) return false;  // full n x n of one matrix: both (i, j) and (j, i) - not worth a special walk
+  return hg_narrow_shape_ok(hv_d, d_a, d_b) == HG_OK;
+}
+
+// Single-plane dist with the rows arriving in chunks.  same: ONE matrix, symmetric all-vs-all - chunk c is
+// compared against every row up to its own end (j in the chunk, i < j).  Otherwise the queries go first, whole,
+// and every ref chunk is compared against all of them.  Returns HG_E_UNSUPPORTED (with max |hv|) if the rows turn
+// out not to be narrow: by then both matrices are complete in HBM and the caller runs another kernel on them.
+static int dist_stream(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
+                       hg_hit *d_hits, uint64_t cap, unsigned long long *d_cnt, int32_t *absmax, uint64_t *outliers,
+                       uint32_t *n_chunks_out) {
+  int rc;
+  if (!c->copy_stream) {
+    HG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      HG_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+      HG_CUDA(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  if (!c->ev_chunk[0])
+    for (int i = 0; i < 10; i++) HG_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+  const size_t mq = hg_narrow_meta_bytes(Q.n), mr = same ? 0 : hg_narrow_meta_bytes(R.n);
+  void *p_meta;
+  if ((rc = hg_scratch(c, HG_S_NARROW_META, mq + mr, &p_meta))) return rc;
+  hg_narrow_mat Qm, Rm;
+  if ((rc = hg_narrow_setup(c, Q.d_hv, Q.n, hv_d, HG_S_QRY_LIMBS, p_meta, &Qm))) return rc;
+  if (!same && (rc = hg_narrow_setup(c, R.d_hv, R.n, hv_d, HG_S_REF_LIMBS, (uint8_t *)p_meta + mq, &Rm))) return rc;
+  HG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c->stream));
+  auto small = [&](HostRows &S) -> int {
+    HG_CUDA(cudaMemcpyAsync(S.d_norm, S.norm, (size_t)S.n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (S.bits) HG_CUDA(cudaMemcpyAsync(S.d_bits, S.bits, S.n, cudaMemcpyHostToDevice, c->stream));
+    return HG_OK;
+  };
+  if ((rc = small(R))) return rc;
+  if (!same && (rc = small(Q))) return rc;
+  // the copy stream starts once the compute stream has got here (the buffers may still be in use by an earlier call)
+  HG_CUDA(cudaEventRecord(c->ev_chunk[0], c->stream));
+  HG_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[0], 0));
+  auto stage = [&](HostRows &S, uint32_t a, uint32_t rows, cudaEvent_t ev) -> int {  // copy stream
+    HG_CUDA(cudaMemcpy2DAsync(S.d_stage + (size_t)a * S.width, S.width, S.base + (size_t)a * S.stride, S.stride, S.width, rows,
+                              cudaMemcpyHostToDevice, c->copy_stream));
+    HG_CUDA(cudaEventRecord(ev, c->copy_stream));
+    return HG_OK;
+  };
+  auto ready = [&](HostRows &S, const hg_narrow_mat &M, uint32_t a, uint32_t rows, cudaEvent_t ev) -> int {  // compute stream
+    HG_CUDA(cudaStreamWaitEvent(c->stream, ev, 0));
+    if (S.bits) {
+      int r2 = hg_launch_unpack(c, S.d_stage + (size_t)a * S.width, S.width, S.d_bits + a, rows, hv_d, S.d_hv + (size_t)a * hv_d);
+      if (r2) return r2;
+    }
+    return hg_narrow_prep_rows(c, &M, a, rows);
+  };
+  uint32_t chunk_rows = 0;
+  if (const char *e = getenv("HG_DIST_CHUNK_ROWS")) chunk_rows = (uint32_t)std::max(0, atoi(e));
+  if (chunk_rows == 0) {
+    const uint32_t want = std::min<uint32_t>(8, std::max<uint32_t>(1, R.n / 2048));
+    chunk_rows = (R.n + want - 1) / want;
+  }
+  chunk_rows = std::max<uint32_t>(256, (chunk_rows + 255) & ~255u);
+  if ((uint64_t)chunk_rows * 8 < R.n) chunk_rows = (uint32_t)((((uint64_t)R.n + 7) / 8 + 255) & ~255ull);  // at most 8 chunks
+  // all copies are queued first so that PCIe never waits for the host
+  std::vector<std::pair<uint32_t, uint32_t>> chunks;
+  for (uint32_t a = 0; a < R.n; a += chunk_rows) chunks.push_back({a, std::min(chunk_rows, R.n - a)});
+  if (!same && (rc = stage(Q, 0, Q.n, c->ev_chunk[1]))) return rc;
+  for (size_t k = 0; k < chunks.size(); k++)
+    if ((rc = stage(R, chunks[k].first, chunks[k].second, c->ev_chunk[2 + k]))) return rc;
+  if (!same && (rc = ready(Q, Qm, 0, Q.n, c->ev_chunk[1]))) return rc;
+  for (size_t k = 0; k < chunks.size(); k++) {
+    const uint32_t a = chunks[k].first, rows = chunks[k].second;
+    if ((rc = ready(R, same ? Qm : Rm, a, rows, c->ev_chunk[2 + k]))) return rc;
+    if (same)  // pairs (i, j): j in this chunk, i < j
+      rc = hg_narrow_launch(c, &Qm, 0, a + rows, 0, R.d_norm, &Qm, a, rows, a, R.d_norm + a, ksize, ani_th, 1, d_hits, cap, d_cnt);
+    else
+      rc = hg_narrow_launch(c, &Rm, a, rows, a, R.d_norm + a, &Qm, 0, Q.n, 0, Q.d_norm, ksize, ani_th, symmetric, d_hits, cap, d_cnt);
+    if (rc) return rc;
+  }
+  if (n_chunks_out) *n_chunks_out = (uint32_t)chunks.size();
+  return hg_narrow_verdict(c, &Qm, same ? nullptr : &Rm, absmax, outliers);
+}
+
+// common driver of the host entries: streamed single-plane path if eligible, else (or if it declines) whole
+// copies + the kernel the rows call for
+static int dist_from_host(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
+                          int path, bool try_stream, hg_hit *hits, uint64_t cap, uint64_t *n_hits, bool sorted, uint32_t *ani_milli) {
+  int rc;
+  bool allow_narrow = true;
+  int32_t absmax = -1;
+  if (try_stream && dist_stream_eligible(path, same, symmetric, R.n, Q.n, hv_d, R.d_hv, Q.d_hv)) {
+    void *d_hits, *d_cnt;
+    if ((rc = dist_out_buffers(c, cap, &d_hits, &d_cnt))) return rc;
+    uint64_t outliers = 0;
+    uint32_t n_chunks = 0;
+    rc = dist_stream(c, R, Q, same, hv_d, ksize, ani_th, symmetric, (hg_hit *)d_hits, cap, (unsigned long long *)d_cnt, &absmax,
+                     &outliers, &n_chunks);
+    if (rc == HG_OK) {
+      c->dist_path = 3;
+      c->ev_used &= ~(3 << 4);
+      snprintf(c->dist_reason, sizeof(c->dist_reason),
+               "tensor-narrow%s: rows fit one s8 plane as x = 2a + s (max |hv| = %d, %llu outlier elements corrected per candidate); "
+               "tcgen05 kind::i8, one MMA per K step; %u row chunk(s) overlapping their H2D",
+               path == 3 ? " (forced)" : "", absmax, (unsigned long long)outliers, n_chunks);
+      return dist_tail(c, d_hits, d_cnt, hits, cap, n_hits, sorted, ani_milli);
+    }
+    if (rc != HG_E_UNSUPPORTED || path == 3) return rc;
+    allow_narrow = false;  // both matrices are complete in HBM now: another kernel on the same data
+  } else {
+    auto whole = [&](HostRows &S) -> int {
+      HG_CUDA(cudaMemcpy2DAsync(S.d_stage, S.width, S.base, S.stride, S.width, S.n, cudaMemcpyHostToDevice, c->stream));
+      HG_CUDA(cudaMemcpyAsync(S.d_norm, S.norm, (size_t)S.n * 4, cudaMemcpyHostToDevice, c->stream));
+      if (S.bits) {
+        HG_CUDA(cudaMemcpyAsync(S.d_bits, S.bits, S.n, cudaMemcpyHostToDevice, c->stream));
+        return hg_launch_unpack(c, S.d_stage, S.width, S.d_bits, S.n, hv_d, S.d_hv);
+      }
+      return HG_OK;
+    };
+    if ((rc = whole(R))) return rc;
+    if (!same && (rc = whole(Q))) return rc;
+  }
+  return dist_finish(c, R.d_hv, R.d_norm, R.n, Q.d_hv, Q.d_norm, Q.n, hv_d, ksize, ani_th, symmetric, path, hits, cap, n_hits, sorted,
+                     ani_milli, allow_narrow, absmax);
 }
 
 static int dist_host(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uint32_t n_ref, const int16_t *qry,
@@ -903,14 +1071,9 @@ static int dist_host(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uin
   const size_t rb_al = (rb + 255) & ~(size_t)255;
   int16_t *d_qry = same ? d_ref : (int16_t *)((uint8_t *)d_mat + rb_al);
   int32_t *d_rn = (int32_t *)d_norm, *d_qn = same ? d_rn : d_rn + n_ref;
-  HG_CUDA(cudaMemcpyAsync(d_ref, ref, rb, cudaMemcpyHostToDevice, c->stream));
-  HG_CUDA(cudaMemcpyAsync(d_rn, ref_norm, (size_t)n_ref * 4, cudaMemcpyHostToDevice, c->stream));
-  if (!same) {
-    HG_CUDA(cudaMemcpyAsync(d_qry, qry, qb, cudaMemcpyHostToDevice, c->stream));
-    HG_CUDA(cudaMemcpyAsync(d_qn, qry_norm, (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));
-  }
-  return dist_finish(c, d_ref, d_rn, n_ref, d_qry, d_qn, n_qry, hv_d, ksize, ani_th, symmetric, path, hits, cap, n_hits, sorted,
-                     ani_milli);
+  HostRows R = {(const uint8_t *)ref, (uint64_t)hv_d * 2, (uint64_t)hv_d * 2, nullptr, ref_norm, n_ref, (uint8_t *)d_ref, nullptr, d_ref, d_rn};
+  HostRows Q = {(const uint8_t *)qry, (uint64_t)hv_d * 2, (uint64_t)hv_d * 2, nullptr, qry_norm, n_qry, (uint8_t *)d_qry, nullptr, d_qry, d_qn};
+  return dist_from_host(c, R, same ? R : Q, same, hv_d, ksize, ani_th, symmetric, path, true, hits, cap, n_hits, sorted, ani_milli);
 }
 
 // `dist` straight from what the sketch file holds (FileSketch.hv bit-packed + hv_quant_bits + hv_norm_2,
@@ -955,29 +1118,20 @@ extern "C" int hg_dist_packed(hg_ctx *c, const uint8_t *ref_packed, uint64_t ref
   int32_t *d_rn = (int32_t *)d_small, *d_qn = same ? d_rn : d_rn + n_ref;
   uint8_t *d_rbits = (uint8_t *)d_small + ((size_t)n_ref + n_qry) * 4, *d_qbits = same ? d_rbits : d_rbits + n_ref;
   uint8_t *d_rp = (uint8_t *)d_pk, *d_qp = d_rp + rp;
-  HG_CUDA(cudaMemcpy2DAsync(d_rp, rw, ref_packed, ref_stride, rw, n_ref, cudaMemcpyHostToDevice, c->stream));
-  HG_CUDA(cudaMemcpyAsync(d_rbits, ref_bits, n_ref, cudaMemcpyHostToDevice, c->stream));
-  HG_CUDA(cudaMemcpyAsync(d_rn, ref_norm, (size_t)n_ref * 4, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = hg_launch_unpack(c, d_rp, rw, d_rbits, n_ref, hv_d, d_ref))) return rc;
-  if (!same) {
-    HG_CUDA(cudaMemcpy2DAsync(d_qp, qw, qry_packed, qry_stride, qw, n_qry, cudaMemcpyHostToDevice, c->stream));
-    HG_CUDA(cudaMemcpyAsync(d_qbits, qry_bits, n_qry, cudaMemcpyHostToDevice, c->stream));
-    HG_CUDA(cudaMemcpyAsync(d_qn, qry_norm, (size_t)n_qry * 4, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = hg_launch_unpack(c, d_qp, qw, d_qbits, n_qry, hv_d, d_qry))) return rc;
-  }
+  HostRows R = {ref_packed, ref_stride, rw, ref_bits, ref_norm, n_ref, d_rp, d_rbits, d_ref, d_rn};
+  HostRows Q = {qry_packed, qry_stride, qw, qry_bits, qry_norm, n_qry, d_qp, d_qbits, d_qry, d_qn};
   // b-bit two's-complement values are below 2^(b-1): with b > 10 no row can fit the single s8 plane
   // (x = 2a + s spans 510), and with b <= 13 every element fits the int8 limb split, so that case needs no scan
-  if (path == 0 && std::max(rmax, qmax) > 10 && std::max(rmax, qmax) <= 13 && (uint64_t)n_ref * n_qry >= 128ull * 128ull) {
-    path = 2;
-    rc = dist_finish(c, d_ref, d_rn, n_ref, d_qry, d_qn, n_qry, hv_d, ksize, ani_th, symmetric, path, hits, cap, n_hits, sorted != 0,
-                     ani_milli);
+  const uint32_t bmax = std::max(rmax, qmax);
+  const bool wide = bmax > 10;
+  if (path == 0 && wide && bmax <= 13 && (uint64_t)n_ref * n_qry >= 128ull * 128ull) {
+    rc = dist_from_host(c, R, same ? R : Q, same, hv_d, ksize, ani_th, symmetric, 2, false, hits, cap, n_hits, sorted != 0, ani_milli);
     if (c->dist_path == 2)
-      snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor: hv_quant_bits <= %u fits two s8 limbs; tcgen05 kind::i8",
-               std::max(rmax, qmax));
+      snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor: hv_quant_bits <= %u fits two s8 limbs; tcgen05 kind::i8", bmax);
     return rc;
   }
-  return dist_finish(c, d_ref, d_rn, n_ref, d_qry, d_qn, n_qry, hv_d, ksize, ani_th, symmetric, path, hits, cap, n_hits, sorted != 0,
-                     ani_milli);
+  return dist_from_host(c, R, same ? R : Q, same, hv_d, ksize, ani_th, symmetric, path, !wide, hits, cap, n_hits, sorted != 0,
+                        ani_milli);
 }
 
 extern "C" int hg_dist(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uint32_t n_ref, const int16_t *qry,

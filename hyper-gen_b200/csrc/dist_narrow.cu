@@ -388,7 +388,7 @@ __device__ __forceinline__ uint32_t n1_drain(const hg::DistEpilogue &ep, const N
 template <int NACC>
 __global__ void __launch_bounds__(N1_THREADS, 1)
 dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_qry, uint32_t ref_row_base,
-               hg::DistEpilogue ep, NarrowArgs na) {
+               uint32_t qry_row_base, hg::DistEpilogue ep, NarrowArgs na) {
   using Cfg = N1Cfg<NACC>;
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr uint32_t TILE_ROWS = Cfg::TILE_ROWS;
@@ -450,7 +450,7 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
 #pragma unroll
         for (int a = 0; a < NACC; ++a)  // 128 of my ref rows per accumulator (accumulator a: tile rows 256 a .. 256 a + 255)
           tma_load_2d_pair(st + a * N1_A_BYTES, &tm_ref, fb, k0, (int)(ref_row_base + row0 + 256u * a), on);
-        tma_load_2d_pair(st + NACC * N1_A_BYTES, &tm_qry, fb, k0, (int)colh, on);  // my half of the query rows
+        tma_load_2d_pair(st + NACC * N1_A_BYTES, &tm_qry, fb, k0, (int)(qry_row_base + colh), on);  // my half of the query rows
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
@@ -555,108 +555,113 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
   }
 }
 
-struct PrepBuffers {  // one matrix: plane + constants + entries, carved out of two scratch slots
-  int8_t *plane;
-  PrepOut out;
-  uint32_t h_stats[4];
-};
+void carve(hg_narrow_mat &m, void *plane, void *meta) {
+  uint32_t *w = (uint32_t *)meta;
+  const size_t n = m.n_rows;
+  m.plane = (int8_t *)plane;
+  m.stats = w;  // 4 words: max |x|, max (|s| + 256), entries used, declined
+  m.s = (int32_t *)(w + 4);
+  m.a2 = (int32_t *)(w + 4 + n);
+  m.e = w + 4 + 2 * n;
+  m.out_off = w + 4 + 3 * n;
+  m.out_cnt = w + 4 + 4 * n;
+  m.entries = w + 4 + 5 * n;
+}
 
-size_t meta_bytes(uint32_t n_rows, uint32_t cap) { return ((size_t)n_rows * 5 + cap + 4) * 4 + 256; }
+PrepOut prep_out(const hg_narrow_mat &m, uint32_t row0) {
+  PrepOut o;
+  o.plane = m.plane + (size_t)row0 * m.hv_d;
+  o.s = m.s + row0;
+  o.a2 = m.a2 + row0;
+  o.e = m.e + row0;
+  o.out_off = m.out_off + row0;
+  o.out_cnt = m.out_cnt + row0;
+  o.entries = m.entries;
+  o.cap = m.cap;
+  o.stats = m.stats;
+  return o;
+}
 
-void carve(PrepBuffers &pb, void *plane, void *meta, uint32_t n_rows, uint32_t cap) {
-  pb.plane = (int8_t *)plane;
-  uint32_t *m = (uint32_t *)meta;
-  pb.out.plane = pb.plane;
-  pb.out.stats = m;  // 4 words, zeroed before the launch
-  pb.out.s = (int32_t *)(m + 4);
-  pb.out.a2 = (int32_t *)(m + 4 + (size_t)n_rows);
-  pb.out.e = m + 4 + 2 * (size_t)n_rows;
-  pb.out.out_off = m + 4 + 3 * (size_t)n_rows;
-  pb.out.out_cnt = m + 4 + 4 * (size_t)n_rows;
-  pb.out.entries = m + 4 + 5 * (size_t)n_rows;
-  pb.out.cap = cap;
+uint32_t narrow_budget() {  // outlier entries per row on average (HG_NARROW_BUDGET overrides; tests use it to force the correction path)
+  uint32_t per_row = 4;
+  if (const char *e = getenv("HG_NARROW_BUDGET")) per_row = (uint32_t)std::max(0, atoi(e));
+  return per_row;
 }
 
 }  // namespace
 
-// Returns HG_OK when the narrow kernel was launched; HG_E_UNSUPPORTED when it declines (shape, or the rows need
-// more outlier entries than the budget) — *absmax_out then holds max |hv| if the scan ran, else -1.
-int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref, uint32_t i0,
-                          const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry, uint32_t j0, uint32_t hv_d,
-                          uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
-                          unsigned long long *d_n_hits, int32_t *absmax_out, uint64_t *outliers_out) {
-  if (absmax_out) *absmax_out = -1;
-  if (outliers_out) *outliers_out = 0;
-  if (n_ref == 0 || n_qry == 0) return HG_OK;
+// ---- one matrix in single-plane form; its rows may be prepared piecewise, as they arrive ------
+int hg_narrow_shape_ok(uint32_t hv_d, const void *d_a, const void *d_b) {
   if (hv_d % TC_BK != 0 || hv_d > 32768) {
     hg_set_error("narrow tensor path needs hv_d %% 128 == 0 and hv_d <= 32768, got %u", hv_d);
     return HG_E_UNSUPPORTED;
   }
-  if (((uintptr_t)d_ref | (uintptr_t)d_qry) & 15) {
+  if (((uintptr_t)d_a | (uintptr_t)d_b) & 15) {
     hg_set_error("narrow tensor path needs 16-byte aligned HV matrices");
     return HG_E_UNSUPPORTED;
   }
+  return HG_OK;
+}
+
+size_t hg_narrow_meta_bytes(uint32_t n_rows) {
+  return ((((size_t)n_rows * 5 + ((size_t)n_rows * narrow_budget() + 1024) + 4) * 4 + 256) + 255) & ~(size_t)255;
+}
+
+// plane in scratch slot `plane_slot`, constants at `meta` (hg_narrow_meta_bytes); the statistics are zeroed on the stream
+int hg_narrow_setup(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d, int plane_slot, void *meta,
+                    hg_narrow_mat *m) {
+  const uint64_t cap64 = (uint64_t)n_rows * narrow_budget() + 1024;
+  if (cap64 > 0x7FFFFFFFull) { hg_set_error("narrow tensor path: outlier budget too large"); return HG_E_UNSUPPORTED; }
+  void *plane;
   int rc;
-  const uint64_t ref_elems = (uint64_t)n_ref * hv_d, qry_elems = (uint64_t)n_qry * hv_d;
-  // the query block may alias the ref block (all-vs-all) or contain it (row shard of the same matrix)
-  const bool qry_covers_ref = d_ref >= d_qry && d_ref + ref_elems <= d_qry + qry_elems && ((d_ref - d_qry) % hv_d) == 0;
-  // outlier budget: entries per row on average (HG_NARROW_BUDGET overrides; tests use it to force the correction path)
-  uint32_t per_row = 4;
-  if (const char *e = getenv("HG_NARROW_BUDGET")) per_row = (uint32_t)std::max(0, atoi(e));
-  const uint64_t cap_q64 = (uint64_t)n_qry * per_row + 1024, cap_r64 = (uint64_t)n_ref * per_row + 1024;
-  if (cap_q64 > 0x7FFFFFFFull || cap_r64 > 0x7FFFFFFFull) { hg_set_error("narrow tensor path: outlier budget too large"); return HG_E_UNSUPPORTED; }
-  const uint32_t cap_q = (uint32_t)cap_q64, cap_r = (uint32_t)cap_r64;
-
-  PrepBuffers pq, pr;
-  void *p_plane_q, *p_plane_r = nullptr, *p_meta;
-  const size_t mq = (meta_bytes(n_qry, cap_q) + 255) & ~(size_t)255, mr = qry_covers_ref ? 0 : meta_bytes(n_ref, cap_r);
-  if ((rc = hg_scratch(ctx, HG_S_QRY_LIMBS, qry_elems + 1024, &p_plane_q))) return rc;
-  if (!qry_covers_ref && (rc = hg_scratch(ctx, HG_S_REF_LIMBS, ref_elems + 1024, &p_plane_r))) return rc;
-  if ((rc = hg_scratch(ctx, HG_S_NARROW_META, mq + mr, &p_meta))) return rc;
-  carve(pq, p_plane_q, p_meta, n_qry, cap_q);
-  if (!qry_covers_ref) carve(pr, p_plane_r, (uint8_t *)p_meta + mq, n_ref, cap_r);
-
+  if ((rc = hg_scratch(ctx, plane_slot, (uint64_t)n_rows * hv_d + 1024, &plane))) return rc;
+  m->hv = d_hv;
+  m->n_rows = n_rows;
+  m->hv_d = hv_d;
+  m->cap = (uint32_t)cap64;
+  carve(*m, plane, meta);
+  HG_CUDA(cudaMemsetAsync(m->stats, 0, 16, ctx->stream));
   if (!ctx->n1_attr_set) {
     HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
     HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
     ctx->n1_attr_set = 1;
   }
-  // ---- GPU work starts here ----
-  HG_PROF(ctx, 4);
-  auto prep = [&](const int16_t *src, uint32_t rows, PrepBuffers &pb) -> int {
-    HG_CUDA(cudaMemsetAsync(pb.out.stats, 0, 16, ctx->stream));
-    const uint32_t blocks = (rows + PREP_THREADS / 32 - 1) / (PREP_THREADS / 32);
-    narrow_prep_kernel<<<blocks, PREP_THREADS, 0, ctx->stream>>>(src, rows, hv_d, pb.out);
-    ctx->launches++;
-    return HG_OK;
-  };
-  if ((rc = prep(d_qry, n_qry, pq))) return rc;
-  if (!qry_covers_ref && (rc = prep(d_ref, n_ref, pr))) return rc;
-  HG_CUDA(cudaGetLastError());
+  return HG_OK;
+}
 
+// pre-pass over rows [row0, row0 + rows) of the matrix (asynchronous)
+int hg_narrow_prep_rows(hg_ctx *ctx, const hg_narrow_mat *m, uint32_t row0, uint32_t rows) {
+  if (rows == 0) return HG_OK;
+  const uint32_t blocks = (rows + PREP_THREADS / 32 - 1) / (PREP_THREADS / 32);
+  narrow_prep_kernel<<<blocks, PREP_THREADS, 0, ctx->stream>>>(m->hv + (size_t)row0 * m->hv_d, rows, m->hv_d, prep_out(*m, row0));
+  ctx->launches++;
+  HG_CUDA(cudaGetLastError());
+  return HG_OK;
+}
+
+// rows [r0, r0 + n_ref) of R against rows [q0, q0 + n_qry) of Q (both prepared); norms point at the windows' first rows.
+// Asynchronous; the kernel does nothing if a pre-pass so far has declined (hg_narrow_verdict tells the host).
+int hg_narrow_launch(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
+                     const hg_narrow_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm,
+                     uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
+                     unsigned long long *d_n_hits) {
+  if (n_ref == 0 || n_qry == 0) return HG_OK;
+  int rc;
+  const uint32_t hv_d = R->hv_d;
   CUtensorMap tm_ref, tm_qry;
-  if ((rc = make_plane_map(&tm_qry, pq.plane, n_qry, hv_d, 128))) return rc;
-  uint32_t ref_row_off = 0;
+  if ((rc = make_plane_map(&tm_qry, Q->plane, Q->n_rows, hv_d, 128))) return rc;
+  if (R == Q || R->plane == Q->plane) tm_ref = tm_qry;
+  else if ((rc = make_plane_map(&tm_ref, R->plane, R->n_rows, hv_d, 128))) return rc;
   NarrowArgs na;
-  na.q = {pq.out.s, pq.out.a2, pq.out.e, pq.out.out_off, pq.out.out_cnt};
-  na.q_out = pq.out.entries;
-  na.q_hv = d_qry;
+  na.r = {R->s + r0, R->a2 + r0, R->e + r0, R->out_off + r0, R->out_cnt + r0};
+  na.q = {Q->s + q0, Q->a2 + q0, Q->e + q0, Q->out_off + q0, Q->out_cnt + q0};
+  na.r_out = R->entries;
+  na.q_out = Q->entries;
+  na.r_plane = R->plane + (size_t)r0 * hv_d;
+  na.q_hv = Q->hv + (size_t)q0 * hv_d;
   na.hv_d = hv_d;
-  na.q_stats = pq.out.stats;
-  na.r_stats = qry_covers_ref ? pq.out.stats : pr.out.stats;
-  if (qry_covers_ref) {  // the ref rows are a window of the query plane
-    ref_row_off = (uint32_t)((d_ref - d_qry) / hv_d);
-    tm_ref = tm_qry;
-    na.r = {pq.out.s + ref_row_off, pq.out.a2 + ref_row_off, pq.out.e + ref_row_off, pq.out.out_off + ref_row_off,
-            pq.out.out_cnt + ref_row_off};
-    na.r_out = pq.out.entries;
-    na.r_plane = pq.plane + (size_t)ref_row_off * hv_d;
-  } else {
-    if ((rc = make_plane_map(&tm_ref, pr.plane, n_ref, hv_d, 128))) return rc;
-    na.r = {pr.out.s, pr.out.a2, pr.out.e, pr.out.out_off, pr.out.out_cnt};
-    na.r_out = pr.out.entries;
-    na.r_plane = pr.plane;
-  }
+  na.q_stats = Q->stats;
+  na.r_stats = R->stats;
 
   hg::DistEpilogue ep;
   ep.ref_norm = d_ref_norm;
@@ -694,22 +699,60 @@ int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_re
   const uint32_t n_pairs = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)std::max(ctx->sm_count / 2, 1));
   cfg.gridDim = dim3(2 * n_pairs, 1, 1);
   cfg.dynamicSmemBytes = N1_SMEM_BYTES;
-  if (nacc == 2) HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<2>, tm_ref, tm_qry, ref_row_off, ep, na));
-  else HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<1>, tm_ref, tm_qry, ref_row_off, ep, na));
+  if (nacc == 2) HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<2>, tm_ref, tm_qry, r0, q0, ep, na));
+  else HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<1>, tm_ref, tm_qry, r0, q0, ep, na));
   ctx->launches++;
-  HG_PROF(ctx, 5);
   HG_CUDA(cudaGetLastError());
-  // The kernel itself honours the pre-pass's verdict (it does nothing when the rows are not narrow), so the
-  // host learns it only now, with no bubble between pre-pass and kernel.
-  HG_CUDA(cudaMemcpyAsync(pq.h_stats, pq.out.stats, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  if (!qry_covers_ref) HG_CUDA(cudaMemcpyAsync(pr.h_stats, pr.out.stats, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  return HG_OK;
+}
+
+// Reads the pre-pass statistics (synchronises the stream): HG_OK if every row prepared so far fits the single
+// plane within the budget, else HG_E_UNSUPPORTED (then the kernels launched so far have done nothing useful and
+// the caller must discard their hits).  B may be NULL or equal to A.
+int hg_narrow_verdict(hg_ctx *ctx, const hg_narrow_mat *A, const hg_narrow_mat *B, int32_t *absmax_out, uint64_t *outliers_out) {
+  uint32_t sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+  HG_CUDA(cudaMemcpyAsync(sa, A->stats, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  if (B && B != A && B->stats != A->stats) HG_CUDA(cudaMemcpyAsync(sb, B->stats, 16, cudaMemcpyDeviceToHost, ctx->stream));
   HG_CUDA(cudaStreamSynchronize(ctx->stream));
-  const uint32_t *sq = pq.h_stats, *sr = qry_covers_ref ? pq.h_stats : pr.h_stats;
-  if (absmax_out) *absmax_out = (int32_t)std::max(sq[0], sr[0]);
-  if (outliers_out) *outliers_out = (uint64_t)sq[2] + (qry_covers_ref ? 0 : sr[2]);
-  if (sq[3] || sr[3]) {
-    hg_set_error("rows are not narrow: more than %u outlier entries per row on average (x = 2a + s, a in s8)", per_row);
+  if (absmax_out) *absmax_out = (int32_t)std::max(sa[0], sb[0]);
+  if (outliers_out) *outliers_out = (uint64_t)sa[2] + sb[2];
+  if (sa[3] || sb[3]) {
+    hg_set_error("rows are not narrow: more than %u outlier entries per row on average (x = 2a + s, a in s8)", narrow_budget());
     return HG_E_UNSUPPORTED;
   }
   return HG_OK;
+}
+
+// One-shot form: both matrices already in HBM.  Returns HG_OK when the narrow kernel ran; HG_E_UNSUPPORTED when it
+// declines (shape, or the rows need more outlier entries than the budget) — *absmax_out then holds max |hv| if the
+// scan ran, else -1.
+int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref, uint32_t i0,
+                          const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry, uint32_t j0, uint32_t hv_d,
+                          uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
+                          unsigned long long *d_n_hits, int32_t *absmax_out, uint64_t *outliers_out) {
+  if (absmax_out) *absmax_out = -1;
+  if (outliers_out) *outliers_out = 0;
+  if (n_ref == 0 || n_qry == 0) return HG_OK;
+  int rc;
+  if ((rc = hg_narrow_shape_ok(hv_d, d_ref, d_qry))) return rc;
+  const uint64_t ref_elems = (uint64_t)n_ref * hv_d, qry_elems = (uint64_t)n_qry * hv_d;
+  // the query block may alias the ref block (all-vs-all) or contain it (row shard of the same matrix)
+  const bool qry_covers_ref = d_ref >= d_qry && d_ref + ref_elems <= d_qry + qry_elems && ((d_ref - d_qry) % hv_d) == 0;
+  const size_t mq = hg_narrow_meta_bytes(n_qry), mr = qry_covers_ref ? 0 : hg_narrow_meta_bytes(n_ref);
+  void *p_meta;
+  if ((rc = hg_scratch(ctx, HG_S_NARROW_META, mq + mr, &p_meta))) return rc;
+  hg_narrow_mat Q, R;
+  if ((rc = hg_narrow_setup(ctx, d_qry, n_qry, hv_d, HG_S_QRY_LIMBS, p_meta, &Q))) return rc;
+  if (!qry_covers_ref && (rc = hg_narrow_setup(ctx, d_ref, n_ref, hv_d, HG_S_REF_LIMBS, (uint8_t *)p_meta + mq, &R))) return rc;
+  HG_PROF(ctx, 4);
+  if ((rc = hg_narrow_prep_rows(ctx, &Q, 0, n_qry))) return rc;
+  if (!qry_covers_ref && (rc = hg_narrow_prep_rows(ctx, &R, 0, n_ref))) return rc;
+  const uint32_t ref_row_off = qry_covers_ref ? (uint32_t)((d_ref - d_qry) / hv_d) : 0u;
+  if ((rc = hg_narrow_launch(ctx, qry_covers_ref ? &Q : &R, ref_row_off, n_ref, i0, d_ref_norm, &Q, 0, n_qry, j0, d_qry_norm, ksize,
+                             ani_th, symmetric, d_hits, cap, d_n_hits)))
+    return rc;
+  HG_PROF(ctx, 5);
+  // The kernel itself honours the pre-pass's verdict (it does nothing when the rows are not narrow), so the
+  // host learns it only now, with no bubble between pre-pass and kernel.
+  return hg_narrow_verdict(ctx, &Q, qry_covers_ref ? nullptr : &R, absmax_out, outliers_out);
 }

@@ -149,6 +149,7 @@ struct hg_ctx {
   const uint64_t *d_actual_len;  // optional per-genome true lengths for the next k-mer launch (raw-FASTA path)
   cudaStream_t copy_stream;
   cudaEvent_t ev_copied[2], ev_done[2];
+  cudaEvent_t ev_chunk[10];  // dist streaming: fork + one per row chunk (created with the copy stream)
 };
 
 // stage boundaries: 0 start, 1 after staging/memsets, 2 after k-mer hash, 3 after encode,
@@ -222,7 +223,26 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
                       uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
                       uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
                       hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits);
-// single s8 plane (x = 2a + s) + sparse outlier corrections; HG_E_UNSUPPORTED when the rows are not narrow
+// single s8 plane (x = 2a + s) + sparse outlier corrections (dist_narrow.cu): one matrix in that form, prepared
+// piecewise (rows as they arrive over PCIe) or at once
+struct hg_narrow_mat {
+  const int16_t *hv;  // the i16 matrix in HBM (n_rows x hv_d); rows need to be there only when they are prepared
+  int8_t *plane;
+  int32_t *s, *a2;
+  uint32_t *e, *out_off, *out_cnt, *entries, *stats;
+  uint32_t cap, n_rows, hv_d;
+};
+int hg_narrow_shape_ok(uint32_t hv_d, const void *d_a, const void *d_b);
+size_t hg_narrow_meta_bytes(uint32_t n_rows);
+int hg_narrow_setup(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d, int plane_slot, void *meta,
+                    hg_narrow_mat *m);
+int hg_narrow_prep_rows(hg_ctx *ctx, const hg_narrow_mat *m, uint32_t row0, uint32_t rows);
+int hg_narrow_launch(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
+                     const hg_narrow_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm,
+                     uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
+                     unsigned long long *d_n_hits);
+int hg_narrow_verdict(hg_ctx *ctx, const hg_narrow_mat *A, const hg_narrow_mat *B, int32_t *absmax_out, uint64_t *outliers_out);
+// one-shot form of the above; HG_E_UNSUPPORTED when the rows are not narrow
 int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref,
                           uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
                           uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,

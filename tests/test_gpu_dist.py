@@ -278,8 +278,13 @@ def test_narrow_short_and_mid_k(ctx, hg, oracle, hv_d):
     assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32))
 
 
-def test_narrow_random_sweep(ctx, hg, oracle):
-    """random shapes, thresholds, symmetric or not, outliers sprinkled on both sides: auto path == oracle"""
+@pytest.mark.parametrize("chunk_rows", [0, 256])
+def test_narrow_random_sweep(ctx, hg, oracle, chunk_rows, monkeypatch):
+    """random shapes, thresholds, symmetric or not, outliers sprinkled on both sides: auto path == oracle.
+    chunk_rows = 256: the host entry streams the rows in 256-row chunks (H2D of one chunk under the kernels of the
+    previous one), i.e. several partial launches appending to one hit list; 0: its default chunking"""
+    if chunk_rows:
+        monkeypatch.setenv("HG_DIST_CHUNK_ROWS", str(chunk_rows))
     rng = np.random.default_rng(2026)
     for trial in range(8):
         D = int(rng.choice([256, 512, 1024, 2048]))
@@ -308,3 +313,21 @@ def test_narrow_random_sweep(ctx, hg, oracle):
         assert np.array_equal(np.sort(idx), want), (trial, D, R, Q, sym, th)
         assert np.array_equal(hits["dot"], dot[idx]), trial
         assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32)), trial
+
+
+def test_streamed_dist_declines_midway_and_falls_back(ctx, hg, oracle, monkeypatch):
+    """narrow rows first, wide rows in the last chunk: the chunks already computed are discarded and the two-limb
+    kernel runs on the matrices that are complete in HBM by then"""
+    monkeypatch.setenv("HG_DIST_CHUNK_ROWS", "256")
+    rng = np.random.default_rng(77)
+    D = 512
+    hv = _narrow_rows(rng, 700, D)
+    hv[600:] = (2 * rng.binomial(40000, 0.5, (100, D)) - 40000).astype(np.int16)
+    norm = _norms(oracle, hv)
+    ani, dot = oracle.dist_all(hv, norm, hv, norm, symmetric=True)
+    hits = ctx.dist(hv, norm, hv, norm, ani_th=0.0, symmetric=True, path=0, cap=ani.size + 16)
+    assert ctx.dist_last_path == 2, ctx.dist_last_reason
+    idx = _as_pairs(hits, 700, 700, True)
+    assert np.array_equal(np.sort(idx), np.arange(ani.size))
+    assert np.array_equal(hits["dot"], dot[idx])
+    assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32))

@@ -143,3 +143,31 @@ def test_dist_packed_equals_unpack_then_dist(ctx, hg, oracle):
             assert ctx.dist_last_path == 3 and "narrow" in ctx.dist_last_reason, ctx.dist_last_reason
         else:     # 140 x 70 pairs do not fill one 128 x 128 tile: exact SIMT path
             assert ctx.dist_last_path == 1
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_dist_packed_streamed_in_chunks(ctx, hg, oracle, sym, monkeypatch):
+    """hg_dist_packed with the packed rows arriving in several chunks (copy stream) while the earlier chunks are
+    unpacked, pre-passed and compared: same sorted output as the oracle"""
+    from hypergen_b200 import synth, dist as hdist
+    monkeypatch.setenv("HG_DIST_CHUNK_ROWS", "256")
+    D = 1024
+    seq, off = synth.family_batch(600, 30_000, first=900)
+    sk = oracle.sketch_batch(seq.numpy(), off, scaled=100, hv_d=D)
+    hv, norm, bits, packed = sk["hv"], sk["norm2"], sk["quant_bits"], sk["packed"]
+    if sym:
+        args = (packed, bits, norm, packed, bits, norm)
+        qh, qn = hv, norm
+    else:
+        q = np.arange(37, 337)
+        args = (packed, bits, norm, packed[q].copy(), bits[q].copy(), norm[q].copy())
+        qh, qn = hv[q], norm[q]
+    ani, dot = oracle.dist_all(hv, norm, qh, qn, symmetric=sym)
+    for th in (90.0, 0.0):
+        hits, milli = ctx.dist_packed(*args, D, ani_th=th, symmetric=sym, cap=ani.size + 16)
+        assert ctx.dist_last_path == 3 and "chunk" in ctx.dist_last_reason, ctx.dist_last_reason
+        want = oracle.ani_output_order(ani, th)
+        idx = hdist.pair_index(hits["i"].astype(np.int64), hits["j"].astype(np.int64), qh.shape[0], sym)
+        assert np.array_equal(idx, want), (sym, th)
+        assert np.array_equal(hits["ani"].view(np.uint32), ani[want].view(np.uint32))
+        assert np.array_equal(hits["dot"], dot[want])
