@@ -984,7 +984,7 @@ static int dist_stream(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32_t 
   uint32_t chunk_rows = 0;
   if (const char *e = getenv("HG_DIST_CHUNK_ROWS")) chunk_rows = (uint32_t)std::max(0, atoi(e));
   if (chunk_rows == 0) {
-    const uint32_t want = std::min<uint32_t>(8, std::max<uint32_t>(1, R.n / 2048));
+    const uint32_t want = std::min<uint32_t>(8, std::max<uint32_t>(1, R.n / 1280));  // measured on config 3: 6-8 chunks beat 2-4
     chunk_rows = (R.n + want - 1) / want;
   }
   chunk_rows = std::max<uint32_t>(256, (chunk_rows + 255) & ~255u);

@@ -135,7 +135,7 @@ struct hg_ctx {
   size_t h_pinned_bytes[4];
   // last dist decision
   int dist_path;
-  char dist_reason[160];
+  char dist_reason[288];
   // status words of the last sketch batch (device + host copy)
   uint32_t *d_status;  // [0] table overflow, [1] quant range overflow
   uint32_t h_status[4];
