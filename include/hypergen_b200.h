@@ -174,7 +174,9 @@ HG_API int hg_unpack_dev(hg_ctx *ctx, const uint8_t *d_packed, uint64_t row_stri
  *             bits, else SIMT; fewer than 128 x 128 pairs go to SIMT directly,
  *         1 = force SIMT (CUDA-core) path, 2 = force the two-limb tensor path,
  *         3 = force the single-plane tensor path (HG_E_UNSUPPORTED if the rows are not narrow).
- *   Every path is exact: identical i32 dots and f32 ANI bits. */
+ *   Every path is exact: identical i32 dots and f32 ANI bits.
+ *   The host-pointer entries (hg_dist, hg_dist_sorted, hg_dist_packed) with path 0 or 3 stream the rows
+ *   in chunks: the H2D copy of one chunk runs under the unpack / pre-pass / kernel of the previous ones. */
 HG_API int hg_dist(hg_ctx *ctx, const int16_t *ref_hv, const int32_t *ref_norm2, uint32_t n_ref,
                    const int16_t *qry_hv, const int32_t *qry_norm2, uint32_t n_qry, uint32_t hv_d,
                    uint32_t ksize, float ani_th, int symmetric, int path, hg_hit *hits, uint64_t cap,
