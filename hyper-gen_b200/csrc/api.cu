@@ -926,19 +926,20 @@ struct HostRows {
 
 static bool dist_stream_eligible(int path, bool same, int symmetric, uint32_t n_ref, uint32_t n_qry, uint32_t hv_d,
                                  const void *d_a, const void *d_b) {
-  if (const char *e = getenv("HG_DIST_STREAM")) if (atoi(e) == 0) return false;
   if (path != 0 && path != 3) return false;
   if ((uint64_t)n_ref * n_qry < 128ull * 128ull && path == 0) return false;  // SIMT territory
   if (same && !symmetric) return false;  // full n x n of one matrix: both (i, j) and (j, i) - not worth a special walk
   return hg_narrow_shape_ok(hv_d, d_a, d_b) == HG_OK;
 }
 
-// Single-plane dist with the rows arriving in chunks.  same: ONE matrix, symmetric all-vs-all - chunk c is
-// compared against every row up to its own end (j in the chunk, i < j).  Otherwise the queries go first, whole,
-// and every ref chunk is compared against all of them.  Returns HG_E_UNSUPPORTED (with max |hv|) if the rows turn
-// out not to be narrow: by then both matrices are complete in HBM and the caller runs another kernel on them.
+// Dist with the rows arriving in chunks.  same: ONE matrix, symmetric all-vs-all - chunk c is compared against
+// every row up to its own end (j in the chunk, i < j).  Otherwise the queries go first, whole, and every ref chunk
+// is compared against all of them.
+//   narrow = true: single-plane kernel; returns HG_E_UNSUPPORTED (with max |hv|) if the rows turn out not to be
+//     narrow: by then both matrices are complete in HBM and the caller runs another kernel on them.
+//   narrow = false: two-limb kernel (the caller knows every |hv| fits 13 bits: packed rows of <= 13 bits).
 static int dist_stream(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
-                       hg_hit *d_hits, uint64_t cap, unsigned long long *d_cnt, int32_t *absmax, uint64_t *outliers,
+                       bool narrow, hg_hit *d_hits, uint64_t cap, unsigned long long *d_cnt, int32_t *absmax, uint64_t *outliers,
                        uint32_t *n_chunks_out) {
   int rc;
   if (!c->copy_stream) {
@@ -950,12 +951,18 @@ static int dist_stream(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32_t 
   }
   if (!c->ev_chunk[0])
     for (int i = 0; i < 10; i++) HG_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
-  const size_t mq = hg_narrow_meta_bytes(Q.n), mr = same ? 0 : hg_narrow_meta_bytes(R.n);
-  void *p_meta;
-  if ((rc = hg_scratch(c, HG_S_NARROW_META, mq + mr, &p_meta))) return rc;
   hg_narrow_mat Qm, Rm;
-  if ((rc = hg_narrow_setup(c, Q.d_hv, Q.n, hv_d, HG_S_QRY_LIMBS, p_meta, &Qm))) return rc;
-  if (!same && (rc = hg_narrow_setup(c, R.d_hv, R.n, hv_d, HG_S_REF_LIMBS, (uint8_t *)p_meta + mq, &Rm))) return rc;
+  if (narrow) {
+    const size_t mq = hg_narrow_meta_bytes(Q.n), mr = same ? 0 : hg_narrow_meta_bytes(R.n);
+    void *p_meta;
+    if ((rc = hg_scratch(c, HG_S_NARROW_META, mq + mr, &p_meta))) return rc;
+    if ((rc = hg_narrow_setup(c, Q.d_hv, Q.n, hv_d, HG_S_QRY_LIMBS, p_meta, &Qm))) return rc;
+    if (!same && (rc = hg_narrow_setup(c, R.d_hv, R.n, hv_d, HG_S_REF_LIMBS, (uint8_t *)p_meta + mq, &Rm))) return rc;
+  } else {  // the limb planes of the largest launch, so that no launch has to grow them mid-pipeline
+    void *p;
+    if ((rc = hg_scratch(c, HG_S_QRY_LIMBS, 2 * (size_t)Q.n * hv_d + 1024, &p))) return rc;
+    if ((rc = hg_scratch(c, HG_S_REF_LIMBS, 2 * (size_t)R.n * hv_d + 1024, &p))) return rc;
+  }
   HG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c->stream));
   auto small = [&](HostRows &S) -> int {
     HG_CUDA(cudaMemcpyAsync(S.d_norm, S.norm, (size_t)S.n * 4, cudaMemcpyHostToDevice, c->stream));
@@ -973,13 +980,13 @@ static int dist_stream(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32_t 
     HG_CUDA(cudaEventRecord(ev, c->copy_stream));
     return HG_OK;
   };
-  auto ready = [&](HostRows &S, const hg_narrow_mat &M, uint32_t a, uint32_t rows, cudaEvent_t ev) -> int {  // compute stream
+  auto ready = [&](HostRows &S, const hg_narrow_mat *M, uint32_t a, uint32_t rows, cudaEvent_t ev) -> int {  // compute stream
     HG_CUDA(cudaStreamWaitEvent(c->stream, ev, 0));
     if (S.bits) {
       int r2 = hg_launch_unpack(c, S.d_stage + (size_t)a * S.width, S.width, S.d_bits + a, rows, hv_d, S.d_hv + (size_t)a * hv_d);
       if (r2) return r2;
     }
-    return hg_narrow_prep_rows(c, &M, a, rows);
+    return M ? hg_narrow_prep_rows(c, M, a, rows) : HG_OK;
   };
   uint32_t chunk_rows = 0;
   if (const char *e = getenv("HG_DIST_CHUNK_ROWS")) chunk_rows = (uint32_t)std::max(0, atoi(e));
@@ -995,33 +1002,47 @@ static int dist_stream(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32_t 
   if (!same && (rc = stage(Q, 0, Q.n, c->ev_chunk[1]))) return rc;
   for (size_t k = 0; k < chunks.size(); k++)
     if ((rc = stage(R, chunks[k].first, chunks[k].second, c->ev_chunk[2 + k]))) return rc;
-  if (!same && (rc = ready(Q, Qm, 0, Q.n, c->ev_chunk[1]))) return rc;
+  if (!same && (rc = ready(Q, narrow ? &Qm : nullptr, 0, Q.n, c->ev_chunk[1]))) return rc;
   for (size_t k = 0; k < chunks.size(); k++) {
     const uint32_t a = chunks[k].first, rows = chunks[k].second;
-    if ((rc = ready(R, same ? Qm : Rm, a, rows, c->ev_chunk[2 + k]))) return rc;
-    if (same)  // pairs (i, j): j in this chunk, i < j
-      rc = hg_narrow_launch(c, &Qm, 0, a + rows, 0, R.d_norm, &Qm, a, rows, a, R.d_norm + a, ksize, ani_th, 1, d_hits, cap, d_cnt);
-    else
-      rc = hg_narrow_launch(c, &Rm, a, rows, a, R.d_norm + a, &Qm, 0, Q.n, 0, Q.d_norm, ksize, ani_th, symmetric, d_hits, cap, d_cnt);
+    if ((rc = ready(R, narrow ? (same ? &Qm : &Rm) : nullptr, a, rows, c->ev_chunk[2 + k]))) return rc;
+    if (narrow) {
+      if (same)  // pairs (i, j): j in this chunk, i < j
+        rc = hg_narrow_launch(c, &Qm, 0, a + rows, 0, R.d_norm, &Qm, a, rows, a, R.d_norm + a, ksize, ani_th, 1, d_hits, cap, d_cnt);
+      else
+        rc = hg_narrow_launch(c, &Rm, a, rows, a, R.d_norm + a, &Qm, 0, Q.n, 0, Q.d_norm, ksize, ani_th, symmetric, d_hits, cap, d_cnt);
+    } else if (same) {  // the same pairs as two launches: the rows before the chunk against it, and the chunk against itself
+      const int16_t *ch = R.d_hv + (size_t)a * hv_d;
+      rc = a ? hg_launch_dist_tc(c, R.d_hv, R.d_norm, a, 0, ch, R.d_norm + a, rows, a, hv_d, ksize, ani_th, 0, d_hits, cap, d_cnt) : HG_OK;
+      if (!rc) rc = hg_launch_dist_tc(c, ch, R.d_norm + a, rows, a, ch, R.d_norm + a, rows, a, hv_d, ksize, ani_th, 1, d_hits, cap, d_cnt);
+    } else {
+      rc = hg_launch_dist_tc(c, R.d_hv + (size_t)a * hv_d, R.d_norm + a, rows, a, Q.d_hv, Q.d_norm, Q.n, 0, hv_d, ksize, ani_th, symmetric,
+                             d_hits, cap, d_cnt);
+    }
     if (rc) return rc;
   }
   if (n_chunks_out) *n_chunks_out = (uint32_t)chunks.size();
+  if (!narrow) return HG_OK;
   return hg_narrow_verdict(c, &Qm, same ? nullptr : &Rm, absmax, outliers);
 }
 
 // common driver of the host entries: streamed single-plane path if eligible, else (or if it declines) whole
 // copies + the kernel the rows call for
 static int dist_from_host(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
-                          int path, bool try_stream, hg_hit *hits, uint64_t cap, uint64_t *n_hits, bool sorted, uint32_t *ani_milli) {
+                          int path, int stream_mode /*0 no, 1 single-plane, 2 two-limb*/, hg_hit *hits, uint64_t cap,
+                          uint64_t *n_hits, bool sorted, uint32_t *ani_milli) {
   int rc;
   bool allow_narrow = true;
   int32_t absmax = -1;
-  if (try_stream && dist_stream_eligible(path, same, symmetric, R.n, Q.n, hv_d, R.d_hv, Q.d_hv)) {
+  const bool shape_ok = !(same && !symmetric) && hg_narrow_shape_ok(hv_d, R.d_hv, Q.d_hv) == HG_OK;
+  bool stream_on = true;
+  if (const char *e = getenv("HG_DIST_STREAM")) stream_on = atoi(e) != 0;
+  if (stream_on && stream_mode == 1 && dist_stream_eligible(path, same, symmetric, R.n, Q.n, hv_d, R.d_hv, Q.d_hv)) {
     void *d_hits, *d_cnt;
     if ((rc = dist_out_buffers(c, cap, &d_hits, &d_cnt))) return rc;
     uint64_t outliers = 0;
     uint32_t n_chunks = 0;
-    rc = dist_stream(c, R, Q, same, hv_d, ksize, ani_th, symmetric, (hg_hit *)d_hits, cap, (unsigned long long *)d_cnt, &absmax,
+    rc = dist_stream(c, R, Q, same, hv_d, ksize, ani_th, symmetric, true, (hg_hit *)d_hits, cap, (unsigned long long *)d_cnt, &absmax,
                      &outliers, &n_chunks);
     if (rc == HG_OK) {
       c->dist_path = 3;
@@ -1034,6 +1055,18 @@ static int dist_from_host(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32
     }
     if (rc != HG_E_UNSUPPORTED || path == 3) return rc;
     allow_narrow = false;  // both matrices are complete in HBM now: another kernel on the same data
+  } else if (stream_on && stream_mode == 2 && shape_ok && hv_d % 512 == 0 && (uint64_t)R.n * Q.n >= 128ull * 128ull) {
+    void *d_hits, *d_cnt;
+    if ((rc = dist_out_buffers(c, cap, &d_hits, &d_cnt))) return rc;
+    uint32_t n_chunks = 0;
+    rc = dist_stream(c, R, Q, same, hv_d, ksize, ani_th, symmetric, false, (hg_hit *)d_hits, cap, (unsigned long long *)d_cnt, nullptr,
+                     nullptr, &n_chunks);
+    if (rc) return rc;
+    c->dist_path = 2;
+    c->ev_used &= ~(3 << 4);
+    snprintf(c->dist_reason, sizeof(c->dist_reason),
+             "tensor: hv_quant_bits fit two s8 limbs; tcgen05 kind::i8; %u row chunk(s) overlapping their H2D", n_chunks);
+    return dist_tail(c, d_hits, d_cnt, hits, cap, n_hits, sorted, ani_milli);
   } else {
     auto whole = [&](HostRows &S) -> int {
       HG_CUDA(cudaMemcpy2DAsync(S.d_stage, S.width, S.base, S.stride, S.width, S.n, cudaMemcpyHostToDevice, c->stream));
@@ -1073,7 +1106,7 @@ static int dist_host(hg_ctx *c, const int16_t *ref, const int32_t *ref_norm, uin
   int32_t *d_rn = (int32_t *)d_norm, *d_qn = same ? d_rn : d_rn + n_ref;
   HostRows R = {(const uint8_t *)ref, (uint64_t)hv_d * 2, (uint64_t)hv_d * 2, nullptr, ref_norm, n_ref, (uint8_t *)d_ref, nullptr, d_ref, d_rn};
   HostRows Q = {(const uint8_t *)qry, (uint64_t)hv_d * 2, (uint64_t)hv_d * 2, nullptr, qry_norm, n_qry, (uint8_t *)d_qry, nullptr, d_qry, d_qn};
-  return dist_from_host(c, R, same ? R : Q, same, hv_d, ksize, ani_th, symmetric, path, true, hits, cap, n_hits, sorted, ani_milli);
+  return dist_from_host(c, R, same ? R : Q, same, hv_d, ksize, ani_th, symmetric, path, 1, hits, cap, n_hits, sorted, ani_milli);
 }
 
 // `dist` straight from what the sketch file holds (FileSketch.hv bit-packed + hv_quant_bits + hv_norm_2,
@@ -1125,12 +1158,12 @@ extern "C" int hg_dist_packed(hg_ctx *c, const uint8_t *ref_packed, uint64_t ref
   const uint32_t bmax = std::max(rmax, qmax);
   const bool wide = bmax > 10;
   if (path == 0 && wide && bmax <= 13 && (uint64_t)n_ref * n_qry >= 128ull * 128ull) {
-    rc = dist_from_host(c, R, same ? R : Q, same, hv_d, ksize, ani_th, symmetric, 2, false, hits, cap, n_hits, sorted != 0, ani_milli);
-    if (c->dist_path == 2)
+    rc = dist_from_host(c, R, same ? R : Q, same, hv_d, ksize, ani_th, symmetric, 2, 2, hits, cap, n_hits, sorted != 0, ani_milli);
+    if (c->dist_path == 2 && !strstr(c->dist_reason, "chunk"))
       snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor: hv_quant_bits <= %u fits two s8 limbs; tcgen05 kind::i8", bmax);
     return rc;
   }
-  return dist_from_host(c, R, same ? R : Q, same, hv_d, ksize, ani_th, symmetric, path, !wide, hits, cap, n_hits, sorted != 0,
+  return dist_from_host(c, R, same ? R : Q, same, hv_d, ksize, ani_th, symmetric, path, wide ? 0 : 1, hits, cap, n_hits, sorted != 0,
                         ani_milli);
 }
 

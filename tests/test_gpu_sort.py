@@ -171,3 +171,34 @@ def test_dist_packed_streamed_in_chunks(ctx, hg, oracle, sym, monkeypatch):
         assert np.array_equal(idx, want), (sym, th)
         assert np.array_equal(hits["ani"].view(np.uint32), ani[want].view(np.uint32))
         assert np.array_equal(hits["dot"], dot[want])
+
+
+@pytest.mark.parametrize("sym", [True, False])
+def test_dist_packed_wide_rows_streamed_two_limb(ctx, hg, oracle, sym, monkeypatch):
+    """rows stored at 11 bits (wider than one s8 plane can hold): hg_dist_packed streams them through the two-limb
+    tensor kernel, one partial launch per chunk"""
+    from hypergen_b200 import synth, dist as hdist
+    monkeypatch.setenv("HG_DIST_CHUNK_ROWS", "256")
+    D = 1024
+    seq, off = synth.family_batch(560, 30_000, first=1700)
+    sk = oracle.sketch_batch(seq.numpy(), off, scaled=100, hv_d=D)
+    hv, norm = sk["hv"], sk["norm2"]
+    bits = np.full(560, 11, np.uint8)
+    rp = np.zeros((560, 11 * D // 8), np.uint8)
+    for g in range(560):
+        rp[g] = _pack_bits(hv[g], 11)
+    if sym:
+        args = (rp, bits, norm, rp, bits, norm)
+        qh, qn = hv, norm
+    else:
+        q = np.arange(11, 311)
+        args = (rp, bits, norm, rp[q].copy(), bits[q].copy(), norm[q].copy())
+        qh, qn = hv[q], norm[q]
+    ani, dot = oracle.dist_all(hv, norm, qh, qn, symmetric=sym)
+    hits, milli = ctx.dist_packed(*args, D, ani_th=0.0, symmetric=sym, cap=ani.size + 16)
+    assert ctx.dist_last_path == 2 and "chunk" in ctx.dist_last_reason, ctx.dist_last_reason
+    want = oracle.ani_output_order(ani, 0.0)
+    idx = hdist.pair_index(hits["i"].astype(np.int64), hits["j"].astype(np.int64), qh.shape[0], sym)
+    assert np.array_equal(idx, want), sym
+    assert np.array_equal(hits["ani"].view(np.uint32), ani[want].view(np.uint32))
+    assert np.array_equal(hits["dot"], dot[want])
