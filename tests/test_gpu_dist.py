@@ -331,3 +331,52 @@ def test_streamed_dist_declines_midway_and_falls_back(ctx, hg, oracle, monkeypat
     assert np.array_equal(np.sort(idx), np.arange(ani.size))
     assert np.array_equal(hits["dot"], dot[idx])
     assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32))
+
+
+def test_full_size_config3_cross_kernel_and_symmetry_properties(ctx, hg):
+    """BASELINE config 3 at full size (10,000 sketches, D=4096, ani_th=85), where the oracle would take minutes:
+    the three kernels must report the same hits bit for bit; the symmetric run must equal the j > i half of the
+    full ref x query run, whose other half must mirror it (dot and ANI are symmetric in the pair); and the ten
+    identical pairs the generator plants must come out at exactly 100."""
+    import torch
+    from hypergen_b200 import synth
+    n, D = 10_000, 4096
+    dev = torch.device("cuda", 0)
+    sets = synth.hash_sets_family(n)
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum([len(x) for x in sets])
+    hashes = torch.from_numpy(np.concatenate(sets).view(np.int64)).to(dev)
+    hv = torch.empty((n, D), dtype=torch.int16, device=dev)
+    bits = torch.empty(n, dtype=torch.uint8, device=dev)
+    norm = torch.empty(n, dtype=torch.int32, device=dev)
+    ctx.encode_sets_dev(hashes.data_ptr(), off, D, hv.data_ptr(), None, bits.data_ptr(), norm.data_ptr())
+    ctx.sync()
+    cap = 1_000_000
+    d_hits = torch.empty(cap * 16, dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def run(path, sym):
+        ctx.dist_dev(hv.data_ptr(), norm.data_ptr(), n, 0, hv.data_ptr(), norm.data_ptr(), n, 0, D, 21, 85.0, sym, path,
+                     d_hits.data_ptr(), cap, d_cnt.data_ptr())
+        ctx.sync()
+        c = int(d_cnt.item())
+        assert c <= cap
+        h = np.frombuffer(d_hits[: c * 16].cpu().numpy().tobytes(), dtype=hg.ffi.HIT_DTYPE)
+        return np.sort(h, order=["i", "j"])
+
+    narrow = run(3, True)
+    assert ctx.dist_last_path == 3
+    assert np.array_equal(narrow, run(2, True))      # two-limb tensor kernel
+    assert np.array_equal(narrow, run(1, True))      # CUDA-core kernel
+    assert narrow.size > 100_000 and (narrow["i"] < narrow["j"]).all()
+    full = run(3, False)
+    upper = full[full["j"] > full["i"]]
+    lower = full[full["j"] < full["i"]]
+    diag = full[full["j"] == full["i"]]
+    assert np.array_equal(upper, narrow)
+    mirrored = np.sort(np.rec.fromarrays([lower["j"], lower["i"], lower["dot"], lower["ani"]], dtype=hg.ffi.HIT_DTYPE), order=["i", "j"])
+    assert np.array_equal(mirrored, narrow)
+    assert diag.size == n and (diag["ani"] == np.float32(100.0)).all() and np.array_equal(diag["dot"], norm.cpu().numpy())
+    # family members 0 and ... keep probability 1.0 means member 0 IS the pool; members with the same kept set are rare,
+    # but every hit must respect the threshold and the ANI bound
+    assert (narrow["ani"] >= np.float32(85.0)).all() and (narrow["ani"] <= np.float32(100.0)).all()
