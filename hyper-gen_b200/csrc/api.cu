@@ -937,7 +937,8 @@ static bool dist_stream_eligible(int path, bool same, int symmetric, uint32_t n_
 // is compared against all of them.
 //   narrow = true: single-plane kernel; returns HG_E_UNSUPPORTED (with max |hv|) if the rows turn out not to be
 //     narrow: by then both matrices are complete in HBM and the caller runs another kernel on them.
-//   narrow = false: two-limb kernel (the caller knows every |hv| fits 13 bits: packed rows of <= 13 bits).
+//   narrow = false: two-limb kernel (the caller knows every |hv| fits 13 bits: packed rows of <= 13 bits), the
+//     rows of a chunk split into the matrix-wide limb planes when they arrive.
 static int dist_stream(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
                        bool narrow, hg_hit *d_hits, uint64_t cap, unsigned long long *d_cnt, int32_t *absmax, uint64_t *outliers,
                        uint32_t *n_chunks_out) {
@@ -952,16 +953,16 @@ static int dist_stream(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32_t 
   if (!c->ev_chunk[0])
     for (int i = 0; i < 10; i++) HG_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
   hg_narrow_mat Qm, Rm;
+  hg_tc_mat Qt, Rt;
   if (narrow) {
     const size_t mq = hg_narrow_meta_bytes(Q.n), mr = same ? 0 : hg_narrow_meta_bytes(R.n);
     void *p_meta;
     if ((rc = hg_scratch(c, HG_S_NARROW_META, mq + mr, &p_meta))) return rc;
     if ((rc = hg_narrow_setup(c, Q.d_hv, Q.n, hv_d, HG_S_QRY_LIMBS, p_meta, &Qm))) return rc;
     if (!same && (rc = hg_narrow_setup(c, R.d_hv, R.n, hv_d, HG_S_REF_LIMBS, (uint8_t *)p_meta + mq, &Rm))) return rc;
-  } else {  // the limb planes of the largest launch, so that no launch has to grow them mid-pipeline
-    void *p;
-    if ((rc = hg_scratch(c, HG_S_QRY_LIMBS, 2 * (size_t)Q.n * hv_d + 1024, &p))) return rc;
-    if ((rc = hg_scratch(c, HG_S_REF_LIMBS, 2 * (size_t)R.n * hv_d + 1024, &p))) return rc;
+  } else {
+    if ((rc = hg_tc_setup(c, Q.d_hv, Q.n, hv_d, HG_S_QRY_LIMBS, &Qt))) return rc;
+    if (!same && (rc = hg_tc_setup(c, R.d_hv, R.n, hv_d, HG_S_REF_LIMBS, &Rt))) return rc;
   }
   HG_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c->stream));
   auto small = [&](HostRows &S) -> int {
@@ -980,13 +981,13 @@ static int dist_stream(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32_t 
     HG_CUDA(cudaEventRecord(ev, c->copy_stream));
     return HG_OK;
   };
-  auto ready = [&](HostRows &S, const hg_narrow_mat *M, uint32_t a, uint32_t rows, cudaEvent_t ev) -> int {  // compute stream
+  auto ready = [&](HostRows &S, const hg_narrow_mat *M, const hg_tc_mat *T, uint32_t a, uint32_t rows, cudaEvent_t ev) -> int {  // compute stream
     HG_CUDA(cudaStreamWaitEvent(c->stream, ev, 0));
     if (S.bits) {
       int r2 = hg_launch_unpack(c, S.d_stage + (size_t)a * S.width, S.width, S.d_bits + a, rows, hv_d, S.d_hv + (size_t)a * hv_d);
       if (r2) return r2;
     }
-    return M ? hg_narrow_prep_rows(c, M, a, rows) : HG_OK;
+    return M ? hg_narrow_prep_rows(c, M, a, rows) : hg_tc_split_rows(c, T, a, rows);
   };
   uint32_t chunk_rows = 0;
   if (const char *e = getenv("HG_DIST_CHUNK_ROWS")) chunk_rows = (uint32_t)std::max(0, atoi(e));
@@ -1002,22 +1003,19 @@ static int dist_stream(hg_ctx *c, HostRows &R, HostRows &Q, bool same, uint32_t 
   if (!same && (rc = stage(Q, 0, Q.n, c->ev_chunk[1]))) return rc;
   for (size_t k = 0; k < chunks.size(); k++)
     if ((rc = stage(R, chunks[k].first, chunks[k].second, c->ev_chunk[2 + k]))) return rc;
-  if (!same && (rc = ready(Q, narrow ? &Qm : nullptr, 0, Q.n, c->ev_chunk[1]))) return rc;
+  if (!same && (rc = ready(Q, narrow ? &Qm : nullptr, &Qt, 0, Q.n, c->ev_chunk[1]))) return rc;
   for (size_t k = 0; k < chunks.size(); k++) {
     const uint32_t a = chunks[k].first, rows = chunks[k].second;
-    if ((rc = ready(R, narrow ? (same ? &Qm : &Rm) : nullptr, a, rows, c->ev_chunk[2 + k]))) return rc;
+    if ((rc = ready(R, narrow ? (same ? &Qm : &Rm) : nullptr, same ? &Qt : &Rt, a, rows, c->ev_chunk[2 + k]))) return rc;
     if (narrow) {
       if (same)  // pairs (i, j): j in this chunk, i < j
         rc = hg_narrow_launch(c, &Qm, 0, a + rows, 0, R.d_norm, &Qm, a, rows, a, R.d_norm + a, ksize, ani_th, 1, d_hits, cap, d_cnt);
       else
         rc = hg_narrow_launch(c, &Rm, a, rows, a, R.d_norm + a, &Qm, 0, Q.n, 0, Q.d_norm, ksize, ani_th, symmetric, d_hits, cap, d_cnt);
-    } else if (same) {  // the same pairs as two launches: the rows before the chunk against it, and the chunk against itself
-      const int16_t *ch = R.d_hv + (size_t)a * hv_d;
-      rc = a ? hg_launch_dist_tc(c, R.d_hv, R.d_norm, a, 0, ch, R.d_norm + a, rows, a, hv_d, ksize, ani_th, 0, d_hits, cap, d_cnt) : HG_OK;
-      if (!rc) rc = hg_launch_dist_tc(c, ch, R.d_norm + a, rows, a, ch, R.d_norm + a, rows, a, hv_d, ksize, ani_th, 1, d_hits, cap, d_cnt);
+    } else if (same) {
+      rc = hg_tc_launch(c, &Qt, 0, a + rows, 0, R.d_norm, &Qt, a, rows, a, R.d_norm + a, ksize, ani_th, 1, d_hits, cap, d_cnt);
     } else {
-      rc = hg_launch_dist_tc(c, R.d_hv + (size_t)a * hv_d, R.d_norm + a, rows, a, Q.d_hv, Q.d_norm, Q.n, 0, hv_d, ksize, ani_th, symmetric,
-                             d_hits, cap, d_cnt);
+      rc = hg_tc_launch(c, &Rt, a, rows, a, R.d_norm + a, &Qt, 0, Q.n, 0, Q.d_norm, ksize, ani_th, symmetric, d_hits, cap, d_cnt);
     }
     if (rc) return rc;
   }

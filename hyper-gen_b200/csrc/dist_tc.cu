@@ -152,7 +152,7 @@ __device__ __forceinline__ uint32_t tc_drain(const hg::DistEpilogue &ep, uint32_
 // ---- fallback kernel: one stand-alone CTA per 128 x 128 tile ----------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_qry,
-               uint32_t ref_plane_rows, uint32_t ref_row_base, uint32_t qry_plane_rows, uint32_t hv_d,
+               uint32_t ref_plane_rows, uint32_t ref_row_base, uint32_t qry_plane_rows, uint32_t qry_row_base, uint32_t hv_d,
                hg::DistEpilogue ep) {
   const uint32_t row0 = blockIdx.y * TC_BM, col0 = blockIdx.x * TC_BN;
   // symmetric: a tile whose largest global j is not above its smallest global i is empty
@@ -198,8 +198,8 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
         const int k0 = (int)(kb * TC_BK);
         tma_load_2d(st + 0 * TC_TILE_BYTES, &tm_ref, full_bar(s), k0, (int)(ref_row_base + row0), on);  // ref hi limbs
         tma_load_2d(st + 1 * TC_TILE_BYTES, &tm_ref, full_bar(s), k0, (int)(ref_plane_rows + ref_row_base + row0), on);  // ref lo
-        tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_qry, full_bar(s), k0, (int)col0, on);                    // qry hi limbs
-        tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_qry, full_bar(s), k0, (int)(qry_plane_rows + col0), on);  // qry lo limbs
+        tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_qry, full_bar(s), k0, (int)(qry_row_base + col0), on);                    // qry hi limbs
+        tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_qry, full_bar(s), k0, (int)(qry_plane_rows + qry_row_base + col0), on);  // qry lo limbs
       }
     }
   } else if (warp == 1) {
@@ -307,7 +307,7 @@ struct PairTiles {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_qry,
-                uint32_t ref_plane_rows, uint32_t ref_row_base, uint32_t qry_plane_rows, uint32_t hv_d,
+                uint32_t ref_plane_rows, uint32_t ref_row_base, uint32_t qry_plane_rows, uint32_t qry_row_base, uint32_t hv_d,
                 hg::DistEpilogue ep) {
   uint32_t rank;  // 0 = leader (issues the MMAs, owns the full / tmem-empty barriers), 1 = peer
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -365,8 +365,8 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
           const int k0 = (int)(kb * TC_BK);
           tma_load_2d_pair(st, &tm_ref, fb, k0, (int)(ref_row_base + row0), on);                                  // ref hi
           tma_load_2d_pair(st + T2_A_BYTES, &tm_ref, fb, k0, (int)(ref_plane_rows + ref_row_base + row0), on);    // ref lo
-          tma_load_2d_pair(st + 2 * T2_A_BYTES, &tm_qry, fb, k0, (int)colh, on);                                  // qry hi, my half
-          tma_load_2d_pair(st + 2 * T2_A_BYTES + T2_B_BYTES, &tm_qry, fb, k0, (int)(qry_plane_rows + colh), on);  // qry lo
+          tma_load_2d_pair(st + 2 * T2_A_BYTES, &tm_qry, fb, k0, (int)(qry_row_base + colh), on);                 // qry hi, my half
+          tma_load_2d_pair(st + 2 * T2_A_BYTES + T2_B_BYTES, &tm_qry, fb, k0, (int)(qry_plane_rows + qry_row_base + colh), on);  // qry lo
         }
       }
     }
@@ -447,7 +447,9 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
 }
 
 // i16 -> two s8 limb planes: out[0][r][d] = h, out[1][r][d] = l  (plane stride = rows * hv_d)
-__global__ void split_limbs_kernel(const int16_t *__restrict__ hv, uint64_t n_elems, int8_t *__restrict__ planes) {
+// i16 -> two s8 limb planes: plane 0 = h, plane 1 = l, `plane_stride` bytes apart; `out` points at the first element
+// of plane 0 that belongs to `hv`
+__global__ void split_limbs_kernel(const int16_t *__restrict__ hv, uint64_t n_elems, int8_t *__restrict__ out, uint64_t plane_stride) {
   const uint64_t n8 = n_elems / 8;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint4 v = reinterpret_cast<const uint4 *>(hv)[i];
@@ -461,72 +463,70 @@ __global__ void split_limbs_kernel(const int16_t *__restrict__ hv, uint64_t n_el
       hi[e >> 2] |= (uint32_t)(h & 0xFF) << (8 * (e & 3));
       lo[e >> 2] |= (uint32_t)(l & 0xFF) << (8 * (e & 3));
     }
-    reinterpret_cast<uint2 *>(planes)[i] = make_uint2(hi[0], hi[1]);
-    reinterpret_cast<uint2 *>(planes + n_elems)[i] = make_uint2(lo[0], lo[1]);
+    reinterpret_cast<uint2 *>(out)[i] = make_uint2(hi[0], hi[1]);
+    reinterpret_cast<uint2 *>(out + plane_stride)[i] = make_uint2(lo[0], lo[1]);
   }
 }
 
-
 }  // namespace
 
-int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref, uint32_t i0,
-                      const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry, uint32_t j0, uint32_t hv_d,
-                      uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
-                      unsigned long long *d_n_hits) {
-  if (n_ref == 0 || n_qry == 0) return HG_OK;
+// ---- one matrix as two s8 limb planes [2][n_rows][hv_d]; its rows may be split piecewise, as they arrive ----
+int hg_tc_shape_ok(uint32_t hv_d, const void *d_a, const void *d_b) {
   if (hv_d % TC_BK != 0 || hv_d > 32768) {
     hg_set_error("tensor path needs hv_d %% 128 == 0 and hv_d <= 32768 (s32 accumulator bound), got %u", hv_d);
     return HG_E_UNSUPPORTED;
   }
-  if (((uintptr_t)d_ref | (uintptr_t)d_qry) & 15) {
+  if (((uintptr_t)d_a | (uintptr_t)d_b) & 15) {
     hg_set_error("tensor path needs 16-byte aligned HV matrices");
     return HG_E_UNSUPPORTED;
   }
+  return HG_OK;
+}
+
+int hg_tc_setup(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d, int plane_slot, hg_tc_mat *m) {
+  void *p;
   int rc;
-  // ---- limb planes (scratch 8 / 9) ----
-  const uint64_t ref_elems = (uint64_t)n_ref * hv_d, qry_elems = (uint64_t)n_qry * hv_d;
-  // the query block may alias the ref block (all-vs-all) or contain it (row shard of the same matrix)
-  const bool qry_covers_ref = d_ref >= d_qry && d_ref + ref_elems <= d_qry + qry_elems &&
-                              ((d_ref - d_qry) % hv_d) == 0;
-  void *p_q, *p_r = nullptr;
-  if ((rc = hg_scratch(ctx, HG_S_QRY_LIMBS, 2 * qry_elems + 1024, &p_q))) return rc;
-  if (!qry_covers_ref && (rc = hg_scratch(ctx, HG_S_REF_LIMBS, 2 * ref_elems + 1024, &p_r))) return rc;
-  const uint32_t gx = (n_qry + TC_BN - 1) / TC_BN, gy_total = (n_ref + TC_BM - 1) / TC_BM;
-  // HG_DIST_KERNEL=1 selects the stand-alone-CTA fallback; default is the persistent CTA-pair kernel
-  int pair_kernel = 1;
-  if (const char *e = getenv("HG_DIST_KERNEL")) pair_kernel = atoi(e) == 1 ? 0 : 1;
-  if (hv_d % (TC_BK * T2_STAGES) != 0) pair_kernel = 0;  // the pair kernel walks whole trips of its 4-stage ring
-
-  CUtensorMap tm_ref, tm_qry;
-  if ((rc = make_plane_map(&tm_qry, (const int8_t *)p_q, 2ull * n_qry, hv_d, pair_kernel ? 64 : 128))) return rc;
-  uint32_t ref_plane_rows = n_ref, ref_row_off = 0;
-  const int8_t *ref_planes = (const int8_t *)p_r;
-  uint64_t ref_rows2 = 2ull * n_ref;
-  if (qry_covers_ref) {  // the ref rows are a window of the query planes
-    ref_planes = (const int8_t *)p_q;
-    ref_rows2 = 2ull * n_qry;
-    ref_plane_rows = n_qry;
-    ref_row_off = (uint32_t)((d_ref - d_qry) / hv_d);
-  }
-  if ((rc = make_plane_map(&tm_ref, ref_planes, ref_rows2, hv_d, 128))) return rc;
-
+  if ((rc = hg_scratch(ctx, plane_slot, 2 * (uint64_t)n_rows * hv_d + 1024, &p))) return rc;
+  m->hv = d_hv;
+  m->planes = (int8_t *)p;
+  m->n_rows = n_rows;
+  m->hv_d = hv_d;
   if (!ctx->tc_attr_set) {
     HG_CUDA(cudaFuncSetAttribute(dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
     ctx->tc_attr_set = 1;
   }
-  // ---- GPU work starts here (stage timer 4..5 brackets exactly this) ----
-  auto split = [&](const int16_t *src, uint64_t elems, void *dst) {
-    uint64_t blocks = (elems / 8 + 255) / 256;
-    if (blocks > (uint64_t)ctx->sm_count * 16) blocks = (uint64_t)ctx->sm_count * 16;
-    split_limbs_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(src, elems, (int8_t *)dst);
-    ctx->launches++;
-  };
+  return HG_OK;
+}
 
-  HG_PROF(ctx, 4);
-  split(d_qry, qry_elems, p_q);
-  if (!qry_covers_ref) split(d_ref, ref_elems, p_r);
+// limb split of rows [row0, row0 + rows) (asynchronous)
+int hg_tc_split_rows(hg_ctx *ctx, const hg_tc_mat *m, uint32_t row0, uint32_t rows) {
+  if (rows == 0) return HG_OK;
+  const uint64_t elems = (uint64_t)rows * m->hv_d;
+  uint64_t blocks = (elems / 8 + 255) / 256;
+  if (blocks > (uint64_t)ctx->sm_count * 16) blocks = (uint64_t)ctx->sm_count * 16;
+  split_limbs_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(m->hv + (size_t)row0 * m->hv_d, elems, m->planes + (size_t)row0 * m->hv_d,
+                                                                (uint64_t)m->n_rows * m->hv_d);
+  ctx->launches++;
   HG_CUDA(cudaGetLastError());
+  return HG_OK;
+}
+
+// rows [r0, r0 + n_ref) of R against rows [q0, q0 + n_qry) of Q (both split); norms point at the windows' first rows
+int hg_tc_launch(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
+                 const hg_tc_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm, uint32_t ksize,
+                 float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits) {
+  if (n_ref == 0 || n_qry == 0) return HG_OK;
+  int rc;
+  const uint32_t hv_d = R->hv_d;
+  const uint32_t gx = (n_qry + TC_BN - 1) / TC_BN, gy_total = (n_ref + TC_BM - 1) / TC_BM;
+  // HG_DIST_KERNEL=1 selects the stand-alone-CTA fallback; default is the persistent CTA-pair kernel
+  int pair_kernel = 1;
+  if (const char *e = getenv("HG_DIST_KERNEL")) pair_kernel = atoi(e) == 1 ? 0 : 1;
+  if (hv_d % (TC_BK * T2_STAGES) != 0) pair_kernel = 0;  // the pair kernel walks whole trips of its 4-stage ring
+  CUtensorMap tm_ref, tm_qry;
+  if ((rc = make_plane_map(&tm_qry, Q->planes, 2ull * Q->n_rows, hv_d, pair_kernel ? 64 : 128))) return rc;
+  if ((rc = make_plane_map(&tm_ref, R->planes, 2ull * R->n_rows, hv_d, 128))) return rc;
   auto make_ep = [&](uint32_t y0) {
     hg::DistEpilogue ep;
     ep.ref_norm = d_ref_norm + (size_t)y0 * TC_BM;
@@ -561,7 +561,7 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
     cfg.gridDim = dim3(2 * n_pairs, 1, 1);
     cfg.dynamicSmemBytes = T2_SMEM_BYTES;
     attr[0].val.clusterDim.x = 2;
-    HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel, tm_ref, tm_qry, ref_plane_rows, ref_row_off, n_qry, hv_d, make_ep(0)));
+    HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel, tm_ref, tm_qry, R->n_rows, r0, Q->n_rows, q0, hv_d, make_ep(0)));
     ctx->launches++;
   } else {
     const uint32_t y_step = 65534;  // <= the gridDim.y limit
@@ -570,12 +570,35 @@ int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_no
       cfg.gridDim = dim3(gx, gy, 1);
       cfg.dynamicSmemBytes = TC_SMEM_BYTES;
       attr[0].val.clusterDim.x = 1;
-      HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc_kernel, tm_ref, tm_qry, ref_plane_rows, ref_row_off + y0 * TC_BM, n_qry, hv_d,
-                                 make_ep(y0)));
+      HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc_kernel, tm_ref, tm_qry, R->n_rows, r0 + y0 * TC_BM, Q->n_rows, q0, hv_d, make_ep(y0)));
       ctx->launches++;
     }
   }
-  HG_PROF(ctx, 5);
   HG_CUDA(cudaGetLastError());
   return HG_OK;
+}
+
+// one-shot form: both matrices already in HBM
+int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref, uint32_t i0,
+                      const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry, uint32_t j0, uint32_t hv_d,
+                      uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
+                      unsigned long long *d_n_hits) {
+  if (n_ref == 0 || n_qry == 0) return HG_OK;
+  int rc;
+  if ((rc = hg_tc_shape_ok(hv_d, d_ref, d_qry))) return rc;
+  const uint64_t ref_elems = (uint64_t)n_ref * hv_d, qry_elems = (uint64_t)n_qry * hv_d;
+  // the query block may alias the ref block (all-vs-all) or contain it (row shard of the same matrix)
+  const bool qry_covers_ref = d_ref >= d_qry && d_ref + ref_elems <= d_qry + qry_elems && ((d_ref - d_qry) % hv_d) == 0;
+  hg_tc_mat Q, R;
+  if ((rc = hg_tc_setup(ctx, d_qry, n_qry, hv_d, HG_S_QRY_LIMBS, &Q))) return rc;
+  if (!qry_covers_ref && (rc = hg_tc_setup(ctx, d_ref, n_ref, hv_d, HG_S_REF_LIMBS, &R))) return rc;
+  // ---- GPU work starts here (stage timer 4..5 brackets exactly this) ----
+  HG_PROF(ctx, 4);
+  if ((rc = hg_tc_split_rows(ctx, &Q, 0, n_qry))) return rc;
+  if (!qry_covers_ref && (rc = hg_tc_split_rows(ctx, &R, 0, n_ref))) return rc;
+  const uint32_t ref_row_off = qry_covers_ref ? (uint32_t)((d_ref - d_qry) / hv_d) : 0u;
+  rc = hg_tc_launch(ctx, qry_covers_ref ? &Q : &R, ref_row_off, n_ref, i0, d_ref_norm, &Q, 0, n_qry, j0, d_qry_norm, ksize, ani_th,
+                    symmetric, d_hits, cap, d_n_hits);
+  HG_PROF(ctx, 5);
+  return rc;
 }

@@ -219,6 +219,18 @@ int hg_launch_dist_simt(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_
                         uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
                         uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
                         hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits);
+// two s8 limb planes of one matrix (dist_tc.cu), split piecewise or at once
+struct hg_tc_mat {
+  const int16_t *hv;
+  int8_t *planes;  // [2][n_rows][hv_d]
+  uint32_t n_rows, hv_d;
+};
+int hg_tc_shape_ok(uint32_t hv_d, const void *d_a, const void *d_b);
+int hg_tc_setup(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d, int plane_slot, hg_tc_mat *m);
+int hg_tc_split_rows(hg_ctx *ctx, const hg_tc_mat *m, uint32_t row0, uint32_t rows);
+int hg_tc_launch(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
+                 const hg_tc_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm, uint32_t ksize,
+                 float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits);
 int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref,
                       uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
                       uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
