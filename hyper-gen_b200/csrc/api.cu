@@ -134,6 +134,19 @@ extern "C" int hg_int_peak(hg_ctx *c, int which, double *lane_ops_per_s) {
   return HG_OK;
 }
 
+extern "C" int hg_host_alloc(uint64_t bytes, void **out) {
+  if (!out) { hg_set_error("hg_host_alloc: out is NULL"); return HG_E_INVALID; }
+  *out = nullptr;
+  if (bytes == 0) return HG_OK;
+  HG_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+  return HG_OK;
+}
+
+extern "C" int hg_host_free(void *p) {
+  if (p) HG_CUDA(cudaFreeHost(p));
+  return HG_OK;
+}
+
 int hg_scratch(hg_ctx *c, int slot, size_t bytes, void **out) {
   if (bytes == 0) bytes = 256;
   if (c->d_scratch_bytes[slot] < bytes) {

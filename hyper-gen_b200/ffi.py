@@ -16,7 +16,7 @@ from . import _build
 HG_OK, HG_E_INVALID, HG_E_CUDA, HG_E_CAPACITY, HG_E_RANGE, HG_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 EXPORTS = [
-    "hg_init", "hg_destroy", "hg_sync", "hg_last_error", "hg_version", "hg_stream_handle", "hg_launch_count",
+    "hg_init", "hg_destroy", "hg_sync", "hg_host_alloc", "hg_host_free", "hg_last_error", "hg_version", "hg_stream_handle", "hg_launch_count",
     "hg_set_profiling", "hg_stage_ms", "hg_int_peak", "hg_encode_sets", "hg_encode_sets_dev",
     "hg_fasta_merge", "hg_sketch_fasta_batch",
     "hg_kmer_hash", "hg_sketch_batch", "hg_sketch_batch_dev", "hg_sketch_status", "hg_unpack", "hg_unpack_dev",
@@ -63,6 +63,8 @@ def load() -> C.CDLL:
     L.hg_init.restype = i32; L.hg_init.argtypes = [i32, C.POINTER(vp)]
     L.hg_destroy.restype = None; L.hg_destroy.argtypes = [vp]
     L.hg_sync.restype = i32; L.hg_sync.argtypes = [vp]
+    L.hg_host_alloc.restype = i32; L.hg_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
+    L.hg_host_free.restype = i32; L.hg_host_free.argtypes = [vp]
     L.hg_last_error.restype = C.c_char_p; L.hg_last_error.argtypes = []
     L.hg_version.restype = C.c_char_p; L.hg_version.argtypes = []
     L.hg_stream_handle.restype = u64; L.hg_stream_handle.argtypes = [vp]

@@ -22,6 +22,7 @@
 #include <fstream>
 #include <glob.h>
 #include <string>
+#include <functional>
 #include <thread>
 #include <vector>
 
@@ -130,10 +131,18 @@ std::vector<types::FileSketch> load_sketch(const std::string &path) {
 
 namespace fastx_reader {
 
-std::vector<uint8_t> read_raw(const std::string &file_name) {
+uint64_t file_size(const std::string &file_name) {
+  std::ifstream f(file_name, std::ios::binary | std::ios::ate);
+  if (!f) die("Opening .fna files failed: " + file_name);
+  return (uint64_t)f.tellg();
+}
+
+// the file's bytes as they are, straight into (pinned) staging memory: the GPU does read_merge_seq's job
+void read_raw_into(const std::string &file_name, uint8_t *dst, uint64_t size) {
   std::ifstream f(file_name, std::ios::binary);
   if (!f) die("Opening .fna files failed: " + file_name);
-  return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  f.read(reinterpret_cast<char *>(dst), (std::streamsize)size);
+  if ((uint64_t)f.gcount() != size) die("Reading .fna file failed: " + file_name);
 }
 
 std::vector<uint8_t> read_merge_seq(const std::string &file_name) {
@@ -174,35 +183,49 @@ void sketch_cuda(const types::SketchParams &params) {
   const size_t D = params.hv_d;
   std::vector<types::FileSketch> all(n_file);
   const size_t batch_files = 256;
+  // By default the raw file bytes go to the GPU, which does read_merge_seq's job itself (hg_sketch_fasta_batch);
+  // HG_HOST_PARSE=1 keeps the reference's host-side reader in the loop instead.
+  const bool host_parse = getenv("HG_HOST_PARSE") != nullptr;
+  // one page-locked staging buffer for the whole run (H2D from it runs at the PCIe rate and overlaps the kernels):
+  // the reader threads put every file at its offset, no per-file vectors in between
+  uint8_t *stage = nullptr;
+  uint64_t stage_cap = 0;
   for (size_t b0 = 0; b0 < n_file; b0 += batch_files) {
     const size_t b1 = std::min(n_file, b0 + batch_files), m = b1 - b0;
-    // host file reading in parallel (the reference's rayon par_iter over files).  By default the raw
-    // file bytes go to the GPU, which does read_merge_seq's job itself (hg_sketch_fasta_batch);
-    // HG_HOST_PARSE=1 keeps the reference's host-side reader in the loop instead.
-    const bool host_parse = getenv("HG_HOST_PARSE") != nullptr;
-    std::vector<std::vector<uint8_t>> seqs(m);
-    {
-      std::vector<std::thread> th;
-      const int nt = std::max(1, std::min<int>(params.threads, (int)m));
-      for (int t = 0; t < nt; t++)
-        th.emplace_back([&, t] {
-          for (size_t i = (size_t)t; i < m; i += (size_t)nt)
-            seqs[i] = host_parse ? fastx_reader::read_merge_seq(files[b0 + i]) : fastx_reader::read_raw(files[b0 + i]);
-        });
-      for (auto &x : th) x.join();
-    }
     std::vector<uint64_t> seg_off(m + 1, 0);
-    for (size_t i = 0; i < m; i++) seg_off[i + 1] = seg_off[i] + seqs[i].size();
-    std::vector<uint8_t> seq(seg_off[m]);
-    for (size_t i = 0; i < m; i++) if (!seqs[i].empty()) memcpy(seq.data() + seg_off[i], seqs[i].data(), seqs[i].size());
+    std::vector<std::vector<uint8_t>> seqs(host_parse ? m : 0);
+    const int nt = std::max(1, std::min<int>(params.threads, (int)m));
+    auto parallel = [&](const std::function<void(size_t)> &fn) {  // the reference's rayon par_iter over files
+      std::vector<std::thread> th;
+      for (int t = 0; t < nt; t++)
+        th.emplace_back([&, t] { for (size_t i = (size_t)t; i < m; i += (size_t)nt) fn(i); });
+      for (auto &x : th) x.join();
+    };
+    if (host_parse) {
+      parallel([&](size_t i) { seqs[i] = fastx_reader::read_merge_seq(files[b0 + i]); });
+      for (size_t i = 0; i < m; i++) seg_off[i + 1] = seg_off[i] + seqs[i].size();
+    } else {
+      std::vector<uint64_t> sz(m);
+      parallel([&](size_t i) { sz[i] = fastx_reader::file_size(files[b0 + i]); });
+      for (size_t i = 0; i < m; i++) seg_off[i + 1] = seg_off[i] + sz[i];
+    }
+    if (seg_off[m] > stage_cap) {
+      check(hg_host_free(stage), "hg_host_free");
+      stage_cap = seg_off[m] + seg_off[m] / 4 + 4096;
+      check(hg_host_alloc(stage_cap, (void **)&stage), "hg_host_alloc");
+    }
+    if (host_parse)
+      parallel([&](size_t i) { if (!seqs[i].empty()) memcpy(stage + seg_off[i], seqs[i].data(), seqs[i].size()); });
+    else
+      parallel([&](size_t i) { fastx_reader::read_raw_into(files[b0 + i], stage + seg_off[i], seg_off[i + 1] - seg_off[i]); });
     std::vector<uint8_t> packed(m * 2 * D), bits(m);
     std::vector<int32_t> norm2(m);
     std::vector<uint32_t> nh(m);
     if (host_parse)
-      check(hg_sketch_batch(ctx, seq.data(), seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
+      check(hg_sketch_batch(ctx, stage, seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
                             norm2.data(), nh.data()), "hg_sketch_batch");
     else
-      check(hg_sketch_fasta_batch(ctx, seq.data(), seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
+      check(hg_sketch_fasta_batch(ctx, stage, seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
                                   norm2.data(), nh.data()), "hg_sketch_fasta_batch");
     for (size_t i = 0; i < m; i++) {
       types::FileSketch &s = all[b0 + i];
@@ -213,6 +236,7 @@ void sketch_cuda(const types::SketchParams &params) {
       memcpy(s.hv.data(), packed.data() + i * 2 * D, nbytes);  // hd.rs:155-157: bytes viewed as i16
     }
   }
+  check(hg_host_free(stage), "hg_host_free");
   hg_destroy(ctx);
   utils::dump_sketch(all, params.out_file);
 }

@@ -72,6 +72,13 @@ typedef struct hg_hit {
 HG_API int hg_init(int device, hg_ctx **out);
 HG_API void hg_destroy(hg_ctx *ctx);
 HG_API int hg_sync(hg_ctx *ctx);
+
+/* Page-locked host memory for the buffers the host entries read from / write to (FASTA bytes, sequences, packed
+ * sketches, hits): from such memory the H2D copies run at the PCIe rate and overlap with the kernels; from
+ * ordinary (pageable) memory they are staged by the driver at a fraction of it.  A Rust host reads its files
+ * straight into a buffer from hg_host_alloc instead of a Vec.  hg_host_free(NULL) is a no-op. */
+HG_API int hg_host_alloc(uint64_t bytes, void **out);
+HG_API int hg_host_free(void *p);
 HG_API const char *hg_last_error(void);
 HG_API const char *hg_version(void);
 /* cudaStream_t of the context as an integer handle, so a host framework (torch) can order
