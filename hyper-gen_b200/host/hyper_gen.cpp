@@ -15,6 +15,7 @@
 //   hyper-gen dist   -r <ref sketch> -q <query sketch> -o <out> [-a 85.0]
 // The GPU path is the only path (`-D gpu` is implied): there is no CPU fallback.
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -171,61 +172,87 @@ std::vector<uint8_t> read_merge_seq(const std::string &file_name) {
 
 namespace sketch_cuda {
 
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 void sketch_cuda(const types::SketchParams &params) {
   const auto files = utils::get_fasta_files(params.path);
   const size_t n_file = files.size();
   fprintf(stdout, "Start GPU sketching...\n");
+  const bool timing = getenv("HG_CLI_TIMING") != nullptr;  // per-phase wall clock on stderr
+  double t_mark = now_s(), t_init = 0, t_stat = 0, t_alloc = 0, t_read = 0, t_gpu = 0, t_collect = 0, t_dump = 0;
+  auto lap = [&](double &acc) { const double t = now_s(); acc += t - t_mark; t_mark = t; };
   hg_ctx *ctx = nullptr;
   check(hg_init(0, &ctx), "hg_init");
+  lap(t_init);
   hg_sketch_params p{};
   p.scaled = params.scaled; p.seed = params.seed; p.hv_d = (uint32_t)params.hv_d;
   p.ksize = params.ksize; p.canonical = params.canonical ? 1 : 0;
   const size_t D = params.hv_d;
   std::vector<types::FileSketch> all(n_file);
-  const size_t batch_files = 256;
   // By default the raw file bytes go to the GPU, which does read_merge_seq's job itself (hg_sketch_fasta_batch);
   // HG_HOST_PARSE=1 keeps the reference's host-side reader in the loop instead.
   const bool host_parse = getenv("HG_HOST_PARSE") != nullptr;
-  // one page-locked staging buffer for the whole run (H2D from it runs at the PCIe rate and overlaps the kernels):
-  // the reader threads put every file at its offset, no per-file vectors in between
-  uint8_t *stage = nullptr;
-  uint64_t stage_cap = 0;
-  for (size_t b0 = 0; b0 < n_file; b0 += batch_files) {
-    const size_t b1 = std::min(n_file, b0 + batch_files), m = b1 - b0;
-    std::vector<uint64_t> seg_off(m + 1, 0);
-    std::vector<std::vector<uint8_t>> seqs(host_parse ? m : 0);
-    const int nt = std::max(1, std::min<int>(params.threads, (int)m));
-    auto parallel = [&](const std::function<void(size_t)> &fn) {  // the reference's rayon par_iter over files
-      std::vector<std::thread> th;
-      for (int t = 0; t < nt; t++)
-        th.emplace_back([&, t] { for (size_t i = (size_t)t; i < m; i += (size_t)nt) fn(i); });
-      for (auto &x : th) x.join();
-    };
-    if (host_parse) {
-      parallel([&](size_t i) { seqs[i] = fastx_reader::read_merge_seq(files[b0 + i]); });
-      for (size_t i = 0; i < m; i++) seg_off[i + 1] = seg_off[i] + seqs[i].size();
-    } else {
-      std::vector<uint64_t> sz(m);
-      parallel([&](size_t i) { sz[i] = fastx_reader::file_size(files[b0 + i]); });
-      for (size_t i = 0; i < m; i++) seg_off[i + 1] = seg_off[i] + sz[i];
-    }
-    if (seg_off[m] > stage_cap) {
-      check(hg_host_free(stage), "hg_host_free");
-      stage_cap = seg_off[m] + seg_off[m] / 4 + 4096;
-      check(hg_host_alloc(stage_cap, (void **)&stage), "hg_host_alloc");
-    }
+  const int nt_all = std::max(1, params.threads);
+  auto parallel = [&](size_t count, const std::function<void(size_t)> &fn) {  // the reference's rayon par_iter over files
+    const int nt = (int)std::min<size_t>((size_t)nt_all, std::max<size_t>(count, 1));
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+      th.emplace_back([&, t] { for (size_t i = (size_t)t; i < count; i += (size_t)nt) fn(i); });
+    for (auto &x : th) x.join();
+  };
+  // batches of about 256 MB of file bytes: two page-locked staging buffers of that size (pinning memory costs
+  // ~0.4 s per GB, H2D from it runs at the PCIe rate) - the reader threads fill one while the GPU works on the other
+  std::vector<uint64_t> fsize(n_file, 0);
+  std::vector<std::vector<uint8_t>> parsed(host_parse ? n_file : 0);
+  if (host_parse) {
+    parallel(n_file, [&](size_t i) { parsed[i] = fastx_reader::read_merge_seq(files[i]); fsize[i] = parsed[i].size(); });
+  } else {
+    parallel(n_file, [&](size_t i) { fsize[i] = fastx_reader::file_size(files[i]); });
+  }
+  lap(t_stat);
+  const uint64_t batch_bytes = 256ull << 20;
+  std::vector<std::pair<size_t, size_t>> batches;  // [first, last)
+  uint64_t max_batch = 0;
+  for (size_t b0 = 0; b0 < n_file;) {
+    size_t b1 = b0;
+    uint64_t sum = 0;
+    do { sum += fsize[b1]; ++b1; } while (b1 < n_file && sum + fsize[b1] <= batch_bytes && b1 - b0 < 65535);
+    batches.push_back({b0, b1});
+    max_batch = std::max(max_batch, sum);
+    b0 = b1;
+  }
+  uint8_t *stage[2] = {nullptr, nullptr};
+  for (int i = 0; i < (batches.size() > 1 ? 2 : 1); i++) check(hg_host_alloc(max_batch + 4096, (void **)&stage[i]), "hg_host_alloc");
+  lap(t_alloc);
+  std::vector<std::vector<uint64_t>> seg_offs(batches.size());
+  auto fill = [&](size_t bi) {  // batch bi into staging buffer bi % 2
+    const size_t b0 = batches[bi].first, m = batches[bi].second - b0;
+    std::vector<uint64_t> &seg_off = seg_offs[bi];
+    seg_off.assign(m + 1, 0);
+    for (size_t i = 0; i < m; i++) seg_off[i + 1] = seg_off[i] + fsize[b0 + i];
+    uint8_t *dst = stage[bi & 1];
     if (host_parse)
-      parallel([&](size_t i) { if (!seqs[i].empty()) memcpy(stage + seg_off[i], seqs[i].data(), seqs[i].size()); });
+      parallel(m, [&](size_t i) { if (fsize[b0 + i]) memcpy(dst + seg_off[i], parsed[b0 + i].data(), fsize[b0 + i]); });
     else
-      parallel([&](size_t i) { fastx_reader::read_raw_into(files[b0 + i], stage + seg_off[i], seg_off[i + 1] - seg_off[i]); });
+      parallel(m, [&](size_t i) { fastx_reader::read_raw_into(files[b0 + i], dst + seg_off[i], fsize[b0 + i]); });
+  };
+  if (!batches.empty()) fill(0);
+  lap(t_read);
+  for (size_t bi = 0; bi < batches.size(); bi++) {
+    const size_t b0 = batches[bi].first, m = batches[bi].second - b0;
+    std::thread next;
+    if (bi + 1 < batches.size()) next = std::thread(fill, bi + 1);  // overlaps the GPU call below
+    const std::vector<uint64_t> &seg_off = seg_offs[bi];
     std::vector<uint8_t> packed(m * 2 * D), bits(m);
     std::vector<int32_t> norm2(m);
     std::vector<uint32_t> nh(m);
     if (host_parse)
-      check(hg_sketch_batch(ctx, stage, seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
+      check(hg_sketch_batch(ctx, stage[bi & 1], seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
                             norm2.data(), nh.data()), "hg_sketch_batch");
     else
-      check(hg_sketch_fasta_batch(ctx, stage, seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
+      check(hg_sketch_fasta_batch(ctx, stage[bi & 1], seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
                                   norm2.data(), nh.data()), "hg_sketch_fasta_batch");
     for (size_t i = 0; i < m; i++) {
       types::FileSketch &s = all[b0 + i];
@@ -235,10 +262,18 @@ void sketch_cuda(const types::SketchParams &params) {
       s.hv.resize(nbytes / 2);
       memcpy(s.hv.data(), packed.data() + i * 2 * D, nbytes);  // hd.rs:155-157: bytes viewed as i16
     }
+    if (next.joinable()) next.join();
   }
-  check(hg_host_free(stage), "hg_host_free");
+  lap(t_gpu);
+  check(hg_host_free(stage[0]), "hg_host_free");
+  check(hg_host_free(stage[1]), "hg_host_free");
   hg_destroy(ctx);
+  lap(t_collect);
   utils::dump_sketch(all, params.out_file);
+  lap(t_dump);
+  if (timing)
+    fprintf(stderr, "[hyper-gen sketch] init %.3f s, stat %.3f, pinned alloc %.3f, first batch read %.3f, GPU calls (+ overlapped reads) %.3f, free %.3f, dump %.3f\n",
+            t_init, t_stat, t_alloc, t_read, t_gpu, t_collect, t_dump);
 }
 
 }  // namespace sketch_cuda
