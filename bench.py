@@ -543,7 +543,10 @@ def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, m
                if path_sel[0] == 3 else "the two-limb split executes 4x these MACs, so frac tops out at 0.25"))
     out["roofline"] = {"bound": "tensor", "achieved": alg_ops / (kms * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s",
                        "frac": alg_ops / (kms * 1e-3) / 1e12 / int8_peak, "note": note,
-                       "executed_frac": mac_mult * alg_ops / (kms * 1e-3) / 1e12 / int8_peak}
+                       "executed_frac": mac_mult * alg_ops / (kms * 1e-3) / 1e12 / int8_peak,
+                       # DRAM bytes of one config-3 step from the ncu captures (profiles/r1_dist_narrow_full.md,
+                       # r1_narrow_prep_full.md): pre-pass 82 MB read + 41 MB written, kernel 41.3 MB read + 0.6 MB written
+                       "traffic": (165.0e6 if (path_sel[0] == 3 and nq == 10000 and world == 1) else None)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # CPU port of dist::compute_hv_ani (dist.rs:231-294) on a bounded sample of the same sketches
         import oracle as O
