@@ -8,9 +8,9 @@ and the one-process-per-GPU sharding (``multigpu``).  The directory is named
 shim module at the repository root.
 """
 from . import _build, ffi  # noqa: F401
-from .ffi import Context, HyperGenError, make_params  # noqa: F401
+from .ffi import Context, Group, HyperGenError, Peer, make_params  # noqa: F401
 
-__all__ = ["Context", "HyperGenError", "make_params", "ffi", "build"]
+__all__ = ["Context", "Group", "Peer", "HyperGenError", "make_params", "ffi", "build"]
 
 
 def build(force: bool = False) -> str:

@@ -778,8 +778,9 @@ static const int32_t HG_TC_MAX_ABS = 8127;  // |x| <= 8127 splits into two s8 li
 static int dist_dev_impl(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref, uint32_t i0,
                          const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry, uint32_t j0,
                          uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path, hg_hit *d_hits,
-                         uint64_t cap, unsigned long long *d_n_hits, bool allow_narrow, int32_t absmax) {
+                         uint64_t cap, unsigned long long *d_n_hits, bool allow_narrow, int32_t absmax, bool defer_forced = false) {
   if (!c || !d_n_hits) { hg_set_error("hg_dist_dev: NULL argument"); return HG_E_INVALID; }
+  c->pending_stats[0] = c->pending_stats[1] = nullptr;
   if ((n_ref && (!d_ref || !d_ref_norm)) || (n_qry && (!d_qry || !d_qry_norm)) || (cap && !d_hits)) {
     hg_set_error("hg_dist_dev: NULL argument"); return HG_E_INVALID;
   }
@@ -805,11 +806,11 @@ static int dist_dev_impl(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref_n
     // the narrow path's own pre-pass (one read of both matrices) tells whether the rows fit one s8 plane
     uint64_t outliers = 0;
     rc = hg_launch_dist_narrow(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th, symmetric,
-                               d_hits, cap, d_n_hits, &absmax, &outliers);
+                               d_hits, cap, d_n_hits, &absmax, &outliers, path == 3 && defer_forced);
     if (rc == HG_OK) {
       c->dist_path = 3;
       if (path == 3)
-        snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor-narrow: forced by caller");
+        snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor-narrow: forced by caller%s", defer_forced ? " (verdict deferred to hg_dist_status)" : "");
       else
         snprintf(c->dist_reason, sizeof(c->dist_reason),
                  "tensor-narrow: rows fit one s8 plane as x = 2a + s (max |hv| = %d, %llu outlier elements corrected per candidate); "
@@ -853,7 +854,7 @@ static int dist_dev_impl(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref_n
   if (use == 2) {
     rc2 = hg_launch_dist_tc(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th,
                             symmetric, d_hits, cap, d_n_hits);
-    if (rc2 == HG_E_UNSUPPORTED && path == 0) {  // shape outside the tensor kernel's tiling: exact SIMT path
+    if (rc2 == HG_E_UNSUPPORTED && (path == 0 || c->tc_is_hint)) {  // shape outside the tensor kernel's tiling: exact SIMT path
       use = c->dist_path = 1;
       snprintf(c->dist_reason, sizeof(c->dist_reason), "SIMT: tensor kernel declined this shape (%s)", hg_last_error());
     }
@@ -872,7 +873,25 @@ extern "C" int hg_dist_dev(hg_ctx *c, const int16_t *d_ref, const int32_t *d_ref
                            uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path, hg_hit *d_hits,
                            uint64_t cap, unsigned long long *d_n_hits) {
   return dist_dev_impl(c, d_ref, d_ref_norm, n_ref, i0, d_qry, d_qry_norm, n_qry, j0, hv_d, ksize, ani_th, symmetric, path, d_hits,
-                       cap, d_n_hits, true, -1);
+                       cap, d_n_hits, true, -1, true);
+}
+
+// After hg_dist_dev(path = 3): the pre-pass verdict that call did not wait for.
+extern "C" int hg_dist_status(hg_ctx *c) {
+  if (!c) { hg_set_error("ctx is NULL"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(c->device));
+  uint32_t st[2][4 * HG_MAX_PEERS] = {{0}, {0}};
+  for (int k = 0; k < 2; ++k)
+    if (c->pending_stats[k] && c->pending_nsets[k] <= HG_MAX_PEERS)
+      HG_CUDA(cudaMemcpyAsync(st[k], c->pending_stats[k], 16 * c->pending_nsets[k], cudaMemcpyDeviceToHost, c->stream));
+  HG_CUDA(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 2; ++k)
+    for (uint32_t t = 0; c->pending_stats[k] && t < c->pending_nsets[k]; ++t)
+      if (st[k][4 * t + 3]) {
+        hg_set_error("the forced single-plane dist did nothing: its rows are not narrow (outlier budget exceeded)");
+        return HG_E_UNSUPPORTED;
+      }
+  return HG_OK;
 }
 
 extern "C" int hg_dist_last_path(hg_ctx *c) { return c ? c->dist_path : 0; }
@@ -1169,7 +1188,9 @@ extern "C" int hg_dist_packed(hg_ctx *c, const uint8_t *ref_packed, uint64_t ref
   const uint32_t bmax = std::max(rmax, qmax);
   const bool wide = bmax > 10;
   if (path == 0 && wide && bmax <= 13 && (uint64_t)n_ref * n_qry >= 128ull * 128ull) {
+    c->tc_is_hint = 1;  // the caller asked for auto: if the tensor kernel declines the shape (hv_d > 32768 ...) SIMT takes over
     rc = dist_from_host(c, R, same ? R : Q, same, hv_d, ksize, ani_th, symmetric, 2, 2, hits, cap, n_hits, sorted != 0, ani_milli);
+    c->tc_is_hint = 0;
     if (c->dist_path == 2 && !strstr(c->dist_reason, "chunk"))
       snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor: hv_quant_bits <= %u fits two s8 limbs; tcgen05 kind::i8", bmax);
     return rc;

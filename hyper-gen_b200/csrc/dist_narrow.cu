@@ -75,10 +75,15 @@ struct NarrowArgs {
   NarrowSide r, q;
   const uint32_t *r_out, *q_out;  // outlier entries: (d << 16) | (eps & 0xffff)
   const int8_t *r_plane;          // s8 plane of the ref rows (first row of the launch)
-  const int16_t *q_hv;            // the query matrix itself
+  const int8_t *q_plane;          // s8 plane of the query rows (first row of the launch)
   uint32_t hv_d;
-  // written by the pre-pass: [0] max |x|, [1] max (|s| + 256) >= max |x~|, [2] entries used, [3] declined
+  // written by the pre-pass, one set of 4 words per contributor (a multi-GPU matrix has one per member):
+  // [0] max |x|, [1] max (|s| + 256) >= max |x~|, [2] entry cursor, [3] declined
   const uint32_t *q_stats, *r_stats;
+  uint32_t q_nsets, r_nsets;
+  // tile walk: this launch takes the non-empty tiles walk_add, walk_add + walk_mul, ... of the row-major
+  // enumeration (single GPU: 0, 1, 2, ...; member r of w GPUs: r, r + w, ...), dealt round-robin to its CTA pairs
+  uint32_t walk_mul, walk_add;
 };
 
 // ---- i16 rows -> s8 plane + per-row constants + outlier lists ---------------------------------
@@ -281,24 +286,26 @@ __device__ __forceinline__ int32_t n1_loosen(int32_t t, uint32_t e, uint32_t m, 
   return (int32_t)((int64_t)t - (int64_t)M);  // t >= -1, so this stays far above both sentinels
 }
 
-// exact i32 correction of candidate (li, lj): sum eps_r[d] y[d] + sum eps_q[d] x~[d]
+// exact i32 correction of candidate (li, lj): with x = x~ + eps_x, y = y~ + eps_y
+//   x . y - x~ . y~ = sum eps_x[d] y~[d] + sum eps_y[d] x~[d] + sum eps_x[d] eps_y[d]
+// from the planes and the (short) outlier lists alone - the i16 rows of a remote member are not needed
 __device__ __noinline__ int32_t n1_correction(const NarrowArgs &na, uint32_t li, uint32_t lj, uint32_t er, uint32_t eq) {
   uint32_t c = 0;
-  if (er) {
-    const uint32_t off = na.r.out_off[li], cnt = na.r.out_cnt[li];
-    const int16_t *y = na.q_hv + (size_t)lj * na.hv_d;
-    for (uint32_t t = 0; t < cnt; ++t) {
-      const uint32_t w = na.r_out[off + t];
-      c += (uint32_t)((int32_t)(int16_t)(w & 0xFFFFu) * (int32_t)y[w >> 16]);
-    }
+  const int8_t *a = na.r_plane + (size_t)li * na.hv_d;
+  const int8_t *b = na.q_plane + (size_t)lj * na.hv_d;
+  const int32_t sr = na.r.s[li], sq = na.q.s[lj];
+  const uint32_t roff = na.r.out_off[li], rcnt = er ? na.r.out_cnt[li] : 0u;
+  const uint32_t qoff = na.q.out_off[lj], qcnt = eq ? na.q.out_cnt[lj] : 0u;
+  for (uint32_t t = 0; t < rcnt; ++t) {
+    const uint32_t w = na.r_out[roff + t];
+    c += (uint32_t)((int32_t)(int16_t)(w & 0xFFFFu) * (2 * (int32_t)b[w >> 16] + sq));
   }
-  if (eq) {
-    const uint32_t off = na.q.out_off[lj], cnt = na.q.out_cnt[lj];
-    const int8_t *a = na.r_plane + (size_t)li * na.hv_d;
-    const int32_t s = na.r.s[li];
-    for (uint32_t t = 0; t < cnt; ++t) {
-      const uint32_t w = na.q_out[off + t];
-      c += (uint32_t)((int32_t)(int16_t)(w & 0xFFFFu) * (2 * (int32_t)a[w >> 16] + s));
+  for (uint32_t u = 0; u < qcnt; ++u) {
+    const uint32_t w = na.q_out[qoff + u];
+    c += (uint32_t)((int32_t)(int16_t)(w & 0xFFFFu) * (2 * (int32_t)a[w >> 16] + sr));
+    for (uint32_t t = 0; t < rcnt; ++t) {  // both rows have a residual in the same dimension
+      const uint32_t v = na.r_out[roff + t];
+      if ((v >> 16) == (w >> 16)) c += (uint32_t)((int32_t)(int16_t)(v & 0xFFFFu) * (int32_t)(int16_t)(w & 0xFFFFu));
     }
   }
   return (int32_t)c;
@@ -395,11 +402,14 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
   constexpr uint32_t NBUF = NACC == 1 ? 2 : 1;  // accumulator sets in TMEM
   // the pre-pass ran on this stream just before: if it found the rows not narrow (outlier budget exceeded)
   // nothing is computed here and the host, which reads the same flag after this launch, takes another path
-  if (na.q_stats[3] | na.r_stats[3]) return;
-  const uint32_t q_absmax = na.q_stats[0], r_tmax = na.r_stats[1];
+  uint32_t declined = 0, q_absmax = 0, r_tmax = 0;
+  for (uint32_t t = 0; t < na.q_nsets; ++t) { declined |= na.q_stats[4 * t + 3]; q_absmax = max(q_absmax, na.q_stats[4 * t]); }
+  for (uint32_t t = 0; t < na.r_nsets; ++t) { declined |= na.r_stats[4 * t + 3]; r_tmax = max(r_tmax, na.r_stats[4 * t + 1]); }
+  if (declined) return;
   uint32_t rank;  // 0 = leader (issues the MMAs, owns the full / tmem-empty barriers), 1 = peer
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  // this pair's tiles: first, first + n_pairs, ... of the launch's share of the tile enumeration
+  const uint32_t pair = (blockIdx.x >> 1) * na.walk_mul + na.walk_add, n_pairs = (gridDim.x >> 1) * na.walk_mul;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B swizzle wants 1024 B alignment
@@ -555,17 +565,14 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
   }
 }
 
-void carve(hg_narrow_mat &m, void *plane, void *meta) {
-  uint32_t *w = (uint32_t *)meta;
+void carve_arrays(hg_narrow_mat &m, void *arrays) {
+  uint32_t *w = (uint32_t *)arrays;
   const size_t n = m.n_rows;
-  m.plane = (int8_t *)plane;
-  m.stats = w;  // 4 words: max |x|, max (|s| + 256), entries used, declined
-  m.s = (int32_t *)(w + 4);
-  m.a2 = (int32_t *)(w + 4 + n);
-  m.e = w + 4 + 2 * n;
-  m.out_off = w + 4 + 3 * n;
-  m.out_cnt = w + 4 + 4 * n;
-  m.entries = w + 4 + 5 * n;
+  m.s = (int32_t *)w;
+  m.a2 = (int32_t *)(w + n);
+  m.e = w + 2 * n;
+  m.out_off = w + 3 * n;
+  m.out_cnt = w + 4 * n;
 }
 
 PrepOut prep_out(const hg_narrow_mat &m, uint32_t row0) {
@@ -580,6 +587,10 @@ PrepOut prep_out(const hg_narrow_mat &m, uint32_t row0) {
   o.cap = m.cap;
   o.stats = m.stats;
   return o;
+}
+
+__global__ void narrow_stats_init_kernel(uint32_t *stats, uint32_t entry_base) {
+  if (threadIdx.x < 4) stats[threadIdx.x] = threadIdx.x == 2 ? entry_base : 0u;
 }
 
 uint32_t narrow_budget() {  // outlier entries per row on average (HG_NARROW_BUDGET overrides; tests use it to force the correction path)
@@ -606,6 +617,39 @@ int hg_narrow_shape_ok(uint32_t hv_d, const void *d_a, const void *d_b) {
 size_t hg_narrow_meta_bytes(uint32_t n_rows) {
   return ((((size_t)n_rows * 5 + ((size_t)n_rows * narrow_budget() + 1024) + 4) * 4 + 256) + 255) & ~(size_t)255;
 }
+size_t hg_narrow_arrays_bytes(uint32_t n_rows) { return (size_t)n_rows * 5 * 4; }
+uint32_t hg_narrow_set_cap(uint32_t n_rows) { return (uint32_t)std::min<uint64_t>((uint64_t)n_rows * narrow_budget() + 1024, 0x0FFFFFFFull); }
+
+static int narrow_attrs(hg_ctx *ctx) {
+  if (!ctx->n1_attr_set) {
+    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
+    ctx->n1_attr_set = 1;
+  }
+  return HG_OK;
+}
+
+// the matrix lives in caller-provided memory (a peer window shared by `n_sets` members); this context prepares some of
+// its rows, records its statistics in set `my_set` and may use entries [entry_base, entry_base + set_cap)
+int hg_narrow_attach(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d, int8_t *plane, void *arrays,
+                     uint32_t *entries, uint32_t *stats_all, uint32_t n_sets, uint32_t my_set, uint32_t entry_base,
+                     uint32_t set_cap, hg_narrow_mat *m) {
+  m->hv = d_hv;
+  m->n_rows = n_rows;
+  m->hv_d = hv_d;
+  m->plane = plane;
+  carve_arrays(*m, arrays);
+  m->entries = entries;
+  m->stats_all = stats_all;
+  m->stats = stats_all + 4 * my_set;
+  m->n_sets = n_sets;
+  m->entry_base = entry_base;
+  m->cap = entry_base + set_cap;
+  narrow_stats_init_kernel<<<1, 32, 0, ctx->stream>>>(m->stats, entry_base);
+  ctx->launches++;
+  HG_CUDA(cudaGetLastError());
+  return narrow_attrs(ctx);
+}
 
 // plane in scratch slot `plane_slot`, constants at `meta` (hg_narrow_meta_bytes); the statistics are zeroed on the stream
 int hg_narrow_setup(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d, int plane_slot, void *meta,
@@ -618,15 +662,16 @@ int hg_narrow_setup(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t 
   m->hv = d_hv;
   m->n_rows = n_rows;
   m->hv_d = hv_d;
+  m->plane = (int8_t *)plane;
+  uint32_t *w = (uint32_t *)meta;  // 4 statistics words | the five per-row arrays | entries
+  m->stats = m->stats_all = w;
+  m->n_sets = 1;
+  m->entry_base = 0;
   m->cap = (uint32_t)cap64;
-  carve(*m, plane, meta);
+  carve_arrays(*m, w + 4);
+  m->entries = w + 4 + 5 * (size_t)n_rows;
   HG_CUDA(cudaMemsetAsync(m->stats, 0, 16, ctx->stream));
-  if (!ctx->n1_attr_set) {
-    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
-    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
-    ctx->n1_attr_set = 1;
-  }
-  return HG_OK;
+  return narrow_attrs(ctx);
 }
 
 // pre-pass over rows [row0, row0 + rows) of the matrix (asynchronous)
@@ -645,7 +690,16 @@ int hg_narrow_launch(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t 
                      const hg_narrow_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm,
                      uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
                      unsigned long long *d_n_hits) {
+  return hg_narrow_launch_ex(ctx, R, r0, n_ref, i0, d_ref_norm, Q, q0, n_qry, j0, d_qry_norm, ksize, ani_th, symmetric, d_hits, cap,
+                             d_n_hits, 1, 0);
+}
+
+int hg_narrow_launch_ex(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
+                        const hg_narrow_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm,
+                        uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
+                        unsigned long long *d_n_hits, uint32_t walk_mul, uint32_t walk_add) {
   if (n_ref == 0 || n_qry == 0) return HG_OK;
+  if (walk_mul == 0 || walk_add >= walk_mul) { hg_set_error("hg_narrow_launch: tile walk %u / %u", walk_add, walk_mul); return HG_E_INVALID; }
   int rc;
   const uint32_t hv_d = R->hv_d;
   CUtensorMap tm_ref, tm_qry;
@@ -658,10 +712,14 @@ int hg_narrow_launch(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t 
   na.r_out = R->entries;
   na.q_out = Q->entries;
   na.r_plane = R->plane + (size_t)r0 * hv_d;
-  na.q_hv = Q->hv + (size_t)q0 * hv_d;
+  na.q_plane = Q->plane + (size_t)q0 * hv_d;
   na.hv_d = hv_d;
-  na.q_stats = Q->stats;
-  na.r_stats = R->stats;
+  na.q_stats = Q->stats_all;
+  na.r_stats = R->stats_all;
+  na.q_nsets = Q->n_sets;
+  na.r_nsets = R->n_sets;
+  na.walk_mul = walk_mul;
+  na.walk_add = walk_add;
 
   hg::DistEpilogue ep;
   ep.ref_norm = d_ref_norm;
@@ -695,7 +753,8 @@ int hg_narrow_launch(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t 
   int nacc = 1;
   if (const char *e = getenv("HG_NARROW_NACC")) nacc = atoi(e) == 2 ? 2 : 1;
   const uint32_t tile_rows = 256u * nacc;
-  const uint64_t tiles = (uint64_t)((n_qry + N1_BN - 1) / N1_BN) * ((n_ref + tile_rows - 1) / tile_rows);
+  const uint64_t tiles_all = (uint64_t)((n_qry + N1_BN - 1) / N1_BN) * ((n_ref + tile_rows - 1) / tile_rows);
+  const uint64_t tiles = (tiles_all + walk_mul - 1) / walk_mul;  // this launch's share (an upper bound when symmetric)
   const uint32_t n_pairs = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)std::max(ctx->sm_count / 2, 1));
   cfg.gridDim = dim3(2 * n_pairs, 1, 1);
   cfg.dynamicSmemBytes = N1_SMEM_BYTES;
@@ -710,13 +769,22 @@ int hg_narrow_launch(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t 
 // plane within the budget, else HG_E_UNSUPPORTED (then the kernels launched so far have done nothing useful and
 // the caller must discard their hits).  B may be NULL or equal to A.
 int hg_narrow_verdict(hg_ctx *ctx, const hg_narrow_mat *A, const hg_narrow_mat *B, int32_t *absmax_out, uint64_t *outliers_out) {
-  uint32_t sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
-  HG_CUDA(cudaMemcpyAsync(sa, A->stats, 16, cudaMemcpyDeviceToHost, ctx->stream));
-  if (B && B != A && B->stats != A->stats) HG_CUDA(cudaMemcpyAsync(sb, B->stats, 16, cudaMemcpyDeviceToHost, ctx->stream));
+  uint32_t sa[4 * 8] = {0}, sb[4 * 8] = {0};
+  if (A->n_sets > 8 || (B && B->n_sets > 8)) { hg_set_error("hg_narrow_verdict: more than 8 statistic sets"); return HG_E_INVALID; }
+  HG_CUDA(cudaMemcpyAsync(sa, A->stats_all, 16 * A->n_sets, cudaMemcpyDeviceToHost, ctx->stream));
+  const bool two = B && B != A && B->stats_all != A->stats_all;
+  if (two) HG_CUDA(cudaMemcpyAsync(sb, B->stats_all, 16 * B->n_sets, cudaMemcpyDeviceToHost, ctx->stream));
   HG_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (absmax_out) *absmax_out = (int32_t)std::max(sa[0], sb[0]);
-  if (outliers_out) *outliers_out = (uint64_t)sa[2] + sb[2];
-  if (sa[3] || sb[3]) {
+  uint32_t amax = 0, declined = 0;
+  uint64_t used = 0;
+  for (uint32_t t = 0; t < A->n_sets; ++t) { amax = std::max(amax, sa[4 * t]); declined |= sa[4 * t + 3]; }
+  for (uint32_t t = 0; two && t < B->n_sets; ++t) { amax = std::max(amax, sb[4 * t]); declined |= sb[4 * t + 3]; }
+  // entries used: the cursors start at each set's base (a single-set matrix: 0)
+  used += A->n_sets == 1 ? sa[2] - A->entry_base : 0;
+  used += two && B->n_sets == 1 ? sb[2] - B->entry_base : 0;
+  if (absmax_out) *absmax_out = (int32_t)amax;
+  if (outliers_out) *outliers_out = used;
+  if (declined) {
     hg_set_error("rows are not narrow: more than %u outlier entries per row on average (x = 2a + s, a in s8)", narrow_budget());
     return HG_E_UNSUPPORTED;
   }
@@ -729,7 +797,8 @@ int hg_narrow_verdict(hg_ctx *ctx, const hg_narrow_mat *A, const hg_narrow_mat *
 int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref, uint32_t i0,
                           const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry, uint32_t j0, uint32_t hv_d,
                           uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
-                          unsigned long long *d_n_hits, int32_t *absmax_out, uint64_t *outliers_out) {
+                          unsigned long long *d_n_hits, int32_t *absmax_out, uint64_t *outliers_out, int defer_verdict) {
+  ctx->pending_stats[0] = ctx->pending_stats[1] = nullptr;
   if (absmax_out) *absmax_out = -1;
   if (outliers_out) *outliers_out = 0;
   if (n_ref == 0 || n_qry == 0) return HG_OK;
@@ -753,6 +822,14 @@ int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_re
     return rc;
   HG_PROF(ctx, 5);
   // The kernel itself honours the pre-pass's verdict (it does nothing when the rows are not narrow), so the
-  // host learns it only now, with no bubble between pre-pass and kernel.
+  // host learns it only now, with no bubble between pre-pass and kernel - or, when the caller has asserted the
+  // path (defer_verdict), not at all here: hg_dist_status reads it whenever the caller synchronises anyway.
+  if (defer_verdict) {
+    ctx->pending_stats[0] = Q.stats_all;
+    ctx->pending_nsets[0] = Q.n_sets;
+    ctx->pending_stats[1] = qry_covers_ref ? nullptr : R.stats_all;
+    ctx->pending_nsets[1] = qry_covers_ref ? 0 : R.n_sets;
+    return HG_OK;
+  }
   return hg_narrow_verdict(ctx, &Q, qry_covers_ref ? nullptr : &R, absmax_out, outliers_out);
 }

@@ -308,10 +308,12 @@ struct PairTiles {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_qry,
                 uint32_t ref_plane_rows, uint32_t ref_row_base, uint32_t qry_plane_rows, uint32_t qry_row_base, uint32_t hv_d,
-                hg::DistEpilogue ep) {
+                hg::DistEpilogue ep, uint32_t walk_mul, uint32_t walk_add) {
   uint32_t rank;  // 0 = leader (issues the MMAs, owns the full / tmem-empty barriers), 1 = peer
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  // this launch takes tiles walk_add, walk_add + walk_mul, ... of the enumeration (member walk_add of walk_mul GPUs),
+  // dealt round-robin to its CTA pairs
+  const uint32_t pair = (blockIdx.x >> 1) * walk_mul + walk_add, n_pairs = (gridDim.x >> 1) * walk_mul;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -516,7 +518,29 @@ int hg_tc_split_rows(hg_ctx *ctx, const hg_tc_mat *m, uint32_t row0, uint32_t ro
 int hg_tc_launch(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
                  const hg_tc_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm, uint32_t ksize,
                  float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits) {
+  return hg_tc_launch_ex(ctx, R, r0, n_ref, i0, d_ref_norm, Q, q0, n_qry, j0, d_qry_norm, ksize, ani_th, symmetric, d_hits, cap,
+                         d_n_hits, 1, 0);
+}
+
+int hg_tc_attach(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d, int8_t *planes, hg_tc_mat *m) {
+  m->hv = d_hv;
+  m->planes = planes;
+  m->n_rows = n_rows;
+  m->hv_d = hv_d;
+  if (!ctx->tc_attr_set) {
+    HG_CUDA(cudaFuncSetAttribute(dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    ctx->tc_attr_set = 1;
+  }
+  return HG_OK;
+}
+
+int hg_tc_launch_ex(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
+                    const hg_tc_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm, uint32_t ksize,
+                    float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits, uint32_t walk_mul,
+                    uint32_t walk_add) {
   if (n_ref == 0 || n_qry == 0) return HG_OK;
+  if (walk_mul == 0 || walk_add >= walk_mul) { hg_set_error("hg_tc_launch: tile walk %u / %u", walk_add, walk_mul); return HG_E_INVALID; }
   int rc;
   const uint32_t hv_d = R->hv_d;
   const uint32_t gx = (n_qry + TC_BN - 1) / TC_BN, gy_total = (n_ref + TC_BM - 1) / TC_BM;
@@ -524,6 +548,7 @@ int hg_tc_launch(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref, u
   int pair_kernel = 1;
   if (const char *e = getenv("HG_DIST_KERNEL")) pair_kernel = atoi(e) == 1 ? 0 : 1;
   if (hv_d % (TC_BK * T2_STAGES) != 0) pair_kernel = 0;  // the pair kernel walks whole trips of its 4-stage ring
+  if (!pair_kernel && walk_mul != 1) { hg_set_error("a shared tile walk needs the pair kernel (hv_d %% 512 == 0)"); return HG_E_UNSUPPORTED; }
   CUtensorMap tm_ref, tm_qry;
   if ((rc = make_plane_map(&tm_qry, Q->planes, 2ull * Q->n_rows, hv_d, pair_kernel ? 64 : 128))) return rc;
   if ((rc = make_plane_map(&tm_ref, R->planes, 2ull * R->n_rows, hv_d, 128))) return rc;
@@ -556,12 +581,12 @@ int hg_tc_launch(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref, u
   cfg.stream = ctx->stream;
   if (pair_kernel) {
     // one CTA pair per TPC, each walking the 256 x 128 tiles with stride n_pairs
-    const uint64_t tiles = (uint64_t)gx * ((n_ref + 255) / 256);
+    const uint64_t tiles = ((uint64_t)gx * ((n_ref + 255) / 256) + walk_mul - 1) / walk_mul;
     const uint32_t n_pairs = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)std::max(ctx->sm_count / 2, 1));
     cfg.gridDim = dim3(2 * n_pairs, 1, 1);
     cfg.dynamicSmemBytes = T2_SMEM_BYTES;
     attr[0].val.clusterDim.x = 2;
-    HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel, tm_ref, tm_qry, R->n_rows, r0, Q->n_rows, q0, hv_d, make_ep(0)));
+    HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel, tm_ref, tm_qry, R->n_rows, r0, Q->n_rows, q0, hv_d, make_ep(0), walk_mul, walk_add));
     ctx->launches++;
   } else {
     const uint32_t y_step = 65534;  // <= the gridDim.y limit

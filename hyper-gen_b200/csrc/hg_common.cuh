@@ -145,11 +145,15 @@ struct hg_ctx {
   int ev_used;           // which stage boundaries were recorded in the last call
   // H2D pipeline of the host-pointer sketch entry
   int tc_attr_set;
+  int tc_is_hint;   // the two-limb path was chosen by the library (packed rows of 11..13 bits), not forced by the caller: SIMT fallback allowed
   int n1_attr_set;
   const uint64_t *d_actual_len;  // optional per-genome true lengths for the next k-mer launch (raw-FASTA path)
   cudaStream_t copy_stream;
   cudaEvent_t ev_copied[2], ev_done[2];
   cudaEvent_t ev_chunk[10];  // dist streaming: fork + one per row chunk (created with the copy stream)
+  // hg_dist_dev with the single-plane path forced: the pre-pass verdict is not waited for (hg_dist_status reads it)
+  const uint32_t *pending_stats[2];
+  uint32_t pending_nsets[2];
 };
 
 // stage boundaries: 0 start, 1 after staging/memsets, 2 after k-mer hash, 3 after encode,
@@ -231,6 +235,11 @@ int hg_tc_split_rows(hg_ctx *ctx, const hg_tc_mat *m, uint32_t row0, uint32_t ro
 int hg_tc_launch(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
                  const hg_tc_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm, uint32_t ksize,
                  float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits);
+int hg_tc_attach(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d, int8_t *planes, hg_tc_mat *m);
+int hg_tc_launch_ex(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
+                    const hg_tc_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm, uint32_t ksize,
+                    float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits, uint32_t walk_mul,
+                    uint32_t walk_add);
 int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref,
                       uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
                       uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
@@ -241,25 +250,43 @@ struct hg_narrow_mat {
   const int16_t *hv;  // the i16 matrix in HBM (n_rows x hv_d); rows need to be there only when they are prepared
   int8_t *plane;
   int32_t *s, *a2;
-  uint32_t *e, *out_off, *out_cnt, *entries, *stats;
-  uint32_t cap, n_rows, hv_d;
+  uint32_t *e, *out_off, *out_cnt, *entries;
+  // pre-pass statistics, 4 words per set: [0] max |x|, [1] max (|s| + 256), [2] entry cursor, [3] declined.
+  // `stats` is the set THIS context's pre-pass writes; the dist kernel and the verdict reduce over the
+  // n_sets sets at stats_all (one per member when the rows of the matrix were prepared on several GPUs).
+  uint32_t *stats, *stats_all;
+  uint32_t n_sets;
+  uint32_t entry_base;  // first entry index this context's pre-pass may use ...
+  uint32_t cap;         // ... and the limit (exclusive)
+  uint32_t n_rows, hv_d;
 };
 int hg_narrow_shape_ok(uint32_t hv_d, const void *d_a, const void *d_b);
 size_t hg_narrow_meta_bytes(uint32_t n_rows);
 int hg_narrow_setup(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d, int plane_slot, void *meta,
                     hg_narrow_mat *m);
+// the same over caller-provided memory (a peer window): nothing is allocated; entries_per_set as hg_narrow_set_cap()
+size_t hg_narrow_arrays_bytes(uint32_t n_rows);  // s | a2 | e | out_off | out_cnt, n_rows words each
+uint32_t hg_narrow_set_cap(uint32_t n_rows);
+int hg_narrow_attach(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d, int8_t *plane, void *arrays,
+                     uint32_t *entries, uint32_t *stats_all, uint32_t n_sets, uint32_t my_set, uint32_t entry_base,
+                     uint32_t set_cap, hg_narrow_mat *m);
 int hg_narrow_prep_rows(hg_ctx *ctx, const hg_narrow_mat *m, uint32_t row0, uint32_t rows);
 int hg_narrow_launch(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
                      const hg_narrow_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm,
                      uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
                      unsigned long long *d_n_hits);
+// as hg_narrow_launch for one member of `walk_mul` GPUs sharing the tile enumeration (takes tiles walk_add, walk_add + walk_mul, ...)
+int hg_narrow_launch_ex(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
+                        const hg_narrow_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm,
+                        uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
+                        unsigned long long *d_n_hits, uint32_t walk_mul, uint32_t walk_add);
 int hg_narrow_verdict(hg_ctx *ctx, const hg_narrow_mat *A, const hg_narrow_mat *B, int32_t *absmax_out, uint64_t *outliers_out);
 // one-shot form of the above; HG_E_UNSUPPORTED when the rows are not narrow
 int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref,
                           uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
                           uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
                           hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits, int32_t *absmax_out,
-                          uint64_t *outliers_out);
+                          uint64_t *outliers_out, int defer_verdict);
 int hg_launch_int_peak(hg_ctx *ctx, int which, uint32_t iters, uint32_t *d_sink, uint32_t blocks);
 // max |hv| over a device matrix (decides the dist path); result in *d_out (int32)
 int hg_launch_sort_hits(hg_ctx *ctx, hg_hit *d_hits, uint64_t n, uint32_t *d_milli);

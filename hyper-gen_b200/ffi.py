@@ -20,8 +20,12 @@ EXPORTS = [
     "hg_set_profiling", "hg_stage_ms", "hg_int_peak", "hg_encode_sets", "hg_encode_sets_dev",
     "hg_fasta_merge", "hg_sketch_fasta_batch",
     "hg_kmer_hash", "hg_sketch_batch", "hg_sketch_batch_dev", "hg_sketch_status", "hg_unpack", "hg_unpack_dev",
-    "hg_dist", "hg_dist_dev", "hg_dist_last_path", "hg_dist_last_reason", "hg_sort_hits_dev", "hg_dist_sorted", "hg_dist_packed",
+    "hg_dist", "hg_dist_dev", "hg_dist_status", "hg_dist_last_path", "hg_dist_last_reason", "hg_sort_hits_dev", "hg_dist_sorted", "hg_dist_packed",
+    "hg_group_create", "hg_group_destroy", "hg_group_size", "hg_group_ctx", "hg_group_sketch_fasta_batch", "hg_group_dist_packed",
+    "hg_peer_window_need", "hg_peer_create", "hg_peer_connect", "hg_peer_create_local", "hg_peer_destroy", "hg_peer_rank",
+    "hg_peer_world", "hg_peer_barrier", "hg_dist_sharded_dev", "hg_dist_sharded_hits", "hg_peer_hit_buffers",
 ]
+HG_MAX_PEERS, HG_IPC_HANDLE_BYTES = 8, 64
 
 
 class SketchParams(C.Structure):
@@ -86,12 +90,33 @@ def load() -> C.CDLL:
     L.hg_dist.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, u32, C.c_float, i32, i32, vp, u64, C.POINTER(u64)]
     L.hg_dist_dev.restype = i32
     L.hg_dist_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp, u32, u32, u32, u32, C.c_float, i32, i32, vp, u64, vp]
+    L.hg_dist_status.restype = i32; L.hg_dist_status.argtypes = [vp]
     L.hg_sort_hits_dev.restype = i32; L.hg_sort_hits_dev.argtypes = [vp, vp, u64, vp]
     L.hg_dist_sorted.restype = i32
     L.hg_dist_sorted.argtypes = [vp, vp, vp, u32, vp, vp, u32, u32, u32, C.c_float, i32, i32, vp, vp, u64, C.POINTER(u64)]
     L.hg_dist_packed.restype = i32
     L.hg_dist_packed.argtypes = [vp, vp, u64, vp, vp, u32, vp, u64, vp, vp, u32, u32, u32, C.c_float, i32, i32, i32, vp, vp,
                                  u64, C.POINTER(u64)]
+    L.hg_group_create.restype = i32; L.hg_group_create.argtypes = [i32, vp, C.POINTER(vp)]
+    L.hg_group_destroy.restype = None; L.hg_group_destroy.argtypes = [vp]
+    L.hg_group_size.restype = i32; L.hg_group_size.argtypes = [vp]
+    L.hg_group_ctx.restype = vp; L.hg_group_ctx.argtypes = [vp, i32]
+    L.hg_group_sketch_fasta_batch.restype = i32; L.hg_group_sketch_fasta_batch.argtypes = [vp, vp, vp, u32, pp, vp, vp, vp, vp, vp]
+    L.hg_group_dist_packed.restype = i32
+    L.hg_group_dist_packed.argtypes = [vp, vp, u64, vp, vp, u32, vp, u64, vp, vp, u32, u32, u32, C.c_float, i32, i32, vp, vp, u64,
+                                       C.POINTER(u64)]
+    L.hg_peer_window_need.restype = u64; L.hg_peer_window_need.argtypes = [u32, u32, u64]
+    L.hg_peer_create.restype = i32; L.hg_peer_create.argtypes = [vp, i32, i32, u64, vp, C.POINTER(vp)]
+    L.hg_peer_connect.restype = i32; L.hg_peer_connect.argtypes = [vp, vp]
+    L.hg_peer_create_local.restype = i32; L.hg_peer_create_local.argtypes = [vp, i32, u64, vp]
+    L.hg_peer_destroy.restype = None; L.hg_peer_destroy.argtypes = [vp]
+    L.hg_peer_rank.restype = i32; L.hg_peer_rank.argtypes = [vp]
+    L.hg_peer_world.restype = i32; L.hg_peer_world.argtypes = [vp]
+    L.hg_peer_barrier.restype = i32; L.hg_peer_barrier.argtypes = [vp]
+    L.hg_dist_sharded_dev.restype = i32
+    L.hg_dist_sharded_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp, u32, u32, u32, u32, u32, C.c_float, i32, i32, i32, u64]
+    L.hg_dist_sharded_hits.restype = i32; L.hg_dist_sharded_hits.argtypes = [vp, i32, vp, vp, u64, C.POINTER(u64)]
+    L.hg_peer_hit_buffers.restype = i32; L.hg_peer_hit_buffers.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
     L.hg_dist_last_path.restype = i32; L.hg_dist_last_path.argtypes = [vp]
     L.hg_dist_last_reason.restype = C.c_char_p; L.hg_dist_last_reason.argtypes = [vp]
     _lib = L
@@ -313,6 +338,10 @@ class Context:
         _check(load().hg_dist_dev(self._h, d_ref, d_ref_norm2, n_ref, i0, d_qry, d_qry_norm2, n_qry, j0, hv_d, ksize,
                                   ani_th, int(symmetric), path, d_hits, cap, d_n_hits))
 
+    def dist_status(self):
+        """hg_dist_status: the verdict a dist_dev(path=3) did not wait for"""
+        _check(load().hg_dist_status(self._h))
+
     def dist_packed(self, ref_packed, ref_bits, ref_norm2, qry_packed, qry_bits, qry_norm2, hv_d, ksize=21, ani_th=85.0,
                     symmetric=False, path=0, sorted_output=True, cap=None):
         """hg_dist_packed: packed sketch rows (n x stride uint8) + quant bits + norms -> (hits, ani_milli)."""
@@ -338,7 +367,8 @@ class Context:
                 cap = int(n_hits.value)
                 continue
             _check(rc)
-            return hits[: n_hits.value].copy(), milli[: n_hits.value].copy()
+            # ani_milli is written by the output-stage sort only (hypergen_b200.h): unsorted calls get None
+            return hits[: n_hits.value].copy(), (milli[: n_hits.value].copy() if sorted_output else None)
 
     def sort_hits_dev(self, d_hits, n, d_ani_milli=None):
         """hg_sort_hits_dev: device records to the reference's output order, in place."""
@@ -351,3 +381,125 @@ class Context:
     @property
     def dist_last_reason(self) -> str:
         return load().hg_dist_last_reason(self._h).decode()
+
+
+class Peer:
+    """hg_peer: this process's GPU as one member of a group of GPUs on the box (one process per GPU).
+
+    `exchange(handle: bytes) -> list[bytes]` is the host's own all-gather of the 64-byte window handles
+    (multigpu.PeerGroup passes one built on torch.distributed); world == 1 needs none."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, window_bytes: int, exchange=None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._h = C.c_void_p()
+        handle = (C.c_uint8 * HG_IPC_HANDLE_BYTES)()
+        _check(load().hg_peer_create(ctx._h, rank, world, window_bytes, handle, C.byref(self._h)))
+        if world > 1:
+            allh = exchange(bytes(handle))
+            buf = (C.c_uint8 * (HG_IPC_HANDLE_BYTES * world)).from_buffer_copy(b"".join(allh))
+            _check(load().hg_peer_connect(self._h, buf))
+
+    def close(self):
+        if self._h:
+            load().hg_peer_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def barrier(self):
+        _check(load().hg_peer_barrier(self._h))
+
+    def dist_sharded_dev(self, d_ref, d_ref_norm2, n_ref_local, ref_row0, d_qry, d_qry_norm2, n_qry_local, qry_row0,
+                         n_qry_total, hv_d, ksize, ani_th, symmetric, path, root, cap):
+        """hg_dist_sharded_dev (collective; device pointers as ints)."""
+        _check(load().hg_dist_sharded_dev(self._h, d_ref, d_ref_norm2, n_ref_local, ref_row0, d_qry, d_qry_norm2, n_qry_local,
+                                          qry_row0, n_qry_total, hv_d, ksize, ani_th, int(symmetric), path, root, cap))
+
+    def dist_sharded_hits(self, cap: int, sorted_output: bool = False, hits=None, milli=None):
+        """hg_dist_sharded_hits -> (hits, milli or None) on the root, (empty, None) elsewhere.  `hits` / `milli`
+        may be preallocated (pinned) numpy arrays of at least `cap` records."""
+        own = hits is None
+        if own:
+            hits = np.empty(cap, HIT_DTYPE)
+        if sorted_output and milli is None:
+            milli = np.empty(cap, np.uint32)
+        n = C.c_uint64(0)
+        _check(load().hg_dist_sharded_hits(self._h, int(sorted_output), _ptr(hits), _ptr(milli) if sorted_output else None, cap,
+                                           C.byref(n)))
+        h = hits[: n.value]
+        return (h.copy() if own else h), (milli[: n.value] if sorted_output else None)
+
+    def hit_buffers(self, root: int = 0):
+        dh, dc = C.c_void_p(), C.c_void_p()
+        _check(load().hg_peer_hit_buffers(self._h, root, C.byref(dh), C.byref(dc)))
+        return dh.value, dc.value
+
+
+def peer_window_need(gathered_rows: int, hv_d: int, hit_cap: int) -> int:
+    return int(load().hg_peer_window_need(gathered_rows, hv_d, hit_cap))
+
+
+class Group:
+    """hg_group: one process driving several GPUs of the box (what the `hyper-gen` CLI uses)."""
+
+    def __init__(self, n_devices: int = 0, ordinals=None):
+        self._h = C.c_void_p()
+        arr = None
+        if ordinals is not None:
+            arr = (C.c_int * len(ordinals))(*ordinals)
+            n_devices = len(ordinals)
+        _check(load().hg_group_create(n_devices, arr, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            load().hg_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def size(self) -> int:
+        return int(load().hg_group_size(self._h))
+
+    def dist_last_path(self, i: int = 0) -> int:
+        return int(load().hg_dist_last_path(load().hg_group_ctx(self._h, i)))
+
+    def sketch_fasta_batch(self, files, params: SketchParams, want_hv: bool = True):
+        raw, off = Context._concat_files(files)
+        n = len(files)
+        D = int(params.hv_d)
+        hv = np.empty((n, D), np.int16) if want_hv else None
+        packed = np.empty((n, 2 * D), np.uint8)
+        qb = np.empty(n, np.uint8)
+        norm2 = np.empty(n, np.int32)
+        nh = np.empty(n, np.uint32)
+        _check(load().hg_group_sketch_fasta_batch(self._h, _ptr(raw) if raw.size else None, _ptr(off), n, C.byref(params),
+                                                  _ptr(hv), _ptr(packed), _ptr(qb), _ptr(norm2), _ptr(nh)))
+        return dict(hv=hv, packed=packed, quant_bits=qb, norm2=norm2, n_hashes=nh)
+
+    def dist_packed(self, ref_packed, ref_bits, ref_norm2, qry_packed, qry_bits, qry_norm2, hv_d, ksize=21, ani_th=85.0,
+                    symmetric=False, sorted_output=True, cap=None):
+        rp = np.ascontiguousarray(ref_packed, np.uint8)
+        rb = np.ascontiguousarray(ref_bits, np.uint8)
+        rn = np.ascontiguousarray(ref_norm2, np.int32)
+        same = qry_packed is ref_packed
+        qp = rp if same else np.ascontiguousarray(qry_packed, np.uint8)
+        qb = rb if same else np.ascontiguousarray(qry_bits, np.uint8)
+        qn = rn if same else np.ascontiguousarray(qry_norm2, np.int32)
+        R, Q = rp.shape[0], qp.shape[0]
+        if cap is None:
+            cap = max(1024, R * Q // 64)
+        while True:
+            hits = np.empty(cap, HIT_DTYPE)
+            milli = np.empty(cap, np.uint32)
+            n_hits = C.c_uint64(0)
+            rc = load().hg_group_dist_packed(self._h, _ptr(rp), rp.strides[0] if R else 0, _ptr(rb), _ptr(rn), R, _ptr(qp),
+                                             qp.strides[0] if Q else 0, _ptr(qb), _ptr(qn), Q, hv_d, ksize, ani_th,
+                                             int(symmetric), int(sorted_output), _ptr(hits), _ptr(milli), cap, C.byref(n_hits))
+            if rc == HG_E_CAPACITY and n_hits.value > cap:
+                cap = int(n_hits.value)
+                continue
+            _check(rc)
+            return hits[: n_hits.value].copy(), (milli[: n_hits.value].copy() if sorted_output else None)

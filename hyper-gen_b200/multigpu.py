@@ -8,8 +8,13 @@
     For the symmetric all-vs-all case the row boundaries are chosen so every rank owns the
     same number of upper-triangle pairs.
 
-The collective logic is independent of the device: it takes a `compute` callback, so the
-same code runs under NCCL on GPUs and under gloo on CPU tensors in the tests.
+Two transports exist for the dist exchange:
+  * the product path, `PeerGroup`: NVLink windows inside the library (csrc/peer.cu) - every rank turns its
+    own rows into the kernel's operand form and pushes them into all windows, tiles are dealt round-robin,
+    hits are appended straight into rank 0's list.  torch.distributed only carries the 64-byte window
+    handles once, at start-up;
+  * `dist_sharded`, collectives of torch.distributed around a `compute` callback (NCCL on GPUs, gloo on
+    CPU tensors): the reference formulation of the same sharding, kept for the CPU tests of the host logic.
 """
 from __future__ import annotations
 
@@ -241,3 +246,38 @@ def sketch_files_distributed(files, sketch_fn, out_file: str | None = None):
     if out_file:
         fileio.dump_sketch(allsk, out_file)
     return allsk
+
+
+# ---------------------------------------------------------------------------------------------
+# NVLink-window transport (the product path): hg_peer behind torch.distributed's bootstrap
+# ---------------------------------------------------------------------------------------------
+def block_rows(n: int, n_ranks: int, align: int = 4) -> list[int]:
+    """Boundaries of the contiguous row blocks the ranks hold: as even as `align`-row granularity allows."""
+    return [n if r == n_ranks else (n * r // n_ranks) // align * align for r in range(n_ranks + 1)]
+
+
+def exchange_handles(handle: bytes, device=None) -> list[bytes]:
+    """All-gather of one fixed-size byte string per rank over the default process group."""
+    world = dist.get_world_size()
+    t = torch.tensor(list(handle), dtype=torch.uint8, device=device if device is not None else "cpu")
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    return [bytes(x.cpu().tolist()) for x in parts]
+
+
+class PeerGroup:
+    """This rank's GPU as a member of the box's GPUs (one process per GPU, launched by torchrun)."""
+
+    def __init__(self, ctx, window_bytes: int, device=None):
+        from . import ffi
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.peer = ffi.Peer(ctx, self.rank, self.world, window_bytes,
+                             exchange=(lambda h: exchange_handles(h, device)) if self.world > 1 else None)
+        if self.world > 1:
+            dist.barrier()  # every rank has mapped every window before anyone pushes into one
+
+    def close(self):
+        if self.world > 1:
+            dist.barrier()  # nobody unmaps a window a peer may still push into
+        self.peer.close()

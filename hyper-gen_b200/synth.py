@@ -101,3 +101,42 @@ def hash_sets_family(n_sketches: int, n_per: int = 3333, members: int = 10, scal
         priv = rng.integers(0, thr, n_per - mine.size, dtype=np.uint64)
         out.append(np.unique(np.concatenate([mine, priv])))
     return out
+
+
+def _mix64(z: torch.Tensor) -> torch.Tensor:
+    """splitmix64 finaliser on int64 tensors (two's complement of the u64)."""
+    z = (z ^ _lsr(z, 30)) * _s64(_M1)
+    z = (z ^ _lsr(z, 27)) * _s64(_M2)
+    return z ^ _lsr(z, 31)
+
+
+_KEEP = (1.0, 0.98, 0.9, 0.8, 0.65, 0.5, 0.35, 0.2, 0.1, 0.02)
+
+
+def hash_sets_family_dev(n_sketches: int, n_per: int = 3333, members: int = 10, scaled: int = 1500, seed: int = 0xD157,
+                         device="cpu", first: int = 0, chunk: int = 4096):
+    """Controlled-Jaccard hash sets like hash_sets_family, generated with tensor arithmetic so that large
+    collections (config 4: 100,000 sketches, config 5: 20,000 x 10,000 hashes) come straight from the GPU and any
+    block of sketches [first, first + n) can be generated on its own (every value is a pure function of the sketch /
+    family index).  Every set has exactly n_per distinct values < u64::MAX / scaled.
+    Returns (hashes int64[n * n_per] as the bit pattern of the u64 values, hash_off uint64[n + 1])."""
+    thr = (2 ** 64 - 1) // scaled
+    keep = torch.tensor([int(k * (1 << 24)) for k in _KEEP], dtype=torch.int64, device=device)
+    e = torch.arange(n_per, dtype=torch.int64, device=device)[None, :]
+    out = torch.empty((n_sketches, n_per), dtype=torch.int64, device=device)
+    for c0 in range(0, n_sketches, chunk):
+        m = min(chunk, n_sketches - c0)
+        sid = torch.arange(first + c0, first + c0 + m, dtype=torch.int64, device=device)[:, None]
+        fam, mem = sid // members, sid % members
+        pool = _mix64((fam * n_per + e) * _s64(_GAMMA) + _s64(seed))
+        priv = _mix64((sid * n_per + e) * _s64(_GAMMA) + _s64(seed ^ 0x5EED5EED5EED))
+        u = _mix64((sid * n_per + e) * _s64(_GAMMA) + _s64(seed ^ 0x0123456789AB))
+        take = _lsr(u, 40) < keep[mem % len(_KEEP)]
+        v = torch.where(take, pool, priv)
+        v = _lsr(v, 1) % thr
+        vs, _ = torch.sort(v, dim=1)
+        if bool((vs[:, 1:] == vs[:, :-1]).any()):
+            raise RuntimeError("hash_sets_family_dev: duplicate value inside a set (change the seed)")
+        out[c0:c0 + m] = vs
+    off = np.arange(n_sketches + 1, dtype=np.uint64) * np.uint64(n_per)
+    return out.view(-1), off

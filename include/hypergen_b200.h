@@ -192,14 +192,19 @@ HG_API int hg_dist(hg_ctx *ctx, const int16_t *ref_hv, const int32_t *ref_norm2,
 /* Device-resident variant: HVs/norms/hits in HBM, hit order unspecified (atomic append),
  * *d_n_hits counts every passing pair even beyond cap.  (i, j) are offset by i0 / j0 so a
  * row shard of a larger ref matrix reports global indices; with `symmetric` the filter is
- * global_j > global_i.  Work is enqueued on the context stream; paths 1 and 2 return without waiting
- * for it, paths 0 and 3 wait once at the end (the host reads the single-plane pre-pass's verdict
- * there, after the kernel has been enqueued behind it, so the GPU never idles on that read). */
+ * global_j > global_i.  Work is enqueued on the context stream; paths 1, 2 and 3 return without waiting
+ * for it; path 0 waits once at the end (the host reads the single-plane pre-pass's verdict there, after
+ * the kernel has been enqueued behind it, so the GPU never idles on that read).  With path 3 the caller
+ * asserts that the rows are narrow: if they are not, the kernel does nothing and hg_dist_status() says so. */
 HG_API int hg_dist_dev(hg_ctx *ctx, const int16_t *d_ref_hv, const int32_t *d_ref_norm2, uint32_t n_ref,
                        uint32_t i0, const int16_t *d_qry_hv, const int32_t *d_qry_norm2,
                        uint32_t n_qry, uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th,
                        int symmetric, int path, hg_hit *d_hits, uint64_t cap,
                        unsigned long long *d_n_hits);
+
+/* After hg_dist_dev(path = 3) (synchronises the stream): HG_OK, or HG_E_UNSUPPORTED if the rows were not
+ * narrow - the forced call then produced no hits and the caller must use path 0 / 2 / 1. */
+HG_API int hg_dist_status(hg_ctx *ctx);
 
 /* ---- output stage ------------------------------------------------------------------ */
 
@@ -223,12 +228,81 @@ HG_API int hg_dist_sorted(hg_ctx *ctx, const int16_t *ref_hv, const int32_t *ref
  * apart), hv_quant_bits and hv_norm_2.  Only the live bytes cross PCIe; decompress_file_sketch
  * (src/hd.rs:171-232) runs on the device in front of the dist kernel.  sorted != 0: the hits
  * come back in dump_ani_file's order as from hg_dist_sorted (ani_milli may be NULL); otherwise
- * as from hg_dist.  Pass the same pointers for ref and query for the symmetric all-vs-all. */
+ * as from hg_dist and ani_milli is NOT written (the output-stage sort produces it).  Pass the same pointers for ref and query for the symmetric all-vs-all. */
 HG_API int hg_dist_packed(hg_ctx *ctx, const uint8_t *ref_packed, uint64_t ref_stride, const uint8_t *ref_quant_bits,
                           const int32_t *ref_norm2, uint32_t n_ref, const uint8_t *qry_packed,
                           uint64_t qry_stride, const uint8_t *qry_quant_bits, const int32_t *qry_norm2,
                           uint32_t n_qry, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path,
                           int sorted, hg_hit *hits, uint32_t *ani_milli, uint64_t cap, uint64_t *n_hits);
+
+/* ---- several GPUs of one box ---------------------------------------------------------- */
+
+/* The reference drives one GPU (CudaDevice::new(0), src/sketch_cuda.rs:52) and has no GPU dist at all
+ * (src/dist.rs:231-294 is a rayon loop); SURVEY.md 8e shards the path over the GPUs of one box:
+ * genome files split across GPUs for sketching (no exchange), ref rows sharded / queries broadcast /
+ * hits gathered for dist.  The exchange runs over NVLink windows owned by the library (no collective
+ * library on the data path, see csrc/peer.cu).
+ *
+ * hg_group: ONE process driving all GPUs - what `hyper-gen sketch -D gpu` and `hyper-gen dist` call. */
+typedef struct hg_group hg_group;
+#define HG_MAX_PEERS 8
+/* n_devices <= 0: every visible GPU (at most HG_MAX_PEERS); ordinals may be NULL (0 .. n-1). */
+HG_API int hg_group_create(int n_devices, const int *ordinals, hg_group **out);
+HG_API void hg_group_destroy(hg_group *g);
+HG_API int hg_group_size(const hg_group *g);
+HG_API hg_ctx *hg_group_ctx(hg_group *g, int i);
+/* hg_sketch_fasta_batch with the files split into one contiguous run per GPU of about equal bytes
+ * (sketch_cuda's par_iter over files, src/sketch_cuda.rs:79, across GPUs); same arguments and outputs. */
+HG_API int hg_group_sketch_fasta_batch(hg_group *g, const uint8_t *raw, const uint64_t *file_off, uint32_t n_files,
+                                       const hg_sketch_params *p, int16_t *hv, uint8_t *packed, uint8_t *quant_bits,
+                                       int32_t *norm2, uint32_t *n_hashes);
+/* hg_dist_packed with the rows of both sketch files split into one block per GPU: each block crosses its
+ * own GPU's PCIe link, is unpacked and brought into operand form there, the query operands are pushed to
+ * every GPU, the output tiles are shared out, the hits land on GPU 0 (sorted there if asked).  Results are
+ * identical to hg_dist_packed (the unsorted order is unspecified in both). */
+HG_API int hg_group_dist_packed(hg_group *g, const uint8_t *ref_packed, uint64_t ref_stride, const uint8_t *ref_quant_bits,
+                                const int32_t *ref_norm2, uint32_t n_ref, const uint8_t *qry_packed, uint64_t qry_stride,
+                                const uint8_t *qry_quant_bits, const int32_t *qry_norm2, uint32_t n_qry, uint32_t hv_d,
+                                uint32_t ksize, float ani_th, int symmetric, int sorted, hg_hit *hits, uint32_t *ani_milli,
+                                uint64_t cap, uint64_t *n_hits);
+
+/* hg_peer: one member of a group of GPUs, for hosts that run ONE PROCESS PER GPU.  Every member
+ * allocates a window (hg_peer_create), the host exchanges the HG_IPC_HANDLE_BYTES-byte handles by its
+ * own means (an all-gather), and every member maps the others' windows (hg_peer_connect). */
+typedef struct hg_peer hg_peer;
+#define HG_IPC_HANDLE_BYTES 64
+/* bytes a window needs for a sharded dist whose gathered (query) matrix has `gathered_rows` rows */
+HG_API uint64_t hg_peer_window_need(uint32_t gathered_rows, uint32_t hv_d, uint64_t hit_cap);
+HG_API int hg_peer_create(hg_ctx *ctx, int rank, int world, uint64_t window_bytes, uint8_t handle_out[HG_IPC_HANDLE_BYTES],
+                          hg_peer **out);
+HG_API int hg_peer_connect(hg_peer *p, const uint8_t *handles /* world x HG_IPC_HANDLE_BYTES, rank order */);
+/* members of one process instead (what hg_group uses): out[0 .. world) */
+HG_API int hg_peer_create_local(hg_ctx *const *ctxs, int world, uint64_t window_bytes, hg_peer **out);
+HG_API void hg_peer_destroy(hg_peer *p);
+HG_API int hg_peer_rank(const hg_peer *p);
+HG_API int hg_peer_world(const hg_peer *p);
+/* enqueue a barrier among the members on this member's stream (bounded wait: HG_PEER_TIMEOUT_MS, default 10 s) */
+HG_API int hg_peer_barrier(hg_peer *p);
+/* Collective sharded dist, rows resident in HBM (compute_hv_ani, src/dist.rs:231-294, over several GPUs).
+ * Every member calls it with the same scalars and ITS rows:
+ *   symmetric != 0  all-vs-all (j > i, src/dist.rs:253-265) over ONE matrix of n_qry_total rows, of which this
+ *                   member holds rows [qry_row0, qry_row0 + n_qry_local); the ref arguments are ignored.  The
+ *                   non-empty output tiles are dealt round-robin to the members;
+ *   symmetric == 0  this member's n_ref_local ref rows (global index ref_row0 + row) against ALL n_qry_total
+ *                   query rows, of which this member contributes [qry_row0, +n_qry_local) - none, some or all.
+ *   path  0 auto (one host read of all members' pre-pass verdict; two-limb kernel if the rows are not narrow),
+ *         3 / 2 single-plane / two-limb tensor kernel asserted by the caller: the call only enqueues.
+ * Hits carry global (i, j) and accumulate in member `root`'s window (capacity `cap`, same on every member). */
+HG_API int hg_dist_sharded_dev(hg_peer *p, const int16_t *d_ref_hv, const int32_t *d_ref_norm2, uint32_t n_ref_local,
+                               uint32_t ref_row0, const int16_t *d_qry_hv, const int32_t *d_qry_norm2, uint32_t n_qry_local,
+                               uint32_t qry_row0, uint32_t n_qry_total, uint32_t hv_d, uint32_t ksize, float ani_th,
+                               int symmetric, int path, int root, uint64_t cap);
+/* Waits for this member's part.  On the root: *n_hits and the hits copied to HOST memory, in dump_ani_file's
+ * order if `sorted` (ani_milli as in hg_dist_sorted; may be NULL); HG_E_CAPACITY with the need if they exceed
+ * cap.  On the other members *n_hits = 0 and hits may be NULL. */
+HG_API int hg_dist_sharded_hits(hg_peer *p, int sorted, hg_hit *hits, uint32_t *ani_milli, uint64_t cap, uint64_t *n_hits);
+/* the root's hit list and counter as this member addresses them (device pointers) */
+HG_API int hg_peer_hit_buffers(hg_peer *p, int root, hg_hit **d_hits, unsigned long long **d_count);
 
 /* Which path the last hg_dist / hg_dist_dev took (1 SIMT, 2 two-limb tensor, 3 single-plane tensor) and why. */
 HG_API int hg_dist_last_path(hg_ctx *ctx);

@@ -18,7 +18,11 @@ def timeit(fn, n=10):
 t_b = timeit(lambda: dist.broadcast(buf, src=0))
 t_g = timeit(lambda: dist.all_gather_into_tensor(recv, small))
 t_ar = timeit(lambda: dist.all_reduce(small[:8].view(torch.int64)))
+plane = torch.empty(41_000_000 // world, dtype=torch.uint8, device=dev)
+plane_all = torch.empty(plane.numel() * world, dtype=torch.uint8, device=dev)
+t_ag = timeit(lambda: dist.all_gather_into_tensor(plane_all, plane))
 if rank == 0:
     print("world %d: broadcast 82 MB %.3f ms (%.1f GB/s), all_gather 1 MiB/rank %.3f ms, all_reduce 8 B %.3f ms" %
           (world, t_b, 82e6 / t_b / 1e6, t_g, t_ar))
+    print("all_gather of a 41 MB s8 plane (%.1f MB per rank): %.3f ms" % (plane.numel() / 1e6, t_ag))
 dist.destroy_process_group()
