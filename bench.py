@@ -9,9 +9,12 @@ sketches its own 1,000 genomes, no collective on the data path).  A "step" is on
 the sketch hot path (k-mer hash -> set -> HV encode -> norm -> quantise -> bit-pack) over the
 whole batch with the sequence bytes already resident in HBM.  `e2e` is the same pass through
 the host-pointer C-ABI call (pinned host buffers, H2D of the FASTA bytes and D2H of the
-sketches inside the timed region).  The `dist` object carries the second half of the
-metric: ANI pairs/s for the all-vs-all over 10,000 sketches (config[2]), ref rows sharded
-over the ranks, queries broadcast and hits gathered with NCCL.
+sketches inside the timed region).  The `dist`, `dist_cfg4` and `dist_cfg5` objects carry the
+second half of the metric, ANI pairs/s, on configs[2] (10,000 all-vs-all), configs[3]
+(100,000 refs x 1,000 queries) and configs[4] (20,000 all-vs-all at scaled=500, D=8192), each
+with its own roofline, oracle parity check and CPU baseline; at N > 1 the rows are sharded over
+the ranks and exchanged through the library's NVLink windows (csrc/peer.cu).
+`reference_gpu_kernel` times the reference's own CUDA kernel (oracle/_ref) on the same GPU.
 
 `--impl reference` times the reference's CPU path restated in C (oracle/hg_oracle.c — the
 Rust crate cannot be built here: no cargo/rustc) on the host cores.
@@ -121,18 +124,61 @@ def cpu_sketch_baseline(seq_host: np.ndarray, n_avail: int, seconds_hint: float 
 def parity_sample(seq_host, packed, bits, norm, n):
     """Checker leg: the e2e results of a few genomes of the timed batch against the oracle."""
     import oracle as O
-    pick = sorted(set([0, 1, n // 2, n - 1]))
+    pick = sorted(set(list(range(0, n, 50)) + [1, n - 1]))  # every 50th genome of the batch + the ends
+    O.set_threads(os.cpu_count() or 1)
+    sub = np.concatenate([seq_host[g * GENOME_LEN:(g + 1) * GENOME_LEN] for g in pick])
+    off = np.arange(len(pick) + 1, dtype=np.uint64) * np.uint64(GENOME_LEN)
+    w = O.sketch_batch(sub, off, k=K, scaled=SCALED, seed=SEED, hv_d=HV_D, want_hv=False)
     bad = 0
-    for g in pick:
-        s = seq_host[g * GENOME_LEN:(g + 1) * GENOME_LEN]
-        w = O.sketch_batch(s, np.array([0, GENOME_LEN], np.uint64), k=K, scaled=SCALED, seed=SEED, hv_d=HV_D, want_hv=False)
-        nb = int(w["quant_bits"][0]) * HV_D // 8
-        ok = (int(w["quant_bits"][0]) == int(bits[g]) and int(w["norm2"][0]) == int(norm[g])
-              and np.array_equal(w["packed"][0, :nb], packed[g, :nb]))
+    for t, g in enumerate(pick):
+        nb = int(w["quant_bits"][t]) * HV_D // 8
+        ok = (int(w["quant_bits"][t]) == int(bits[g]) and int(w["norm2"][t]) == int(norm[g])
+              and np.array_equal(w["packed"][t, :nb], packed[g, :nb]))
         bad += 0 if ok else 1
     if bad:
         raise RuntimeError("parity check failed on %d of %d sampled genomes" % (bad, len(pick)))
-    return "ok: %d sampled genomes of the timed batch bit-identical to the oracle (packed HV, bits, norm)" % len(pick)
+    return "ok: %d genomes of the timed batch (every 50th) bit-identical to the oracle (packed HV, bits, norm)" % len(pick)
+
+
+def reference_gpu_leg(ctx, params, seq_dev, seq_host, n, our_resident_per_gpu, our_e2e_per_gpu, n_ref_genomes=32):
+    """The reference's own GPU kernel (cuda_kmer_t1ha2, /root/reference/src/cuda_kernel.cu:250-321, built by
+    oracle/Makefile into oracle/_ref) with its launch geometry (src/sketch_cuda.rs:130-154) on genomes of the timed batch."""
+    try:
+        from oracle import ref_gpu
+        if not ref_gpu.available():
+            return {"unavailable": "oracle/_ref holds no GPU image of the reference kernel (built where /root/reference is mounted)"}
+        m = min(n, n_ref_genomes)
+        out = {}
+        sets = None
+        for image in ("cubin", "ptx"):
+            try:
+                r, sets_i = ref_gpu.time_reference_kernel(seq_dev, seq_host, GENOME_LEN, m, K, SCALED, SEED, image=image)
+                out[image] = r
+                sets = sets or sets_i
+            except Exception as ex:  # noqa: BLE001
+                out[image] = {"error": str(ex)[:200]}
+        best = min((v for v in out.values() if "kernel_ms_per_genome" in v), key=lambda v: v["kernel_ms_per_genome"], default=None)
+        if best is None:
+            return out
+        # its hash sets against ours (set semantics; the reference drops samples beyond 8 per 512-k-mer chunk and h == 0)
+        sh = seq_host.numpy()
+        missing = extra = 0
+        for g, rs in enumerate(sets):
+            ours, _ = ctx.kmer_hash(sh[g * GENOME_LEN:(g + 1) * GENOME_LEN], np.array([0, GENOME_LEN], np.uint64), params)
+            missing += int((~np.isin(rs, ours)).sum())
+            extra += int((~np.isin(ours, rs)).sum())
+        out.update({
+            "kernel": "cuda_kmer_t1ha2 (reference, unmodified, compiled from /root/reference/src/cuda_kernel.cu where it lies)",
+            "genomes_s": best["kernel_genomes_per_s"], "ms": best["kernel_ms_per_genome"], "e2e_genomes_s": best["e2e_genomes_per_s"],
+            "scope": "k-mer hashing only (the reference encodes, norms and packs on the CPU afterwards, src/sketch_cuda.rs:85-100)",
+            "ours_over_reference_kernel": our_resident_per_gpu / best["kernel_genomes_per_s"],
+            "ours_over_reference_e2e": our_e2e_per_gpu / best["e2e_genomes_per_s"],
+            "set_check": {"genomes": len(sets), "reference_hashes_missing_from_ours": missing, "ours_not_in_reference": extra,
+                          "note": "ours_not_in_reference are the samples the reference kernel drops (more than 8 per 512-k-mer "
+                                  "chunk, src/cuda_kernel.cu:316) or h == 0 (src/sketch_cuda.rs:159)"}})
+        return out
+    except Exception as ex:  # noqa: BLE001
+        return {"error": str(ex)[:300]}
 
 
 def run_reference(args, rank):
@@ -193,7 +239,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genomes", type=int, default=1000, help="genomes per GPU per step (config[1]: 1000)")
-    ap.add_argument("--dist-n", type=int, default=10000, help="sketches in the all-vs-all (config[2]: 10000)")
+    ap.add_argument("--dist-configs", default="dist,dist_cfg4,dist_cfg5",
+                    help="which dist workloads to run: dist (configs[2]), dist_cfg4 (configs[3]), dist_cfg5 (configs[4])")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the reference's own GPU kernel (oracle/_ref)")
     ap.add_argument("--no-dist", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fasta", action="store_true", help="skip the raw-FASTA end-to-end leg")
@@ -224,9 +272,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa = multigpu.bind_to_gpu_numa(local_rank) if os.environ.get("HG_NUMA_BIND", "1") != "0" else {"bound": False}
+    host_pg = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        host_pg = dist.new_group(backend="gloo")  # host-only waits (an NCCL barrier would park a kernel on the waiting GPUs)
 
     def barrier():
         if world > 1:
@@ -405,24 +455,65 @@ def main():
     }
 
     # auxiliary INT32 roofline (denominator measured live with the library's probe kernels)
+    int_peak = float("nan")
     try:
         int_peak = ctx.int_peak(2)
         line["roofline_int32"] = {"bound": "int32_issue", "achieved": kmers_per_s * KMER_INST_PER_KMER * 1.0,
                                   "peak": int_peak, "unit": "lane-instr/s", "frac": kmers_per_s * KMER_INST_PER_KMER / int_peak,
                                   "kmers_per_s": kmers_per_s, "inst_per_kmer": KMER_INST_PER_KMER,
-                                  "peak_imad_only": ctx.int_peak(0), "peak_alu_only": ctx.int_peak(1)}
+                                  "peak_imad_only": ctx.int_peak(0), "peak_alu_only": ctx.int_peak(1),
+                                  "peak_source": "measured live by this build's own probe (hg_int_peak, csrc/probe.cu), not a published figure"}
     except Exception as ex:  # pragma: no cover
         line["roofline_int32"] = {"error": str(ex)}
 
-    # ---------------- dist: all-vs-all ANI over dist_n sketches ----------------
-    if not args.no_dist:
-        line["dist"] = bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, max_over_ranks, peaks)
+    # ---------------- encode: INT32 roofline (north star: "INT32 ALU for encode") ----------------
+    try:
+        nh_sum = float(d_nh.sum().item())
+        enc_updates = nh_sum * HV_D * (1.0 + 1.0 / 64.0)  # n*D counter updates + n*D/64 wyrng words per genome
+        line["roofline_encode"] = {"bound": "int32_alu", "kernel": "encode_kernel", "achieved": enc_updates / (enc_ms * 1e-3),
+                                   "peak": int_peak, "unit": "counter updates/s vs lane-instr/s", "frac": enc_updates / (enc_ms * 1e-3) / int_peak,
+                                   "ms_per_launch": enc_ms, "alg_updates_per_launch": enc_updates,
+                                   "note": "algorithmic work n*D counter updates + n*D/64 wyrng words over the measured dual-pipe INT32 "
+                                           "lane-instruction rate; the kernel counts bit-sliced (carry-save adders retire 32 one-bit "
+                                           "updates per LOP3), so this is a work-rate ratio, not a pipe utilisation (ncu: profiles/r1_encode_full.md)"}
+    except Exception as ex:  # pragma: no cover
+        line["roofline_encode"] = {"error": str(ex)}
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_sketch_baseline(seq_host.numpy(), n)
+    # ---------------- the reference's own GPU kernel on this GPU (rank 0) ----------------
+    if rank == 0 and not args.no_ref_gpu:
+        line["reference_gpu_kernel"] = reference_gpu_leg(ctx, params, seq_dev, seq_host, n, value / world, e2e_value / world)
+    barrier()
+
+    # ---------------- dist: configs[2], [3], [4] ----------------
+    if not args.no_dist:
+        try:
+            i8_peak = {"tops": ctx.tensor_peak() / 1e12,
+                       "source": "measured live: hg_tensor_peak (tcgen05 kind::i8 256x256x32 MMAs back to back on every TPC)"}
+        except Exception as ex:  # pragma: no cover
+            i8_peak = {"tops": 2.0 * peaks["bf16_tflops"], "source": "2 x measured bf16 (probe failed: %s)" % ex}
+        if world > 1:  # every rank reports its own; the denominators use the slowest
+            t = torch.tensor([i8_peak["tops"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            i8_peak["tops"] = float(t.item())
+        line["int8_tensor_peak"] = dict(i8_peak, unit="TOP/s per GPU", vs_2x_bf16=i8_peak["tops"] / (2.0 * peaks["bf16_tflops"]))
+        wanted = [c for c in DIST_CONFIGS if c["key"] in args.dist_configs.split(",")]
+        pg = None
+        if world > 1 and wanted:
+            need = max(hg.ffi.peer_window_need(c.get("n", c.get("n_qry")), c["hv_d"], 4_000_000) for c in wanted)
+            pg = multigpu.PeerGroup(ctx, need, dev)
+        for cfg in wanted:
+            line[cfg["key"]] = bench_dist_config(cfg, args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, max_over_ranks,
+                                                 i8_peak, pg, host_pg)
+            torch.cuda.empty_cache()
+        if pg is not None:
+            pg.close()
+
+    if rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_sketch_baseline(seq_host.numpy(), n) if world == 1 else None
         line["parity_check"] = parity_sample(seq_host.numpy(), h_packed.numpy(), h_bits.numpy(), h_norm.numpy(), n)
-    elif rank == 0:
-        line["cpu_baseline"] = None
+        line["config"]["reference_arm"] = ("same_config: false by construction - the CPU reference arm sketches a bounded sample "
+                                           "(2 x cores genomes per step) of the same 5 Mbp / k=21 / D=4096 genomes; both report genomes/s; "
+                                           "ratios against it scale with the host's %d cores" % (os.cpu_count() or 1))
 
     if rank == 0:
         _emit(line)
@@ -433,212 +524,321 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_dist(args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, max_over_ranks, peaks):
+DIST_CONFIGS = [
+    dict(key="dist", label="BASELINE configs[2]", n=10000, hv_d=4096, n_per=3333, scaled=1500, symmetric=True, seed=0xD157,
+         metric="ANI pairs/sec (all-vs-all, D=4096, ani_th=85)"),
+    dict(key="dist_cfg4", label="BASELINE configs[3]", n_ref=100000, n_qry=1000, hv_d=4096, n_per=3333, scaled=1500, symmetric=False,
+         seed=0xD157, metric="ANI pairs/sec (database search 100,000 refs x 1,000 queries, D=4096, ani_th=85)"),
+    dict(key="dist_cfg5", label="BASELINE configs[4]", n=20000, hv_d=8192, n_per=10000, scaled=500, symmetric=True, seed=0xD158,
+         metric="ANI pairs/sec (all-vs-all, scaled=500 D=8192, ani_th=85)"),
+]
+
+
+def encode_family(ctx, synth, dev, n, D, n_per, scaled, seed, want_packed=False):
+    """n family-structured sketches encoded on this GPU from device-generated hash sets (never random i16: quant bits and
+    norms stay realistic).  Deterministic: every rank builds the same matrix."""
     import torch
-    import torch.distributed as dist
-    nq = args.dist_n
-    D = HV_D
-    # sketches with controlled Jaccard, encoded on the GPU from hash sets (rank 0), then broadcast
-    if rank == 0:
-        sets = synth.hash_sets_family(nq)
-        off = np.zeros(nq + 1, np.uint64)
-        off[1:] = np.cumsum([len(s) for s in sets])
-        hashes = torch.from_numpy(np.concatenate(sets).view(np.int64)).to(dev)
-        hv = torch.empty((nq, D), dtype=torch.int16, device=dev)
-        bits = torch.empty(nq, dtype=torch.uint8, device=dev)
-        norm = torch.empty(nq, dtype=torch.int32, device=dev)
-        ctx.encode_sets_dev(hashes.data_ptr(), off, D, hv.data_ptr(), None, bits.data_ptr(), norm.data_ptr())
+    hv = torch.empty((n, D), dtype=torch.int16, device=dev)
+    norm = torch.empty(n, dtype=torch.int32, device=dev)
+    bits = torch.empty(n, dtype=torch.uint8, device=dev)
+    packed = torch.empty((n, 2 * D), dtype=torch.uint8, device=dev) if want_packed else None
+    chunk = max(256, min(n, (1 << 28) // (8 * n_per)))
+    for c0 in range(0, n, chunk):
+        m = min(chunk, n - c0)
+        hashes, off = synth.hash_sets_family_dev(m, n_per=n_per, scaled=scaled, seed=seed, device=dev, first=c0)
+        ctx.encode_sets_dev(hashes.data_ptr(), off, D, hv[c0:].data_ptr(), packed[c0:].data_ptr() if want_packed else None,
+                            bits[c0:].data_ptr(), norm[c0:].data_ptr())
         ctx.sync()
         del hashes
+    return hv, norm, bits, packed
+
+
+def dist_parity(cfg, hits, ref_hv, ref_norm, qry_hv, qry_norm, th=85.0, sample_rows=64):
+    """Checker leg (rank 0): the hit list of the last timed step against the oracle - the hit set, the exact i32 dots and
+    the f32 ANI bits.  Config 3 in full (every one of the 49,995,000 pairs); configs 4 / 5 on `sample_rows` ref rows."""
+    import oracle as O
+    O.set_threads(os.cpu_count() or 1)
+    R, Q = ref_hv.shape[0], qry_hv.shape[0]
+    sym = cfg["symmetric"]
+    t0 = time.perf_counter()
+    hi, hj = hits["i"].astype(np.int64), hits["j"].astype(np.int64)
+    if sym and R <= 10000:
+        r, rn = ref_hv.cpu().numpy(), ref_norm.cpu().numpy()
+        ani, dot = O.dist_all(r, rn, r, rn, k=K, symmetric=True)
+        dt = time.perf_counter() - t0
+        idx = hi * (Q - 1) - hi * (hi - 1) // 2 + (hj - hi - 1)
+        want = np.nonzero(ani >= np.float32(th))[0]
+        order = np.argsort(idx, kind="stable")
+        ok = (idx.size == want.size and np.array_equal(idx[order], want) and np.array_equal(hits["dot"][order], dot[want])
+              and np.array_equal(hits["ani"][order].view(np.uint32), ani[want].view(np.uint32)))
+        if not ok:
+            raise RuntimeError("dist parity failed (%s): GPU hits differ from the oracle" % cfg["key"])
+        return ("ok: all %d pairs against the oracle - %d hits, same set, i32 dots equal, f32 ANI bit-identical"
+                % (ani.size, want.size)), dict(pairs=int(ani.size), seconds=dt)
+    rows = np.unique(np.linspace(0, R - 1, sample_rows).astype(np.int64))
+    q, qn = qry_hv.cpu().numpy(), qry_norm.cpu().numpy()
+    r, rn = ref_hv[torch_index(rows, ref_hv)].cpu().numpy(), ref_norm[torch_index(rows, ref_norm)].cpu().numpy()
+    ani, dot = O.dist_all(r, rn, q, qn, k=K, symmetric=False)
+    dt = time.perf_counter() - t0
+    ani, dot = ani.reshape(rows.size, Q), dot.reshape(rows.size, Q)
+    n_checked = 0
+    for t, i in enumerate(rows):
+        keep = ani[t] >= np.float32(th)
+        if sym:
+            keep &= np.arange(Q) > i
+        wj = np.nonzero(keep)[0]
+        sel = np.nonzero(hi == i)[0]
+        sel = sel[np.argsort(hj[sel], kind="stable")]
+        ok = (sel.size == wj.size and np.array_equal(hj[sel], wj) and np.array_equal(hits["dot"][sel], dot[t, wj])
+              and np.array_equal(hits["ani"][sel].view(np.uint32), ani[t, wj].view(np.uint32)))
+        if not ok:
+            raise RuntimeError("dist parity failed (%s): ref row %d differs from the oracle" % (cfg["key"], i))
+        n_checked += wj.size
+    return ("ok: %d sampled ref rows x all %d queries against the oracle - %d hits, same set, i32 dots equal, f32 ANI bit-identical"
+            % (rows.size, Q, n_checked)), dict(pairs=int(rows.size * Q), seconds=dt)
+
+
+def torch_index(rows, like):
+    import torch
+    return torch.from_numpy(rows).to(like.device)
+
+
+def bench_dist_config(cfg, args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, max_over_ranks, i8_peak, pg, host_pg):
+    """One dist configuration at this world size.  N = 1: hg_dist_dev, hits written by the kernel straight into pinned
+    host memory.  N > 1: hg_dist_sharded_dev over the NVLink windows (every rank holds a block of the rows, turns it
+    into operand planes, pushes them; tiles dealt round-robin; hits appended into rank 0's list) + the D2H on rank 0."""
+    import torch
+    import torch.distributed as dist
+    D, sym = cfg["hv_d"], cfg["symmetric"]
+    want_packed = rank == 0 and (cfg["key"] == "dist" or (cfg["key"] == "dist_cfg4" and world > 1))  # the e2e legs' input
+    if sym:
+        n_ref = n_qry = cfg["n"]
+        hv, norm, bits, packed = encode_family(ctx, synth, dev, n_ref, D, cfg["n_per"], cfg["scaled"], cfg["seed"], want_packed)
+        ref_hv, ref_norm, qry_hv, qry_norm = hv, norm, hv, norm
+        n_pairs = n_ref * (n_ref - 1) // 2
     else:
-        hv = norm = None
+        n_ref, n_qry = cfg["n_ref"], cfg["n_qry"]
+        ref_hv, ref_norm, bits, packed = encode_family(ctx, synth, dev, n_ref, D, cfg["n_per"], cfg["scaled"], cfg["seed"], want_packed)
+        q_idx = torch.arange(5, n_ref, n_ref // n_qry, device=dev)[:n_qry]  # queries with relatives among the refs
+        qry_hv, qry_norm = ref_hv[q_idx].contiguous(), ref_norm[q_idx].contiguous()
+        n_pairs = n_ref * n_qry
     cap = 4_000_000
-    # counter and hit array live in one buffer laid out as the multi-GPU gather sends it (no staging copy)
-    hit_blk, d_cnt, d_hits = multigpu.hit_block(cap, dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     hits_pin = torch.empty(cap * 16, dtype=torch.uint8, pin_memory=True)
-    bounds = multigpu.triangle_rows(nq, world, align=128)
-    a, b = bounds[rank], bounds[rank + 1]
-    n_pairs = nq * (nq - 1) // 2
+    hits_np = hits_pin.numpy().view(hg.ffi.HIT_DTYPE)
+    qb = multigpu.block_rows(n_qry, world)
+    rb = multigpu.block_rows(n_ref, world)
+    if world == 1:
+        d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        cnt_pin = torch.zeros(1, dtype=torch.int64, pin_memory=True)
 
-    # multi-GPU: one fused broadcast buffer (HVs + norms) and one fixed-size gather per step
-    if world > 1:
-        qbuf = torch.empty(nq * D * 2 + nq * 4, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            qbuf[: nq * D * 2] = hv.view(torch.uint8).view(-1)
-            qbuf[nq * D * 2:] = norm.view(torch.uint8).view(-1)
-        gather_cap = 1 << 18  # hits per rank carried by the one-shot gather (4 MiB per rank)
-        gather_pin = torch.empty(cap * 16, dtype=torch.uint8, pin_memory=True)
-        gather_recv = torch.empty(world * (16 + gather_cap * 16), dtype=torch.uint8, device=dev)
+        def step(path):
+            ctx.dist_dev(ref_hv.data_ptr(), ref_norm.data_ptr(), n_ref, 0, qry_hv.data_ptr(), qry_norm.data_ptr(), n_qry, 0, D, K,
+                         85.0, sym, path, hits_pin.data_ptr(), cap, d_cnt.data_ptr())  # hits land in host memory as they are found
+            cnt_pin.copy_(d_cnt, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            c = int(cnt_pin.item())
+            if c > cap:
+                raise RuntimeError("hit buffer too small: %d > %d" % (c, cap))
+            return hits_np[:c]
+    else:
+        a, b = qb[rank], qb[rank + 1]
+        ra, rbb = rb[rank], rb[rank + 1]
 
-    def step():
-        """broadcast queries -> local shard -> hits gathered on rank 0; returns device ms"""
-        nonlocal hv, norm
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        with torch.cuda.stream(ext):  # collectives and kernels ordered on the context's stream
-            e0.record()
-            dbg = os.environ.get("HG_BENCH_DEBUG") and rank == 0
-            if dbg:
-                torch.cuda.synchronize(); tA = time.perf_counter()
-            if world > 1:
-                hv, norm = multigpu.broadcast_queries_fused(qbuf, nq, D)
-            if dbg:
-                torch.cuda.synchronize(); tB = time.perf_counter()
-            ctx.dist_dev(hv[a:b].data_ptr(), norm[a:b].data_ptr(), b - a, a, hv.data_ptr(), norm.data_ptr(), nq, 0, D, K,
-                         85.0, True, path_sel[0], d_hits.data_ptr(), cap, d_cnt.data_ptr())
-            if dbg:
-                torch.cuda.synchronize(); ctx.sync(); tC = time.perf_counter()
-            if world > 1:
-                allh, overflow = multigpu.gather_hits_fixed(None, None, gather_cap, host_buf=gather_pin, block=hit_blk,
-                                                            recv=gather_recv)
-                if overflow:  # some shard produced more hits than the one-shot block carries
-                    cnt = int(d_cnt.item())
-                    allh = multigpu.gather_hits(d_hits, dev, count=min(cnt, cap))
-            else:
-                cnt = int(d_cnt.item())  # D2H of the hit count
-                if cnt > cap:
-                    raise RuntimeError("hit buffer too small: %d > %d" % (cnt, cap))
-                hits_pin[: cnt * 16].copy_(d_hits[: cnt * 16], non_blocking=True)  # D2H of the hit list
-                torch.cuda.current_stream().synchronize()
-                allh = hits_pin[: cnt * 16].numpy().view(hg.ffi.HIT_DTYPE)
-            if dbg:
-                torch.cuda.synchronize(); tD = time.perf_counter()
-                print("[dist step] bcast %.3f ms, dist_dev %.3f ms, gather %.3f ms" % ((tB - tA) * 1e3, (tC - tB) * 1e3, (tD - tC) * 1e3), file=sys.stderr)
-            e1.record()
-        e1.synchronize()
-        return e0.elapsed_time(e1), ctx.stage_ms()[3], (allh.size if allh is not None else 0)
+        def step(path):
+            if sym:
+                pg.peer.dist_sharded_dev(None, None, 0, 0, qry_hv[a:b].data_ptr(), qry_norm[a:b].data_ptr(), b - a, a, n_qry, D, K,
+                                         85.0, True, path, 0, cap)
+            else:  # refs: this rank's resident block; queries: all held by rank 0, which pushes their operand plane to everyone
+                mine = n_qry if rank == 0 else 0
+                pg.peer.dist_sharded_dev(ref_hv[ra:rbb].data_ptr(), ref_norm[ra:rbb].data_ptr(), rbb - ra, ra,
+                                         qry_hv.data_ptr() if mine else None, qry_norm.data_ptr() if mine else None, mine, 0, n_qry,
+                                         D, K, 85.0, False, path, 0, cap)
+            h, _ = pg.peer.dist_sharded_hits(cap, hits=hits_np)
+            return h
 
     ctx.set_profiling(True)
-    # first call: path 0 = auto (single-plane tensor kernel if the rows are narrow, else two-limb tensor
-    # kernel, else SIMT; records why); the timed steps pass the chosen path directly
-    path_sel = [0]
-    step()
-    path_sel[0], path_reason = ctx.dist_last_path, ctx.dist_last_reason
+    with torch.cuda.stream(ext):
+        step(0)  # auto: single-plane tensor kernel if the rows are narrow, else two-limb; records why
+    path, path_reason = ctx.dist_last_path, ctx.dist_last_reason
     for _ in range(3):
-        step()
+        with torch.cuda.stream(ext):
+            step(path)
     steps = max(5, args.steps)
-    tot_ms, kern_ms, n_hits = 0.0, [], 0
+    tot_ms, kern_ms, hits = 0.0, [], None
     barrier()
     for _ in range(steps):
-        flush.fill_(1)  # inputs (82 MB) fit in L2: flush it between timed iterations
+        flush.fill_(1)  # the operands of config 3 fit in L2: flush it between timed iterations
         barrier()
-        ms, kms, n_hits = step()
-        tot_ms += max_over_ranks(ms)
-        kern_ms.append(max_over_ranks(kms))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ext):
+            e0.record()
+            hits = step(path)
+            e1.record()
+        e1.synchronize()
+        tot_ms += max_over_ranks(e0.elapsed_time(e1))
+        kern_ms.append(max_over_ranks(ctx.stage_ms()[3]))
+    if world == 1 and path == 3:
+        ctx.dist_status()  # the verdict the forced single-plane calls did not wait for
     kms = statistics.mean(kern_ms)
+    del flush
     out = {
-        "metric": "ANI pairs/sec (all-vs-all, D=4096, ani_th=85)", "unit": "pairs/s",
-        "value": n_pairs * steps / (tot_ms * 1e-3), "kernel_value": n_pairs / (kms * 1e-3),
-        "ms_per_step": tot_ms / steps, "kernel_ms": kms, "steps": steps, "hits": int(n_hits), "pairs": n_pairs,
-        "config": {"workload": "all-vs-all dist over %d synthetic sketches (BASELINE configs[2]), D=4096, ani_th=85" % nq,
-                   "rows_per_rank": [bounds[r + 1] - bounds[r] for r in range(world)], "l2": "flushed between iterations"},
-        "path": path_sel[0], "path_reason": path_reason,
+        "metric": cfg["metric"], "unit": "pairs/s", "value": n_pairs * steps / (tot_ms * 1e-3), "kernel_value": n_pairs / (kms * 1e-3),
+        "ms_per_step": tot_ms / steps, "kernel_ms": kms, "steps": steps, "hits": int(hits.size) if rank == 0 else None, "pairs": n_pairs,
+        "n_gpus": world, "path": path, "path_reason": path_reason,
+        "config": {"workload": ("all-vs-all dist over %d synthetic sketches (%s), D=%d, ani_th=85" % (n_ref, cfg["label"], D)) if sym else
+                   ("%d ref sketches x %d queries (%s), D=%d, ani_th=85" % (n_ref, n_qry, cfg["label"], D)),
+                   "rows_per_rank": ([qb[r + 1] - qb[r] for r in range(world)] if sym else [rb[r + 1] - rb[r] for r in range(world)]),
+                   "sharding": ("single GPU" if world == 1 else
+                                ("rows sharded in blocks; operand planes pushed to every GPU over NVLink windows; output tiles dealt "
+                                 "round-robin; hits appended into rank 0's list" if sym else
+                                 "ref rows sharded and resident; rank 0 pushes the query operand plane to every GPU; hits appended "
+                                 "into rank 0's list")),
+                   "step": "i16 rows resident in HBM -> operand form -> dist kernel -> hit list in rank 0's host memory",
+                   "l2": "flushed between iterations"},
     }
     alg_ops = 2.0 * D * n_pairs
-    int8_peak = 2.0 * peaks["bf16_tflops"] * world  # kind::i8 runs at twice the bf16 MMA rate; all ranks' tensor pipes
-    mac_mult = 1.0 if path_sel[0] == 3 else 4.0  # MMAs executed per algorithmic MAC
-    note = ("algorithmic 2*D ops per pair; peak = n_gpus x 2 x measured bf16 (kind::i8 runs at twice the bf16 MMA rate); "
-            + ("single s8 plane (x = 2a + s): executed MACs = algorithmic MACs; kernel_ms includes the i16 -> s8 pre-pass and its host sync"
-               if path_sel[0] == 3 else "the two-limb split executes 4x these MACs, so frac tops out at 0.25"))
-    out["roofline"] = {"bound": "tensor", "achieved": alg_ops / (kms * 1e-3) / 1e12, "peak": int8_peak, "unit": "TOP/s",
-                       "frac": alg_ops / (kms * 1e-3) / 1e12 / int8_peak, "note": note,
-                       "executed_frac": mac_mult * alg_ops / (kms * 1e-3) / 1e12 / int8_peak,
-                       # DRAM bytes of one config-3 step from the ncu captures (profiles/r1_dist_narrow_full.md,
-                       # r1_narrow_prep_full.md): pre-pass 82 MB read + 41 MB written, kernel 41.3 MB read + 0.6 MB written
-                       "traffic": (165.0e6 if (path_sel[0] == 3 and nq == 10000 and world == 1) else None)}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        # CPU port of dist::compute_hv_ani (dist.rs:231-294) on a bounded sample of the same sketches
-        import oracle as O
+    mac_mult = 1.0 if path == 3 else 4.0
+    peak = i8_peak["tops"] * world
+    out["roofline"] = {"bound": "tensor", "achieved": alg_ops / (kms * 1e-3) / 1e12, "peak": peak, "unit": "TOP/s",
+                       "frac": alg_ops / (kms * 1e-3) / 1e12 / peak, "executed_frac": mac_mult * alg_ops / (kms * 1e-3) / 1e12 / peak,
+                       "frac_of_step": alg_ops / (tot_ms / steps * 1e-3) / 1e12 / peak, "peak_source": i8_peak["source"],
+                       "note": "algorithmic 2*D integer ops per pair over kernel_ms (operand pre-pass" +
+                               (", NVLink push and barrier" if world > 1 else "") + " + dist kernel, max over ranks); peak = n_gpus x " +
+                               "tcgen05 kind::i8 rate; " + ("single s8 plane: executed MACs = algorithmic MACs" if path == 3 else
+                                                            "two s8 limbs: 4 MMAs per algorithmic MAC, frac tops out at 0.25"),
+                       "traffic": (165.0e6 if (path == 3 and cfg["key"] == "dist" and world == 1) else None)}
+    # ---- parity of the timed step's result + CPU baseline (rank 0) ----
+    if rank == 0 and not args.no_cpu_baseline:
+        msg, cost = dist_parity(cfg, hits.copy(), ref_hv, ref_norm, qry_hv, qry_norm)
+        out["parity_check"] = msg
         cores = os.cpu_count() or 1
-        O.set_threads(cores)
-        m = min(nq, 10000)
-        hv_s, norm_s = hv[:m].cpu().numpy(), norm[:m].cpu().numpy()
-        t0 = time.perf_counter()
-        ani_s, _ = O.dist_all(hv_s, norm_s, hv_s, norm_s, k=K, symmetric=True, want_dot=False)
-        dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": (m * (m - 1) // 2) / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-                               "sample": "all-vs-all over the first %d of the %d sketches (%d pairs), oracle/hg_oracle.c, %d threads, %.1f s"
-                               % (m, nq, m * (m - 1) // 2, cores, dt)}
-    # e2e through the host-pointer C-ABI call (N=1 only): pinned host matrices in, hits out
-    if world == 1:
-        import ctypes as C
-        lib = hg.ffi.load()
-        hv_h = torch.empty((nq, D), dtype=torch.int16, pin_memory=True)
-        norm_h = torch.empty(nq, dtype=torch.int32, pin_memory=True)
-        hv_h.copy_(hv)
-        norm_h.copy_(norm)
-        hits_h = torch.empty(cap * 16, dtype=torch.uint8, pin_memory=True)
-        torch.cuda.synchronize()
-        n_hits_c = C.c_uint64(0)
+        out["cpu_baseline"] = {"value": cost["pairs"] / cost["seconds"], "unit": "pairs/s", "cores": cores, "kind": "port",
+                               "sample": "%d pairs of this workload, oracle/hg_oracle.c (dist.rs:139-161,231-294 restated), %d threads, %.1f s"
+                               % (cost["pairs"], cores, cost["seconds"])}
+    # ---- end to end through the host-pointer C ABI ----
+    import ctypes as C
+    lib = hg.ffi.load()
+    if world == 1 and cfg["key"] == "dist":
+        out.update(dist_e2e_single(ctx, hg, lib, ref_hv, ref_norm, bits, packed, n_ref, D, cap, path, n_pairs, hits))
+    if cfg["key"] in ("dist", "dist_cfg4") and world > 1:
+        # `hyper-gen dist` with all GPUs behind one process (hg_group_dist_packed): rank 0 drives the N GPUs from packed
+        # sketch rows in pinned host memory while the other ranks wait on the host
+        if rank == 0:
+            width = int(bits.max().item()) * D // 8
+            rp = torch.empty((n_ref, width), dtype=torch.uint8, pin_memory=True); rp.copy_(packed[:, :width])
+            rbt = torch.empty(n_ref, dtype=torch.uint8, pin_memory=True); rbt.copy_(bits)
+            rn = torch.empty(n_ref, dtype=torch.int32, pin_memory=True); rn.copy_(ref_norm)
+            if sym:
+                qp, qbt, qn, nq = rp, rbt, rn, n_ref
+            else:
+                qi = q_idx.cpu()
+                qp = torch.empty((n_qry, width), dtype=torch.uint8, pin_memory=True); qp.copy_(rp[qi])
+                qbt = torch.empty(n_qry, dtype=torch.uint8, pin_memory=True); qbt.copy_(rbt[qi])
+                qn = torch.empty(n_qry, dtype=torch.int32, pin_memory=True); qn.copy_(rn[qi])
+                nq = n_qry
+            milli = torch.empty(cap, dtype=torch.int32, pin_memory=True)
+            nh = C.c_uint64(0)
+            torch.cuda.synchronize()
+            grp = hg.Group(world)
 
-        def e2e():
-            rc = lib.hg_dist(ctx._h, hv_h.data_ptr(), norm_h.data_ptr(), nq, hv_h.data_ptr(), norm_h.data_ptr(), nq, D, K,
-                             85.0, 1, path_sel[0], hits_h.data_ptr(), cap, C.byref(n_hits_c))
-            if rc != 0:
-                raise RuntimeError(lib.hg_last_error().decode())
+            def gcall():
+                rc = lib.hg_group_dist_packed(grp._h, rp.data_ptr(), width, rbt.data_ptr(), rn.data_ptr(), n_ref, qp.data_ptr(), width,
+                                              qbt.data_ptr(), qn.data_ptr(), nq, D, K, 85.0, int(sym), 1, hits_pin.data_ptr(),
+                                              milli.data_ptr(), cap, C.byref(nh))
+                if rc != 0:
+                    raise RuntimeError(lib.hg_last_error().decode())
 
+            gcall(); gcall()
+            t0 = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                gcall()
+            dtg = (time.perf_counter() - t0) / reps
+            out["e2e"] = {"value": n_pairs / dtg, "unit": "pairs/s", "ms_per_step": dtg * 1e3,
+                          "h2d_bytes_per_step": int(rp.numel() + (0 if sym else qp.numel()) + (n_ref + (0 if sym else nq)) * 5),
+                          "d2h_bytes_per_step": int(nh.value * 20 + 8), "hits": int(nh.value),
+                          "same_hit_count_as_resident_step": bool(nh.value == hits.size),
+                          "call": "hg_group_dist_packed: one process, %d GPUs, packed sketch rows in pinned host memory -> sorted hits" % world}
+            grp.close()
+        dist.barrier(group=host_pg)
+    return out
+
+
+def dist_e2e_single(ctx, hg, lib, hv, norm, bits, packed_d, nq, D, cap, path, n_pairs, hits_ref):
+    """config 3 through the single-GPU host-pointer entries (hg_dist, hg_dist_sorted, hg_dist_packed)"""
+    import ctypes as C
+    import torch
+    out = {}
+    hv_h = torch.empty((nq, D), dtype=torch.int16, pin_memory=True)
+    norm_h = torch.empty(nq, dtype=torch.int32, pin_memory=True)
+    hv_h.copy_(hv)
+    norm_h.copy_(norm)
+    hits_h = torch.empty(cap * 16, dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+    n_hits_c = C.c_uint64(0)
+
+    def e2e():
+        rc = lib.hg_dist(ctx._h, hv_h.data_ptr(), norm_h.data_ptr(), nq, hv_h.data_ptr(), norm_h.data_ptr(), nq, D, K,
+                         85.0, 1, path, hits_h.data_ptr(), cap, C.byref(n_hits_c))
+        if rc != 0:
+            raise RuntimeError(lib.hg_last_error().decode())
+
+    e2e()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
         e2e()
-        t0 = time.perf_counter()
-        reps = 5
-        for _ in range(reps):
-            e2e()
-        dt = (time.perf_counter() - t0) / reps
-        assert n_hits_c.value == n_hits
-        out["e2e"] = {"value": n_pairs / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(hv_h.numel() * 2 + norm_h.numel() * 4),
-                      "d2h_bytes_per_step": int(n_hits_c.value * 16 + 8), "ms_per_step": dt * 1e3}
-        # the same call with the output stage on the GPU (hits come back in the reference's TSV order)
-        milli_h = torch.empty(cap, dtype=torch.int32, pin_memory=True)
+    dt = (time.perf_counter() - t0) / reps
+    assert n_hits_c.value == hits_ref.size
+    out["e2e"] = {"value": n_pairs / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(hv_h.numel() * 2 + norm_h.numel() * 4),
+                  "d2h_bytes_per_step": int(n_hits_c.value * 16 + 8), "ms_per_step": dt * 1e3,
+                  "call": "hg_dist: pinned host i16 matrices -> hits"}
+    milli_h = torch.empty(cap, dtype=torch.int32, pin_memory=True)
 
-        def e2e_sorted():
-            rc = lib.hg_dist_sorted(ctx._h, hv_h.data_ptr(), norm_h.data_ptr(), nq, hv_h.data_ptr(), norm_h.data_ptr(), nq, D,
-                                    K, 85.0, 1, path_sel[0], hits_h.data_ptr(), milli_h.data_ptr(), cap, C.byref(n_hits_c))
-            if rc != 0:
-                raise RuntimeError(lib.hg_last_error().decode())
+    def e2e_sorted():
+        rc = lib.hg_dist_sorted(ctx._h, hv_h.data_ptr(), norm_h.data_ptr(), nq, hv_h.data_ptr(), norm_h.data_ptr(), nq, D,
+                                K, 85.0, 1, path, hits_h.data_ptr(), milli_h.data_ptr(), cap, C.byref(n_hits_c))
+        if rc != 0:
+            raise RuntimeError(lib.hg_last_error().decode())
 
+    e2e_sorted()
+    t0 = time.perf_counter()
+    for _ in range(reps):
         e2e_sorted()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            e2e_sorted()
-        dts = (time.perf_counter() - t0) / reps
-        hs = hits_h[: n_hits_c.value * 16].numpy().view(hg.ffi.HIT_DTYPE)
-        ok = bool(np.all((hs["ani"][:-1] > hs["ani"][1:]) | ((hs["ani"][:-1] == hs["ani"][1:]) & (
-            (hs["i"][:-1] > hs["i"][1:]) | ((hs["i"][:-1] == hs["i"][1:]) & (hs["j"][:-1] > hs["j"][1:]))))))
-        out["e2e_sorted"] = {"value": n_pairs / dts, "unit": "pairs/s", "ms_per_step": dts * 1e3, "sort_ms": (dts - dt) * 1e3,
-                             "d2h_bytes_per_step": int(n_hits_c.value * 20 + 8), "order_verified": ok,
-                             "note": "hg_dist_sorted: hits radix-sorted on the GPU into dump_ani_file's order (utils.rs:262-285)"}
-        # the `hyper-gen dist` flow: sketch-file payload (bit-packed rows) in, sorted hits out (hg_dist_packed)
-        bits_np = bits.cpu().numpy()
-        width = int(bits_np.max()) * D // 8
-        packed_d = torch.empty((nq, 2 * D), dtype=torch.uint8, device=dev)
-        hv2 = torch.empty_like(hv)
-        hashes2 = torch.from_numpy(np.concatenate(sets).view(np.int64)).to(dev)
-        ctx.encode_sets_dev(hashes2.data_ptr(), off, D, hv2.data_ptr(), packed_d.data_ptr(), bits.data_ptr(), norm.data_ptr())
-        ctx.sync()
-        del hashes2, hv2
-        packed_h = torch.empty((nq, 2 * D), dtype=torch.uint8, pin_memory=True)
-        packed_h.copy_(packed_d)
-        bits_h = torch.empty(nq, dtype=torch.uint8, pin_memory=True)
-        bits_h.copy_(bits)
-        torch.cuda.synchronize()
+    dts = (time.perf_counter() - t0) / reps
+    hs = hits_h[: n_hits_c.value * 16].numpy().view(hg.ffi.HIT_DTYPE).copy()
+    ok = bool(np.all((hs["ani"][:-1] > hs["ani"][1:]) | ((hs["ani"][:-1] == hs["ani"][1:]) & (
+        (hs["i"][:-1] > hs["i"][1:]) | ((hs["i"][:-1] == hs["i"][1:]) & (hs["j"][:-1] > hs["j"][1:]))))))
+    same = bool(np.array_equal(np.sort(hs, order=["i", "j"]), np.sort(hits_ref, order=["i", "j"])))
+    out["e2e_sorted"] = {"value": n_pairs / dts, "unit": "pairs/s", "ms_per_step": dts * 1e3, "sort_ms": (dts - dt) * 1e3,
+                         "d2h_bytes_per_step": int(n_hits_c.value * 20 + 8), "order_verified": ok, "same_hits_as_resident_step": same,
+                         "note": "hg_dist_sorted: hits radix-sorted on the GPU into dump_ani_file's order (utils.rs:262-285)"}
+    bits_np = bits.cpu().numpy()
+    width = int(bits_np.max()) * D // 8
+    packed_h = torch.empty((nq, 2 * D), dtype=torch.uint8, pin_memory=True)
+    packed_h.copy_(packed_d)
+    bits_h = torch.empty(nq, dtype=torch.uint8, pin_memory=True)
+    bits_h.copy_(bits)
+    torch.cuda.synchronize()
 
-        def e2e_packed():
-            rc = lib.hg_dist_packed(ctx._h, packed_h.data_ptr(), 2 * D, bits_h.data_ptr(), norm_h.data_ptr(), nq,
-                                    packed_h.data_ptr(), 2 * D, bits_h.data_ptr(), norm_h.data_ptr(), nq, D, K, 85.0, 1, 0, 1,
-                                    hits_h.data_ptr(), milli_h.data_ptr(), cap, C.byref(n_hits_c))
-            if rc != 0:
-                raise RuntimeError(lib.hg_last_error().decode())
+    def e2e_packed():
+        rc = lib.hg_dist_packed(ctx._h, packed_h.data_ptr(), 2 * D, bits_h.data_ptr(), norm_h.data_ptr(), nq,
+                                packed_h.data_ptr(), 2 * D, bits_h.data_ptr(), norm_h.data_ptr(), nq, D, K, 85.0, 1, 0, 1,
+                                hits_h.data_ptr(), milli_h.data_ptr(), cap, C.byref(n_hits_c))
+        if rc != 0:
+            raise RuntimeError(lib.hg_last_error().decode())
 
+    e2e_packed()
+    t0 = time.perf_counter()
+    for _ in range(reps):
         e2e_packed()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            e2e_packed()
-        dtp = (time.perf_counter() - t0) / reps
-        hp = hits_h[: n_hits_c.value * 16].numpy().view(hg.ffi.HIT_DTYPE)
-        out["e2e_packed_sorted"] = {"value": n_pairs / dtp, "unit": "pairs/s", "ms_per_step": dtp * 1e3,
-                                    "h2d_bytes_per_step": int(nq * width + nq * 5), "d2h_bytes_per_step": int(n_hits_c.value * 20 + 8),
-                                    "same_hits_as_sorted": bool(n_hits_c.value == hs.size and np.array_equal(hp, hs)),
-                                    "note": "hg_dist_packed: %d-bit packed sketch rows over PCIe, decompress + dist + sort on the GPU" % int(bits_np.max())}
+    dtp = (time.perf_counter() - t0) / reps
+    hp = hits_h[: n_hits_c.value * 16].numpy().view(hg.ffi.HIT_DTYPE)
+    out["e2e_packed_sorted"] = {"value": n_pairs / dtp, "unit": "pairs/s", "ms_per_step": dtp * 1e3,
+                                "h2d_bytes_per_step": int(nq * width + nq * 5), "d2h_bytes_per_step": int(n_hits_c.value * 20 + 8),
+                                "same_hits_as_sorted": bool(n_hits_c.value == hs.size and np.array_equal(hp, hs)),
+                                "note": "hg_dist_packed: %d-bit packed sketch rows over PCIe, decompress + dist + sort on the GPU" % int(bits_np.max())}
     return out
 
 

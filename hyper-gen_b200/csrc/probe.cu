@@ -1,7 +1,10 @@
 // probe.cu — integer issue-rate probe: the INT32 roofline denominator for the k-mer hash and
 // encode kernels (MEASURED_PEAKS.json carries HBM and bf16 tensor peaks only).
 // Eight independent dependency chains per thread, enough warps to hide the 4-cycle latency.
+#include <algorithm>
+
 #include "hg_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -26,7 +29,109 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t iters, uint32_t 
   if (x == 0x12345u) sink[0] = x;  // never true in practice; keeps the chains alive
 }
 
+// ---- tcgen05 kind::i8 issue-rate probe: the dist roofline's denominator --------------------------------------
+// One CTA pair per TPC issues the MMA shape of the dist kernels (cta_group::2, M = 256, N = 256, K = 32, s32
+// accumulators in TMEM) back to back on operands that already sit in shared memory - no TMA, no epilogue - with
+// two accumulator buffers and one commit per 16 MMAs, so the tensor pipe never waits for anything but itself.
+constexpr uint32_t TP_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+constexpr int TP_SMEM = 2 * 128 * hgtc::TC_BK + 1024 + 256;
+
+__global__ void __launch_bounds__(128, 1) tensor_peak_kernel(uint32_t groups) {
+  using namespace hgtc;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *aligned = smem_raw + (base - smem_u32(smem_raw));
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const uint32_t bar0 = base + 2 * 128 * TC_BK;
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(aligned + 2 * 128 * TC_BK + 64);
+  for (uint32_t i = threadIdx.x; i < 2 * 128 * TC_BK / 4; i += blockDim.x)  // operand bytes with every bit toggling
+    reinterpret_cast<uint32_t *>(aligned)[i] = (i * 2654435761u) ^ (blockIdx.x * 40503u);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void *)tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> visible to the tensor core
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 1 && rank == 0 && groups) {
+    const uint32_t on = elect_one();
+    const uint32_t d0 = umma_desc_lo(base);
+    for (uint32_t g = 0; g < groups; ++g) {
+      const uint32_t b = g & 1u;
+      if (g >= 2) mbar_wait(bar0 + 8 * b, ((g >> 1) - 1u) & 1u);  // the group that used this accumulator last is done
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_i8_pair(tmem_base + b * 256u, d0 + (uint32_t)((32 * ks) >> 4), d0 + (uint32_t)((128 * TC_BK + 32 * ks) >> 4), TP_IDESC,
+                       (uint32_t)(rep | ks) != 0u, on);
+      umma_commit_pair(bar0 + 8 * b, on);
+    }
+    for (uint32_t b = 0; b < 2 && b < groups; ++b) {
+      const uint32_t last = ((groups - 1u - b) & ~1u) + b;  // last group on barrier b
+      mbar_wait(bar0 + 8 * b, (last >> 1) & 1u);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 }  // namespace
+
+// tcgen05 kind::i8 dense rate of this GPU in integer ops / s (2 per MAC), best of 5
+extern "C" int hg_tensor_peak(hg_ctx *c, double *ops_per_s) {
+  if (!c || !ops_per_s) { hg_set_error("hg_tensor_peak: NULL argument"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(c->device));
+  const uint32_t pairs = (uint32_t)std::max(c->sm_count / 2, 1), groups = 2048;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.blockDim = dim3(128, 1, 1);
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.dynamicSmemBytes = TP_SMEM;
+  cfg.stream = c->stream;
+  HG_CUDA(cudaLaunchKernelEx(&cfg, tensor_peak_kernel, 32u));  // warm-up
+  cudaEvent_t e0, e1;
+  HG_CUDA(cudaEventCreate(&e0));
+  HG_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    HG_CUDA(cudaEventRecord(e0, c->stream));
+    HG_CUDA(cudaLaunchKernelEx(&cfg, tensor_peak_kernel, groups));
+    HG_CUDA(cudaEventRecord(e1, c->stream));
+    HG_CUDA(cudaEventSynchronize(e1));
+    float ms;
+    HG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  c->launches += 6;
+  *ops_per_s = 2.0 * 256.0 * 256.0 * 32.0 * 16.0 * groups * pairs / (best * 1e-3);
+  return HG_OK;
+}
 
 int hg_launch_int_peak(hg_ctx *ctx, int which, uint32_t iters, uint32_t *d_sink, uint32_t blocks) {
   switch (which) {

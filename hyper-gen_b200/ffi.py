@@ -17,7 +17,7 @@ HG_OK, HG_E_INVALID, HG_E_CUDA, HG_E_CAPACITY, HG_E_RANGE, HG_E_UNSUPPORTED = 0,
 
 EXPORTS = [
     "hg_init", "hg_destroy", "hg_sync", "hg_host_alloc", "hg_host_free", "hg_last_error", "hg_version", "hg_stream_handle", "hg_launch_count",
-    "hg_set_profiling", "hg_stage_ms", "hg_int_peak", "hg_encode_sets", "hg_encode_sets_dev",
+    "hg_set_profiling", "hg_stage_ms", "hg_int_peak", "hg_tensor_peak", "hg_encode_sets", "hg_encode_sets_dev",
     "hg_fasta_merge", "hg_sketch_fasta_batch",
     "hg_kmer_hash", "hg_sketch_batch", "hg_sketch_batch_dev", "hg_sketch_status", "hg_unpack", "hg_unpack_dev",
     "hg_dist", "hg_dist_dev", "hg_dist_status", "hg_dist_last_path", "hg_dist_last_reason", "hg_sort_hits_dev", "hg_dist_sorted", "hg_dist_packed",
@@ -76,6 +76,7 @@ def load() -> C.CDLL:
     L.hg_set_profiling.restype = i32; L.hg_set_profiling.argtypes = [vp, i32]
     L.hg_stage_ms.restype = i32; L.hg_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.hg_int_peak.restype = i32; L.hg_int_peak.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    L.hg_tensor_peak.restype = i32; L.hg_tensor_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.hg_encode_sets.restype = i32; L.hg_encode_sets.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp, vp]
     L.hg_encode_sets_dev.restype = i32; L.hg_encode_sets_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp, vp]
     L.hg_fasta_merge.restype = i32; L.hg_fasta_merge.argtypes = [vp, vp, vp, u32, vp, u64, vp]
@@ -190,6 +191,11 @@ class Context:
     def int_peak(self, which: int = 2) -> float:
         v = C.c_double(0)
         _check(load().hg_int_peak(self._h, which, C.byref(v)))
+        return v.value
+
+    def tensor_peak(self) -> float:
+        v = C.c_double(0)
+        _check(load().hg_tensor_peak(self._h, C.byref(v)))
         return v.value
 
     # -- stage 1 --

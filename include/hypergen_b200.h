@@ -95,6 +95,10 @@ HG_API int hg_stage_ms(hg_ctx *ctx, float out_ms[4]);
 /* Dependent-free integer issue-rate probe used as the INT32 roofline denominator:
  * which = 0 IMAD chain mix, 1 LOP3/IADD3/SHF mix, 2 both interleaved.  Returns lane-ops/s. */
 HG_API int hg_int_peak(hg_ctx *ctx, int which, double *lane_ops_per_s);
+/* tcgen05 kind::i8 issue-rate probe used as the dist roofline denominator: the dist kernels' MMA shape (cta_group::2,
+ * 256 x 256 x 32) back to back from resident shared-memory operands on every TPC.  Returns integer ops / s (2 per MAC).
+ * Both probes are measurement hooks of this build, not part of the interface a host binds. */
+HG_API int hg_tensor_peak(hg_ctx *ctx, double *ops_per_s);
 
 /* ---- stage 1: sketch -------------------------------------------------------------- */
 

@@ -32,8 +32,13 @@ def build(force: bool = False) -> None:
     stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
     if force or stale:
         subprocess.check_call(["make", "-s", "-C", _HERE, "_build/libhg_oracle.so"])
-    if force or (not os.path.exists(_REF_PATH) and os.path.exists("/root/reference/src/cuda_kernel.cu")):
+    have_ref = os.path.exists("/root/reference/src/cuda_kernel.cu")
+    if have_ref and (force or not os.path.exists(_REF_PATH)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    # the reference's GPU kernel as PTX (its own build.rs recipe) and as an sm_100a cubin, for bench.py's
+    # `reference_gpu_kernel` leg on the GPU box (oracle/ref_gpu.py)
+    if have_ref and (force or not os.path.exists(os.path.join(_HERE, "_ref", "cuda_kernel_sm100a.cubin"))):
+        subprocess.call(["make", "-s", "-C", _HERE, "ref_gpu"], stderr=subprocess.DEVNULL)
 
 
 _lib = None
