@@ -147,6 +147,19 @@ extern "C" int hg_host_free(void *p) {
   return HG_OK;
 }
 
+extern "C" int hg_host_register(void *p, uint64_t bytes, void **dev_ptr) {
+  if (!p || !dev_ptr) { hg_set_error("hg_host_register: NULL argument"); return HG_E_INVALID; }
+  *dev_ptr = nullptr;
+  HG_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+  HG_CUDA(cudaHostGetDevicePointer(dev_ptr, p, 0));
+  return HG_OK;
+}
+
+extern "C" int hg_host_unregister(void *p) {
+  if (p) HG_CUDA(cudaHostUnregister(p));
+  return HG_OK;
+}
+
 int hg_scratch(hg_ctx *c, int slot, size_t bytes, void **out) {
   if (bytes == 0) bytes = 256;
   if (c->d_scratch_bytes[slot] < bytes) {

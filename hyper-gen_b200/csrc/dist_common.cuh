@@ -61,6 +61,109 @@ __device__ __forceinline__ void dist_emit(const DistEpilogue &e, bool live, uint
   }
 }
 
+// The same decision without the append: used by the tensor kernels' candidate lists, which evaluate a whole list first
+// and then reserve room for all its survivors with ONE atomic (the counter may live on another GPU: a round trip over
+// NVLink per 32 candidates is what made remote members slow).
+__device__ __forceinline__ bool dist_eval(const DistEpilogue &e, bool live, uint32_t li, uint32_t lj, int32_t dot, float *ani_out) {
+  if (!live) return false;
+  const uint32_t gi = e.i0 + li, gj = e.j0 + lj;
+  if (e.symmetric && gj <= gi) return false;
+  const int32_t nr = e.ref_norm[li], nq = e.qry_norm[lj];
+  if (e.jmin > 0.0f) {
+    const int32_t den = (int32_t)((uint32_t)nr + (uint32_t)nq - (uint32_t)dot);
+    if (!(den <= 0 || __int2float_rn(dot) >= e.jmin * __int2float_rn(den))) return false;
+  }
+  const float ani = ani_from_dot(dot, nr, nq, e.ksize_f);
+  *ani_out = ani;
+  return ani >= e.ani_th;
+}
+
+// ---- arrival flags of a multi-GPU launch (hg_tile_feed) ----
+__device__ __forceinline__ unsigned long long feed_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// whole warp, converged: returns once every flag in `need` is set (`have` caches what has been seen)
+__device__ __forceinline__ void feed_wait(const hg_tile_feed &f, uint32_t need, uint32_t &have) {
+  if ((have & need) == need) return;
+  const uint32_t lane = threadIdx.x & 31;
+  const unsigned long long t0 = feed_ns();
+  for (;;) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.ready + lane) : "memory");
+    have |= __ballot_sync(0xffffffffu, (int32_t)(v - f.seq) >= 0);
+    if ((have & need) == need) break;
+    if (feed_ns() - t0 > f.timeout_ns) {  // a member never delivered: flag the error, stop waiting for good
+      if (lane == 0) atomicExch(f.status, 1u);
+      have = 0xffffffffu;
+      break;
+    }
+    __nanosleep(200);
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");  // the TMA (async proxy) reads that follow see what the flags published
+}
+// whole warp, converged: one look at the flags, no waiting
+__device__ __forceinline__ bool feed_poll(const hg_tile_feed &f, uint32_t need, uint32_t &have) {
+  if ((have & need) == need) return true;
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.ready + (threadIdx.x & 31)) : "memory");
+  have |= __ballot_sync(0xffffffffu, (int32_t)(v - f.seq) >= 0);
+  return (have & need) == need;
+}
+
+// One pusher warp's share of this member's chunk pushes (hg_push_plan); `me` of `n_pushers` warps in the grid.
+__device__ __forceinline__ void push_my_chunks(const hg_push_plan *__restrict__ pp, uint32_t me, uint32_t n_pushers) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t seq = *pp->seq;
+  const int rank = pp->rank, world = pp->world;
+  const size_t tid = (size_t)me * 32 + lane, nth = (size_t)n_pushers * 32;
+  for (int ch = 0; ch < HG_PUSH_CHUNKS; ++ch) {
+    for (int k = 0; k < pp->n[ch]; ++k) {
+      const uint64_t off = pp->off[ch][k];
+      const uint32_t bytes = pp->bytes[ch][k];
+      if (((off | bytes) & 15) == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(pp->win[rank] + off);
+        const size_t n16 = bytes / 16;
+        for (size_t i = tid; i < n16; i += 8 * nth) {  // eight loads in flight per lane, then their stores to every peer
+          uint4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (i + u * nth < n16) v[u] = src[i + u * nth];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (i + u * nth < n16)
+              for (int m = 0; m < world; ++m)
+                if (m != rank) reinterpret_cast<uint4 *>(pp->win[m] + off)[i + u * nth] = v[u];
+        }
+      } else {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(pp->win[rank] + off);
+        for (size_t i = tid; i < bytes / 4; i += nth) {
+          const uint32_t v = src[i];
+          for (int m = 0; m < world; ++m)
+            if (m != rank) reinterpret_cast<uint32_t *>(pp->win[m] + off)[i] = v;
+        }
+      }
+    }
+    // the last pusher warp of the grid through with this chunk raises its arrival flag in every other window
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t prev = atomicAdd(pp->done + ch, 1u);
+      if (prev == n_pushers - 1) {
+        __threadfence_system();
+        pp->done[ch] = 0;
+        for (int m = 0; m < world; ++m)
+          if (m != rank) {
+            uint32_t *f = reinterpret_cast<uint32_t *>(pp->win[m] + pp->ready_off) + (rank * HG_PUSH_CHUNKS + ch);
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+          }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // Host: the Jaccard value below which ANI (dist.rs:154) cannot reach ani_th, lowered by a safety
 // margin (0.01 ANI points and 0.1 % relative) that dwarfs every f32 rounding in the exact path.
 inline float dist_jmin(float ani_th, uint32_t ksize) {

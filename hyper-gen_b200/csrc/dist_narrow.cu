@@ -51,11 +51,13 @@ template <int NACC> struct N1Cfg {
   static constexpr int TILE_ROWS = 256 * NACC;
 };
 constexpr int N1_EPI_WARPS = 8;                         // two per TMEM lane quarter, half the columns each
-constexpr int N1_THREADS = 64 + 32 * N1_EPI_WARPS;
+constexpr int N1_THREADS = 64 + 32 * N1_EPI_WARPS;      // producer, MMA issuer, epilogue warps (+ 32 per pusher warp of a multi-GPU member)
+constexpr int N1_PUSH_WARPS = 2;
 constexpr int N1_LIST_CAP = 256;                        // candidates per warp list (8 B each)
 constexpr int N1_COL_WORDS = 3 * N1_BN;                 // per tile: bound, centre, 2 sum(b) of every column
 constexpr int N1_SMEM_BYTES = 6 * (N1_A_BYTES + N1_B_BYTES) /* == 4 * (2 A + B) */ + 1024 /*align slack*/ + 256 /*barriers*/ +
-                              2 * N1_COL_WORDS * 4 /*column constants, double buffered*/ + N1_EPI_WARPS * N1_LIST_CAP * 8;
+                              2 * N1_COL_WORDS * 4 /*column constants, double buffered*/ + N1_EPI_WARPS * N1_LIST_CAP * 8 +
+                              N1_EPI_WARPS * N1_LIST_CAP * 4 /*ANI of the evaluated candidates*/;
 constexpr uint32_t N1_TMEM_COLS = 512;                  // two accumulator buffers of 256 columns
 // instruction descriptor, kind::i8: D = s32, A = B = signed 8-bit, both K-major, M = 256 (pair), N = 256
 constexpr uint32_t N1_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((N1_BN >> 3) << 17) | ((256u >> 4) << 24);
@@ -250,6 +252,8 @@ struct N1Tiles {
   uint32_t gx, gy, R, C, tile_rows;
   int64_t delta;  // i0 - j0
   int sym;
+  const uint2 *list;  // multi-GPU member: its tiles in the order the host chose (hg_tile_feed); NULL: the arithmetic walk below
+  uint32_t n_list, cur, need;
   __device__ uint32_t cmin(uint32_t r) const {  // symmetric: tiles whose largest j is not above their smallest i are empty
     if (!sym) return 0;
     const int64_t v = delta + (int64_t)tile_rows * (int64_t)r + 1;
@@ -257,7 +261,11 @@ struct N1Tiles {
     const uint64_t c = (uint64_t)v / (uint32_t)N1_BN;
     return c > gx ? gx : (uint32_t)c;
   }
-  __device__ void init(const hg::DistEpilogue &ep, uint32_t rows_per_tile) {
+  __device__ void init(const hg::DistEpilogue &ep, uint32_t rows_per_tile, const hg_tile_feed &f) {
+    list = f.list;
+    n_list = f.n_list;
+    cur = 0;
+    need = 0;
     tile_rows = rows_per_tile;
     gx = (ep.n_qry + N1_BN - 1) / N1_BN;
     gy = (ep.n_ref + tile_rows - 1) / tile_rows;
@@ -267,6 +275,15 @@ struct N1Tiles {
     C = cmin(0);
   }
   __device__ bool advance(uint32_t k) {
+    if (list) {
+      cur += k;
+      if (cur >= n_list) return false;
+      const uint2 e = list[cur];
+      R = e.x & 0xFFFFu;
+      C = e.x >> 16;
+      need = e.y;
+      return true;
+    }
     while (R < gy) {
       const uint32_t avail = gx - C;
       if (k < avail) { C += k; return true; }
@@ -311,20 +328,58 @@ __device__ __noinline__ int32_t n1_correction(const NarrowArgs &na, uint32_t li,
   return (int32_t)c;
 }
 
-__device__ __forceinline__ void n1_process(const hg::DistEpilogue &ep, const NarrowArgs &na, const uint2 *list, uint32_t n,
+// Evaluate a warp's parked candidates and append the survivors: pass 1 runs the exact correction + f32 ANI sequence and
+// leaves (keep flag, dot, ANI) in shared memory, ONE atomic reserves room for all survivors (the counter may sit on another
+// GPU), pass 2 writes the records.
+__device__ __forceinline__ void n1_process(const hg::DistEpilogue &ep, const NarrowArgs &na, uint2 *list, float *anis, uint32_t n,
                                            uint32_t row0, uint32_t col0) {
+  if (n == 0) return;
   const uint32_t lane = threadIdx.x & 31;
-  for (uint32_t e = lane; e < ((n + 31u) & ~31u); e += 32) {
-    const bool live0 = e < n;
-    const uint2 c = live0 ? list[e] : make_uint2(0u, 0u);
+  uint32_t mine = 0;
+  for (uint32_t e = lane; e < n; e += 32) {
+    const uint2 c = list[e];
     const uint32_t li = row0 + (c.x >> 8), lj = col0 + (c.x & 255u);
-    const bool live = live0 && li < ep.n_ref && lj < ep.n_qry;
+    const bool live = li < ep.n_ref && lj < ep.n_qry;
     int32_t dot = (int32_t)c.y;
     if (live) {
       const uint32_t er = na.r.e[li], eq = na.q.e[lj];
       if (er | eq) dot = (int32_t)((uint32_t)dot + (uint32_t)n1_correction(na, li, lj, er, eq));
     }
-    hg::dist_emit(ep, live, li, lj, dot);
+    float ani = 0.0f;
+    const bool keep = hg::dist_eval(ep, live, li, lj, dot, &ani);
+    list[e] = make_uint2(c.x | (keep ? 0x80000000u : 0u), (uint32_t)dot);
+    anis[e] = ani;
+    mine += keep;
+  }
+  uint32_t inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += y;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+  if (total == 0) { __syncwarp(); return; }
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(ep.n_hits, (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  // consecutive lanes write consecutive records: whole 64-byte+ bursts when the list may live in host memory behind PCIe
+  for (uint32_t e0 = 0; e0 < n; e0 += 32) {
+    const uint32_t e = e0 + lane;
+    const uint2 c = e < n ? list[e] : make_uint2(0u, 0u);
+    const bool keep = (c.x & 0x80000000u) != 0u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const unsigned long long idx = base + __popc(bal & ((1u << lane) - 1u));
+      if (idx < ep.cap) {
+        hg_hit h;
+        h.i = ep.i0 + row0 + ((c.x & 0x7FFFFFFFu) >> 8);
+        h.j = ep.j0 + col0 + (c.x & 255u);
+        h.dot = (int32_t)c.y;
+        h.ani = anis[e];
+        ep.hits[idx] = h;
+      }
+    }
+    base += __popc(bal);
   }
   __syncwarp();
 }
@@ -334,7 +389,7 @@ __device__ __forceinline__ void n1_process(const hg::DistEpilogue &ep, const Nar
 // column, the centre s_q and T_q = 2 sum(b).  Candidates (rowl, column, x~ . y~) go to `list`.
 __device__ __forceinline__ uint32_t n1_drain(const hg::DistEpilogue &ep, const NarrowArgs &na, uint32_t taddr, int c_begin,
                                              int c_end, const int32_t *s_col, int32_t tr, int32_t sr, int32_t xr, bool row_live,
-                                             uint32_t rowl, uint32_t row0, uint32_t col0, uint2 *list, uint32_t n_list) {
+                                             uint32_t rowl, uint32_t row0, uint32_t col0, uint2 *list, float *anis, uint32_t n_list) {
   const uint32_t lane = threadIdx.x & 31;
   const bool row_always = tr == ROW_ALWAYS;
   uint32_t nx[16];
@@ -378,7 +433,7 @@ __device__ __forceinline__ uint32_t n1_drain(const hg::DistEpilogue &ep, const N
       const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
       if (total == 0) continue;
       if (n_list + total > N1_LIST_CAP) {  // evaluate what is parked (slow path: the accumulator stays held)
-        n1_process(ep, na, list, n_list, row0, col0);
+        n1_process(ep, na, list, anis, n_list, row0, col0);
         n_list = 0;
       }
       uint32_t pos = n_list + inc - cnt;
@@ -392,22 +447,17 @@ __device__ __forceinline__ uint32_t n1_drain(const hg::DistEpilogue &ep, const N
   return n_list;
 }
 
-template <int NACC>
-__global__ void __launch_bounds__(N1_THREADS, 1)
+template <int NACC, int PUSHW>
+__global__ void __launch_bounds__(N1_THREADS + 32 * PUSHW, 1)
 dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_qry, uint32_t ref_row_base,
-               uint32_t qry_row_base, hg::DistEpilogue ep, NarrowArgs na) {
+               uint32_t qry_row_base, hg::DistEpilogue ep, NarrowArgs na, hg_tile_feed feed, const __grid_constant__ hg_push_plan plan) {
   using Cfg = N1Cfg<NACC>;
   constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr uint32_t TILE_ROWS = Cfg::TILE_ROWS;
   constexpr uint32_t NBUF = NACC == 1 ? 2 : 1;  // accumulator sets in TMEM
-  // the pre-pass ran on this stream just before: if it found the rows not narrow (outlier budget exceeded)
-  // nothing is computed here and the host, which reads the same flag after this launch, takes another path
-  uint32_t declined = 0, q_absmax = 0, r_tmax = 0;
-  for (uint32_t t = 0; t < na.q_nsets; ++t) { declined |= na.q_stats[4 * t + 3]; q_absmax = max(q_absmax, na.q_stats[4 * t]); }
-  for (uint32_t t = 0; t < na.r_nsets; ++t) { declined |= na.r_stats[4 * t + 3]; r_tmax = max(r_tmax, na.r_stats[4 * t + 1]); }
-  if (declined) return;
   uint32_t rank;  // 0 = leader (issues the MMAs, owns the full / tmem-empty barriers), 1 = peer
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  if (feed.seq_ptr) feed.seq = *feed.seq_ptr;
   // this pair's tiles: first, first + n_pairs, ... of the launch's share of the tile enumeration
   const uint32_t pair = (blockIdx.x >> 1) * na.walk_mul + na.walk_add, n_pairs = (gridDim.x >> 1) * na.walk_mul;
 
@@ -441,9 +491,25 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t num_kb = na.hv_d / TC_BK;
 
+  if (PUSHW > 0 && warp >= N1_THREADS / 32) {
+    // ===== pusher warps (a member of several GPUs): my operand rows to every other window, chunk by chunk =====
+    hg::push_my_chunks(&plan, blockIdx.x * PUSHW + (uint32_t)(warp - N1_THREADS / 32), gridDim.x * PUSHW);
+  } else {
+  uint32_t have = 0;  // arrival flags seen so far (warp 0)
+  if (feed.start_need) {  // the other members' pre-pass statistics have arrived, the root has reset its hit counter
+    if (warp == 0) hg::feed_wait(feed, feed.start_need, have);
+    asm volatile("bar.sync 2, %0;" ::"r"(N1_THREADS) : "memory");
+  }
+  // the pre-passes ran before this kernel (on this GPU, and on the others before their statistics were pushed): if they
+  // found the rows not narrow (outlier budget exceeded) nothing is computed here and the host, which reads the same
+  // flags after this launch, takes another path
+  uint32_t declined = 0, q_absmax = 0, r_tmax = 0;
+  for (uint32_t t = 0; t < na.q_nsets; ++t) { declined |= na.q_stats[4 * t + 3]; q_absmax = max(q_absmax, na.q_stats[4 * t]); }
+  for (uint32_t t = 0; t < na.r_nsets; ++t) { declined |= na.r_stats[4 * t + 3]; r_tmax = max(r_tmax, na.r_stats[4 * t + 1]); }
+
   N1Tiles tiles;
-  tiles.init(ep, TILE_ROWS);
-  bool valid = tiles.advance(pair);
+  tiles.init(ep, TILE_ROWS, feed);
+  bool valid = !declined && tiles.advance(pair);
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs; completion bytes go to the LEADER's full barrier) =====
@@ -451,6 +517,7 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
     uint32_t s = 0, ph = 0;
     for (; valid; valid = tiles.advance(n_pairs)) {
       const uint32_t row0 = tiles.R * TILE_ROWS + rank * 128u, colh = tiles.C * N1_BN + rank * 128u;
+      if (tiles.need) hg::feed_wait(feed, tiles.need, have);  // the rows this tile reads have arrived from their owners
       for (uint32_t kb = 0; kb < num_kb; ++kb) {
         mbar_wait_cluster(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES, rank == 0 ? on : 0u);  // the leader expects its bytes and the peer's
@@ -499,47 +566,70 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
     const uint32_t q = warp & 3;  // TMEM lane quarter this warp may read
     const int half = (ew >> 2);   // which 128 columns this warp drains
     uint2 *list = reinterpret_cast<uint2 *>(aligned + STAGES * STAGE_BYTES + 256 + 2 * N1_COL_WORDS * 4) + ew * N1_LIST_CAP;
-    uint32_t tile_n = 0;
+    float *anis = reinterpret_cast<float *>(aligned + STAGES * STAGE_BYTES + 256 + 2 * N1_COL_WORDS * 4 + N1_EPI_WARPS * N1_LIST_CAP * 8) +
+                  ew * N1_LIST_CAP;
+    uint32_t tile_n = 0, have_e = 0, have_l = 0;
+    volatile uint32_t *s_early = reinterpret_cast<volatile uint32_t *>(aligned + STAGES * STAGE_BYTES + 240);
     for (; valid; valid = tiles.advance(n_pairs), ++tile_n) {
       const uint32_t b = tile_n % NBUF, use = tile_n / NBUF;
       const uint32_t row0 = tiles.R * TILE_ROWS + rank * 128u, col0 = tiles.C * N1_BN;
-      int32_t *s_col = s_col_all + (tile_n & 1u) * N1_COL_WORDS;  // double buffered: one barrier per tile is enough
-      {
-        const uint32_t t = threadIdx.x - 64, lj = col0 + t;  // one column per epilogue thread
-        int32_t tq = COL_NEVER, sq = 0, tt = 0;
-        if (lj < ep.n_qry) {
-          tq = COL_ALWAYS;
-          if (ep.cfrac > 0.0f) {
-            const int32_t nq = ep.qry_norm[lj];
-            if (nq > 0) tq = n1_loosen(__float2int_rd(ep.cfrac * __int2float_rz(nq)) - 1, na.q.e[lj], r_tmax, COL_ALWAYS);
-          }
-          sq = na.q.s[lj];
-          tt = na.q.a2[lj];
+      // The per-row / per-column constants are read BEFORE the accumulator is waited for, to hide their latency - in a
+      // multi-GPU launch possibly before the rows they belong to have arrived.  One epilogue warp looks at the arrival
+      // flags (no spinning here: the producer does the waiting) and all eight take the same route: constants now, or
+      // after the accumulator barrier, by when the producer has seen the flags.
+      bool early = true;
+      if (tiles.need) {
+        if (ew == 0) {
+          const bool ok = hg::feed_poll(feed, tiles.need, have_e);
+          if (lane == 0) *s_early = ok ? 1u : 0u;
         }
-        s_col[t] = tq;
-        s_col[N1_BN + t] = sq;
-        s_col[2 * N1_BN + t] = tt;
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * N1_EPI_WARPS) : "memory");
+        early = *s_early != 0u;
       }
-      asm volatile("bar.sync 1, %0;" ::"r"(32 * N1_EPI_WARPS) : "memory");  // epilogue warps only
-      // row constants of my row in every accumulator
+      int32_t *s_col = s_col_all + (tile_n & 1u) * N1_COL_WORDS;  // double buffered: one barrier per tile is enough
       int32_t tr[NACC], sr[NACC], xr[NACC];
       bool live[NACC];
-#pragma unroll
-      for (int a = 0; a < NACC; ++a) {
-        const uint32_t li = row0 + 256u * a + q * 32 + lane;
-        tr[a] = ROW_ALWAYS; sr[a] = 0; xr[a] = 0;
-        live[a] = li < ep.n_ref;
-        if (live[a]) {
-          if (ep.cfrac > 0.0f) {
-            const int32_t nr = ep.ref_norm[li];
-            if (nr > 0) tr[a] = n1_loosen(__float2int_rd(ep.cfrac * __int2float_rz(nr)) - 1, na.r.e[li], q_absmax, ROW_ALWAYS);
+      auto constants = [&]() {
+        {
+          const uint32_t t = threadIdx.x - 64, lj = col0 + t;  // one column per epilogue thread
+          int32_t tq = COL_NEVER, sq = 0, tt = 0;
+          if (lj < ep.n_qry) {
+            tq = COL_ALWAYS;
+            if (ep.cfrac > 0.0f) {
+              const int32_t nq = ep.qry_norm[lj];
+              if (nq > 0) tq = n1_loosen(__float2int_rd(ep.cfrac * __int2float_rz(nq)) - 1, na.q.e[lj], r_tmax, COL_ALWAYS);
+            }
+            sq = na.q.s[lj];
+            tt = na.q.a2[lj];
           }
-          sr[a] = na.r.s[li];
-          xr[a] = (int32_t)((uint32_t)na.r.a2[li] + na.hv_d * (uint32_t)sr[a]);  // sum x~ = 2 sum a + D s
+          s_col[t] = tq;
+          s_col[N1_BN + t] = sq;
+          s_col[2 * N1_BN + t] = tt;
         }
-      }
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * N1_EPI_WARPS) : "memory");  // epilogue warps only
+        // row constants of my row in every accumulator
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+          const uint32_t li = row0 + 256u * a + q * 32 + lane;
+          tr[a] = ROW_ALWAYS; sr[a] = 0; xr[a] = 0;
+          live[a] = li < ep.n_ref;
+          if (live[a]) {
+            if (ep.cfrac > 0.0f) {
+              const int32_t nr = ep.ref_norm[li];
+              if (nr > 0) tr[a] = n1_loosen(__float2int_rd(ep.cfrac * __int2float_rz(nr)) - 1, na.r.e[li], q_absmax, ROW_ALWAYS);
+            }
+            sr[a] = na.r.s[li];
+            xr[a] = (int32_t)((uint32_t)na.r.a2[li] + na.hv_d * (uint32_t)sr[a]);  // sum x~ = 2 sum a + D s
+          }
+        }
+      };
+      if (early) constants();
       mbar_wait_cluster(accum_bar(b), use & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (!early) {  // the producer has seen this tile's arrival flags; so do we now (an acquire, returns at once)
+        hg::feed_wait(feed, tiles.need, have_l);
+        constants();
+      }
       uint32_t n_list = 0;
 #pragma unroll
       for (int a = 0; a < NACC; ++a) {
@@ -549,14 +639,15 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
         if (!mine_empty)
           n_list = n1_drain(ep, na, tmem_base + ((q * 32u) << 16) + (NACC == 1 ? b * N1_BN : a * N1_BN), half * (N1_BN / 2),
                             (half + 1) * (N1_BN / 2), s_col, tr[a], sr[a], xr[a], live[a], 256u * a + q * 32 + lane, row0, col0,
-                            list, n_list);
+                            list, anis, n_list);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(tmem_empty_bar(b), 0));  // this warp's TMEM reads of buffer b are done
-      n1_process(ep, na, list, n_list, row0, col0);                        // exact ANI + append, under the next tiles' MMAs
+      n1_process(ep, na, list, anis, n_list, row0, col0);                  // exact ANI + append, under the next tiles' MMAs
     }
   }
+  }  // compute roles
   __syncthreads();
   cluster_sync_all();  // nobody leaves while the peer may still read its smem or signal its barriers
   if (warp == 2) {
@@ -601,6 +692,8 @@ uint32_t narrow_budget() {  // outlier entries per row on average (HG_NARROW_BUD
 
 }  // namespace
 
+void hg_narrow_tile_shape(uint32_t *rows, uint32_t *cols) { *rows = 256; *cols = N1_BN; }
+
 // ---- one matrix in single-plane form; its rows may be prepared piecewise, as they arrive ------
 int hg_narrow_shape_ok(uint32_t hv_d, const void *d_a, const void *d_b) {
   if (hv_d % TC_BK != 0 || hv_d > 32768) {
@@ -622,8 +715,9 @@ uint32_t hg_narrow_set_cap(uint32_t n_rows) { return (uint32_t)std::min<uint64_t
 
 static int narrow_attrs(hg_ctx *ctx) {
   if (!ctx->n1_attr_set) {
-    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
-    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<1, N1_PUSH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
     ctx->n1_attr_set = 1;
   }
   return HG_OK;
@@ -633,7 +727,7 @@ static int narrow_attrs(hg_ctx *ctx) {
 // its rows, records its statistics in set `my_set` and may use entries [entry_base, entry_base + set_cap)
 int hg_narrow_attach(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d, int8_t *plane, void *arrays,
                      uint32_t *entries, uint32_t *stats_all, uint32_t n_sets, uint32_t my_set, uint32_t entry_base,
-                     uint32_t set_cap, hg_narrow_mat *m) {
+                     uint32_t set_cap, hg_narrow_mat *m, bool init_stats) {
   m->hv = d_hv;
   m->n_rows = n_rows;
   m->hv_d = hv_d;
@@ -645,9 +739,11 @@ int hg_narrow_attach(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t
   m->n_sets = n_sets;
   m->entry_base = entry_base;
   m->cap = entry_base + set_cap;
-  narrow_stats_init_kernel<<<1, 32, 0, ctx->stream>>>(m->stats, entry_base);
-  ctx->launches++;
-  HG_CUDA(cudaGetLastError());
+  if (init_stats) {  // (peer.cu resets the statistics in the first node of its launch sequence instead)
+    narrow_stats_init_kernel<<<1, 32, 0, ctx->stream>>>(m->stats, entry_base);
+    ctx->launches++;
+    HG_CUDA(cudaGetLastError());
+  }
   return narrow_attrs(ctx);
 }
 
@@ -697,7 +793,8 @@ int hg_narrow_launch(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t 
 int hg_narrow_launch_ex(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
                         const hg_narrow_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm,
                         uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
-                        unsigned long long *d_n_hits, uint32_t walk_mul, uint32_t walk_add) {
+                        unsigned long long *d_n_hits, uint32_t walk_mul, uint32_t walk_add, const hg_tile_feed *feed,
+                        const hg_push_plan *push) {
   if (n_ref == 0 || n_qry == 0) return HG_OK;
   if (walk_mul == 0 || walk_add >= walk_mul) { hg_set_error("hg_narrow_launch: tile walk %u / %u", walk_add, walk_mul); return HG_E_INVALID; }
   int rc;
@@ -754,12 +851,25 @@ int hg_narrow_launch_ex(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32
   if (const char *e = getenv("HG_NARROW_NACC")) nacc = atoi(e) == 2 ? 2 : 1;
   const uint32_t tile_rows = 256u * nacc;
   const uint64_t tiles_all = (uint64_t)((n_qry + N1_BN - 1) / N1_BN) * ((n_ref + tile_rows - 1) / tile_rows);
-  const uint64_t tiles = (tiles_all + walk_mul - 1) / walk_mul;  // this launch's share (an upper bound when symmetric)
+  hg_tile_feed fd = {};
+  if (feed) fd = *feed;
+  if (fd.list && nacc != 1) { hg_set_error("a tile list is built for 256-row tiles (HG_NARROW_NACC=2 is a single-GPU experiment)"); return HG_E_UNSUPPORTED; }
+  // this launch's share of the tiles (an upper bound when symmetric)
+  const uint64_t tiles = fd.list ? fd.n_list : (tiles_all + walk_mul - 1) / walk_mul;
+  if (tiles == 0) return HG_OK;
   const uint32_t n_pairs = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)std::max(ctx->sm_count / 2, 1));
   cfg.gridDim = dim3(2 * n_pairs, 1, 1);
   cfg.dynamicSmemBytes = N1_SMEM_BYTES;
-  if (nacc == 2) HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<2>, tm_ref, tm_qry, r0, q0, ep, na));
-  else HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<1>, tm_ref, tm_qry, r0, q0, ep, na));
+  static const hg_push_plan no_push = {};
+  if (push) {  // a member of several GPUs: the launch carries pusher warps that send my operand rows while the tiles are computed
+    if (nacc != 1) { hg_set_error("pusher warps come with the 256-row tile kernel"); return HG_E_UNSUPPORTED; }
+    cfg.blockDim = dim3(N1_THREADS + 32 * N1_PUSH_WARPS, 1, 1);
+    HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<1, N1_PUSH_WARPS>, tm_ref, tm_qry, r0, q0, ep, na, fd, *push));
+  } else if (nacc == 2) {
+    HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<2, 0>, tm_ref, tm_qry, r0, q0, ep, na, fd, no_push));
+  } else {
+    HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<1, 0>, tm_ref, tm_qry, r0, q0, ep, na, fd, no_push));
+  }
   ctx->launches++;
   HG_CUDA(cudaGetLastError());
   return HG_OK;

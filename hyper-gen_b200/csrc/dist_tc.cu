@@ -39,9 +39,10 @@ constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = 128 * TC_BK;            // one operand tile
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;     // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_EPI_WARPS = 8;                      // two per TMEM lane quarter, half the columns each
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // producer, MMA issuer, epilogue warps (+ 32 per pusher warp of a multi-GPU member)
+constexpr int TC_PUSH_WARPS = 2;
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 512 /*col bounds*/ +
-                              8 * 256 * 8 /*candidate lists: TC_EPI_WARPS x TC_LIST_CAP x 8 B*/;
+                              8 * 256 * 8 /*candidate lists: TC_EPI_WARPS x TC_LIST_CAP x 8 B*/ + 8 * 256 * 4 /*their ANIs*/;
 constexpr uint32_t TC_TMEM_COLS = 512;
 
 // instruction descriptor, kind::i8: D = s32, A = B = signed 8-bit, both K-major, M = 128, N = 128
@@ -73,13 +74,50 @@ __device__ __forceinline__ int32_t tc_row_bound(const hg::DistEpilogue &ep, uint
 // it also balances the lanes (hits cluster on a few rows of the diagonal tiles).
 constexpr int TC_LIST_CAP = 256;  // candidates per warp list (8 B each); a full list is evaluated in place
 
-__device__ __forceinline__ void tc_process(const hg::DistEpilogue &ep, const uint2 *list, uint32_t n, uint32_t row0, uint32_t col0) {
+// pass 1: exact f32 ANI of every parked candidate; ONE atomic reserves room for the survivors (the counter may sit on
+// another GPU); pass 2 writes the records
+__device__ __forceinline__ void tc_process(const hg::DistEpilogue &ep, uint2 *list, float *anis, uint32_t n, uint32_t row0, uint32_t col0) {
+  if (n == 0) return;
   const uint32_t lane = threadIdx.x & 31;
-  for (uint32_t e = lane; e < ((n + 31u) & ~31u); e += 32) {
-    const bool live = e < n;
-    const uint2 c = live ? list[e] : make_uint2(0u, 0u);
+  uint32_t mine = 0;
+  for (uint32_t e = lane; e < n; e += 32) {
+    const uint2 c = list[e];
     const uint32_t li = row0 + (c.x >> 8), lj = col0 + (c.x & 255u);
-    hg::dist_emit(ep, live && li < ep.n_ref && lj < ep.n_qry, li, lj, (int32_t)c.y);
+    float ani = 0.0f;
+    const bool keep = hg::dist_eval(ep, li < ep.n_ref && lj < ep.n_qry, li, lj, (int32_t)c.y, &ani);
+    if (keep) list[e].x = c.x | 0x80000000u;
+    anis[e] = ani;
+    mine += keep;
+  }
+  uint32_t inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += y;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+  if (total == 0) { __syncwarp(); return; }
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(ep.n_hits, (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  // consecutive lanes write consecutive records: whole 64-byte+ bursts when the list may live in host memory behind PCIe
+  for (uint32_t e0 = 0; e0 < n; e0 += 32) {
+    const uint32_t e = e0 + lane;
+    const uint2 c = e < n ? list[e] : make_uint2(0u, 0u);
+    const bool keep = (c.x & 0x80000000u) != 0u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const unsigned long long idx = base + __popc(bal & ((1u << lane) - 1u));
+      if (idx < ep.cap) {
+        hg_hit h;
+        h.i = ep.i0 + row0 + ((c.x & 0x7FFFFFFFu) >> 8);
+        h.j = ep.j0 + col0 + (c.x & 255u);
+        h.dot = (int32_t)c.y;
+        h.ani = anis[e];
+        ep.hits[idx] = h;
+      }
+    }
+    base += __popc(bal);
   }
   __syncwarp();
 }
@@ -89,7 +127,7 @@ __device__ __forceinline__ void tc_process(const hg::DistEpilogue &ep, const uin
 // Appends the candidates to list[0..n_list); returns the new n_list.
 __device__ __forceinline__ uint32_t tc_drain(const hg::DistEpilogue &ep, uint32_t taddr, int c_begin, int c_end,
                                              const int32_t *s_tq, int32_t tr, bool row_live, uint32_t rowl, uint32_t row0,
-                                             uint32_t col0, uint2 *list, uint32_t n_list) {
+                                             uint32_t col0, uint2 *list, float *anis, uint32_t n_list) {
   const uint32_t lane = threadIdx.x & 31;
   // software pipelined: the loads of chunk c + 16 are in flight while chunk c is tested
   uint32_t nh[16], nc[16], nl[16];
@@ -135,7 +173,7 @@ __device__ __forceinline__ uint32_t tc_drain(const hg::DistEpilogue &ep, uint32_
       const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
       if (total == 0) continue;
       if (n_list + total > TC_LIST_CAP) {  // evaluate what is parked (slow path: TMEM stays held)
-        tc_process(ep, list, n_list, row0, col0);
+        tc_process(ep, list, anis, n_list, row0, col0);
         n_list = 0;
       }
       uint32_t pos = n_list + inc - cnt;
@@ -248,10 +286,11 @@ dist_tc_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     uint2 *list = reinterpret_cast<uint2 *>(aligned + TC_STAGES * TC_STAGE_BYTES + 256 + 512) + ew * TC_LIST_CAP;
+    float *anis = reinterpret_cast<float *>(aligned + TC_STAGES * TC_STAGE_BYTES + 256 + 512 + TC_EPI_WARPS * TC_LIST_CAP * 8) + ew * TC_LIST_CAP;
     const uint32_t n_list = tc_drain(ep, tmem_base + ((q * 32u) << 16), half * (TC_BN / 2), (half + 1) * (TC_BN / 2), s_tq, tr,
-                                     li < ep.n_ref, q * 32 + lane, row0, col0, list, 0u);
+                                     li < ep.n_ref, q * 32 + lane, row0, col0, list, anis, 0u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    tc_process(ep, list, n_list, row0, col0);
+    tc_process(ep, list, anis, n_list, row0, col0);
   }
   __syncthreads();
   if (warp == 2) {
@@ -266,7 +305,7 @@ constexpr int T2_A_BYTES = 128 * TC_BK;               // my 128 ref rows, one li
 constexpr int T2_B_BYTES = 64 * TC_BK;                // my half of the 128 query rows, one limb plane
 constexpr int T2_STAGE_BYTES = 2 * T2_A_BYTES + 2 * T2_B_BYTES;  // 48 KB
 constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 1024 /*col bounds x 2*/ +
-                              8 * 256 * 8 /*candidate lists*/;
+                              8 * 256 * 8 /*candidate lists*/ + 8 * 256 * 4 /*their ANIs*/;
 // instruction descriptor as TC_IDESC with M = 256 (the pair's rows)
 constexpr uint32_t T2_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((256u >> 4) << 24);
 
@@ -278,6 +317,8 @@ struct PairTiles {
   uint32_t gx, gy2, R, C;
   int64_t delta;  // i0 - j0
   int sym;
+  const uint2 *list;  // multi-GPU member: its tiles in the order the host chose (hg_tile_feed); NULL: the arithmetic walk below
+  uint32_t n_list, cur, need;
   __device__ uint32_t cmin(uint32_t r) const {
     if (!sym) return 0;
     const int64_t v = delta + 256ll * (int64_t)r + 1;
@@ -285,7 +326,11 @@ struct PairTiles {
     const uint64_t c = (uint64_t)v / 128u;
     return c > gx ? gx : (uint32_t)c;
   }
-  __device__ void init(const hg::DistEpilogue &ep) {
+  __device__ void init(const hg::DistEpilogue &ep, const hg_tile_feed &f) {
+    list = f.list;
+    n_list = f.n_list;
+    cur = 0;
+    need = 0;
     gx = (ep.n_qry + TC_BN - 1) / TC_BN;
     gy2 = (ep.n_ref + 255) / 256;
     delta = (int64_t)ep.i0 - (int64_t)ep.j0;
@@ -294,6 +339,15 @@ struct PairTiles {
     C = cmin(0);
   }
   __device__ bool advance(uint32_t k) {  // k non-empty tiles forward; false past the end
+    if (list) {
+      cur += k;
+      if (cur >= n_list) return false;
+      const uint2 e = list[cur];
+      R = e.x & 0xFFFFu;
+      C = e.x >> 16;
+      need = e.y;
+      return true;
+    }
     while (R < gy2) {
       const uint32_t avail = gx - C;
       if (k < avail) { C += k; return true; }
@@ -305,12 +359,14 @@ struct PairTiles {
   }
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int PUSHW>
+__global__ void __launch_bounds__(TC_THREADS + 32 * PUSHW, 1)
 dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant__ CUtensorMap tm_qry,
                 uint32_t ref_plane_rows, uint32_t ref_row_base, uint32_t qry_plane_rows, uint32_t qry_row_base, uint32_t hv_d,
-                hg::DistEpilogue ep, uint32_t walk_mul, uint32_t walk_add) {
+                hg::DistEpilogue ep, uint32_t walk_mul, uint32_t walk_add, hg_tile_feed feed, const __grid_constant__ hg_push_plan plan) {
   uint32_t rank;  // 0 = leader (issues the MMAs, owns the full / tmem-empty barriers), 1 = peer
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  if (feed.seq_ptr) feed.seq = *feed.seq_ptr;
   // this launch takes tiles walk_add, walk_add + walk_mul, ... of the enumeration (member walk_add of walk_mul GPUs),
   // dealt round-robin to its CTA pairs
   const uint32_t pair = (blockIdx.x >> 1) * walk_mul + walk_add, n_pairs = (gridDim.x >> 1) * walk_mul;
@@ -346,9 +402,18 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t num_kb = hv_d / TC_BK;
 
+  if (PUSHW > 0 && warp >= TC_THREADS / 32) {
+    // ===== pusher warps (a member of several GPUs): my limb-plane rows to every other window, chunk by chunk =====
+    hg::push_my_chunks(&plan, blockIdx.x * PUSHW + (uint32_t)(warp - TC_THREADS / 32), gridDim.x * PUSHW);
+  } else {
   PairTiles tiles;
-  tiles.init(ep);
+  tiles.init(ep, feed);
   bool valid = tiles.advance(pair);
+  uint32_t have = 0;  // arrival flags seen so far (the producer warp)
+  if (feed.start_need) {  // a member of several GPUs: nothing is appended before the root has reset its hit counter
+    if (warp == 0) hg::feed_wait(feed, feed.start_need, have);
+    asm volatile("bar.sync 2, %0;" ::"r"(TC_THREADS) : "memory");
+  }
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs; completion bytes go to the LEADER's full barrier) =====
@@ -357,6 +422,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
       uint32_t it = 0;
       for (; valid; valid = tiles.advance(n_pairs)) {
         const uint32_t row0 = tiles.R * 256u + rank * 128u, colh = tiles.C * TC_BN + rank * 64u;
+        if (tiles.need) hg::feed_wait(feed, tiles.need, have);  // the rows this tile reads have arrived from their owners
         for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % T2_STAGES;
           const uint32_t ph = (it / T2_STAGES) & 1u;
@@ -415,31 +481,53 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
     const int half = (ew >> 2);
     const uint32_t te = mapa_u32(tmem_empty_bar, 0);
     uint2 *list = reinterpret_cast<uint2 *>(aligned + T2_STAGES * T2_STAGE_BYTES + 256 + 1024) + ew * TC_LIST_CAP;
-    uint32_t tile_n = 0;
+    float *anis = reinterpret_cast<float *>(aligned + T2_STAGES * T2_STAGE_BYTES + 256 + 1024 + TC_EPI_WARPS * TC_LIST_CAP * 8) + ew * TC_LIST_CAP;
+    uint32_t tile_n = 0, have_e = 0, have_l = 0;
+    volatile uint32_t *s_early = reinterpret_cast<volatile uint32_t *>(aligned + T2_STAGES * T2_STAGE_BYTES + 240);
     for (; valid; valid = tiles.advance(n_pairs), ++tile_n) {
       const uint32_t row0 = tiles.R * 256u + rank * 128u, col0 = tiles.C * TC_BN;
+      // The bounds below read the norms of this tile's rows / columns before the accumulators are waited for - in a
+      // multi-GPU launch possibly before those rows have arrived.  One epilogue warp looks at the arrival flags (no
+      // spinning here: the producer does the waiting) and all eight take the same route: bounds now, or after the
+      // accumulator barrier, by when the producer has seen the flags.
+      bool early = true;
+      if (tiles.need) {
+        if (ew == 0) {
+          const bool ok = hg::feed_poll(feed, tiles.need, have_e);
+          if (lane == 0) *s_early = ok ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
+        early = *s_early != 0u;
+      }
       int32_t *s_tq = s_tq_all + (tile_n & 1u) * TC_BN;  // double buffered: one barrier per tile is enough
-      {
+      const uint32_t li = row0 + q * 32 + lane;
+      int32_t tr = 0;
+      auto bounds = [&]() {
         const int t = threadIdx.x - 64;
         if (t < TC_BN) s_tq[t] = tc_col_bound(ep, col0 + t);
-      }
-      asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
-      const uint32_t li = row0 + q * 32 + lane;
-      const int32_t tr = tc_row_bound(ep, li);
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * TC_EPI_WARPS) : "memory");
+        tr = tc_row_bound(ep, li);
+      };
+      if (early) bounds();
       // my 128 x 128 part of the tile may be empty (below the diagonal, or past the last ref row)
       const bool mine_empty = row0 >= ep.n_ref || (ep.symmetric && (uint64_t)ep.j0 + col0 + TC_BN - 1 <= (uint64_t)ep.i0 + row0);
       mbar_wait_cluster(accum_bar, tile_n & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (!early) {  // the producer has seen this tile's arrival flags; so do we now (an acquire, returns at once)
+        hg::feed_wait(feed, tiles.need, have_l);
+        bounds();
+      }
       uint32_t n_list = 0;
       if (!mine_empty)
         n_list = tc_drain(ep, tmem_base + ((q * 32u) << 16), half * (TC_BN / 2), (half + 1) * (TC_BN / 2), s_tq, tr,
-                          li < ep.n_ref, q * 32 + lane, row0, col0, list, 0u);
+                          li < ep.n_ref, q * 32 + lane, row0, col0, list, anis, 0u);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(te);  // this warp's TMEM reads are done: the next tile's MMAs may start
-      tc_process(ep, list, n_list, row0, col0);  // exact ANI + append, under the next tile's mainloop
+      tc_process(ep, list, anis, n_list, row0, col0);  // exact ANI + append, under the next tile's mainloop
     }
   }
+  }  // compute roles
   __syncthreads();
   cluster_sync_all();  // nobody leaves while the peer may still read its smem or signal its barriers
   if (warp == 2) {
@@ -472,6 +560,8 @@ __global__ void split_limbs_kernel(const int16_t *__restrict__ hv, uint64_t n_el
 
 }  // namespace
 
+void hg_tc_tile_shape(uint32_t *rows, uint32_t *cols) { *rows = 256; *cols = TC_BN; }
+
 // ---- one matrix as two s8 limb planes [2][n_rows][hv_d]; its rows may be split piecewise, as they arrive ----
 int hg_tc_shape_ok(uint32_t hv_d, const void *d_a, const void *d_b) {
   if (hv_d % TC_BK != 0 || hv_d > 32768) {
@@ -495,7 +585,8 @@ int hg_tc_setup(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d
   m->hv_d = hv_d;
   if (!ctx->tc_attr_set) {
     HG_CUDA(cudaFuncSetAttribute(dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<TC_PUSH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
     ctx->tc_attr_set = 1;
   }
   return HG_OK;
@@ -529,7 +620,8 @@ int hg_tc_attach(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_
   m->hv_d = hv_d;
   if (!ctx->tc_attr_set) {
     HG_CUDA(cudaFuncSetAttribute(dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<TC_PUSH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
     ctx->tc_attr_set = 1;
   }
   return HG_OK;
@@ -538,8 +630,10 @@ int hg_tc_attach(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_
 int hg_tc_launch_ex(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
                     const hg_tc_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm, uint32_t ksize,
                     float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits, uint32_t walk_mul,
-                    uint32_t walk_add) {
+                    uint32_t walk_add, const hg_tile_feed *feed, const hg_push_plan *push) {
   if (n_ref == 0 || n_qry == 0) return HG_OK;
+  hg_tile_feed fd = {};
+  if (feed) fd = *feed;
   if (walk_mul == 0 || walk_add >= walk_mul) { hg_set_error("hg_tc_launch: tile walk %u / %u", walk_add, walk_mul); return HG_E_INVALID; }
   int rc;
   const uint32_t hv_d = R->hv_d;
@@ -548,7 +642,7 @@ int hg_tc_launch_ex(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref
   int pair_kernel = 1;
   if (const char *e = getenv("HG_DIST_KERNEL")) pair_kernel = atoi(e) == 1 ? 0 : 1;
   if (hv_d % (TC_BK * T2_STAGES) != 0) pair_kernel = 0;  // the pair kernel walks whole trips of its 4-stage ring
-  if (!pair_kernel && walk_mul != 1) { hg_set_error("a shared tile walk needs the pair kernel (hv_d %% 512 == 0)"); return HG_E_UNSUPPORTED; }
+  if (!pair_kernel && (walk_mul != 1 || fd.list || push)) { hg_set_error("a shared tile walk needs the pair kernel (hv_d %% 512 == 0)"); return HG_E_UNSUPPORTED; }
   CUtensorMap tm_ref, tm_qry;
   if ((rc = make_plane_map(&tm_qry, Q->planes, 2ull * Q->n_rows, hv_d, pair_kernel ? 64 : 128))) return rc;
   if ((rc = make_plane_map(&tm_ref, R->planes, 2ull * R->n_rows, hv_d, 128))) return rc;
@@ -581,12 +675,21 @@ int hg_tc_launch_ex(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref
   cfg.stream = ctx->stream;
   if (pair_kernel) {
     // one CTA pair per TPC, each walking the 256 x 128 tiles with stride n_pairs
-    const uint64_t tiles = ((uint64_t)gx * ((n_ref + 255) / 256) + walk_mul - 1) / walk_mul;
+    const uint64_t tiles = fd.list ? fd.n_list : ((uint64_t)gx * ((n_ref + 255) / 256) + walk_mul - 1) / walk_mul;
+    if (tiles == 0) return HG_OK;
     const uint32_t n_pairs = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)std::max(ctx->sm_count / 2, 1));
     cfg.gridDim = dim3(2 * n_pairs, 1, 1);
     cfg.dynamicSmemBytes = T2_SMEM_BYTES;
     attr[0].val.clusterDim.x = 2;
-    HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel, tm_ref, tm_qry, R->n_rows, r0, Q->n_rows, q0, hv_d, make_ep(0), walk_mul, walk_add));
+    static const hg_push_plan no_push = {};
+    if (push) {  // a member of several GPUs: pusher warps send my limb-plane rows while the tiles are computed
+      cfg.blockDim = dim3(TC_THREADS + 32 * TC_PUSH_WARPS, 1, 1);
+      HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel<TC_PUSH_WARPS>, tm_ref, tm_qry, R->n_rows, r0, Q->n_rows, q0, hv_d, make_ep(0), walk_mul,
+                                 walk_add, fd, *push));
+    } else {
+      HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel<0>, tm_ref, tm_qry, R->n_rows, r0, Q->n_rows, q0, hv_d, make_ep(0), walk_mul, walk_add,
+                                 fd, no_push));
+    }
     ctx->launches++;
   } else {
     const uint32_t y_step = 65534;  // <= the gridDim.y limit

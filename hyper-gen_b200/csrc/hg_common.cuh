@@ -128,8 +128,8 @@ struct hg_ctx {
   cudaStream_t stream;
   unsigned long long launches;
   // grow-only device scratch
-  void *d_scratch[13];        // indexed by hg_scratch_slot
-  size_t d_scratch_bytes[13];
+  void *d_scratch[14];        // indexed by hg_scratch_slot
+  size_t d_scratch_bytes[14];
   // pinned host scratch
   void *h_pinned[4];
   size_t h_pinned_bytes[4];
@@ -190,7 +190,8 @@ enum hg_scratch_slot {
   HG_S_SORT_TMP = 10,  // ping-pong buffer of the hit sort
   HG_S_SORT_CNT = 11,  // digit counters of the hit sort
   HG_S_NARROW_META = 12,  // per-row constants + outlier lists of the single-plane dist path (dist_narrow)
-  HG_S_COUNT = 13
+  HG_S_TILES = 13,        // tile list of a multi-GPU dist launch (peer.cu)
+  HG_S_COUNT = 14
 };
 // scratch slot `slot` grown to at least `bytes` (contents not preserved)
 int hg_scratch(hg_ctx *ctx, int slot, size_t bytes, void **out);
@@ -223,6 +224,36 @@ int hg_launch_dist_simt(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_
                         uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
                         uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
                         hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits);
+// A dist launch that is one member of several GPUs (csrc/peer.cu) walks a host-built list of ITS tiles instead of the
+// arithmetic enumeration, ordered by when the rows they read arrive, and its TMA producer waits for the arrival flags
+// of those rows: the operand exchange over NVLink overlaps the tile computation.
+// What a multi-GPU member pushes to the other members WHILE its dist kernel runs: the kernel carries extra "pusher"
+// warps that copy this member's operand rows (byte ranges of its window, in HG_PUSH_CHUNKS chunks) to the same offsets
+// of every other window with 16-byte stores over NVLink and raise the chunk's arrival flag there when all pusher warps
+// of the grid are through with it.  One kernel computes tiles and moves operands; nothing has to be co-scheduled.
+#define HG_PUSH_CHUNKS 4
+#define HG_PUSH_RANGES 10
+struct hg_push_plan {
+  uint8_t *win[HG_MAX_PEERS];  // every member's window as this member addresses it
+  int rank, world;
+  uint64_t off[HG_PUSH_CHUNKS][HG_PUSH_RANGES];   // byte ranges (relative to the window base), 4-byte granular
+  uint32_t bytes[HG_PUSH_CHUNKS][HG_PUSH_RANGES];
+  int n[HG_PUSH_CHUNKS];
+  uint32_t *done;       // HG_PUSH_CHUNKS counters in this member's window: pusher warps through with the chunk
+  uint64_t ready_off;   // offset of the arrival flags in every window; chunk c raises flag rank * HG_PUSH_CHUNKS + c
+  const uint32_t *seq;  // the call's sequence number lives in device memory (the launch sequence is replayed as a CUDA graph)
+};
+struct hg_tile_feed {
+  const uint2 *list;        // x = tile row | tile column << 16, y = mask of the arrival flags the tile needs; NULL: arithmetic walk
+  uint32_t n_list;
+  const uint32_t *ready;    // 32 arrival flags (in this member's window); a flag is set when (int)(flag - seq) >= 0
+  const uint32_t *seq_ptr;  // where the call's sequence number lives (device memory: the launch sequence is replayed as a CUDA graph)
+  uint32_t seq;             // filled in by the kernel from *seq_ptr
+  uint32_t start_need;      // flags to wait for before the kernel reads anything (the members' pre-pass statistics)
+  uint32_t *status;         // set to 1 if a wait times out (the host turns it into an error)
+  unsigned long long timeout_ns;
+};
+
 // two s8 limb planes of one matrix (dist_tc.cu), split piecewise or at once
 struct hg_tc_mat {
   const int16_t *hv;
@@ -239,7 +270,8 @@ int hg_tc_attach(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_
 int hg_tc_launch_ex(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
                     const hg_tc_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm, uint32_t ksize,
                     float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap, unsigned long long *d_n_hits, uint32_t walk_mul,
-                    uint32_t walk_add);
+                    uint32_t walk_add, const hg_tile_feed *feed = nullptr, const hg_push_plan *push = nullptr);
+void hg_tc_tile_shape(uint32_t *rows, uint32_t *cols);
 int hg_launch_dist_tc(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref,
                       uint32_t i0, const int16_t *d_qry, const int32_t *d_qry_norm, uint32_t n_qry,
                       uint32_t j0, uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric,
@@ -269,7 +301,7 @@ size_t hg_narrow_arrays_bytes(uint32_t n_rows);  // s | a2 | e | out_off | out_c
 uint32_t hg_narrow_set_cap(uint32_t n_rows);
 int hg_narrow_attach(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d, int8_t *plane, void *arrays,
                      uint32_t *entries, uint32_t *stats_all, uint32_t n_sets, uint32_t my_set, uint32_t entry_base,
-                     uint32_t set_cap, hg_narrow_mat *m);
+                     uint32_t set_cap, hg_narrow_mat *m, bool init_stats = true);
 int hg_narrow_prep_rows(hg_ctx *ctx, const hg_narrow_mat *m, uint32_t row0, uint32_t rows);
 int hg_narrow_launch(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
                      const hg_narrow_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm,
@@ -279,7 +311,9 @@ int hg_narrow_launch(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t 
 int hg_narrow_launch_ex(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32_t n_ref, uint32_t i0, const int32_t *d_ref_norm,
                         const hg_narrow_mat *Q, uint32_t q0, uint32_t n_qry, uint32_t j0, const int32_t *d_qry_norm,
                         uint32_t ksize, float ani_th, int symmetric, hg_hit *d_hits, uint64_t cap,
-                        unsigned long long *d_n_hits, uint32_t walk_mul, uint32_t walk_add);
+                        unsigned long long *d_n_hits, uint32_t walk_mul, uint32_t walk_add, const hg_tile_feed *feed = nullptr,
+                        const hg_push_plan *push = nullptr);
+void hg_narrow_tile_shape(uint32_t *rows, uint32_t *cols);
 int hg_narrow_verdict(hg_ctx *ctx, const hg_narrow_mat *A, const hg_narrow_mat *B, int32_t *absmax_out, uint64_t *outliers_out);
 // one-shot form of the above; HG_E_UNSUPPORTED when the rows are not narrow
 int hg_launch_dist_narrow(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_norm, uint32_t n_ref,

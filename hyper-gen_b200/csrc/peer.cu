@@ -4,20 +4,26 @@
 //
 // Every member GPU owns a "window" of device memory that all other members can address over NVLink
 // (one process per GPU: cudaIpc handles; one process driving several GPUs: peer access).  A sharded
-// dist then needs no collective library on its data path:
+// dist then needs no collective library on its data path, and the exchange overlaps the compute:
 //   1. each member turns ITS rows into the operand form of the tensor kernel (one s8 plane + per-row
-//      constants, or two s8 limb planes) inside its own window and PUSHES that slice, with plain
-//      16-byte stores over NVLink, to the same offsets of every other window - the "all-gather" (or,
-//      when one member holds all queries, the "broadcast") of what the kernel actually reads: 1 byte
-//      per element instead of the 2 of the int16 rows, and no pre-pass replicated on every GPU;
-//   2. a flag barrier (st.release.sys / ld.acquire.sys on words in the windows, bounded spin);
-//   3. every member runs the dist kernel on its share of the output tiles - the non-empty tiles of the
-//      all-vs-all are dealt round-robin (tile t to member t mod N), which balances the triangle to
-//      within one tile; ref x query keeps the member's own ref rows - and appends its hits straight
-//      into the ROOT's hit list over NVLink (warp-aggregated atomic on the root's counter);
-//   4. a second flag barrier; the root's stream then owns the complete hit list.
-// Measured on 2 B200s (tools/ipc_probe.cu): push of a 21 MB slice + both barriers 49 us (NCCL
-// all_gather of the same plane 69 us), flag barrier 6.3 us.
+//      constants, or two s8 limb planes) inside its own window and PUSHES them, in 4 chunks, with plain
+//      16-byte stores over NVLink to the same offsets of every other window - the "all-gather" of what
+//      the kernel actually reads: 1 byte per element instead of the 2 of the int16 rows, no pre-pass
+//      replicated on every GPU.  The last CTA of a chunk's push raises that chunk's ARRIVAL FLAG in
+//      every window (fence + st.release.sys);
+//   2. every member launches the dist kernel at once.  Its tiles come from a host-built list: the
+//      non-empty tiles of the all-vs-all dealt round-robin (tile t to member t mod N - balances the
+//      triangle to within one tile), each member's share ordered by when the rows it reads arrive (own
+//      rows first, then chunk 0 of everybody, chunk 1 ...).  The kernel's TMA producer waits for the
+//      arrival flags a tile needs (ld.acquire.sys on its own window, bounded) - so tiles are computed
+//      while later chunks are still crossing NVLink.  ref x query: the member's own (resident) ref rows
+//      against all queries, same mechanism on the query side;
+//   3. hits are appended straight into the ROOT's hit list - its window, or a host buffer every member
+//      has mapped - with one atomic on the root's counter per evaluated candidate list;
+//   4. one flag barrier at the end (st.release.sys / ld.acquire.sys, bounded spin); the root's stream
+//      then owns the complete hit list.
+// Measured on 2 B200s (tools/ipc_probe.cu): push of a 21 MB slice + two barriers 49 us (NCCL all_gather
+// of the same plane 69 us), flag barrier 6.3 us.
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -29,10 +35,15 @@
 namespace {
 
 constexpr size_t OFF_FLAGS = 0;      // u32[HG_MAX_PEERS]: flags[r] = last barrier epoch member r has reached
-constexpr size_t OFF_STATUS = 64;    // u32: a barrier of this member timed out
-constexpr size_t OFF_COUNT = 128;    // u64: hit counter (the root's is the one in use)
+constexpr size_t OFF_SEQ = 32;       // u32[2]: [0] sharded dist launches so far (what the arrival flags count), [1] barriers so far
+constexpr size_t OFF_STATUS = 64;    // u32: a barrier / an arrival wait of this member timed out
+constexpr size_t OFF_COUNT = 128;    // u64: hits in THIS member's list
+constexpr size_t OFF_TOTAL = 136;    // u64: hits of all members gathered so far (the root's is the one in use)
 constexpr size_t OFF_STATS_Q = 256;  // u32[HG_MAX_PEERS][4]: pre-pass statistics of the gathered (query) matrix, one set per member
 constexpr size_t OFF_STATS_R = 384;  // u32[HG_MAX_PEERS][4]: ... of the members' own ref rows (ref x query)
+constexpr size_t OFF_READY = 512;    // u32[32]: arrival flags, flag m * 4 + c = sequence number of the last call for which chunk c of member m's rows is here
+constexpr size_t OFF_DONE = 640;     // u32[4]: CTAs of this member's chunk pushes that have finished (local use)
+constexpr int N_CHUNKS = 4;
 constexpr size_t OFF_HITS = 4096;    // hg_hit[cap]
 constexpr int32_t TC_MAX_ABS = 8127; // |x| <= 8127 splits into two s8 limbs
 
@@ -48,8 +59,12 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // Everything this stream wrote before (its pushes) is complete when the kernel starts; the fence + release
 // order it before the flag.  The spin is bounded: a member that never arrives (a failed launch, a dead
 // process) turns into an error status instead of a hung GPU.
-__global__ void peer_barrier_kernel(PeerPtrs w, int rank, int world, uint32_t epoch, unsigned long long timeout_ns) {
+__global__ void peer_barrier_kernel(PeerPtrs w, int rank, int world, unsigned long long timeout_ns) {
   const int t = threadIdx.x;
+  uint32_t *ep = reinterpret_cast<uint32_t *>(w.p[rank] + OFF_SEQ) + 1;  // barriers so far: device-resident, so that the
+  uint32_t epoch = 0;                                                    // launch sequence can be replayed as a CUDA graph
+  if (t == 0) { epoch = *ep + 1; *ep = epoch; }
+  epoch = __shfl_sync(0xffffffffu, epoch, 0);
   if (t >= world) return;
   __threadfence_system();
   uint32_t *theirs = reinterpret_cast<uint32_t *>(w.p[t] + OFF_FLAGS) + rank;
@@ -67,20 +82,65 @@ __global__ void peer_barrier_kernel(PeerPtrs w, int rank, int world, uint32_t ep
   }
 }
 
+// First node of a sharded dist on every member: next sequence number, my hit counter and my pre-pass statistics reset
+// (the cursor of my outlier entries starts at my share of the entry space), the root's gather counter reset.
+__global__ void peer_tick_kernel(uint8_t *W, int rank, int is_root, uint32_t entry_base) {
+  if (threadIdx.x == 0) {
+    uint32_t *seq = reinterpret_cast<uint32_t *>(W + OFF_SEQ);
+    *seq = *seq + 1;
+    *reinterpret_cast<unsigned long long *>(W + OFF_COUNT) = 0ull;
+    if (is_root) *reinterpret_cast<unsigned long long *>(W + OFF_TOTAL) = 0ull;
+  }
+  if (threadIdx.x < 4) {
+    reinterpret_cast<uint32_t *>(W + OFF_STATS_Q)[4 * rank + threadIdx.x] = threadIdx.x == 2 ? entry_base : 0u;
+    reinterpret_cast<uint32_t *>(W + OFF_STATS_R)[4 * rank + threadIdx.x] = 0u;
+  }
+}
+
+// After a member's dist kernel: its hit list (in its own window - local atomics, local stores while the tiles were
+// computed) moves to the root in ONE piece: one atomic on the root's counter reserves the room, then coalesced 16-byte
+// stores - over NVLink into the root's gather list, or over this GPU's own PCIe link into a host buffer that every
+// member has mapped.
+__global__ void peer_flush_kernel(const uint8_t *W, unsigned long long *root_total, hg_hit *dst, unsigned long long cap) {
+  __shared__ unsigned long long s_base;
+  const unsigned long long cnt = *reinterpret_cast<const unsigned long long *>(W + OFF_COUNT);
+  const unsigned long long n = cnt < cap ? cnt : cap;  // records beyond my list's capacity were counted, not stored
+  // every block moves a contiguous slice of my list and reserves exactly that much room on the root
+  const unsigned long long per = (n + gridDim.x - 1) / gridDim.x;
+  const unsigned long long lo = per * blockIdx.x < n ? per * blockIdx.x : n, hi = lo + per < n ? lo + per : n;
+  const unsigned long long extra = blockIdx.x == 0 ? cnt - n : 0;  // overflow of my own list still counts towards the need
+  if (hi == lo && extra == 0) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(root_total, hi - lo + extra);
+  __syncthreads();
+  const unsigned long long base = s_base;
+  const uint4 *src = reinterpret_cast<const uint4 *>(W + OFF_HITS);
+  uint4 *out = reinterpret_cast<uint4 *>(dst);
+  for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x)
+    if (base + (i - lo) < cap) out[base + (i - lo)] = src[i];
+}
+
 // Copies byte ranges of this member's window to the same offsets of every other window.
 struct PushRange { uint64_t off, bytes; };  // 4-byte granular; ranges that are 16-byte aligned go as uint4
 struct PushArgs { PushRange r[10]; int n; };
 
-__global__ void peer_push_kernel(PeerPtrs w, int rank, int world, PushArgs a) {
+__global__ void __launch_bounds__(256) peer_push_kernel(PeerPtrs w, int rank, int world, PushArgs a, uint32_t flag_index, uint32_t *done) {
+  const uint32_t seq = *reinterpret_cast<const uint32_t *>(w.p[rank] + OFF_SEQ);
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
   for (int k = 0; k < a.n; ++k) {
     const uint64_t off = a.r[k].off, bytes = a.r[k].bytes;
     if (((off | bytes) & 15) == 0) {
       const uint4 *src = reinterpret_cast<const uint4 *>(w.p[rank] + off);
-      for (size_t i = tid; i < bytes / 16; i += nth) {
-        const uint4 v = src[i];
-        for (int m = 0; m < world; ++m)
-          if (m != rank) reinterpret_cast<uint4 *>(w.p[m] + off)[i] = v;
+      const size_t n16 = bytes / 16;
+      for (size_t i = tid; i < n16; i += 4 * nth) {  // four loads in flight per thread, then their stores to every peer
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i + u * nth < n16) v[u] = src[i + u * nth];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i + u * nth < n16)
+            for (int m = 0; m < world; ++m)
+              if (m != rank) reinterpret_cast<uint4 *>(w.p[m] + off)[i + u * nth] = v[u];
       }
     } else {
       const uint32_t *src = reinterpret_cast<const uint32_t *>(w.p[rank] + off);
@@ -91,18 +151,35 @@ __global__ void peer_push_kernel(PeerPtrs w, int rank, int world, PushArgs a) {
       }
     }
   }
+  // the last CTA to finish raises this chunk's arrival flag in every other window
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence_system();
+      *done = 0;
+      for (int m = 0; m < world; ++m)
+        if (m != rank) {
+          uint32_t *f = reinterpret_cast<uint32_t *>(w.p[m] + OFF_READY) + flag_index;
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+        }
+    }
+  }
 }
 
 inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
 
 // where the pieces of one sharded dist live inside every window (same call arguments -> same layout everywhere)
 struct ShardLayout {
-  uint64_t norm, arrays, entries, plane, end;
+  uint64_t gather, norm, arrays, entries, plane, end;
   uint32_t set_cap;
 };
-ShardLayout make_layout(int world, uint32_t n_total, uint32_t hv_d, uint64_t cap, int n_planes) {
+// [header | my hit list | gathered hit list (root; absent when the hits go to a mapped host buffer) | norms | operands]
+ShardLayout make_layout(int world, uint32_t n_total, uint32_t hv_d, uint64_t cap, int n_planes, bool mapped) {
   ShardLayout l;
-  l.norm = align_up(OFF_HITS + cap * sizeof(hg_hit), 1024);
+  l.gather = align_up(OFF_HITS + cap * sizeof(hg_hit), 1024);
+  l.norm = align_up(l.gather + (mapped ? 0 : cap * sizeof(hg_hit)), 1024);
   l.arrays = align_up(l.norm + (uint64_t)n_total * 4, 256);
   l.set_cap = n_planes == 1 ? hg_narrow_set_cap(n_total) : 0;
   l.entries = align_up(l.arrays + (n_planes == 1 ? hg_narrow_arrays_bytes(n_total) : 0), 256);
@@ -113,20 +190,50 @@ ShardLayout make_layout(int world, uint32_t n_total, uint32_t hv_d, uint64_t cap
 
 }  // namespace
 
-struct hg_peer {
-  hg_ctx *ctx;
-  int rank, world;
-  int local;                     // members driven by one process (peer access) rather than one process per GPU (cudaIpc)
-  uint64_t window_bytes;
-  uint8_t *win[HG_MAX_PEERS];    // every member's window as THIS member addresses it (win[rank] = its own allocation)
-  bool opened[HG_MAX_PEERS];
-  bool connected;
-  uint32_t epoch;
-  unsigned long long timeout_ns;
-  // the last sharded dist
-  int root;
-  uint64_t cap;
+struct TileKey {  // what a cached tile list was built for
+  int sym, path;
+  uint32_t n_ref, n_qry, tr, tc;
+  uint32_t qb[HG_MAX_PEERS + 1];
 };
+
+struct hg_peer {
+  hg_ctx *ctx = nullptr;
+  int rank = 0, world = 1;
+  int local = 0;                 // members driven by one process (peer access) rather than one process per GPU (cudaIpc)
+  uint64_t window_bytes = 0;
+  uint8_t *win[HG_MAX_PEERS] = {};  // every member's window as THIS member addresses it (win[rank] = its own allocation)
+  bool opened[HG_MAX_PEERS] = {};
+  bool connected = false;
+  unsigned long long timeout_ns = 0;
+  uint8_t *h_hdr = nullptr;  // pinned copy of window bytes [OFF_STATUS, OFF_STATUS + 128): status word and hit counters of the
+                             // last call, written by the call's last node
+  // The launch sequence of a sharded dist with asserted path (same pointers, same shapes, call after call) is captured
+  // once and replayed as a CUDA graph: one launch instead of ~10, no gaps between the nodes.
+  cudaGraphExec_t graph = nullptr;
+  std::vector<uint8_t> graph_key, last_key;
+  unsigned graph_nodes = 0;
+  // the last sharded dist
+  int root = 0;
+  uint64_t cap = 0;
+  hg_hit *mapped_hits = nullptr;  // hits went to a host buffer every member has mapped, not to the root's window
+  uint64_t gather_off = 0;        // where the root's gathered list starts in its window
+  // this member's tile list (host copy + what it was built for; the device copy lives in scratch slot HG_S_TILES)
+  std::vector<uint2> tiles;
+  TileKey tiles_key = {};
+  bool tiles_valid = false, tiles_on_device = false;
+  // stage boundaries of the last sharded dist (recorded when the context profiles): start | operands ready | pushed |
+  // kernel done | final barrier passed
+  cudaEvent_t ev[6] = {};
+  int ev_n = 0;
+};
+#define PEER_PROF(p, i)                                                      \
+  do {                                                                       \
+    if ((p)->ctx->prof) {                                                    \
+      if (!(p)->ev[i]) cudaEventCreate(&(p)->ev[i]);                         \
+      cudaEventRecord((p)->ev[i], (p)->ctx->stream);                         \
+      (p)->ev_n = (i) + 1;                                                   \
+    }                                                                        \
+  } while (0)
 
 static PeerPtrs peer_ptrs(const hg_peer *p) {
   PeerPtrs w;
@@ -135,7 +242,7 @@ static PeerPtrs peer_ptrs(const hg_peer *p) {
 }
 
 extern "C" uint64_t hg_peer_window_need(uint32_t gathered_rows, uint32_t hv_d, uint64_t hit_cap) {
-  const ShardLayout a = make_layout(HG_MAX_PEERS, gathered_rows, hv_d, hit_cap, 1), b = make_layout(HG_MAX_PEERS, gathered_rows, hv_d, hit_cap, 2);
+  const ShardLayout a = make_layout(HG_MAX_PEERS, gathered_rows, hv_d, hit_cap, 1, false), b = make_layout(HG_MAX_PEERS, gathered_rows, hv_d, hit_cap, 2, false);
   return std::max(a.end, b.end) + 4096;
 }
 
@@ -145,7 +252,6 @@ static int peer_alloc(hg_ctx *ctx, int rank, int world, uint64_t window_bytes, h
   if (window_bytes < OFF_HITS + 4096) window_bytes = OFF_HITS + 4096;
   HG_CUDA(cudaSetDevice(ctx->device));
   hg_peer *p = new hg_peer();
-  memset(p, 0, sizeof(*p));
   p->ctx = ctx;
   p->rank = rank;
   p->world = world;
@@ -159,6 +265,9 @@ static int peer_alloc(hg_ctx *ctx, int rank, int world, uint64_t window_bytes, h
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { cudaFree(w); delete p; return hg_cuda_fail(e, "cudaMemset(window)", __FILE__, __LINE__); }
   p->win[rank] = (uint8_t *)w;
+  e = cudaMallocHost(&p->h_hdr, 128);
+  if (e != cudaSuccess) { cudaFree(w); delete p; return hg_cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__); }
+  memset(p->h_hdr, 0, 128);
   *out = p;
   return HG_OK;
 }
@@ -235,6 +344,9 @@ extern "C" void hg_peer_destroy(hg_peer *p) {
   for (int r = 0; r < p->world; ++r)
     if (p->opened[r]) cudaIpcCloseMemHandle(p->win[r]);
   if (p->win[p->rank]) cudaFree(p->win[p->rank]);
+  for (int i = 0; i < 6; ++i) if (p->ev[i]) cudaEventDestroy(p->ev[i]);
+  if (p->graph) cudaGraphExecDestroy(p->graph);
+  if (p->h_hdr) cudaFreeHost(p->h_hdr);
   delete p;
 }
 
@@ -242,7 +354,7 @@ extern "C" int hg_peer_rank(const hg_peer *p) { return p ? p->rank : -1; }
 extern "C" int hg_peer_world(const hg_peer *p) { return p ? p->world : 0; }
 
 static int peer_barrier(hg_peer *p) {
-  peer_barrier_kernel<<<1, 32, 0, p->ctx->stream>>>(peer_ptrs(p), p->rank, p->world, ++p->epoch, p->timeout_ns);
+  peer_barrier_kernel<<<1, 32, 0, p->ctx->stream>>>(peer_ptrs(p), p->rank, p->world, p->timeout_ns);
   p->ctx->launches++;
   HG_CUDA(cudaGetLastError());
   return HG_OK;
@@ -254,12 +366,15 @@ extern "C" int hg_peer_barrier(hg_peer *p) {
   return peer_barrier(p);
 }
 
-static int peer_push(hg_peer *p, const PushArgs &a) {
-  if (p->world == 1 || a.n == 0) return HG_OK;
+// Stand-alone push of one chunk (a member that has rows to contribute but no tile to compute - otherwise the dist
+// kernel's pusher warps do this, see hg_push_plan): the ranges, then arrival flag `flag_index` in every other window
+static int peer_push(hg_peer *p, const PushArgs &a, uint32_t flag_index) {
+  if (p->world == 1) return HG_OK;
   uint64_t bytes = 0;
   for (int k = 0; k < a.n; ++k) bytes += a.r[k].bytes;
   const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(bytes / (16 * 256 * 4), 1), (uint64_t)p->ctx->sm_count * 4);
-  peer_push_kernel<<<blocks, 256, 0, p->ctx->stream>>>(peer_ptrs(p), p->rank, p->world, a);
+  uint32_t *done = reinterpret_cast<uint32_t *>(p->win[p->rank] + OFF_DONE) + (flag_index % N_CHUNKS);
+  peer_push_kernel<<<blocks, 256, 0, p->ctx->stream>>>(peer_ptrs(p), p->rank, p->world, a, flag_index, done);
   p->ctx->launches++;
   HG_CUDA(cudaGetLastError());
   return HG_OK;
@@ -271,21 +386,48 @@ static int peer_push(hg_peer *p, const PushArgs &a) {
 namespace {
 struct ShardCall {
   const int16_t *d_ref_hv; const int32_t *d_ref_norm; uint32_t n_ref_local, ref_row0;
-  const int16_t *d_qry_hv; const int32_t *d_qry_norm; uint32_t n_qry_local, qry_row0, n_qry_total;
+  const int16_t *d_qry_hv; const int32_t *d_qry_norm;
+  uint32_t qb[HG_MAX_PEERS + 1];  // rows [qb[m], qb[m + 1]) of the gathered (query) matrix are member m's
   uint32_t hv_d, ksize; float ani_th; int symmetric, root; uint64_t cap;
+  hg_hit *mapped_hits;
+  uint32_t n_qry_total(int world) const { return qb[world]; }
 };
+
+// chunk c of member m's block: rows [chunk_lo(c), chunk_lo(c + 1))
+inline uint32_t chunk_lo(const uint32_t *qb, int m, int c) {
+  if (c >= N_CHUNKS) return qb[m + 1];
+  return qb[m] + (uint32_t)(((uint64_t)(qb[m + 1] - qb[m]) * c / N_CHUNKS) & ~3ull);
+}
+
+// arrival flags (other members' chunks) that rows [x0, x1) of the gathered matrix depend on
+uint32_t need_mask(const uint32_t *qb, int world, int rank, uint64_t x0, uint64_t x1) {
+  uint32_t m_ = 0;
+  for (int m = 0; m < world; ++m) {
+    if (m == rank || qb[m + 1] <= x0 || qb[m] >= x1) continue;
+    for (int c = 0; c < N_CHUNKS; ++c) {
+      const uint64_t lo = chunk_lo(qb, m, c), hi = chunk_lo(qb, m, c + 1);
+      if (lo < hi && lo < x1 && hi > x0) m_ |= 1u << (m * N_CHUNKS + c);
+    }
+  }
+  return m_;
+}
 }  // namespace
 
 static int shard_check(hg_peer *p, const ShardCall &a) {
   if (!p || !p->connected) { hg_set_error("hg_dist_sharded: the group is not connected"); return HG_E_INVALID; }
   if (a.hv_d == 0 || a.hv_d % 256 != 0) { hg_set_error("hg_dist_sharded: hv_d %u must be a multiple of 256", a.hv_d); return HG_E_INVALID; }
   if (a.root < 0 || a.root >= p->world) { hg_set_error("hg_dist_sharded: root %d of %d", a.root, p->world); return HG_E_INVALID; }
-  if ((uint64_t)a.qry_row0 + a.n_qry_local > a.n_qry_total) { hg_set_error("hg_dist_sharded: query rows [%u, +%u) outside %u", a.qry_row0, a.n_qry_local, a.n_qry_total); return HG_E_INVALID; }
-  if ((a.n_qry_local && (!a.d_qry_hv || !a.d_qry_norm)) || (!a.symmetric && a.n_ref_local && (!a.d_ref_hv || !a.d_ref_norm))) {
+  if (a.qb[0] != 0) { hg_set_error("hg_dist_sharded: qry_bounds[0] must be 0"); return HG_E_INVALID; }
+  for (int m = 0; m < p->world; ++m)
+    if (a.qb[m + 1] < a.qb[m]) { hg_set_error("hg_dist_sharded: qry_bounds not monotone at member %d", m); return HG_E_INVALID; }
+  const uint32_t nl = a.qb[p->rank + 1] - a.qb[p->rank];
+  if ((nl && (!a.d_qry_hv || !a.d_qry_norm)) || (!a.symmetric && a.n_ref_local && (!a.d_ref_hv || !a.d_ref_norm))) {
     hg_set_error("hg_dist_sharded: NULL argument"); return HG_E_INVALID;
   }
   if (((uintptr_t)a.d_qry_hv | (uintptr_t)a.d_ref_hv) & 15) { hg_set_error("hg_dist_sharded: HV rows must be 16-byte aligned"); return HG_E_INVALID; }
-  const uint64_t need = std::max(make_layout(p->world, a.n_qry_total, a.hv_d, a.cap, 1).end, make_layout(p->world, a.n_qry_total, a.hv_d, a.cap, 2).end);
+  if (a.qb[p->world] > 65535u * 128u) { hg_set_error("hg_dist_sharded: more than %u gathered rows", 65535u * 128u); return HG_E_UNSUPPORTED; }
+  const bool mp = a.mapped_hits != nullptr;
+  const uint64_t need = std::max(make_layout(p->world, a.qb[p->world], a.hv_d, a.cap, 1, mp).end, make_layout(p->world, a.qb[p->world], a.hv_d, a.cap, 2, mp).end);
   if (need > p->window_bytes) {
     hg_set_error("hg_dist_sharded: the windows hold %llu bytes, this call needs %llu (hg_peer_window_need)", (unsigned long long)p->window_bytes,
                  (unsigned long long)need);
@@ -294,16 +436,62 @@ static int shard_check(hg_peer *p, const ShardCall &a) {
   return HG_OK;
 }
 
+// This member's tiles for kernel `use_path` (3: 256 x 256 tiles, 2: 256 x 128), ordered by arrival of what they read.
+static void build_tiles(hg_peer *p, const ShardCall &a, int use_path) {
+  TileKey k = {};
+  k.sym = a.symmetric;
+  k.path = use_path;
+  k.n_ref = a.symmetric ? a.qb[p->world] : a.n_ref_local;
+  k.n_qry = a.qb[p->world];
+  if (use_path == 3) hg_narrow_tile_shape(&k.tr, &k.tc); else hg_tc_tile_shape(&k.tr, &k.tc);
+  memcpy(k.qb, a.qb, sizeof(k.qb));
+  for (int m = p->world + 1; m <= HG_MAX_PEERS; ++m) k.qb[m] = 0;
+  if (p->tiles_valid && memcmp(&k, &p->tiles_key, sizeof(k)) == 0) return;
+  p->tiles_key = k;
+  p->tiles_valid = true;
+  p->tiles_on_device = false;
+  const uint32_t gx = (k.n_qry + k.tc - 1) / k.tc, gy = (k.n_ref + k.tr - 1) / k.tr;
+  struct T { uint2 e; uint32_t key; };
+  std::vector<T> v;
+  uint64_t t = 0;
+  for (uint32_t R = 0; R < gy; ++R) {
+    // symmetric (i0 = j0 = 0): tiles whose largest j is not above their smallest i are empty (as the kernels' cmin)
+    uint32_t c0 = 0;
+    if (a.symmetric) c0 = (uint32_t)std::min<uint64_t>(((uint64_t)k.tr * R + 1) / k.tc, gx);
+    for (uint32_t C = c0; C < gx; ++C, ++t) {
+      if (a.symmetric && (int)(t % (uint64_t)p->world) != p->rank) continue;
+      uint32_t need = need_mask(a.qb, p->world, p->rank, (uint64_t)C * k.tc, std::min<uint64_t>((uint64_t)(C + 1) * k.tc, k.n_qry));
+      if (a.symmetric) need |= need_mask(a.qb, p->world, p->rank, (uint64_t)R * k.tr, std::min<uint64_t>((uint64_t)(R + 1) * k.tr, k.n_ref));
+      uint32_t key = 0;
+      for (int b = 0; b < 32; ++b) if (need >> b & 1u) key = std::max<uint32_t>(key, 1 + b % N_CHUNKS);
+      v.push_back({make_uint2(R | (C << 16), need), key});
+    }
+  }
+  // all-vs-all: tiles that read only my own rows first, then in the order the other members' chunks arrive (row-major
+  // within each group).  ref x query stays row-major: the queries are few and arrive early, while a column-wise sweep
+  // would stream my whole ref plane from HBM once per query tile column.
+  if (a.symmetric && !getenv("HG_PEER_NOSORT")) std::stable_sort(v.begin(), v.end(), [](const T &x, const T &y) { return x.key < y.key; });
+  p->tiles.resize(v.size());
+  for (size_t i = 0; i < v.size(); ++i) p->tiles[i] = v[i].e;
+}
+
 // every allocation of the call, before anything that waits for another member is enqueued (growing a scratch
-// buffer synchronises the device)
-static int shard_reserve(hg_peer *p, const ShardCall &a) {
+// buffer synchronises the device); also builds this member's tile list for kernel `use_path`
+static int shard_reserve(hg_peer *p, const ShardCall &a, int use_path) {
   hg_ctx *c = p->ctx;
   HG_CUDA(cudaSetDevice(c->device));
+  void *x;
+  int rc;
   if (!a.symmetric && a.n_ref_local) {
-    void *x;
-    int rc;
     if ((rc = hg_scratch(c, HG_S_REF_LIMBS, 2 * (uint64_t)a.n_ref_local * a.hv_d + 1024, &x))) return rc;
     if ((rc = hg_scratch(c, HG_S_NARROW_META, hg_narrow_arrays_bytes(a.n_ref_local) + (uint64_t)hg_narrow_set_cap(a.n_ref_local) * 4 + 256, &x))) return rc;
+  }
+  if (p->world > 1 || getenv("HG_PEER_FORCE_LIST")) {
+    build_tiles(p, a, use_path);
+    const size_t bytes = p->tiles.size() * sizeof(uint2) + 256;
+    if ((rc = hg_scratch(c, HG_S_TILES, bytes, &x))) return rc;
+    if ((rc = hg_pinned(c, 2, bytes, &x))) return rc;
+    if (!p->tiles_on_device) memcpy(x, p->tiles.data(), p->tiles.size() * sizeof(uint2));
   }
   return HG_OK;
 }
@@ -314,90 +502,165 @@ static const int16_t *matrix_base(const int16_t *d_rows, uint32_t row0, uint32_t
 }
 
 // use_path 3: single s8 plane; 2: two s8 limb planes.  Enqueues everything on the member's stream; returns without waiting.
-static int shard_enqueue(hg_peer *p, const ShardCall &a, int use_path, hg_narrow_mat *Qn_out, hg_narrow_mat *Rn_out) {
+static int shard_enqueue(hg_peer *p, const ShardCall &a, int use_path) {
   hg_ctx *c = p->ctx;
   HG_CUDA(cudaSetDevice(c->device));
   int rc;
   const int rank = p->rank, world = p->world;
+  const uint32_t n_total = a.qb[world], r0 = a.qb[rank], nl = a.qb[rank + 1] - a.qb[rank];
   uint8_t *W = p->win[rank];
-  const ShardLayout lay = make_layout(world, a.n_qry_total, a.hv_d, a.cap, use_path == 3 ? 1 : 2);
+  const ShardLayout lay = make_layout(world, n_total, a.hv_d, a.cap, use_path == 3 ? 1 : 2, a.mapped_hits != nullptr);
   int32_t *normW = (int32_t *)(W + lay.norm);
-  hg_hit *hits = (hg_hit *)(p->win[a.root] + OFF_HITS);
-  unsigned long long *counter = (unsigned long long *)(p->win[a.root] + OFF_COUNT);
+  // every member appends to ITS OWN list (local atomics and stores); peer_flush_kernel moves the list to the root afterwards
+  hg_hit *hits = (hg_hit *)(W + OFF_HITS);
+  unsigned long long *counter = (unsigned long long *)(W + OFF_COUNT);
   p->root = a.root;
   p->cap = a.cap;
+  p->mapped_hits = a.mapped_hits;
+  p->gather_off = lay.gather;
   c->ev_used &= ~(3 << 4);
   HG_PROF(c, 4);
-  if (rank == a.root) HG_CUDA(cudaMemsetAsync(W + OFF_COUNT, 0, 8, c->stream));
-  if (a.n_qry_local)
-    HG_CUDA(cudaMemcpyAsync(normW + a.qry_row0, a.d_qry_norm, (size_t)a.n_qry_local * 4, cudaMemcpyDeviceToDevice, c->stream));
-  PushArgs pa;
-  pa.n = 0;
-  auto add = [&](uint64_t off, uint64_t bytes) { if (bytes) { pa.r[pa.n].off = off; pa.r[pa.n].bytes = bytes; pa.n++; } };
-  const uint64_t r0 = a.qry_row0, nl = a.n_qry_local;
-  add(lay.norm + r0 * 4, nl * 4);
+  p->ev_n = 0;
+  PEER_PROF(p, 0);
+  // sequence number + 1, my hit counter and statistics reset, the root's gather counter reset
+  peer_tick_kernel<<<1, 32, 0, c->stream>>>(W, rank, rank == a.root, use_path == 3 ? (uint32_t)rank * lay.set_cap : 0u);
+  c->launches++;
+  HG_CUDA(cudaGetLastError());
+  hg_tile_feed feed = {};
+  const bool use_list = world > 1 || getenv("HG_PEER_FORCE_LIST");  // (the env: list walk on a single GPU, for measurements)
+  if (use_list) {
+    if (!p->tiles_on_device) {
+      HG_CUDA(cudaMemcpyAsync(c->d_scratch[HG_S_TILES], c->h_pinned[2], p->tiles.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+      p->tiles_on_device = true;
+    }
+    feed.list = (const uint2 *)c->d_scratch[HG_S_TILES];
+    feed.n_list = (uint32_t)p->tiles.size();
+    feed.ready = (const uint32_t *)(W + OFF_READY);
+    feed.seq_ptr = (const uint32_t *)(W + OFF_SEQ);
+    feed.status = (uint32_t *)(W + OFF_STATUS);
+    feed.timeout_ns = p->timeout_ns;
+    if (use_path == 3)  // the pre-pass statistics of every other member travel with its chunk 0
+      for (int m = 0; m < world; ++m) if (m != rank) feed.start_need |= 1u << (m * N_CHUNKS);
+    // nobody moves hits to the root before the root has reset its gather counter for this call: the root raises its
+    // chunk-0 flag (empty chunk or not) after its tick kernel, in stream order
+    if (rank != a.root) feed.start_need |= 1u << (a.root * N_CHUNKS);
+  }
+  if (nl) HG_CUDA(cudaMemcpyAsync(normW + r0, a.d_qry_norm, (size_t)nl * 4, cudaMemcpyDeviceToDevice, c->stream));
+  hg_narrow_mat Qn, Rn;
+  hg_tc_mat Qt, Rt;
   if (use_path == 3) {
-    hg_narrow_mat Q, R;
-    if ((rc = hg_narrow_attach(c, matrix_base(a.d_qry_hv, a.qry_row0, a.hv_d), a.n_qry_total, a.hv_d, (int8_t *)(W + lay.plane), W + lay.arrays,
+    if ((rc = hg_narrow_attach(c, matrix_base(a.d_qry_hv, r0, a.hv_d), n_total, a.hv_d, (int8_t *)(W + lay.plane), W + lay.arrays,
                                (uint32_t *)(W + lay.entries), (uint32_t *)(W + OFF_STATS_Q), (uint32_t)world, (uint32_t)rank,
-                               (uint32_t)rank * lay.set_cap, lay.set_cap, &Q)))
+                               (uint32_t)rank * lay.set_cap, lay.set_cap, &Qn, /*init_stats=*/false)))
       return rc;
-    if ((rc = hg_narrow_prep_rows(c, &Q, a.qry_row0, a.n_qry_local))) return rc;
-    if (!a.symmetric) {
+    if ((rc = hg_narrow_prep_rows(c, &Qn, r0, nl))) return rc;
+    if (!a.symmetric) {  // my own ref rows stay local; only their statistics are shared (the verdict must be the same everywhere)
       void *plane = c->d_scratch[HG_S_REF_LIMBS], *meta = c->d_scratch[HG_S_NARROW_META];
       const uint32_t nr = a.n_ref_local;
       if ((rc = hg_narrow_attach(c, a.d_ref_hv, nr, a.hv_d, (int8_t *)plane, meta, (uint32_t *)((uint8_t *)meta + hg_narrow_arrays_bytes(nr)),
-                                 (uint32_t *)(W + OFF_STATS_R), (uint32_t)world, (uint32_t)rank, 0, hg_narrow_set_cap(nr), &R)))
+                                 (uint32_t *)(W + OFF_STATS_R), (uint32_t)world, (uint32_t)rank, 0, hg_narrow_set_cap(nr), &Rn, /*init_stats=*/false)))
         return rc;
-      if ((rc = hg_narrow_prep_rows(c, &R, 0, nr))) return rc;
+      if ((rc = hg_narrow_prep_rows(c, &Rn, 0, nr))) return rc;
     }
-    add(lay.plane + r0 * a.hv_d, nl * a.hv_d);
-    for (int k = 0; k < 5; ++k) add(lay.arrays + ((uint64_t)k * a.n_qry_total + r0) * 4, nl * 4);
-    if (nl) add(lay.entries + (uint64_t)rank * lay.set_cap * 4, (uint64_t)lay.set_cap * 4);
-    add(OFF_STATS_Q + 16 * (uint64_t)rank, 16);
-    if (!a.symmetric) add(OFF_STATS_R + 16 * (uint64_t)rank, 16);
-    if ((rc = peer_push(p, pa))) return rc;
-    if ((rc = peer_barrier(p))) return rc;
-    if (a.symmetric)
-      rc = hg_narrow_launch_ex(c, &Q, 0, a.n_qry_total, 0, normW, &Q, 0, a.n_qry_total, 0, normW, a.ksize, a.ani_th, 1, hits, a.cap, counter,
-                               (uint32_t)world, (uint32_t)rank);
-    else
-      rc = hg_narrow_launch_ex(c, &R, 0, a.n_ref_local, a.ref_row0, a.d_ref_norm, &Q, 0, a.n_qry_total, 0, normW, a.ksize, a.ani_th, 0, hits,
-                               a.cap, counter, 1, 0);
-    if (rc) return rc;
-    if (Qn_out) *Qn_out = Q;
-    if (Rn_out && !a.symmetric) *Rn_out = R;
   } else {
-    hg_tc_mat Q, R;
     if ((rc = hg_tc_shape_ok(a.hv_d, a.d_qry_hv, a.d_ref_hv))) return rc;
-    if ((rc = hg_tc_attach(c, matrix_base(a.d_qry_hv, a.qry_row0, a.hv_d), a.n_qry_total, a.hv_d, (int8_t *)(W + lay.plane), &Q))) return rc;
-    if ((rc = hg_tc_split_rows(c, &Q, a.qry_row0, a.n_qry_local))) return rc;
+    if ((rc = hg_tc_attach(c, matrix_base(a.d_qry_hv, r0, a.hv_d), n_total, a.hv_d, (int8_t *)(W + lay.plane), &Qt))) return rc;
+    if ((rc = hg_tc_split_rows(c, &Qt, r0, nl))) return rc;
     if (!a.symmetric && a.n_ref_local) {
-      if ((rc = hg_tc_attach(c, a.d_ref_hv, a.n_ref_local, a.hv_d, (int8_t *)c->d_scratch[HG_S_REF_LIMBS], &R))) return rc;
-      if ((rc = hg_tc_split_rows(c, &R, 0, a.n_ref_local))) return rc;
+      if ((rc = hg_tc_attach(c, a.d_ref_hv, a.n_ref_local, a.hv_d, (int8_t *)c->d_scratch[HG_S_REF_LIMBS], &Rt))) return rc;
+      if ((rc = hg_tc_split_rows(c, &Rt, 0, a.n_ref_local))) return rc;
     }
-    add(lay.plane + r0 * a.hv_d, nl * a.hv_d);
-    add(lay.plane + ((uint64_t)a.n_qry_total + r0) * a.hv_d, nl * a.hv_d);
-    if ((rc = peer_push(p, pa))) return rc;
-    if ((rc = peer_barrier(p))) return rc;
-    if (a.symmetric)
-      rc = hg_tc_launch_ex(c, &Q, 0, a.n_qry_total, 0, normW, &Q, 0, a.n_qry_total, 0, normW, a.ksize, a.ani_th, 1, hits, a.cap, counter,
-                           (uint32_t)world, (uint32_t)rank);
-    else
-      rc = hg_tc_launch_ex(c, &R, 0, a.n_ref_local, a.ref_row0, a.d_ref_norm, &Q, 0, a.n_qry_total, 0, normW, a.ksize, a.ani_th, 0, hits, a.cap,
-                           counter, 1, 0);
-    if (rc) return rc;
   }
+  PEER_PROF(p, 1);
+  // ---- what I push to the others, in chunks; every chunk raises its arrival flag in the other windows (also when it is
+  //      empty).  The dist kernel below carries pusher warps that do it while the tiles are computed; a member without a
+  //      tile to compute pushes with a stand-alone kernel instead ----
+  hg_push_plan plan = {};
+  for (int m = 0; m < world; ++m) plan.win[m] = p->win[m];
+  plan.rank = rank;
+  plan.world = world;
+  plan.done = reinterpret_cast<uint32_t *>(W + OFF_DONE);
+  plan.ready_off = OFF_READY;
+  plan.seq = (const uint32_t *)(W + OFF_SEQ);
+  for (int ch = 0; ch < N_CHUNKS && world > 1; ++ch) {
+    const uint64_t lo = chunk_lo(a.qb, rank, ch), n = chunk_lo(a.qb, rank, ch + 1) - lo;
+    auto add = [&](uint64_t off, uint64_t bytes) {
+      if (bytes) { plan.off[ch][plan.n[ch]] = off; plan.bytes[ch][plan.n[ch]] = (uint32_t)bytes; plan.n[ch]++; }
+    };
+    add(lay.norm + lo * 4, n * 4);
+    add(lay.plane + lo * a.hv_d, n * a.hv_d);
+    if (use_path == 3) {
+      for (int k = 0; k < 5; ++k) add(lay.arrays + ((uint64_t)k * n_total + lo) * 4, n * 4);
+      if (ch == 0) {  // the statistics and the outlier entries of ALL my rows (the pre-pass above is complete) go first
+        if (nl) add(lay.entries + (uint64_t)rank * lay.set_cap * 4, (uint64_t)lay.set_cap * 4);
+        add(OFF_STATS_Q + 16 * (uint64_t)rank, 16);
+        if (!a.symmetric) add(OFF_STATS_R + 16 * (uint64_t)rank, 16);
+      }
+    } else {
+      add(lay.plane + ((uint64_t)n_total + lo) * a.hv_d, n * a.hv_d);
+    }
+  }
+  bool have_tiles = world > 1 && !p->tiles.empty() && (a.symmetric || a.n_ref_local > 0);
+  if (const char *e = getenv("HG_PEER_PUSH")) if (!strcmp(e, "standalone")) have_tiles = false;  // A/B: pushes ahead of the kernel
+  if (world > 1 && !have_tiles) {
+    for (int ch = 0; ch < N_CHUNKS; ++ch) {
+      PushArgs pa;
+      pa.n = plan.n[ch];
+      for (int k = 0; k < pa.n; ++k) { pa.r[k].off = plan.off[ch][k]; pa.r[k].bytes = plan.bytes[ch][k]; }
+      if ((rc = peer_push(p, pa, (uint32_t)(rank * N_CHUNKS + ch)))) return rc;
+    }
+  }
+  const hg_push_plan *pp = have_tiles ? &plan : nullptr;
+  PEER_PROF(p, 2);
+  const hg_tile_feed *fp = use_list ? &feed : nullptr;
+  if (use_path == 3) {
+    if (a.symmetric)
+      rc = hg_narrow_launch_ex(c, &Qn, 0, n_total, 0, normW, &Qn, 0, n_total, 0, normW, a.ksize, a.ani_th, 1, hits, a.cap, counter, 1, 0, fp, pp);
+    else
+      rc = hg_narrow_launch_ex(c, &Rn, 0, a.n_ref_local, a.ref_row0, a.d_ref_norm, &Qn, 0, n_total, 0, normW, a.ksize, a.ani_th, 0, hits,
+                               a.cap, counter, 1, 0, fp, pp);
+  } else {
+    if (a.symmetric)
+      rc = hg_tc_launch_ex(c, &Qt, 0, n_total, 0, normW, &Qt, 0, n_total, 0, normW, a.ksize, a.ani_th, 1, hits, a.cap, counter, 1, 0, fp, pp);
+    else
+      rc = hg_tc_launch_ex(c, &Rt, 0, a.n_ref_local, a.ref_row0, a.d_ref_norm, &Qt, 0, n_total, 0, normW, a.ksize, a.ani_th, 0, hits, a.cap,
+                           counter, 1, 0, fp, pp);
+  }
+  if (rc) return rc;
   HG_PROF(c, 5);
-  return peer_barrier(p);
+  PEER_PROF(p, 3);
+  {  // my hits to the root: its gather list (NVLink), or the host buffer every member has mapped (my own PCIe link)
+    hg_hit *dst = a.mapped_hits ? a.mapped_hits : (hg_hit *)(p->win[a.root] + lay.gather);
+    unsigned long long *total = (unsigned long long *)(p->win[a.root] + OFF_TOTAL);
+    peer_flush_kernel<<<64, 256, 0, c->stream>>>(W, total, dst, a.cap);
+    c->launches++;
+    HG_CUDA(cudaGetLastError());
+  }
+  if ((rc = peer_barrier(p))) return rc;  // every member has flushed: the root's list is complete, the windows may be reused
+  HG_CUDA(cudaMemcpyAsync(p->h_hdr, W + OFF_STATUS, 128, cudaMemcpyDeviceToHost, c->stream));  // status word + hit counters
+  PEER_PROF(p, 4);
+  return HG_OK;
 }
 
-static int peer_status(hg_peer *p) {  // after a stream synchronisation
-  uint32_t st = 0;
-  HG_CUDA(cudaMemcpy(&st, p->win[p->rank] + OFF_STATUS, 4, cudaMemcpyDeviceToHost));
-  if (st) {
+// Measurement support (with hg_set_profiling on the member's context): device ms of the last sharded dist's stages -
+// [0] operands (pre-pass / limb split), [1] chunked push to the peers, [2] dist kernel (incl. its waits for the peers'
+// chunks), [3] final barrier (wait for the slowest member).  Synchronises the member's stream.
+extern "C" int hg_peer_stage_ms(hg_peer *p, float out_ms[4]) {
+  if (!p || !out_ms) { hg_set_error("hg_peer_stage_ms: NULL argument"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(p->ctx->device));
+  HG_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  for (int i = 0; i < 4; ++i) {
+    out_ms[i] = -1.0f;
+    if (p->ev_n >= i + 2) HG_CUDA(cudaEventElapsedTime(&out_ms[i], p->ev[i], p->ev[i + 1]));
+  }
+  return HG_OK;
+}
+
+static int peer_status(hg_peer *p) {  // after a stream synchronisation that followed a sharded dist (h_hdr is current)
+  if (*reinterpret_cast<const uint32_t *>(p->h_hdr)) {
     cudaMemset(p->win[p->rank] + OFF_STATUS, 0, 4);
-    hg_set_error("a member of the GPU group did not reach a barrier within %llu ms", p->timeout_ns / 1000000ull);
+    *reinterpret_cast<uint32_t *>(p->h_hdr) = 0;
+    hg_set_error("a member of the GPU group did not deliver its rows / reach a barrier within %llu ms", p->timeout_ns / 1000000ull);
     return HG_E_CUDA;
   }
   return HG_OK;
@@ -427,42 +690,79 @@ static void shard_reason(hg_peer *p, int path, int32_t absmax, bool forced) {
   hg_ctx *c = p->ctx;
   c->dist_path = path;
   if (path == 3)
-    snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor-narrow%s: member %d of %d GPUs, operand planes pushed over NVLink windows, tiles dealt round-robin%s",
-             forced ? " (forced)" : "", p->rank, p->world, forced ? "" : "; rows fit one s8 plane as x = 2a + s");
+    snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor-narrow%s: member %d of %d GPUs, operand planes pushed over NVLink windows in %d chunks, tiles dealt round-robin and ordered by arrival%s",
+             forced ? " (forced)" : "", p->rank, p->world, N_CHUNKS, forced ? "" : "; rows fit one s8 plane as x = 2a + s");
   else
-    snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor%s: member %d of %d GPUs, two s8 limb planes pushed over NVLink windows, tiles dealt round-robin (max |hv| = %d)",
-             forced ? " (forced)" : "", p->rank, p->world, absmax);
+    snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor%s: member %d of %d GPUs, two s8 limb planes pushed over NVLink windows in %d chunks, tiles dealt round-robin and ordered by arrival (max |hv| = %d)",
+             forced ? " (forced)" : "", p->rank, p->world, N_CHUNKS, absmax);
 }
 
-// Collective over the group (every member calls it with the same scalars and its own rows):
-//   symmetric != 0: all-vs-all (j > i) over the n_qry_total-row matrix whose rows [qry_row0, +n_qry_local) this member
-//                   holds (d_qry_hv, d_qry_norm2); the ref arguments are ignored;
-//   symmetric == 0: this member's n_ref_local ref rows (global index ref_row0 + local row) against ALL n_qry_total query
-//                   rows, of which this member contributes [qry_row0, +n_qry_local) - possibly none, possibly all.
-//   path: 0 auto (one host read of the members' pre-pass verdict, then the two-limb kernel if the rows are not narrow),
-//         3 / 2 force the single-plane / two-limb tensor kernel: nothing is waited for, the call only enqueues.
-// The hits (global indices) accumulate in member `root`'s window: hg_dist_sharded_hits reads them.
+// Collective over the group (every member calls it with the same scalars and its own rows); see hypergen_b200.h.
 extern "C" int hg_dist_sharded_dev(hg_peer *p, const int16_t *d_ref_hv, const int32_t *d_ref_norm2, uint32_t n_ref_local,
-                                   uint32_t ref_row0, const int16_t *d_qry_hv, const int32_t *d_qry_norm2, uint32_t n_qry_local,
-                                   uint32_t qry_row0, uint32_t n_qry_total, uint32_t hv_d, uint32_t ksize, float ani_th,
-                                   int symmetric, int path, int root, uint64_t cap) {
-  ShardCall a = {d_ref_hv, d_ref_norm2, symmetric ? 0u : n_ref_local, ref_row0, d_qry_hv, d_qry_norm2, n_qry_local, qry_row0, n_qry_total,
-                 hv_d, ksize, ani_th, symmetric, root, cap};
+                                   uint32_t ref_row0, const int16_t *d_qry_hv, const int32_t *d_qry_norm2, const uint32_t *qry_bounds,
+                                   uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path, int root, uint64_t cap,
+                                   hg_hit *mapped_hits) {
+  if (!p || !qry_bounds) { hg_set_error("hg_dist_sharded_dev: NULL argument"); return HG_E_INVALID; }
+  ShardCall a = {};
+  a.d_ref_hv = d_ref_hv; a.d_ref_norm = d_ref_norm2; a.n_ref_local = symmetric ? 0u : n_ref_local; a.ref_row0 = ref_row0;
+  a.d_qry_hv = d_qry_hv; a.d_qry_norm = d_qry_norm2;
+  for (int m = 0; m <= p->world; ++m) a.qb[m] = qry_bounds[m];
+  a.hv_d = hv_d; a.ksize = ksize; a.ani_th = ani_th; a.symmetric = symmetric; a.root = root; a.cap = cap; a.mapped_hits = mapped_hits;
   int rc;
   if ((rc = shard_check(p, a))) return rc;
   if (path != 0 && path != 2 && path != 3) { hg_set_error("hg_dist_sharded_dev: path %d (0 auto, 2 two-limb, 3 single plane)", path); return HG_E_INVALID; }
-  if (n_qry_total == 0) return HG_OK;
-  if ((rc = shard_reserve(p, a))) return rc;
+  if (a.qb[p->world] == 0) return HG_OK;
   if (path == 2 || path == 3) {
     if (path == 3 && (rc = hg_narrow_shape_ok(hv_d, d_qry_hv, d_ref_hv))) return rc;
-    if ((rc = shard_enqueue(p, a, path, nullptr, nullptr))) return rc;
+    hg_ctx *c = p->ctx;
+    // The same call again (same pointers, shapes and scratch buffers): replay its launch sequence as a CUDA graph.
+    // The first call runs directly, the second is captured, the following ones are one cudaGraphLaunch each.
+    std::vector<uint8_t> key(sizeof(ShardCall) + 4 * sizeof(void *));
+    memcpy(key.data(), &a, sizeof(ShardCall));
+    const void *extra[4] = {c->d_scratch[HG_S_REF_LIMBS], c->d_scratch[HG_S_NARROW_META], c->d_scratch[HG_S_TILES], (const void *)(uintptr_t)path};
+    memcpy(key.data() + sizeof(ShardCall), extra, sizeof(extra));
+    const bool can_graph = !c->prof && !getenv("HG_PEER_NO_GRAPH");
+    if (can_graph && p->graph && key == p->graph_key) {
+      HG_CUDA(cudaSetDevice(c->device));
+      HG_CUDA(cudaGraphLaunch(p->graph, c->stream));
+      c->launches += p->graph_nodes;
+      shard_reason(p, path, -1, true);
+      return HG_OK;
+    }
+    if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; p->graph_key.clear(); }
+    if ((rc = shard_reserve(p, a, path))) return rc;
+    memcpy(key.data() + sizeof(ShardCall), extra, 0);  // (scratch pointers may have changed in shard_reserve: refresh below)
+    const void *extra2[4] = {c->d_scratch[HG_S_REF_LIMBS], c->d_scratch[HG_S_NARROW_META], c->d_scratch[HG_S_TILES], (const void *)(uintptr_t)path};
+    memcpy(key.data() + sizeof(ShardCall), extra2, sizeof(extra2));
+    if (can_graph && key == p->last_key && p->tiles_on_device) {
+      HG_CUDA(cudaSetDevice(c->device));
+      const unsigned long long l0 = c->launches;
+      cudaGraph_t g = nullptr;
+      HG_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      rc = shard_enqueue(p, a, path);
+      const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+      if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+      if (e != cudaSuccess) return hg_cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+      const cudaError_t e2 = cudaGraphInstantiate(&p->graph, g, 0);
+      cudaGraphDestroy(g);
+      if (e2 != cudaSuccess) { p->graph = nullptr; return hg_cuda_fail(e2, "cudaGraphInstantiate", __FILE__, __LINE__); }
+      p->graph_key = key;
+      p->graph_nodes = (unsigned)(c->launches - l0);
+      HG_CUDA(cudaGraphLaunch(p->graph, c->stream));
+    } else {
+      if ((rc = shard_enqueue(p, a, path))) return rc;
+      p->last_key = key;
+    }
     shard_reason(p, path, -1, true);
     return HG_OK;
   }
   int32_t absmax = -1;
+  if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; p->graph_key.clear(); }
+  p->last_key.clear();
   rc = hg_narrow_shape_ok(hv_d, d_qry_hv, d_ref_hv);
   if (rc == HG_OK) {
-    if ((rc = shard_enqueue(p, a, 3, nullptr, nullptr))) return rc;
+    if ((rc = shard_reserve(p, a, 3))) return rc;
+    if ((rc = shard_enqueue(p, a, 3))) return rc;
     rc = shard_verdict(p, a, &absmax);
     if (rc == HG_OK) { shard_reason(p, 3, absmax, false); return HG_OK; }
     if (rc != HG_E_UNSUPPORTED) return rc;
@@ -471,7 +771,8 @@ extern "C" int hg_dist_sharded_dev(hg_peer *p, const int16_t *d_ref_hv, const in
     hg_set_error("hg_dist_sharded_dev: max |hv| = %d exceeds the 13-bit budget of the int8 limb split; the sharded path has no SIMT kernel", absmax);
     return HG_E_UNSUPPORTED;
   }
-  if ((rc = shard_enqueue(p, a, 2, nullptr, nullptr))) return rc;
+  if ((rc = shard_reserve(p, a, 2))) return rc;
+  if ((rc = shard_enqueue(p, a, 2))) return rc;
   shard_reason(p, 2, absmax, false);
   return HG_OK;
 }
@@ -485,9 +786,9 @@ extern "C" int hg_dist_sharded_hits(hg_peer *p, int sorted, hg_hit *hits, uint32
   *n_hits = 0;
   HG_CUDA(cudaSetDevice(c->device));
   int rc;
-  unsigned long long cnt = 0;
-  if (p->rank == p->root) HG_CUDA(cudaMemcpyAsync(&cnt, p->win[p->rank] + OFF_COUNT, 8, cudaMemcpyDeviceToHost, c->stream));
   HG_CUDA(cudaStreamSynchronize(c->stream));
+  const unsigned long long cnt =  // written by the call's last node
+      p->rank == p->root ? *reinterpret_cast<const unsigned long long *>(p->h_hdr + (OFF_TOTAL - OFF_STATUS)) : 0ull;
   if ((rc = peer_status(p))) return rc;
   if (p->rank != p->root) return HG_OK;
   *n_hits = cnt;
@@ -496,8 +797,12 @@ extern "C" int hg_dist_sharded_hits(hg_peer *p, int sorted, hg_hit *hits, uint32
     return HG_E_CAPACITY;
   }
   if (cnt == 0) return HG_OK;
+  if (p->mapped_hits) {  // the kernels wrote the records into the caller's mapped host buffer: nothing to copy
+    if (sorted) { hg_set_error("hg_dist_sharded_hits: hits in a mapped host buffer are not sorted on the device"); return HG_E_UNSUPPORTED; }
+    return HG_OK;
+  }
   if (!hits) { hg_set_error("hg_dist_sharded_hits: hits is NULL"); return HG_E_INVALID; }
-  hg_hit *d_hits = (hg_hit *)(p->win[p->rank] + OFF_HITS);
+  hg_hit *d_hits = (hg_hit *)(p->win[p->rank] + p->gather_off);
   void *d_milli = nullptr;
   if (sorted) {
     if (ani_milli && (rc = hg_scratch(c, HG_S_MISC, cnt * 4 + 256, &d_milli))) return rc;
@@ -512,8 +817,8 @@ extern "C" int hg_dist_sharded_hits(hg_peer *p, int sorted, hg_hit *hits, uint32
 // device pointers of the root's hit list and counter as this member addresses them (benchmarks, callers with their own tail)
 extern "C" int hg_peer_hit_buffers(hg_peer *p, int root, hg_hit **d_hits, unsigned long long **d_count) {
   if (!p || root < 0 || root >= p->world || !p->connected) { hg_set_error("hg_peer_hit_buffers: bad argument"); return HG_E_INVALID; }
-  if (d_hits) *d_hits = (hg_hit *)(p->win[root] + OFF_HITS);
-  if (d_count) *d_count = (unsigned long long *)(p->win[root] + OFF_COUNT);
+  if (d_hits) *d_hits = (hg_hit *)(p->win[root] + p->gather_off);
+  if (d_count) *d_count = (unsigned long long *)(p->win[root] + OFF_TOTAL);
   return HG_OK;
 }
 
@@ -661,6 +966,14 @@ extern "C" int hg_group_dist_packed(hg_group *g, const uint8_t *ref_packed, uint
   auto bound = [&](uint32_t n, int k) -> uint32_t { return k >= N ? n : (uint32_t)(((uint64_t)n * k / N) & ~3ull); };
   struct Member { uint32_t r0, rn, q0, qn; int16_t *d_ref, *d_qry; int32_t *d_rn, *d_qn; };
   std::vector<Member> M(N);
+  auto make_call = [&](const Member &m) {
+    ShardCall a = {};
+    a.d_ref_hv = m.d_ref; a.d_ref_norm = m.d_rn; a.n_ref_local = m.rn; a.ref_row0 = m.r0;
+    a.d_qry_hv = m.d_qry; a.d_qry_norm = m.d_qn;
+    for (int k = 0; k <= N; ++k) a.qb[k] = bound(n_qry, k);
+    a.hv_d = hv_d; a.ksize = ksize; a.ani_th = ani_th; a.symmetric = symmetric; a.root = 0; a.cap = cap; a.mapped_hits = nullptr;
+    return a;
+  };
   // phase 1: every allocation, on every GPU
   for (int k = 0; k < N; ++k) {
     hg_ctx *c = g->ctx[k];
@@ -677,18 +990,20 @@ extern "C" int hg_group_dist_packed(hg_group *g, const uint8_t *ref_packed, uint
     m.d_ref = (int16_t *)((uint8_t *)d_mat + qb);
     m.d_qn = (int32_t *)d_small;
     m.d_rn = m.d_qn + m.qn;
-    ShardCall a = {m.d_ref, m.d_rn, m.rn, m.r0, m.d_qry, m.d_qn, m.qn, m.q0, n_qry, hv_d, ksize, ani_th, symmetric, 0, cap};
+    const ShardCall a = make_call(m);
     if ((rc = shard_check(g->peer[k], a))) return rc;
-    if ((rc = shard_reserve(g->peer[k], a))) return rc;
   }
+  // b-bit values are below 2^(b-1): above 10 bits no row fits the single plane, and up to 13 bits every element fits two limbs
+  int used = bmax > 10 ? 2 : 3;
+  for (int k = 0; k < N; ++k)
+    if ((rc = shard_reserve(g->peer[k], make_call(M[k]), used))) return rc;
   // phase 2: H2D + unpack + sharded dist enqueued on every GPU; nothing here waits for another GPU
   auto enqueue_all = [&](int use_path) -> int {
     for (int k = 0; k < N; ++k) {
       hg_ctx *c = g->ctx[k];
       Member &m = M[k];
       HG_CUDA(cudaSetDevice(c->device));
-      ShardCall a = {m.d_ref, m.d_rn, m.rn, m.r0, m.d_qry, m.d_qn, m.qn, m.q0, n_qry, hv_d, ksize, ani_th, symmetric, 0, cap};
-      int r2 = shard_enqueue(g->peer[k], a, use_path, nullptr, nullptr);
+      int r2 = shard_enqueue(g->peer[k], make_call(m), use_path);
       if (r2) return r2;
     }
     return HG_OK;
@@ -710,21 +1025,20 @@ extern "C" int hg_group_dist_packed(hg_group *g, const uint8_t *ref_packed, uint
     if ((rc = load(qry_packed, qry_stride, qw, qry_bits, qry_norm, m.q0, m.qn, d_pk, d_bits, m.d_qn, m.d_qry))) return rc;
     if ((rc = load(ref_packed, ref_stride, rw, ref_bits, ref_norm, m.r0, m.rn, d_pk + (size_t)m.qn * qw, d_bits + m.qn, m.d_rn, m.d_ref))) return rc;
   }
-  // b-bit values are below 2^(b-1): above 10 bits no row fits the single plane, and up to 13 bits every element fits two limbs
-  int used = bmax > 10 ? 2 : 3;
   int32_t absmax = -1;
   if ((rc = enqueue_all(used))) return rc;
   if (used == 3) {
     int verdict = HG_OK;
     for (int k = 0; k < N; ++k) {
-      ShardCall a = {M[k].d_ref, M[k].d_rn, M[k].rn, M[k].r0, M[k].d_qry, M[k].d_qn, M[k].qn, M[k].q0, n_qry, hv_d, ksize, ani_th, symmetric, 0, cap};
       cudaSetDevice(g->ctx[k]->device);
-      const int v = shard_verdict(g->peer[k], a, &absmax);
+      const int v = shard_verdict(g->peer[k], make_call(M[k]), &absmax);
       if (v != HG_OK && v != HG_E_UNSUPPORTED) return v;
       if (v) verdict = v;
     }
     if (verdict == HG_E_UNSUPPORTED) {  // not narrow (the same answer on every GPU): the two-limb kernel on the rows already in HBM
       used = 2;
+      for (int k = 0; k < N; ++k)
+        if ((rc = shard_reserve(g->peer[k], make_call(M[k]), 2))) return rc;
       if ((rc = enqueue_all(2))) return rc;
     }
   }

@@ -16,14 +16,14 @@ from . import _build
 HG_OK, HG_E_INVALID, HG_E_CUDA, HG_E_CAPACITY, HG_E_RANGE, HG_E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 EXPORTS = [
-    "hg_init", "hg_destroy", "hg_sync", "hg_host_alloc", "hg_host_free", "hg_last_error", "hg_version", "hg_stream_handle", "hg_launch_count",
+    "hg_init", "hg_destroy", "hg_sync", "hg_host_alloc", "hg_host_free", "hg_host_register", "hg_host_unregister", "hg_last_error", "hg_version", "hg_stream_handle", "hg_launch_count",
     "hg_set_profiling", "hg_stage_ms", "hg_int_peak", "hg_tensor_peak", "hg_encode_sets", "hg_encode_sets_dev",
     "hg_fasta_merge", "hg_sketch_fasta_batch",
     "hg_kmer_hash", "hg_sketch_batch", "hg_sketch_batch_dev", "hg_sketch_status", "hg_unpack", "hg_unpack_dev",
     "hg_dist", "hg_dist_dev", "hg_dist_status", "hg_dist_last_path", "hg_dist_last_reason", "hg_sort_hits_dev", "hg_dist_sorted", "hg_dist_packed",
     "hg_group_create", "hg_group_destroy", "hg_group_size", "hg_group_ctx", "hg_group_sketch_fasta_batch", "hg_group_dist_packed",
     "hg_peer_window_need", "hg_peer_create", "hg_peer_connect", "hg_peer_create_local", "hg_peer_destroy", "hg_peer_rank",
-    "hg_peer_world", "hg_peer_barrier", "hg_dist_sharded_dev", "hg_dist_sharded_hits", "hg_peer_hit_buffers",
+    "hg_peer_world", "hg_peer_barrier", "hg_peer_stage_ms", "hg_dist_sharded_dev", "hg_dist_sharded_hits", "hg_peer_hit_buffers",
 ]
 HG_MAX_PEERS, HG_IPC_HANDLE_BYTES = 8, 64
 
@@ -69,6 +69,8 @@ def load() -> C.CDLL:
     L.hg_sync.restype = i32; L.hg_sync.argtypes = [vp]
     L.hg_host_alloc.restype = i32; L.hg_host_alloc.argtypes = [C.c_uint64, C.POINTER(C.c_void_p)]
     L.hg_host_free.restype = i32; L.hg_host_free.argtypes = [vp]
+    L.hg_host_register.restype = i32; L.hg_host_register.argtypes = [vp, C.c_uint64, C.POINTER(C.c_void_p)]
+    L.hg_host_unregister.restype = i32; L.hg_host_unregister.argtypes = [vp]
     L.hg_last_error.restype = C.c_char_p; L.hg_last_error.argtypes = []
     L.hg_version.restype = C.c_char_p; L.hg_version.argtypes = []
     L.hg_stream_handle.restype = u64; L.hg_stream_handle.argtypes = [vp]
@@ -114,8 +116,9 @@ def load() -> C.CDLL:
     L.hg_peer_rank.restype = i32; L.hg_peer_rank.argtypes = [vp]
     L.hg_peer_world.restype = i32; L.hg_peer_world.argtypes = [vp]
     L.hg_peer_barrier.restype = i32; L.hg_peer_barrier.argtypes = [vp]
+    L.hg_peer_stage_ms.restype = i32; L.hg_peer_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.hg_dist_sharded_dev.restype = i32
-    L.hg_dist_sharded_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp, u32, u32, u32, u32, u32, C.c_float, i32, i32, i32, u64]
+    L.hg_dist_sharded_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp, u32, u32, C.c_float, i32, i32, i32, u64, vp]
     L.hg_dist_sharded_hits.restype = i32; L.hg_dist_sharded_hits.argtypes = [vp, i32, vp, vp, u64, C.POINTER(u64)]
     L.hg_peer_hit_buffers.restype = i32; L.hg_peer_hit_buffers.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
     L.hg_dist_last_path.restype = i32; L.hg_dist_last_path.argtypes = [vp]
@@ -413,11 +416,13 @@ class Peer:
     def barrier(self):
         _check(load().hg_peer_barrier(self._h))
 
-    def dist_sharded_dev(self, d_ref, d_ref_norm2, n_ref_local, ref_row0, d_qry, d_qry_norm2, n_qry_local, qry_row0,
-                         n_qry_total, hv_d, ksize, ani_th, symmetric, path, root, cap):
-        """hg_dist_sharded_dev (collective; device pointers as ints)."""
-        _check(load().hg_dist_sharded_dev(self._h, d_ref, d_ref_norm2, n_ref_local, ref_row0, d_qry, d_qry_norm2, n_qry_local,
-                                          qry_row0, n_qry_total, hv_d, ksize, ani_th, int(symmetric), path, root, cap))
+    def dist_sharded_dev(self, d_ref, d_ref_norm2, n_ref_local, ref_row0, d_qry, d_qry_norm2, qry_bounds, hv_d, ksize, ani_th,
+                         symmetric, path, root, cap, mapped_hits=None):
+        """hg_dist_sharded_dev (collective; device pointers as ints; qry_bounds: world + 1 row offsets)."""
+        qb = np.ascontiguousarray(qry_bounds, np.uint32)
+        assert qb.size == self.world + 1
+        _check(load().hg_dist_sharded_dev(self._h, d_ref, d_ref_norm2, n_ref_local, ref_row0, d_qry, d_qry_norm2, _ptr(qb), hv_d,
+                                          ksize, ani_th, int(symmetric), path, root, cap, mapped_hits))
 
     def dist_sharded_hits(self, cap: int, sorted_output: bool = False, hits=None, milli=None):
         """hg_dist_sharded_hits -> (hits, milli or None) on the root, (empty, None) elsewhere.  `hits` / `milli`
@@ -433,10 +438,27 @@ class Peer:
         h = hits[: n.value]
         return (h.copy() if own else h), (milli[: n.value] if sorted_output else None)
 
+    def stage_ms(self):
+        """device ms of the last sharded dist: [operands, chunked push, kernel incl. waits for the peers' chunks, final barrier]"""
+        out = (C.c_float * 4)()
+        _check(load().hg_peer_stage_ms(self._h, out))
+        return [float(x) for x in out]
+
     def hit_buffers(self, root: int = 0):
         dh, dc = C.c_void_p(), C.c_void_p()
         _check(load().hg_peer_hit_buffers(self._h, root, C.byref(dh), C.byref(dc)))
         return dh.value, dc.value
+
+
+def host_register(arr: np.ndarray) -> int:
+    """hg_host_register on a numpy array's memory -> the device pointer kernels of this process use for it"""
+    dev = C.c_void_p()
+    _check(load().hg_host_register(arr.ctypes.data, arr.nbytes, C.byref(dev)))
+    return dev.value
+
+
+def host_unregister(arr: np.ndarray) -> None:
+    _check(load().hg_host_unregister(arr.ctypes.data))
 
 
 def peer_window_need(gathered_rows: int, hv_d: int, hit_cap: int) -> int:

@@ -79,6 +79,10 @@ HG_API int hg_sync(hg_ctx *ctx);
  * straight into a buffer from hg_host_alloc instead of a Vec.  hg_host_free(NULL) is a no-op. */
 HG_API int hg_host_alloc(uint64_t bytes, void **out);
 HG_API int hg_host_free(void *p);
+/* Page-lock and map memory the caller already owns (e.g. a POSIX shared-memory segment several processes have
+ * mmap'ed) so that this process's GPU can write into it; *dev_ptr is the pointer kernels use. */
+HG_API int hg_host_register(void *p, uint64_t bytes, void **dev_ptr);
+HG_API int hg_host_unregister(void *p);
 HG_API const char *hg_last_error(void);
 HG_API const char *hg_version(void);
 /* cudaStream_t of the context as an integer handle, so a host framework (torch) can order
@@ -288,23 +292,32 @@ HG_API int hg_peer_world(const hg_peer *p);
 /* enqueue a barrier among the members on this member's stream (bounded wait: HG_PEER_TIMEOUT_MS, default 10 s) */
 HG_API int hg_peer_barrier(hg_peer *p);
 /* Collective sharded dist, rows resident in HBM (compute_hv_ani, src/dist.rs:231-294, over several GPUs).
- * Every member calls it with the same scalars and ITS rows:
- *   symmetric != 0  all-vs-all (j > i, src/dist.rs:253-265) over ONE matrix of n_qry_total rows, of which this
- *                   member holds rows [qry_row0, qry_row0 + n_qry_local); the ref arguments are ignored.  The
+ * Every member calls it with the same scalars and ITS rows.  qry_bounds (world + 1 entries, [0] = 0) says which rows
+ * of the gathered ("query") matrix each member holds: member m has rows [qry_bounds[m], qry_bounds[m + 1]) - d_qry_hv /
+ * d_qry_norm2 point at this member's block (it may be empty; one member may hold everything: a broadcast).
+ *   symmetric != 0  all-vs-all (j > i, src/dist.rs:253-265) over that ONE matrix; the ref arguments are ignored.  The
  *                   non-empty output tiles are dealt round-robin to the members;
- *   symmetric == 0  this member's n_ref_local ref rows (global index ref_row0 + row) against ALL n_qry_total
- *                   query rows, of which this member contributes [qry_row0, +n_qry_local) - none, some or all.
+ *   symmetric == 0  this member's n_ref_local resident ref rows (global index ref_row0 + row) against ALL gathered rows.
  *   path  0 auto (one host read of all members' pre-pass verdict; two-limb kernel if the rows are not narrow),
  *         3 / 2 single-plane / two-limb tensor kernel asserted by the caller: the call only enqueues.
- * Hits carry global (i, j) and accumulate in member `root`'s window (capacity `cap`, same on every member). */
+ * Hits carry global (i, j) and go to member `root`: into its window (capacity `cap`, same on every member), or - if
+ * mapped_hits is not NULL - into a HOST buffer of `cap` records that every member has mapped (the same physical
+ * memory: hg_host_alloc in a one-process group, a shared-memory segment passed through hg_host_register by every
+ * process otherwise; each member passes ITS device pointer to it).  The records then cross each GPU's own PCIe link
+ * while the kernels run and no copy is left for the end. */
 HG_API int hg_dist_sharded_dev(hg_peer *p, const int16_t *d_ref_hv, const int32_t *d_ref_norm2, uint32_t n_ref_local,
-                               uint32_t ref_row0, const int16_t *d_qry_hv, const int32_t *d_qry_norm2, uint32_t n_qry_local,
-                               uint32_t qry_row0, uint32_t n_qry_total, uint32_t hv_d, uint32_t ksize, float ani_th,
-                               int symmetric, int path, int root, uint64_t cap);
+                               uint32_t ref_row0, const int16_t *d_qry_hv, const int32_t *d_qry_norm2, const uint32_t *qry_bounds,
+                               uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path, int root, uint64_t cap,
+                               hg_hit *mapped_hits);
 /* Waits for this member's part.  On the root: *n_hits and the hits copied to HOST memory, in dump_ani_file's
  * order if `sorted` (ani_milli as in hg_dist_sorted; may be NULL); HG_E_CAPACITY with the need if they exceed
- * cap.  On the other members *n_hits = 0 and hits may be NULL. */
+ * cap.  After a call with mapped_hits the records already are in that buffer: nothing is copied (hits may be NULL,
+ * `sorted` is not available).  On the other members *n_hits = 0 and hits may be NULL. */
 HG_API int hg_dist_sharded_hits(hg_peer *p, int sorted, hg_hit *hits, uint32_t *ani_milli, uint64_t cap, uint64_t *n_hits);
+/* Measurement support (hg_set_profiling on the member's context): device ms of the last sharded dist's stages -
+ * [0] operand form of this member's rows, [1] chunked push to the peers, [2] dist kernel (with its waits for the
+ * peers' chunks), [3] final barrier.  Synchronises the member's stream. */
+HG_API int hg_peer_stage_ms(hg_peer *p, float out_ms[4]);
 /* the root's hit list and counter as this member addresses them (device pointers) */
 HG_API int hg_peer_hit_buffers(hg_peer *p, int root, hg_hit **d_hits, unsigned long long **d_count);
 

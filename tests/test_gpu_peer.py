@@ -55,11 +55,11 @@ def test_world1_sharded_equals_oracle(ctx, hg, oracle, path, symmetric):
     try:
         d_hv, d_n = _dev(hv), _dev(norm)
         if symmetric:
-            peer.dist_sharded_dev(None, None, 0, 0, d_hv.data_ptr(), d_n.data_ptr(), 700, 0, 700, 1024, 21, 80.0, True, path, 0, cap)
+            peer.dist_sharded_dev(None, None, 0, 0, d_hv.data_ptr(), d_n.data_ptr(), [0, 700], 1024, 21, 80.0, True, path, 0, cap)
             hits, _ = peer.dist_sharded_hits(cap)
             _check_hits(oracle, hits, hv, norm, hv, norm, True, 80.0)
         else:
-            peer.dist_sharded_dev(d_hv[:300].data_ptr(), d_n[:300].data_ptr(), 300, 1000, d_hv.data_ptr(), d_n.data_ptr(), 700, 0, 700,
+            peer.dist_sharded_dev(d_hv[:300].data_ptr(), d_n[:300].data_ptr(), 300, 1000, d_hv.data_ptr(), d_n.data_ptr(), [0, 700],
                                   1024, 21, 0.0, False, path, 0, cap)
             hits, _ = peer.dist_sharded_hits(cap)
             _check_hits(oracle, hits, hv[:300], norm[:300], hv, norm, False, 0.0, i0=1000)
@@ -82,7 +82,7 @@ def test_world1_outlier_corrections_from_planes(ctx, hg, oracle, monkeypatch):
     peer = hg.Peer(ctx, 0, 1, hg.ffi.peer_window_need(400, 1024, cap))
     try:
         d_hv, d_n = _dev(hv), _dev(norm)
-        peer.dist_sharded_dev(None, None, 0, 0, d_hv.data_ptr(), d_n.data_ptr(), 400, 0, 400, 1024, 21, 0.0, True, 3, 0, cap)
+        peer.dist_sharded_dev(None, None, 0, 0, d_hv.data_ptr(), d_n.data_ptr(), [0, 400], 1024, 21, 0.0, True, 3, 0, cap)
         hits, _ = peer.dist_sharded_hits(cap)
         _check_hits(oracle, hits, hv, norm, hv, norm, True, 0.0)
         # the plain single-GPU narrow path shares the rewritten correction
@@ -165,15 +165,33 @@ a0, a1 = b[rank], b[rank + 1]
 dev = torch.device("cuda", rank)
 d_hv = torch.from_numpy(hv[a0:a1].copy()).to(dev); d_n = torch.from_numpy(norm[a0:a1].copy()).to(dev)
 out = {}
-for name, sym, path in (("sym", True, 0), ("sym3", True, 3), ("refq", False, 0)):
+for name, sym, path in (("sym", True, 0), ("sym3", True, 3), ("refq", False, 0), ("sym2", True, 2), ("mapped", True, 3)):
+    mapped = None
+    if name == "mapped":  # hits straight into a host buffer both ranks have mapped (POSIX shared memory)
+        from multiprocessing import shared_memory
+        if rank == 0:
+            shm = shared_memory.SharedMemory(name="hg_test_hits", create=True, size=cap * 16)
+        dist.barrier()
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name="hg_test_hits")
+        host_hits = np.ndarray((cap,), dtype=hg.ffi.HIT_DTYPE, buffer=shm.buf)
+        mapped = hg.ffi.host_register(host_hits)
     if sym:
-        pg.peer.dist_sharded_dev(None, None, 0, 0, d_hv.data_ptr(), d_n.data_ptr(), a1 - a0, a0, n, D, 21, 75.0, True, path, 0, cap)
+        pg.peer.dist_sharded_dev(None, None, 0, 0, d_hv.data_ptr(), d_n.data_ptr(), b, D, 21, 75.0, True, path, 0, cap, mapped)
     else:  # refs: this rank's block; queries: all on rank 1 (a "broadcast" from a non-root member)
         q_hv = torch.from_numpy(hv.copy()).to(dev) if rank == 1 else None
         q_n = torch.from_numpy(norm.copy()).to(dev) if rank == 1 else None
         pg.peer.dist_sharded_dev(d_hv.data_ptr(), d_n.data_ptr(), a1 - a0, a0, q_hv.data_ptr() if rank == 1 else None,
-                                 q_n.data_ptr() if rank == 1 else None, n if rank == 1 else 0, 0, n, D, 21, 75.0, False, path, 0, cap)
-    hits, _ = pg.peer.dist_sharded_hits(cap, sorted_output=True)
+                                 q_n.data_ptr() if rank == 1 else None, [0, 0, n], D, 21, 75.0, False, path, 0, cap)
+    hits, _ = pg.peer.dist_sharded_hits(cap, sorted_output=(mapped is None), hits=host_hits if mapped else None)
+    if mapped:
+        hits = np.sort(hits.copy(), order=["i", "j"])
+        dist.barrier()
+        hg.ffi.host_unregister(host_hits)
+        del host_hits
+        shm.close()
+        if rank == 0:
+            shm.unlink()
     out[name] = hits
 if rank == 0:
     np.savez(%(out)r, **out)
@@ -198,5 +216,15 @@ def test_one_process_per_gpu_ipc_windows(hg, oracle, ctx, tmp_path):
     got = np.load(outp)
     from hypergen_b200.ffi import HIT_DTYPE
     _check_hits(oracle, got["sym"].view(HIT_DTYPE), hv, norm, hv, norm, True, 75.0)
-    assert np.array_equal(got["sym3"], got["sym"])
+    def same(a, b, what):
+        if np.array_equal(a, b):
+            return
+        ka = a["i"].astype(np.int64) * 100000 + a["j"]
+        kb = b["i"].astype(np.int64) * 100000 + b["j"]
+        ea, eb = a[~np.isin(ka, kb)], b[~np.isin(kb, ka)]
+        raise AssertionError("%s: %d vs %d hits; %d only in first (e.g. %s), %d only in second (e.g. %s)"
+                             % (what, a.size, b.size, ea.size, ea[:4], eb.size, eb[:4]))
+    same(got["sym3"], got["sym"], "forced single-plane vs auto")
+    same(got["sym2"], got["sym"], "forced two-limb vs auto")
+    same(got["mapped"], np.sort(got["sym"], order=["i", "j"]), "hits in mapped host memory vs window")
     _check_hits(oracle, got["refq"].view(HIT_DTYPE), hv, norm, hv, norm, False, 75.0)
