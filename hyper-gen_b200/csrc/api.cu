@@ -54,7 +54,12 @@ extern "C" int hg_init(int device, hg_ctx **out) {
   cudaDeviceProp prop;
   HG_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
-  HG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {  // highest priority: work other streams of the library run NEXT TO this one (a multi-GPU member's operand pushes,
+     // peer.cu) must not get in front of the kernels launched here
+    int lo = 0, hi = 0;
+    HG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    HG_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+  }
   HG_CUDA(cudaMalloc(&c->d_status, 4 * sizeof(uint32_t)));
   HG_CUDA(cudaMemset(c->d_status, 0, 4 * sizeof(uint32_t)));
   for (int i = 0; i < 8; i++) HG_CUDA(cudaEventCreate(&c->ev[i]));

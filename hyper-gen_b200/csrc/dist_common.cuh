@@ -125,13 +125,13 @@ __device__ __forceinline__ void push_my_chunks(const hg_push_plan *__restrict__ 
       if (((off | bytes) & 15) == 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(pp->win[rank] + off);
         const size_t n16 = bytes / 16;
-        for (size_t i = tid; i < n16; i += 8 * nth) {  // eight loads in flight per lane, then their stores to every peer
-          uint4 v[8];
+        for (size_t i = tid; i < n16; i += 12 * nth) {  // twelve loads in flight per lane, then their stores to every peer
+          uint4 v[12];
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
+          for (int u = 0; u < 12; ++u)
             if (i + u * nth < n16) v[u] = src[i + u * nth];
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
+          for (int u = 0; u < 12; ++u)
             if (i + u * nth < n16)
               for (int m = 0; m < world; ++m)
                 if (m != rank) reinterpret_cast<uint4 *>(pp->win[m] + off)[i + u * nth] = v[u];

@@ -857,7 +857,7 @@ int hg_narrow_launch_ex(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32
   // this launch's share of the tiles (an upper bound when symmetric)
   const uint64_t tiles = fd.list ? fd.n_list : (tiles_all + walk_mul - 1) / walk_mul;
   if (tiles == 0) return HG_OK;
-  const uint32_t n_pairs = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)std::max(ctx->sm_count / 2, 1));
+  const uint32_t n_pairs = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)std::max(ctx->sm_count / 2 - fd.reserve_tpcs, 1));
   cfg.gridDim = dim3(2 * n_pairs, 1, 1);
   cfg.dynamicSmemBytes = N1_SMEM_BYTES;
   static const hg_push_plan no_push = {};

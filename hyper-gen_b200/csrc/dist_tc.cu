@@ -677,7 +677,7 @@ int hg_tc_launch_ex(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref
     // one CTA pair per TPC, each walking the 256 x 128 tiles with stride n_pairs
     const uint64_t tiles = fd.list ? fd.n_list : ((uint64_t)gx * ((n_ref + 255) / 256) + walk_mul - 1) / walk_mul;
     if (tiles == 0) return HG_OK;
-    const uint32_t n_pairs = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)std::max(ctx->sm_count / 2, 1));
+    const uint32_t n_pairs = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)std::max(ctx->sm_count / 2 - fd.reserve_tpcs, 1));
     cfg.gridDim = dim3(2 * n_pairs, 1, 1);
     cfg.dynamicSmemBytes = T2_SMEM_BYTES;
     attr[0].val.clusterDim.x = 2;

@@ -231,6 +231,10 @@ int hg_launch_dist_simt(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_
 // warps that copy this member's operand rows (byte ranges of its window, in HG_PUSH_CHUNKS chunks) to the same offsets
 // of every other window with 16-byte stores over NVLink and raise the chunk's arrival flag there when all pusher warps
 // of the grid are through with it.  One kernel computes tiles and moves operands; nothing has to be co-scheduled.
+// TPCs a multi-GPU dist launch leaves free when this member's chunk pushes run as a kernel of their own NEXT TO it (on a
+// second, lower-priority stream): the dist kernel is resident and waiting for the other members' chunks while they run, so
+// the pushes must never need one of its SMs.
+#define HG_PEER_RESERVED_TPCS 8
 #define HG_PUSH_CHUNKS 4
 #define HG_PUSH_RANGES 10
 struct hg_push_plan {
@@ -252,6 +256,7 @@ struct hg_tile_feed {
   uint32_t start_need;      // flags to wait for before the kernel reads anything (the members' pre-pass statistics)
   uint32_t *status;         // set to 1 if a wait times out (the host turns it into an error)
   unsigned long long timeout_ns;
+  int reserve_tpcs;         // TPCs the launch leaves free (for the push kernel running next to it)
 };
 
 // two s8 limb planes of one matrix (dist_tc.cu), split piecewise or at once
