@@ -449,20 +449,10 @@ static int shard_check(hg_peer *p, const ShardCall &a) {
   return HG_OK;
 }
 
-// This member's tiles for kernel `use_path` (3: 256 x 256 tiles, 2: 256 x 128), ordered by arrival of what they read.
-static void build_tiles(hg_peer *p, const ShardCall &a, int use_path) {
-  TileKey k = {};
-  k.sym = a.symmetric;
-  k.path = use_path;
-  k.n_ref = a.symmetric ? a.qb[p->world] : a.n_ref_local;
-  k.n_qry = a.qb[p->world];
-  if (use_path == 3) hg_narrow_tile_shape(&k.tr, &k.tc); else hg_tc_tile_shape(&k.tr, &k.tc);
-  memcpy(k.qb, a.qb, sizeof(k.qb));
-  for (int m = p->world + 1; m <= HG_MAX_PEERS; ++m) k.qb[m] = 0;
-  if (p->tiles_valid && memcmp(&k, &p->tiles_key, sizeof(k)) == 0) return;
-  p->tiles_key = k;
-  p->tiles_valid = true;
-  p->tiles_on_device = false;
+// Member `rank`'s tiles for a key (pure host logic): the non-empty tiles of the all-vs-all dealt round-robin over the
+// members (ref x query: every tile of the member's own ref rows), each with the mask of arrival flags it reads, ordered
+// by when those arrive.
+static void plan_tiles(const TileKey &k, int world, int rank, std::vector<uint2> &out) {
   const uint32_t gx = (k.n_qry + k.tc - 1) / k.tc, gy = (k.n_ref + k.tr - 1) / k.tr;
   struct T { uint2 e; uint32_t key; };
   std::vector<T> v;
@@ -470,11 +460,11 @@ static void build_tiles(hg_peer *p, const ShardCall &a, int use_path) {
   for (uint32_t R = 0; R < gy; ++R) {
     // symmetric (i0 = j0 = 0): tiles whose largest j is not above their smallest i are empty (as the kernels' cmin)
     uint32_t c0 = 0;
-    if (a.symmetric) c0 = (uint32_t)std::min<uint64_t>(((uint64_t)k.tr * R + 1) / k.tc, gx);
+    if (k.sym) c0 = (uint32_t)std::min<uint64_t>(((uint64_t)k.tr * R + 1) / k.tc, gx);
     for (uint32_t C = c0; C < gx; ++C, ++t) {
-      if (a.symmetric && (int)(t % (uint64_t)p->world) != p->rank) continue;
-      uint32_t need = need_mask(a.qb, p->world, p->rank, (uint64_t)C * k.tc, std::min<uint64_t>((uint64_t)(C + 1) * k.tc, k.n_qry));
-      if (a.symmetric) need |= need_mask(a.qb, p->world, p->rank, (uint64_t)R * k.tr, std::min<uint64_t>((uint64_t)(R + 1) * k.tr, k.n_ref));
+      if (k.sym && (int)(t % (uint64_t)world) != rank) continue;
+      uint32_t need = need_mask(k.qb, world, rank, (uint64_t)C * k.tc, std::min<uint64_t>((uint64_t)(C + 1) * k.tc, k.n_qry));
+      if (k.sym) need |= need_mask(k.qb, world, rank, (uint64_t)R * k.tr, std::min<uint64_t>((uint64_t)(R + 1) * k.tr, k.n_ref));
       uint32_t key = 0;
       for (int b = 0; b < 32; ++b) if (need >> b & 1u) key = std::max<uint32_t>(key, 1 + b % N_CHUNKS);
       v.push_back({make_uint2(R | (C << 16), need), key});
@@ -483,9 +473,45 @@ static void build_tiles(hg_peer *p, const ShardCall &a, int use_path) {
   // all-vs-all: tiles that read only my own rows first, then in the order the other members' chunks arrive (row-major
   // within each group).  ref x query stays row-major: the queries are few and arrive early, while a column-wise sweep
   // would stream my whole ref plane from HBM once per query tile column.
-  if (a.symmetric && !getenv("HG_PEER_NOSORT")) std::stable_sort(v.begin(), v.end(), [](const T &x, const T &y) { return x.key < y.key; });
-  p->tiles.resize(v.size());
-  for (size_t i = 0; i < v.size(); ++i) p->tiles[i] = v[i].e;
+  if (k.sym && !getenv("HG_PEER_NOSORT")) std::stable_sort(v.begin(), v.end(), [](const T &x, const T &y) { return x.key < y.key; });
+  out.resize(v.size());
+  for (size_t i = 0; i < v.size(); ++i) out[i] = v[i].e;
+}
+
+static TileKey tile_key(int world, int symmetric, int use_path, uint32_t n_ref, const uint32_t *qb) {
+  TileKey k = {};
+  k.sym = symmetric;
+  k.path = use_path;
+  k.n_ref = symmetric ? qb[world] : n_ref;
+  k.n_qry = qb[world];
+  if (use_path == 3) hg_narrow_tile_shape(&k.tr, &k.tc); else hg_tc_tile_shape(&k.tr, &k.tc);
+  for (int m = 0; m <= world; ++m) k.qb[m] = qb[m];
+  return k;
+}
+
+// This member's tiles for kernel `use_path` (3: 256 x 256 tiles, 2: 256 x 128), cached while the shapes stay the same.
+static void build_tiles(hg_peer *p, const ShardCall &a, int use_path) {
+  const TileKey k = tile_key(p->world, a.symmetric, use_path, a.n_ref_local, a.qb);
+  if (p->tiles_valid && memcmp(&k, &p->tiles_key, sizeof(k)) == 0) return;
+  p->tiles_key = k;
+  p->tiles_valid = true;
+  p->tiles_on_device = false;
+  plan_tiles(k, p->world, p->rank, p->tiles);
+}
+
+// The plan above without a GPU (host logic only; tests): tiles_out receives (tile row | tile column << 16, need mask)
+// pairs; *n_tiles the count (HG_E_CAPACITY if it exceeds cap).
+extern "C" int hg_peer_plan_tiles(int world, int rank, int symmetric, int path, uint32_t n_ref_local, const uint32_t *qry_bounds,
+                                  uint32_t *tiles_out, uint64_t cap, uint64_t *n_tiles) {
+  if (!qry_bounds || !n_tiles || world < 1 || world > HG_MAX_PEERS || rank < 0 || rank >= world || (path != 2 && path != 3)) {
+    hg_set_error("hg_peer_plan_tiles: bad argument"); return HG_E_INVALID;
+  }
+  std::vector<uint2> v;
+  plan_tiles(tile_key(world, symmetric, path, n_ref_local, qry_bounds), world, rank, v);
+  *n_tiles = v.size();
+  if (v.size() > cap || (!tiles_out && !v.empty())) { hg_set_error("hg_peer_plan_tiles: %zu tiles", v.size()); return HG_E_CAPACITY; }
+  for (size_t i = 0; i < v.size(); ++i) { tiles_out[2 * i] = v[i].x; tiles_out[2 * i + 1] = v[i].y; }
+  return HG_OK;
 }
 
 // every allocation of the call, before anything that waits for another member is enqueued (growing a scratch

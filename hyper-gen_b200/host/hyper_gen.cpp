@@ -67,9 +67,21 @@ static void check(int rc, const char *what) {
   if (rc != HG_OK) die(std::string(what) + ": " + hg_last_error());
 }
 
+// every visible GPU of the box (the reference drives CudaDevice::new(0) only, sketch_cuda.rs:52); HG_GPUS=n limits it
+static hg_group *open_group() {
+  int n = 0;
+  if (const char *e = getenv("HG_GPUS")) n = atoi(e);
+  hg_group *g = nullptr;
+  check(hg_group_create(n, nullptr, &g), "hg_group_create");
+  return g;
+}
+
 namespace utils {
 
-std::vector<std::string> get_fasta_files(const std::string &path) {
+std::vector<std::string> get_fasta_files(const std::string &path_in) {
+  // PathBuf::join (utils.rs:210-212) does not double a trailing separator: "dir/" and "dir" both record "dir/x.fna"
+  std::string path = path_in;
+  while (path.size() > 1 && path.back() == '/') path.pop_back();
   std::vector<std::string> all;
   for (const char *pat : {"*.fna", "*.fa", "*.fasta"}) {
     glob_t g;
@@ -183,8 +195,9 @@ void sketch_cuda(const types::SketchParams &params) {
   const bool timing = getenv("HG_CLI_TIMING") != nullptr;  // per-phase wall clock on stderr
   double t_mark = now_s(), t_init = 0, t_stat = 0, t_alloc = 0, t_read = 0, t_gpu = 0, t_collect = 0, t_dump = 0;
   auto lap = [&](double &acc) { const double t = now_s(); acc += t - t_mark; t_mark = t; };
-  hg_ctx *ctx = nullptr;
-  check(hg_init(0, &ctx), "hg_init");
+  hg_group *group = open_group();
+  hg_ctx *ctx = hg_group_ctx(group, 0);
+  const int n_gpus = hg_group_size(group);
   lap(t_init);
   hg_sketch_params p{};
   p.scaled = params.scaled; p.seed = params.seed; p.hv_d = (uint32_t)params.hv_d;
@@ -212,7 +225,7 @@ void sketch_cuda(const types::SketchParams &params) {
     parallel(n_file, [&](size_t i) { fsize[i] = fastx_reader::file_size(files[i]); });
   }
   lap(t_stat);
-  const uint64_t batch_bytes = 256ull << 20;
+  const uint64_t batch_bytes = (256ull << 20) * (uint64_t)(host_parse ? 1 : n_gpus);  // per call; the library splits it over the GPUs
   std::vector<std::pair<size_t, size_t>> batches;  // [first, last)
   uint64_t max_batch = 0;
   for (size_t b0 = 0; b0 < n_file;) {
@@ -252,8 +265,8 @@ void sketch_cuda(const types::SketchParams &params) {
       check(hg_sketch_batch(ctx, stage[bi & 1], seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
                             norm2.data(), nh.data()), "hg_sketch_batch");
     else
-      check(hg_sketch_fasta_batch(ctx, stage[bi & 1], seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
-                                  norm2.data(), nh.data()), "hg_sketch_fasta_batch");
+      check(hg_group_sketch_fasta_batch(group, stage[bi & 1], seg_off.data(), (uint32_t)m, &p, nullptr, packed.data(), bits.data(),
+                                        norm2.data(), nh.data()), "hg_group_sketch_fasta_batch");
     for (size_t i = 0; i < m; i++) {
       types::FileSketch &s = all[b0 + i];
       s.ksize = params.ksize; s.scaled = params.scaled; s.seed = params.seed; s.canonical = params.canonical;
@@ -267,7 +280,7 @@ void sketch_cuda(const types::SketchParams &params) {
   lap(t_gpu);
   check(hg_host_free(stage[0]), "hg_host_free");
   check(hg_host_free(stage[1]), "hg_host_free");
-  hg_destroy(ctx);
+  hg_group_destroy(group);
   lap(t_collect);
   utils::dump_sketch(all, params.out_file);
   lap(t_dump);
@@ -299,9 +312,8 @@ void dist(const types::SketchDist &sd) {
   if (ref[0].ksize != qry[0].ksize) die("Ref and query sketches use different kmer sizes!");
   if (ref[0].hv_d != qry[0].hv_d) die("Ref and query sketches use different HV dimensions!");
   const size_t D = ref[0].hv_d, R = ref.size(), Q = qry.size();
-  hg_ctx *ctx = nullptr;
-  check(hg_init(0, &ctx), "hg_init");
-  // The packed rows go to the GPU as they sit in the sketch file; decompress_file_sketch (hd.rs:171-232),
+  hg_group *group = open_group();
+  // The packed rows go to the GPUs as they sit in the sketch file, one block of rows per GPU; decompress_file_sketch (hd.rs:171-232),
   // compute_hv_ani (dist.rs:231-294) and the sort of dump_ani_file (utils.rs:262-269) all run there.
   Stacked rs = stack(ref, D), qs;
   if (!if_sym) qs = stack(qry, D);
@@ -312,15 +324,15 @@ void dist(const types::SketchDist &sd) {
   for (;;) {
     hits.resize(cap);
     milli.resize(cap);
-    const int rc = hg_dist_packed(ctx, rs.packed.data(), 2 * D, rs.bits.data(), rs.norm.data(), (uint32_t)R, q.packed.data(),
-                                  2 * D, q.bits.data(), q.norm.data(), (uint32_t)Q, (uint32_t)D, ref[0].ksize,
-                                  sd.ani_threshold, if_sym ? 1 : 0, 0, 1, hits.data(), milli.data(), cap, &n_hits);
+    const int rc = hg_group_dist_packed(group, rs.packed.data(), 2 * D, rs.bits.data(), rs.norm.data(), (uint32_t)R, q.packed.data(),
+                                        2 * D, q.bits.data(), q.norm.data(), (uint32_t)Q, (uint32_t)D, ref[0].ksize,
+                                        sd.ani_threshold, if_sym ? 1 : 0, 1, hits.data(), milli.data(), cap, &n_hits);
     if (rc == HG_E_CAPACITY && n_hits > cap) { cap = n_hits; continue; }
-    check(rc, "hg_dist_packed");
+    check(rc, "hg_group_dist_packed");
     break;
   }
   hits.resize(n_hits);
-  hg_destroy(ctx);
+  hg_group_destroy(group);
   std::string csv;
   char buf[64];
   for (size_t t = 0; t < hits.size(); t++) {

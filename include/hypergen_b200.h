@@ -314,6 +314,11 @@ HG_API int hg_dist_sharded_dev(hg_peer *p, const int16_t *d_ref_hv, const int32_
  * cap.  After a call with mapped_hits the records already are in that buffer: nothing is copied (hits may be NULL,
  * `sorted` is not available).  On the other members *n_hits = 0 and hits may be NULL. */
 HG_API int hg_dist_sharded_hits(hg_peer *p, int sorted, hg_hit *hits, uint32_t *ani_milli, uint64_t cap, uint64_t *n_hits);
+/* Host logic of the sharded dist, no GPU involved: the tiles member `rank` of `world` computes (path 3: 256 x 256
+ * tiles, path 2: 256 x 128), in the order it walks them - tiles_out[2 t] = tile row | tile column << 16,
+ * tiles_out[2 t + 1] = mask of the arrival flags (member m, chunk c -> bit 4 m + c) the tile waits for. */
+HG_API int hg_peer_plan_tiles(int world, int rank, int symmetric, int path, uint32_t n_ref_local, const uint32_t *qry_bounds,
+                              uint32_t *tiles_out, uint64_t cap, uint64_t *n_tiles);
 /* Measurement support (hg_set_profiling on the member's context): device ms of the last sharded dist's stages -
  * [0] operand form of this member's rows, [1] chunked push to the peers, [2] dist kernel (with its waits for the
  * peers' chunks), [3] final barrier.  Synchronises the member's stream. */

@@ -228,3 +228,26 @@ def test_one_process_per_gpu_ipc_windows(hg, oracle, ctx, tmp_path):
     same(got["sym2"], got["sym"], "forced two-limb vs auto")
     same(got["mapped"], np.sort(got["sym"], order=["i", "j"]), "hits in mapped host memory vs window")
     _check_hits(oracle, got["refq"].view(HIT_DTYPE), hv, norm, hv, norm, False, 75.0)
+
+
+def test_cli_all_gpus_writes_the_same_bytes_as_one_gpu(hg, tmp_path):
+    """`hyper-gen sketch` / `hyper-gen dist` over every GPU of the box (hg_group) vs HG_GPUS=1: byte-identical sketch
+    file and TSV (src/main.rs:14-21 drives one GPU; the C++ host mirrors its drivers above the C ABI)"""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from hypergen_b200 import synth, _build
+    exe = _build.build_host()
+    d = tmp_path / "genomes"
+    d.mkdir()
+    for g in range(1200):
+        body = synth.family_member(g, 30_000).numpy()
+        with open(d / ("g%04d.fna" % g), "wb") as f:
+            f.write(b">g%d\n" % g + b"".join(bytes(body[t:t + 80]) + b"\n" for t in range(0, body.size, 80)))
+    outs = {}
+    for name, env in (("one", dict(os.environ, HG_GPUS="1")), ("all", dict(os.environ))):
+        sk, tsv = str(tmp_path / (name + ".sketch")), str(tmp_path / (name + ".tsv"))
+        subprocess.check_call([exe, "sketch", "-p", str(d), "-o", sk, "-s", "200", "-d", "1024", "-t", "8"], env=env)
+        subprocess.check_call([exe, "dist", "-r", sk, "-q", sk, "-o", tsv, "-a", "80.0"], env=env)
+        outs[name] = (open(sk, "rb").read(), open(tsv, "rb").read())
+    assert outs["one"][0] == outs["all"][0]
+    assert outs["one"][1] == outs["all"][1] and len(outs["all"][1]) > 1000

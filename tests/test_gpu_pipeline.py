@@ -85,6 +85,9 @@ def test_cpp_host_cli_matches_python_host(ctx, hg, oracle, tmp_path):
     subprocess.check_call([exe, "sketch", "-p", str(d), "-o", out_hp, "-s", "500", "-d", "1024", "-t", "4"],
                           env=dict(os.environ, HG_HOST_PARSE="1"))
     assert open(out_py, "rb").read() == open(out_hp, "rb").read()          # host-side reader, same bytes
+    out_ts = str(tmp_path / "ts.sketch")  # a trailing separator does not change the recorded file names (PathBuf::join)
+    subprocess.check_call([exe, "sketch", "-p", str(d) + "/", "-o", out_ts, "-s", "500", "-d", "1024", "-t", "4"])
+    assert open(out_py, "rb").read() == open(out_ts, "rb").read()
     tsv_py = dist.dist(dist.SketchDist(out_py, out_py, str(tmp_path / "py.tsv"), ani_threshold=80.0), ctx=ctx)
     subprocess.check_call([exe, "dist", "-r", out_cc, "-q", out_cc, "-o", str(tmp_path / "cc.tsv"), "-a", "80.0"])
     assert open(tmp_path / "cc.tsv").read() == tsv_py and tsv_py
