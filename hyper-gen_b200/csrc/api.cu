@@ -51,6 +51,7 @@ extern "C" int hg_init(int device, hg_ctx **out) {
   hg_ctx *c = new hg_ctx();
   memset(c, 0, sizeof(*c));
   c->device = device;
+  struct Guard { hg_ctx *c; ~Guard() { if (c) hg_destroy(c); } } guard{c};  // nothing leaks when a step below fails
   cudaDeviceProp prop;
   HG_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -63,6 +64,7 @@ extern "C" int hg_init(int device, hg_ctx **out) {
   HG_CUDA(cudaMalloc(&c->d_status, 4 * sizeof(uint32_t)));
   HG_CUDA(cudaMemset(c->d_status, 0, 4 * sizeof(uint32_t)));
   for (int i = 0; i < 8; i++) HG_CUDA(cudaEventCreate(&c->ev[i]));
+  guard.c = nullptr;
   *out = c;
   return HG_OK;
 }
@@ -70,7 +72,8 @@ extern "C" int hg_init(int device, hg_ctx **out) {
 extern "C" void hg_destroy(hg_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 10; i++) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
   for (int i = 0; i < HG_S_COUNT; i++) if (c->d_scratch[i]) cudaFree(c->d_scratch[i]);
   for (int i = 0; i < 4; i++) if (c->h_pinned[i]) cudaFreeHost(c->h_pinned[i]);
   if (c->d_status) cudaFree(c->d_status);
@@ -79,7 +82,7 @@ extern "C" void hg_destroy(hg_ctx *c) {
     cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_copied[i]); cudaEventDestroy(c->ev_done[i]); }
   }
-  cudaStreamDestroy(c->stream);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 

@@ -294,8 +294,8 @@ int hg_launch_encode(hg_ctx *ctx, const hg_genome_desc *d_desc, uint32_t n_genom
                      uint8_t *d_quant_bits, int32_t *d_norm2, uint32_t *d_n_hashes) {
   if (n_genomes == 0) return HG_OK;
   const size_t smem = (size_t)hv_d * 6 + 264 + (size_t)EN_BATCH * 8;
-  if (smem > 220 * 1024) {
-    hg_set_error("hv_d %u too large for on-chip encode (max 32768)", hv_d);
+  if (smem > 220 * 1024) {  // 6 B per dimension + the hash batch: hv_d <= 31744
+    hg_set_error("hv_d %u too large for the on-chip encoder (max 31744; dist accepts up to 32768)", hv_d);
     return HG_E_UNSUPPORTED;
   }
   HG_CUDA(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

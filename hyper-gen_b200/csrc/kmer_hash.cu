@@ -2,8 +2,17 @@
 // set insertion for a batch of genomes, in one pass over the sequence bytes.
 //
 // Replaces cuda_kmer_t1ha2 (reference src/cuda_kernel.cu:250-321) and its host-side result
-// scan (src/sketch_cuda.rs:156-163); the result equals the CPU path's HashSet
-// (src/sketch.rs:71-98).  Design (not the reference's one-thread-per-512-k-mers walk):
+// scan (src/sketch_cuda.rs:156-163).  WHICH reference semantics: those of the reference's GPU path
+// - read_merge_seq bytes (src/fastx_reader.rs:6-29), only ACGT / acgt are bases, every other byte
+// breaks the k-mer run (cuda_kernel.cu:272-296) - with two deliberate deviations: no sample is
+// dropped when a 512-k-mer stretch yields more than 8 (cuda_kernel.cu:316) and h == 0 is kept
+// (sketch_cuda.rs:159).  On ACGT/N input that is also the CPU path's HashSet (src/sketch.rs:71-98);
+// it is NOT needletail's normalize(), which maps U/u to T and iterates per record (recalled, not
+// vendored) - tests/test_gpu_sketch.py documents the difference on IUPAC / U bytes.
+// Survivors are compacted through a per-warp shared-memory queue and inserted with atomicCAS into a
+// per-genome hash table (set semantics), not by the warp-ballot / prefix-sum list the north star
+// sketches: a list would still need a dedup pass, the table is the dedup.
+// Design (not the reference's one-thread-per-512-k-mers walk):
 //   * one CTA per tile of 8192 k-mer start positions of ONE genome; the tile's bytes
 //     (+ k-1 halo) are read once with aligned, coalesced 16-byte loads, converted SWAR-style
 //     to nibble codes + a validity bit per base, and staged in 5 KB of shared memory;

@@ -62,6 +62,31 @@ def test_kmer_hash_edge_cases(ctx, hg, oracle):
             assert np.array_equal(hashes[int(hoff[g]):int(hoff[g + 1])], w), (lead, g)
 
 
+def test_u_and_iupac_bytes_break_kmers_like_the_reference_gpu_path(ctx, hg, oracle):
+    """Which reference semantics are reproduced: those of the reference's GPU path (src/cuda_kernel.cu:272-296) - only
+    ACGT / acgt are bases; U, IUPAC codes and anything else end the k-mer run.  needletail's normalize() on the CPU path
+    (src/sketch.rs:84) would map U/u to T instead: a sequence with U therefore sketches differently there (documented
+    deviation) - here it must equal the same sequence with every U replaced by N, not by T."""
+    rng = np.random.default_rng(21)
+    s = random_dna(rng, 60_000)
+    pos = rng.choice(s.size, 400, replace=False)
+    s_u = s.copy()
+    s_u[pos] = np.frombuffer(b"UuRYKMSWBDHVryn-*", np.uint8)[rng.integers(0, 17, pos.size)]
+    s_n, s_t = s_u.copy(), s_u.copy()
+    s_n[pos] = ord("N")
+    s_t[pos] = ord("T")
+    p = hg.make_params(k=21, scaled=5)
+    off = np.array([0, s.size], np.uint64)
+    got, _ = ctx.kmer_hash(s_u, off, p)
+    as_n, _ = ctx.kmer_hash(s_n, off, p)
+    as_t, _ = ctx.kmer_hash(s_t, off, p)
+    assert np.array_equal(got, as_n) and not np.array_equal(got, as_t)
+    assert np.array_equal(got, _oracle_sets(oracle, s_u, off, k=21, scaled=5)[0])
+    if oracle.ref() is not None:  # the reference kernel itself (host build) agrees, capacity drops aside
+        ref = oracle.ref_kmer_hash_set(s_u, k=21, scaled=5)
+        assert np.isin(ref, got).all()
+
+
 def test_kmer_hash_matches_reference_kernel_compiled_for_host(ctx, hg, oracle):
     """The reference's own cuda_kmer_t1ha2 (compiled as host code in oracle/_ref) agrees too."""
     if oracle.ref() is None:
