@@ -18,8 +18,8 @@
 //     to nibble codes + a validity bit per base, and staged in 5 KB of shared memory;
 //   * each thread then owns 32 consecutive start positions: the forward and reverse-
 //     complement k-mers roll in registers one NIBBLE per base (first base in the low nibble),
-//     canonical = lexicographic min via BREV'd unsigned compares (same order as the
-//     reference's byte compare, cuda_kernel.cu:84-89,306-311), and the chosen k-mer becomes
+//     canonical = lexicographic min via ONE multi-word unsigned compare of the two states (same
+//     choice as the reference's byte compare, cuda_kernel.cu:84-89,306-311), and the chosen k-mer becomes
 //     its upper-case ASCII bytes with two PRMT table lookups per 8 bases (the hash is defined
 //     over the ASCII k-mer, sketch.rs:90); t1ha2_atonce in registers; threshold compare;
 //   * the rare survivors (1/scaled) are inserted into the genome's open-addressing table in
@@ -54,10 +54,18 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 
-// Nibble code of a base (one nibble per base everywhere below):  A=2  C=6  G=1  T=5, 0 = "no
-// base".  Chosen so that (i) complement is XOR 7, (ii) the bit-reversed nibbles order as
-// A<C<G<T, so BREV turns "first base in the low nibble" words into unsigned-comparable keys,
-// and (iii) every code is a PRMT selector (< 8) into an 8-byte ASCII table with 0 -> 0x00.
+// Nibble code of a base (one nibble per base everywhere below):  A=1  C=2  G=3  T=4, 0 = "no
+// base".  Chosen so that (i) the codes order as the letters do, (ii) complement is 5 - code (no
+// borrow between nibbles), and (iii) every code is a PRMT selector (< 8) into an 8-byte ASCII
+// table with 0 -> 0x00, so the unused nibbles of the last word expand to the zero bytes t1ha2's
+// tail read wants.
+//
+// (i) + (ii) make the canonical choice a plain multi-word unsigned compare of the two rolling
+// states, although those hold the FIRST base in the LOW nibble: comparing a k-mer with its own
+// reverse complement from the front tests base[i] against comp(base[K-1-i]); comparing the packed
+// values from the top tests base[K-1-i] against comp(base[i]); and a < 5 - b <=> b < 5 - a.  Both
+// walks meet the same sequence of decisions, so F < R numerically <=> forward < revcomp
+// lexicographically (the reference's strcmp_l, cuda_kernel.cu:84-89,306-311).  No bit reversal.
 //
 // 4 ASCII bytes -> 16 bits of nibble codes (base 0 in the low nibble) + 4 validity bits
 // (only A,C,G,T in either case are bases — cuda_kernel.cu:277-296).
@@ -65,7 +73,7 @@ __device__ __forceinline__ void encode4(uint32_t w, uint32_t &nib16, uint32_t &v
   const uint32_t u = w & 0xDFDFDFDFu;                               // fold case
   const uint32_t code = ((u >> 1) ^ (u >> 2)) & 0x03030303u;        // per byte: A0 C1 G2 T3
   const uint32_t sel = (code | (code >> 12)) & 0xFFFFu;             // nibbles: b0 b2 b1 b3
-  const uint32_t nib = prmt(0x05010602u, 0u, sel);           // bytes n0 n2 n1 n3
+  const uint32_t nib = prmt(0x04030201u, 0u, sel);           // bytes n0 n2 n1 n3
   nib16 = (nib | (nib >> 12)) & 0xFFFFu;                            // n0 n1 n2 n3
   // re-expand the codes to upper-case ASCII and compare: anything else is not a base
   const uint32_t expect = prmt(0x54474341u, 0u, sel);        // 'A','C','G','T'
@@ -212,15 +220,15 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
     // F = X << 4 (so that the first step's shift-right puts base i at nibble i)
 #pragma unroll
     for (int m = NW - 1; m >= 0; --m) F[m] = (X[m] << 4) | (m > 0 ? (X[m - 1] >> 28) : 0u);
-    // R: nibble i = complement(base[K-2-i]), i < K-1.  Complement = XOR 7 on real bases.
+    // R: nibble i = complement(base[K-2-i]), i < K-1.  Complement = 5 - code on real bases.
     if (CANON) {
       constexpr int P = K - 1;
       uint32_t Y[NW];
 #pragma unroll
       for (int m = 0; m < NW; ++m) {
         const int have = P - 8 * m;
-        const uint32_t cm = have <= 0 ? 0u : (have >= 8 ? 0x77777777u : (0x77777777u & ((1u << (4 * (have & 7))) - 1u)));
-        Y[m] = X[m] ^ cm;
+        const uint32_t cm = have <= 0 ? 0u : (have >= 8 ? 0x55555555u : (0x55555555u & ((1u << (4 * (have & 7))) - 1u)));
+        Y[m] = cm - X[m];
       }
       // reverse the nibble order of the whole NW-word value, then shift the P used nibbles down
       uint32_t V[NW + 1];
@@ -247,7 +255,7 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
 #pragma unroll 1
   for (int o = 0; o < KH_PPT / 8; ++o) {
     const uint32_t in32 = window8(nb0 + (K - 1) + 8 * o);  // the 8 incoming bases
-    const uint32_t in32c = in32 ^ 0x77777777u;             // their complements
+    const uint32_t in32c = 0x55555555u - in32;             // their complements (codes <= 4: no borrow between nibbles)
     const uint32_t kv8 = kv32 >> (8 * o);
     // straight-line code for the whole group: the (rare) survivors are only flagged here and
     // inserted after the group, so the scheduler can interleave the ALU-heavy rolling/expansion
@@ -272,23 +280,20 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
         for (int m = NW - 1; m > 0; --m) R[m] = __funnelshift_l(R[m - 1], R[m], 4);
         R[0] = (R[0] << 4) | ((in32c >> (4 * jj)) & 0xFu);
         if (LASTN < 8) R[NW - 1] &= LASTMASK;
-        // ---- canonical = lexicographic min: compare the bit-reversed words, word 0 first ----
-        // borrow chain over the bit-reversed words, least significant (last) word first:
-        // mask = all ones iff F < R
-        uint32_t a[NW], b[NW], mask;
-#pragma unroll
-        for (int m = 0; m < NW; ++m) { a[m] = __brev(F[m]); b[m] = __brev(R[m]); }
+        // ---- canonical = lexicographic min = numeric min of the packed states (see the code table above):
+        //      borrow chain over the words, least significant first; mask = all ones iff F < R ----
+        uint32_t mask;
         if (NW == 1) {
-          asm("{.reg .u32 t; sub.cc.u32 t, %1, %2; subc.u32 %0, 0, 0;}" : "=r"(mask) : "r"(a[0]), "r"(b[0]));
+          asm("{.reg .u32 t; sub.cc.u32 t, %1, %2; subc.u32 %0, 0, 0;}" : "=r"(mask) : "r"(F[0]), "r"(R[0]));
         } else if (NW == 2) {
           asm("{.reg .u32 t; sub.cc.u32 t, %1, %2; subc.cc.u32 t, %3, %4; subc.u32 %0, 0, 0;}"
-              : "=r"(mask) : "r"(a[1]), "r"(b[1]), "r"(a[0]), "r"(b[0]));
+              : "=r"(mask) : "r"(F[0]), "r"(R[0]), "r"(F[1]), "r"(R[1]));
         } else if (NW == 3) {
           asm("{.reg .u32 t; sub.cc.u32 t, %1, %2; subc.cc.u32 t, %3, %4; subc.cc.u32 t, %5, %6; subc.u32 %0, 0, 0;}"
-              : "=r"(mask) : "r"(a[2]), "r"(b[2]), "r"(a[1]), "r"(b[1]), "r"(a[0]), "r"(b[0]));
+              : "=r"(mask) : "r"(F[0]), "r"(R[0]), "r"(F[1]), "r"(R[1]), "r"(F[2]), "r"(R[2]));
         } else {
           asm("{.reg .u32 t; sub.cc.u32 t, %1, %2; subc.cc.u32 t, %3, %4; subc.cc.u32 t, %5, %6; subc.cc.u32 t, %7, %8; subc.u32 %0, 0, 0;}"
-              : "=r"(mask) : "r"(a[NW - 1]), "r"(b[NW - 1]), "r"(a[NW > 2 ? 2 : 0]), "r"(b[NW > 2 ? 2 : 0]), "r"(a[1]), "r"(b[1]), "r"(a[0]), "r"(b[0]));
+              : "=r"(mask) : "r"(F[0]), "r"(R[0]), "r"(F[1]), "r"(R[1]), "r"(F[NW > 2 ? 2 : 0]), "r"(R[NW > 2 ? 2 : 0]), "r"(F[NW - 1]), "r"(R[NW - 1]));
         }
 #pragma unroll
         for (int m = 0; m < NW; ++m) C[m] = (F[m] & mask) | (R[m] & ~mask);
@@ -296,7 +301,7 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
 #pragma unroll
         for (int m = 0; m < NW; ++m) C[m] = F[m];
       }
-      // ---- ASCII expansion: each nibble is a PRMT selector into {0,'G','A',0,0,'T','C',0} ----
+      // ---- ASCII expansion: each nibble is a PRMT selector into {0,'A','C','G','T',0,0,0} ----
       uint64_t w[NW];
 #pragma unroll
       for (int m = 0; m < NW; ++m) {
@@ -347,8 +352,8 @@ int launch_kc(hg_ctx *ctx, uint32_t n_tiles, const uint8_t *d_seq, const hg_geno
   if (rc) return rc;
   tile_map_kernel<<<(n_genomes * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_desc, n_genomes, (uint32_t *)d_map);
   kmer_hash_kernel<K, CANON><<<grid, KH_THREADS, 0, ctx->stream>>>(d_seq, d_desc, n_genomes, n_tiles, threshold, seed,
-                                                                   d_tables, d_counts, ctx->d_status, 0x00414700u,
-                                                                   0x00435400u, (const uint32_t *)d_map, ctx->d_actual_len);
+                                                                   d_tables, d_counts, ctx->d_status, 0x47434100u,
+                                                                   0x00000054u, (const uint32_t *)d_map, ctx->d_actual_len);
   ctx->launches += 2;
   HG_CUDA(cudaGetLastError());
   return HG_OK;
