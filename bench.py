@@ -546,6 +546,9 @@ def encode_family(ctx, synth, dev, n, D, n_per, scaled, seed, want_packed=False)
     for c0 in range(0, n, chunk):
         m = min(chunk, n - c0)
         hashes, off = synth.hash_sets_family_dev(m, n_per=n_per, scaled=scaled, seed=seed, device=dev, first=c0)
+        # the generator's last copies run on torch's stream, the encoder on the library's: without this the encoder can
+        # read the tail of `hashes` before it is written (seen once: one rank's row 13332 of config 5 differed from rank 0's)
+        torch.cuda.current_stream().synchronize()
         ctx.encode_sets_dev(hashes.data_ptr(), off, D, hv[c0:].data_ptr(), packed[c0:].data_ptr() if want_packed else None,
                             bits[c0:].data_ptr(), norm[c0:].data_ptr())
         ctx.sync()
@@ -592,7 +595,8 @@ def dist_parity(cfg, hits, ref_hv, ref_norm, qry_hv, qry_norm, th=85.0, sample_r
         ok = (sel.size == wj.size and np.array_equal(hj[sel], wj) and np.array_equal(hits["dot"][sel], dot[t, wj])
               and np.array_equal(hits["ani"][sel].view(np.uint32), ani[t, wj].view(np.uint32)))
         if not ok:
-            raise RuntimeError("dist parity failed (%s): ref row %d differs from the oracle" % (cfg["key"], i))
+            raise RuntimeError("dist parity failed (%s): ref row %d differs from the oracle: GPU has %d hits (j = %s ...), the oracle %d "
+                               "(j = %s ...)" % (cfg["key"], i, sel.size, hj[sel][:6].tolist(), wj.size, wj[:6].tolist()))
         n_checked += wj.size
     return ("ok: %d sampled ref rows x all %d queries against the oracle - %d hits, same set, i32 dots equal, f32 ANI bit-identical"
             % (rows.size, Q, n_checked)), dict(pairs=int(rows.size * Q), seconds=dt)
@@ -622,6 +626,11 @@ def bench_dist_config(cfg, args, ctx, ext, hg, multigpu, synth, dev, rank, world
         q_idx = torch.arange(5, n_ref, n_ref // n_qry, device=dev)[:n_qry]  # queries with relatives among the refs
         qry_hv, qry_norm = ref_hv[q_idx].contiguous(), ref_norm[q_idx].contiguous()
         n_pairs = n_ref * n_qry
+    if world > 1:  # every rank generated the matrices itself: they must be the same bytes everywhere
+        sums = [None] * world
+        dist.all_gather_object(sums, (int(ref_hv.view(torch.int64).sum().item()), int(ref_norm.to(torch.int64).sum().item())), group=host_pg)
+        if any(x != sums[0] for x in sums):
+            raise RuntimeError("%s: the ranks' synthetic matrices differ: %s" % (cfg["key"], sums))
     cap = 4_000_000
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     hits_pin = torch.empty(cap * 16, dtype=torch.uint8, pin_memory=True)
