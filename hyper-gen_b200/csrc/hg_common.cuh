@@ -24,7 +24,14 @@ __host__ __device__ constexpr uint64_t t1_p4() { return 0x9C06FAF4D023E3ABull; }
 __host__ __device__ constexpr uint64_t t1_p5() { return 0xC060724A8424F345ull; }
 __host__ __device__ constexpr uint64_t t1_p6() { return 0xCB5AF53AE3AAAC31ull; }
 
-__device__ __forceinline__ uint64_t rot64(uint64_t v, unsigned s) { return (v >> s) | (v << (64 - s)); }
+// rotate right by a compile-time amount: two funnel shifts (written out, nvcc makes four instructions of the shift-or form)
+template <unsigned S>
+__device__ __forceinline__ uint64_t rot64(uint64_t v) {
+  static_assert(S > 0 && S < 64 && S != 32, "rot64");
+  const uint32_t lo = S < 32 ? (uint32_t)v : (uint32_t)(v >> 32), hi = S < 32 ? (uint32_t)(v >> 32) : (uint32_t)v;
+  const uint32_t a = __funnelshift_r(lo, hi, S & 31), b = __funnelshift_r(hi, lo, S & 31);
+  return (uint64_t)a | ((uint64_t)b << 32);
+}
 
 __device__ __forceinline__ void mixup64(uint64_t &a, uint64_t &b, uint64_t v, uint64_t prime) {
   const uint64_t t = b + v;
@@ -33,8 +40,8 @@ __device__ __forceinline__ void mixup64(uint64_t &a, uint64_t &b, uint64_t v, ui
 }
 
 __device__ __forceinline__ uint64_t final64(uint64_t a, uint64_t b) {
-  const uint64_t x = (a + rot64(b, 41)) * t1_p0();
-  const uint64_t y = (rot64(a, 23) + b) * t1_p6();
+  const uint64_t x = (a + rot64<41>(b)) * t1_p0();
+  const uint64_t y = (rot64<23>(a) + b) * t1_p6();
   const uint64_t v = x ^ y;
   return (v * t1_p5()) ^ __umul64hi(v, t1_p5());
 }

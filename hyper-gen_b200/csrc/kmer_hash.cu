@@ -84,6 +84,23 @@ __device__ __forceinline__ void encode4(uint32_t w, uint32_t &nib16, uint32_t &v
   valid4 = ((ok * 0x01040208u) >> 24) & 0xFu;                       // back to base order
 }
 
+// 8 ASCII bytes (w0 = bases 0..3, w1 = bases 4..7) -> 8 nibble codes, base i in nibble i; `bad` collects a non-zero
+// byte for every byte that is not a base.  The bytes are first gathered into even / odd bases (two PRMTs on the raw
+// words), so that the per-byte 2-bit codes of the two halves interleave into nibbles with one shift-or; the same
+// nibbles then select the byte each code stands for (one PRMT per four bases) and the comparison with what was read
+// is the validity test.  17 instructions per 8 bases; a byte that is not a base gets SOME code 1..4 - its validity
+// bit, not its code, keeps it out of every k-mer.
+__device__ __forceinline__ uint32_t encode8(uint32_t w0, uint32_t w1, uint32_t &bad, uint32_t k_fold, uint32_t k_lut) {
+  // k_fold = 0xDFDFDFDF, k_lut = 0x15060200 (held in registers by the caller)
+  const uint32_t y0 = (w0 & k_fold) ^ 0x41414141u, y1 = (w1 & k_fold) ^ 0x41414141u;  // A 00, C 02, G 06, T 15, either case
+  const uint32_t e = prmt(y0, y1, 0x6420u), o = prmt(y0, y1, 0x7531u);
+  const uint32_t ce = ((e >> 1) ^ (e >> 2)) & 0x03030303u, co = ((o >> 1) ^ (o >> 2)) & 0x03030303u;  // A0 C1 G2 T3
+  const uint32_t sel = ce | (co << 4);
+  const uint32_t x0 = prmt(k_lut, 0u, sel), x1 = prmt(k_lut, 0u, sel >> 16);
+  bad |= (x0 ^ y0) | (x1 ^ y1);
+  return sel + 0x11111111u;
+}
+
 __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
   return __funnelshift_r(lo, hi, s);
 }
@@ -117,12 +134,12 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
                  uint32_t n_genomes, uint32_t n_tiles, uint64_t threshold, uint64_t seed,
                  uint64_t *__restrict__ tables, uint32_t *__restrict__ counts,
                  uint32_t *__restrict__ status, uint32_t lut_lo, uint32_t lut_hi,
-                 const uint32_t *__restrict__ cta_genome, const uint64_t *__restrict__ actual_len) {
+                 const uint32_t *__restrict__ cta_genome, const uint64_t *__restrict__ actual_len, uint2 consts) {
   constexpr int NW = (K + 7) / 8;          // nibble words == t1ha2 input words (8 bases each)
   constexpr int LASTN = K - 8 * (NW - 1);  // bases in the last word, 1..8
   constexpr uint32_t LASTMASK = LASTN == 8 ? 0xFFFFFFFFu : ((1u << (4 * LASTN)) - 1u);
   // every warp owns a private staging area and runs on its own: no CTA-wide barrier anywhere
-  __shared__ uint32_t s_nib_all[KH_WARPS][KH_CHUNKS * 2 + 8];    // 8 bases per word
+  __shared__ __align__(8) uint32_t s_nib_all[KH_WARPS][KH_CHUNKS * 2 + 8];    // 8 bases per word
   __shared__ uint32_t s_valid_all[KH_WARPS][KH_CHUNKS / 2 + 4];  // 16 bits per chunk
   // survivors are queued here and inserted together at the end of the tile, so the round trip
   // of the global atomicCAS is paid once per tile (all lanes in flight) instead of once per hit
@@ -154,26 +171,35 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
 
   // ---- phase A: bytes -> nibble codes + validity, staged in this warp's shared memory ----
   const uintptr_t p_lo = (uintptr_t)(seq + gd.seq_begin + tile_base);
-  const uintptr_t p_hi = (uintptr_t)(seq + gd.seq_begin + need_end);
   const uintptr_t p_al = p_lo & ~(uintptr_t)15;
-  const uint32_t sh = (uint32_t)(p_lo - p_al);  // 0..15 bases of alignment slack
-  for (int c = lane; c < KH_CHUNKS + 4; c += 32) {
-    const uintptr_t pc = p_al + (uintptr_t)16 * c;
-    uint32_t n0 = 0, n1 = 0, valid = 0;
-    if (c < KH_CHUNKS && pc < p_hi && pc + 16 > p_lo) {
-      const uint4 v = ld_stream16(reinterpret_cast<const void *>(pc));
-      uint32_t n16, v4;
-      encode4(v.x, n16, v4); n0 = n16;        valid = v4;
-      encode4(v.y, n16, v4); n0 |= n16 << 16; valid |= v4 << 4;
-      encode4(v.z, n16, v4); n1 = n16;        valid |= v4 << 8;
-      encode4(v.w, n16, v4); n1 |= n16 << 16; valid |= v4 << 12;
-      // bytes of this chunk outside [p_lo, p_hi) belong to someone else (or nobody)
-      const int first = pc < p_lo ? (int)(p_lo - pc) : 0;
-      const int last = pc + 16 > p_hi ? (int)(p_hi - pc) : 16;
-      valid &= ((1u << last) - 1u) & ~((1u << first) - 1u);
+  const uint32_t sh = (uint32_t)(p_lo - p_al);                     // 0..15 bases of alignment slack
+  const uint32_t hi_off = sh + (uint32_t)(need_end - tile_base);   // bytes [sh, hi_off) of the aligned window are this tile's
+  // constants that must live in registers (as immediates they cost an extra instruction per use)
+  const uint32_t k_fold = consts.x, k_lut = consts.y;  // 0xDFDFDFDF, 0x15060200 (kernel arguments, see launch_kc)
+#pragma unroll
+  for (int it = 0; it < (KH_CHUNKS + 4 + 31) / 32; ++it) {
+    const uint32_t c = lane + 32u * it, off = 16u * c;
+    if (c >= KH_CHUNKS + 4) break;
+    uint2 n = make_uint2(0u, 0u);
+    uint32_t valid = 0;
+    if (c < KH_CHUNKS && off < hi_off) {
+      const uint4 v = ld_stream16(reinterpret_cast<const void *>(p_al + off));
+      uint32_t bad = 0;
+      n.x = encode8(v.x, v.y, bad, k_fold, k_lut);
+      n.y = encode8(v.z, v.w, bad, k_fold, k_lut);
+      valid = 0xFFFFu;
+      if (bad) {  // a byte that is not a base (N runs, IUPAC codes, the bytes past a genome's end): exact validity bits
+        uint32_t n16, v4;
+        encode4(v.x, n16, v4); valid = v4;
+        encode4(v.y, n16, v4); valid |= v4 << 4;
+        encode4(v.z, n16, v4); valid |= v4 << 8;
+        encode4(v.w, n16, v4); valid |= v4 << 12;
+      }
+      // bytes of this chunk outside [sh, hi_off) belong to someone else (or nobody)
+      const uint32_t first = c == 0 ? sh : 0u, last = min(hi_off - off, 16u);
+      valid &= ((1u << last) - 1u) & (0xFFFFFFFFu << first);
     }
-    s_nib[2 * c] = n0;
-    s_nib[2 * c + 1] = n1;
+    *reinterpret_cast<uint2 *>(s_nib + 2 * c) = n;
     s_valid16[c] = (uint16_t)valid;
   }
   __syncwarp();
@@ -251,34 +277,42 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
 
   uint64_t *table = tables + gd.table_begin;
   uint32_t *count = counts + g;
+  const uint32_t thr_hi = (uint32_t)(threshold >> 32);
 
 #pragma unroll 1
   for (int o = 0; o < KH_PPT / 8; ++o) {
     const uint32_t in32 = window8(nb0 + (K - 1) + 8 * o);  // the 8 incoming bases
-    const uint32_t in32c = 0x55555555u - in32;             // their complements (codes <= 4: no borrow between nibbles)
     const uint32_t kv8 = kv32 >> (8 * o);
+    // The eight k-mers of the group are windows of ONE (NW + 1)-word value each: XF = the state before the group with
+    // the incoming bases appended above its K nibbles, YR = the reversed complements of the incoming bases below the
+    // reverse-complement state.  Position jj is that value shifted by 4 (jj + 1) bits - one funnel shift per word, no
+    // chain from position to position (the last one is a plain register move).
+    uint32_t XF[NW + 1], YR[NW + 1];
+#pragma unroll
+    for (int m = 0; m + 1 < NW; ++m) XF[m] = F[m];
+    XF[NW - 1] = LASTN < 8 ? (F[NW - 1] | (in32 << (4 * (LASTN & 7)))) : F[NW - 1];
+    XF[NW] = LASTN < 8 ? (in32 >> (32 - 4 * LASTN)) : in32;
+    if (CANON) {
+      const uint32_t c = 0x55555555u - in32;  // complements (codes <= 4: no borrow between nibbles); 5 where there is no base
+      const uint32_t b = prmt(c, 0u, 0x0123u);  // reverse the nibble order: bytes, then the two nibbles of every byte
+      YR[0] = ((b & 0x0F0F0F0Fu) << 4) | ((b >> 4) & 0x0F0F0F0Fu);
+#pragma unroll
+      for (int m = 0; m < NW; ++m) YR[m + 1] = R[m];
+    }
     // straight-line code for the whole group: the (rare) survivors are only flagged here and
     // inserted after the group, so the scheduler can interleave the ALU-heavy rolling/expansion
     // of one position with the multiply chains of its neighbours
     uint64_t hs[KH_GROUP];
-    uint32_t hitmask = 0;
+    uint32_t min_hi = 0xFFFFFFFFu;  // smallest high word of the group's hashes: one VIMNMX per k-mer instead of a 64-bit compare
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
-      // ---- roll the forward strand: drop the low nibble, append at nibble K-1 ----
 #pragma unroll
-      for (int m = 0; m + 1 < NW; ++m) F[m] = funnel_r(F[m], F[m + 1], 4);
-      {
-        constexpr int TO = 4 * (LASTN - 1);
-        const int from = 4 * jj;
-        const uint32_t moved = TO >= from ? (in32 << (TO - from)) : (in32 >> (from - TO));
-        F[NW - 1] = (F[NW - 1] >> 4) | (moved & (0xFu << TO));
-      }
+      for (int m = 0; m < NW; ++m) F[m] = jj < 7 ? funnel_r(XF[m], XF[m + 1], 4 * (jj + 1)) : XF[m + 1];
+      if (LASTN < 8) F[NW - 1] &= LASTMASK;
       uint32_t C[NW];
       if (CANON) {
-        // ---- roll the reverse complement: shift up one nibble, new complement at nibble 0 ----
 #pragma unroll
-        for (int m = NW - 1; m > 0; --m) R[m] = __funnelshift_l(R[m - 1], R[m], 4);
-        R[0] = (R[0] << 4) | ((in32c >> (4 * jj)) & 0xFu);
+        for (int m = 0; m < NW; ++m) R[m] = jj < 7 ? __funnelshift_l(YR[m], YR[m + 1], 4 * (jj + 1)) : YR[m];
         if (LASTN < 8) R[NW - 1] &= LASTMASK;
         // ---- canonical = lexicographic min = numeric min of the packed states (see the code table above):
         //      borrow chain over the words, least significant first; mask = all ones iff F < R ----
@@ -311,13 +345,15 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
       }
       const uint64_t h = hg::t1ha2_kmer<K>(w, seed);
       hs[jj % KH_GROUP] = h;
-      hitmask |= (uint32_t)(h < threshold) << jj;
+      min_hi = min(min_hi, (uint32_t)(h >> 32));
       if ((jj % KH_GROUP) == KH_GROUP - 1) {
-        const uint32_t gm = (hitmask & kv8) >> (jj + 1 - KH_GROUP);
-        if (gm & ((1u << KH_GROUP) - 1u)) {
+        // some hash of the group may be below the threshold (1 group in ~190 at scaled = 1500): the exact 64-bit test
+        // and the validity of the position are looked at only here
+        if (min_hi <= thr_hi) {
+          const uint32_t gm = kv8 >> (jj + 1 - KH_GROUP);
 #pragma unroll
           for (int e = 0; e < KH_GROUP; ++e)
-            if ((gm >> e) & 1u) {
+            if (((gm >> e) & 1u) && hs[e] < threshold) {
               const uint32_t pos = atomicAdd(s_qn, 1u);
               if (pos < KH_QCAP) s_queue[pos] = hs[e];
               else table_insert(table, gd.table_mask, hs[e], count, status);  // queue full (tiny `scaled`)
@@ -353,7 +389,8 @@ int launch_kc(hg_ctx *ctx, uint32_t n_tiles, const uint8_t *d_seq, const hg_geno
   tile_map_kernel<<<(n_genomes * 32 + 127) / 128, 128, 0, ctx->stream>>>(d_desc, n_genomes, (uint32_t *)d_map);
   kmer_hash_kernel<K, CANON><<<grid, KH_THREADS, 0, ctx->stream>>>(d_seq, d_desc, n_genomes, n_tiles, threshold, seed,
                                                                    d_tables, d_counts, ctx->d_status, 0x47434100u,
-                                                                   0x00000054u, (const uint32_t *)d_map, ctx->d_actual_len);
+                                                                   0x00000054u, (const uint32_t *)d_map, ctx->d_actual_len,
+                                                                   make_uint2(0xDFDFDFDFu, 0x15060200u));
   ctx->launches += 2;
   HG_CUDA(cudaGetLastError());
   return HG_OK;
@@ -379,10 +416,14 @@ int hg_launch_kmer_hash(hg_ctx *ctx, const uint8_t *d_seq, const hg_genome_desc 
   switch (p->ksize) {
 #define HG_K(KK) \
   case KK: return launch_k<KK>(ctx, canon, n_tiles, d_seq, d_desc, n_genomes, threshold, p->seed, d_tables, d_counts);
+#ifdef HG_KMER_ONLY_K21  // (development: one instantiation, for reading its SASS)
+    HG_K(21)
+#else
     HG_K(1) HG_K(2) HG_K(3) HG_K(4) HG_K(5) HG_K(6) HG_K(7) HG_K(8)
     HG_K(9) HG_K(10) HG_K(11) HG_K(12) HG_K(13) HG_K(14) HG_K(15) HG_K(16)
     HG_K(17) HG_K(18) HG_K(19) HG_K(20) HG_K(21) HG_K(22) HG_K(23) HG_K(24)
     HG_K(25) HG_K(26) HG_K(27) HG_K(28) HG_K(29) HG_K(30) HG_K(31) HG_K(32)
+#endif
 #undef HG_K
     default:
       hg_set_error("ksize %u unsupported (1..32)", (unsigned)p->ksize);
