@@ -42,7 +42,20 @@ GENOME_LEN = 5_000_000
 ALG_BYTES_PER_GENOME = GENOME_LEN + 8 * (GENOME_LEN // SCALED)
 # integer instructions the k-mer kernel executes per k-mer (ncu smsp__inst_executed /
 # k-mers, profiles/): used only for the auxiliary INT32 roofline
-KMER_INST_PER_KMER = float(os.environ.get("HG_KMER_INST_PER_KMER", "127"))
+def _kmer_inst_per_kmer():
+    """warp-level instructions per 32 k-mers (= lane instructions per k-mer) of kmer_hash_kernel<21,true>, from the committed
+    ncu capture's smsp__inst_executed.sum (profiles/kmer_traffic.json); HG_KMER_INST_PER_KMER overrides"""
+    if os.environ.get("HG_KMER_INST_PER_KMER"):
+        return float(os.environ["HG_KMER_INST_PER_KMER"])
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "kmer_traffic.json")) as f:
+            tj = json.load(f)
+        return tj["smsp_inst_executed"] / (tj["genomes_per_launch"] * (5_000_000 - 20) / 32.0)
+    except (OSError, KeyError, ValueError):
+        return 127.0
+
+
+KMER_INST_PER_KMER = _kmer_inst_per_kmer()
 
 
 def load_peaks():

@@ -84,6 +84,13 @@ __device__ __forceinline__ unsigned long long feed_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// timeline stamp i of a multi-GPU launch (measurement support): first writer wins for "first", atomicMax for "last"
+__device__ __forceinline__ void feed_stamp(unsigned long long *dbg, int i) {
+  if (dbg) dbg[i] = feed_ns();
+}
+__device__ __forceinline__ void feed_stamp_max(unsigned long long *dbg, int i) {
+  if (dbg) atomicMax(dbg + i, feed_ns());
+}
 // whole warp, converged: returns once every flag in `need` is set (`have` caches what has been seen)
 __device__ __forceinline__ void feed_wait(const hg_tile_feed &f, uint32_t need, uint32_t &have) {
   if ((have & need) == need) return;
@@ -153,6 +160,7 @@ __device__ __forceinline__ void push_my_chunks(const hg_push_plan *__restrict__ 
       if (prev == n_pushers - 1) {
         __threadfence_system();
         pp->done[ch] = 0;
+        feed_stamp(pp->dbg, 8 + ch);
         for (int m = 0; m < world; ++m)
           if (m != rank) {
             uint32_t *f = reinterpret_cast<uint32_t *>(pp->win[m] + pp->ready_off) + (rank * HG_PUSH_CHUNKS + ch);

@@ -458,6 +458,7 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
   uint32_t rank;  // 0 = leader (issues the MMAs, owns the full / tmem-empty barriers), 1 = peer
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   if (feed.seq_ptr) feed.seq = *feed.seq_ptr;
+  if (blockIdx.x == 0 && threadIdx.x == 0) hg::feed_stamp(feed.dbg, 1);
   // this pair's tiles: first, first + n_pairs, ... of the launch's share of the tile enumeration
   const uint32_t pair = (blockIdx.x >> 1) * na.walk_mul + na.walk_add, n_pairs = (gridDim.x >> 1) * na.walk_mul;
 
@@ -498,6 +499,7 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
   uint32_t have = 0;  // arrival flags seen so far (warp 0)
   if (feed.start_need) {  // the other members' pre-pass statistics have arrived, the root has reset its hit counter
     if (warp == 0) hg::feed_wait(feed, feed.start_need, have);
+    if (warp == 0 && blockIdx.x == 0 && lane == 0) hg::feed_stamp(feed.dbg, 2);
     asm volatile("bar.sync 2, %0;" ::"r"(N1_THREADS) : "memory");
   }
   // the pre-passes ran before this kernel (on this GPU, and on the others before their statistics were pushed): if they
@@ -515,9 +517,14 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
     // ===== TMA producer (both CTAs; completion bytes go to the LEADER's full barrier) =====
     const uint32_t on = elect_one();
     uint32_t s = 0, ph = 0;
+    unsigned long long waited = 0;  // (timeline) ns this producer spent waiting for other members' rows
     for (; valid; valid = tiles.advance(n_pairs)) {
       const uint32_t row0 = tiles.R * TILE_ROWS + rank * 128u, colh = tiles.C * N1_BN + rank * 128u;
-      if (tiles.need) hg::feed_wait(feed, tiles.need, have);  // the rows this tile reads have arrived from their owners
+      if (tiles.need) {  // the rows this tile reads have arrived from their owners
+        const unsigned long long w0 = feed.dbg ? hg::feed_ns() : 0ull;
+        hg::feed_wait(feed, tiles.need, have);
+        if (feed.dbg) waited += hg::feed_ns() - w0;
+      }
       for (uint32_t kb = 0; kb < num_kb; ++kb) {
         mbar_wait_cluster(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES, rank == 0 ? on : 0u);  // the leader expects its bytes and the peer's
@@ -531,6 +538,7 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
+    if (feed.dbg && lane == 0) { atomicMax(feed.dbg + 5, waited); if (blockIdx.x == 0) feed.dbg[3] = waited; }
   } else if (warp == 1) {
     // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
     if (rank == 0) {
@@ -649,6 +657,7 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
   }
   }  // compute roles
   __syncthreads();
+  if (threadIdx.x == 0) hg::feed_stamp_max(feed.dbg, 4);
   cluster_sync_all();  // nobody leaves while the peer may still read its smem or signal its barriers
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

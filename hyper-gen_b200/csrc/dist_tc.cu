@@ -367,6 +367,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
   uint32_t rank;  // 0 = leader (issues the MMAs, owns the full / tmem-empty barriers), 1 = peer
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   if (feed.seq_ptr) feed.seq = *feed.seq_ptr;
+  if (blockIdx.x == 0 && threadIdx.x == 0) hg::feed_stamp(feed.dbg, 1);
   // this launch takes tiles walk_add, walk_add + walk_mul, ... of the enumeration (member walk_add of walk_mul GPUs),
   // dealt round-robin to its CTA pairs
   const uint32_t pair = (blockIdx.x >> 1) * walk_mul + walk_add, n_pairs = (gridDim.x >> 1) * walk_mul;
@@ -412,6 +413,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
   uint32_t have = 0;  // arrival flags seen so far (the producer warp)
   if (feed.start_need) {  // a member of several GPUs: nothing is appended before the root has reset its hit counter
     if (warp == 0) hg::feed_wait(feed, feed.start_need, have);
+    if (warp == 0 && blockIdx.x == 0 && lane == 0) hg::feed_stamp(feed.dbg, 2);
     asm volatile("bar.sync 2, %0;" ::"r"(TC_THREADS) : "memory");
   }
 
@@ -420,9 +422,14 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
     {
       const uint32_t on = elect_one();
       uint32_t it = 0;
+      unsigned long long waited = 0;  // (timeline) ns this producer spent waiting for other members' rows
       for (; valid; valid = tiles.advance(n_pairs)) {
         const uint32_t row0 = tiles.R * 256u + rank * 128u, colh = tiles.C * TC_BN + rank * 64u;
-        if (tiles.need) hg::feed_wait(feed, tiles.need, have);  // the rows this tile reads have arrived from their owners
+        if (tiles.need) {  // the rows this tile reads have arrived from their owners
+          const unsigned long long w0 = feed.dbg ? hg::feed_ns() : 0ull;
+          hg::feed_wait(feed, tiles.need, have);
+          if (feed.dbg) waited += hg::feed_ns() - w0;
+        }
         for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % T2_STAGES;
           const uint32_t ph = (it / T2_STAGES) & 1u;
@@ -437,6 +444,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
           tma_load_2d_pair(st + 2 * T2_A_BYTES + T2_B_BYTES, &tm_qry, fb, k0, (int)(qry_plane_rows + qry_row_base + colh), on);  // qry lo
         }
       }
+      if (feed.dbg && lane == 0) { atomicMax(feed.dbg + 5, waited); if (blockIdx.x == 0) feed.dbg[3] = waited; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
@@ -529,6 +537,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
   }
   }  // compute roles
   __syncthreads();
+  if (threadIdx.x == 0) hg::feed_stamp_max(feed.dbg, 4);
   cluster_sync_all();  // nobody leaves while the peer may still read its smem or signal its barriers
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

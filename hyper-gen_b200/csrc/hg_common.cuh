@@ -253,6 +253,7 @@ struct hg_push_plan {
   uint32_t *done;       // HG_PUSH_CHUNKS counters in this member's window: pusher warps through with the chunk
   uint64_t ready_off;   // offset of the arrival flags in every window; chunk c raises flag rank * HG_PUSH_CHUNKS + c
   const uint32_t *seq;  // the call's sequence number lives in device memory (the launch sequence is replayed as a CUDA graph)
+  unsigned long long *dbg;  // timeline stamps (HG_PEER_TIMELINE=1, hg_peer_timeline), else NULL
 };
 struct hg_tile_feed {
   const uint2 *list;        // x = tile row | tile column << 16, y = mask of the arrival flags the tile needs; NULL: arithmetic walk
@@ -264,6 +265,7 @@ struct hg_tile_feed {
   uint32_t *status;         // set to 1 if a wait times out (the host turns it into an error)
   unsigned long long timeout_ns;
   int reserve_tpcs;         // TPCs the launch leaves free (for the push kernel running next to it)
+  unsigned long long *dbg;  // timeline stamps (HG_PEER_TIMELINE=1, hg_peer_timeline), else NULL
 };
 
 // two s8 limb planes of one matrix (dist_tc.cu), split piecewise or at once

@@ -30,14 +30,20 @@
 
 namespace {
 
-constexpr int KH_THREADS = 128;
+#ifndef HG_KH_THREADS
+#define HG_KH_THREADS 128
+#endif
+constexpr int KH_THREADS = HG_KH_THREADS;
 constexpr int KH_WARPS = KH_THREADS / 32;
 constexpr int KH_PPT = 32;                       // k-mer start positions per thread
 constexpr int KH_TILE = 32 * KH_PPT;             // start positions per WARP tile
 constexpr int KH_CHUNKS = (KH_TILE + 64) / 16;   // 16-base chunks staged per tile (halo + align)
 constexpr int KH_QCAP = 64;                      // per-warp queue of survivors, flushed once per tile
 constexpr int KH_GROUP = 8;                      // positions hashed back to back before survivors are handled
-constexpr int KH_MIN_CTAS = 8;                   // 32 resident warps per SM at <= 64 registers (measured: occupancy beyond this does not help)
+#ifndef HG_KH_MIN_CTAS
+#define HG_KH_MIN_CTAS 8
+#endif
+constexpr int KH_MIN_CTAS = HG_KH_MIN_CTAS;                   // 32 resident warps per SM at <= 64 registers (measured: occupancy beyond this does not help)
 
 __device__ __forceinline__ uint4 ld_stream16(const void *p) {
   uint4 r;

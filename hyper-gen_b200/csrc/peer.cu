@@ -43,6 +43,7 @@ constexpr size_t OFF_STATS_Q = 256;  // u32[HG_MAX_PEERS][4]: pre-pass statistic
 constexpr size_t OFF_STATS_R = 384;  // u32[HG_MAX_PEERS][4]: ... of the members' own ref rows (ref x query)
 constexpr size_t OFF_READY = 512;    // u32[32]: arrival flags, flag m * 4 + c = sequence number of the last call for which chunk c of member m's rows is here
 constexpr size_t OFF_DONE = 640;     // u32[4]: CTAs of this member's chunk pushes that have finished (local use)
+constexpr size_t OFF_DBG = 768;      // u64[32]: timeline stamps of the last sharded dist (globaltimer ns; HG_PEER_TIMELINE=1)
 constexpr int N_CHUNKS = 4;
 constexpr size_t OFF_HITS = 4096;    // hg_hit[cap]
 constexpr int32_t TC_MAX_ABS = 8127; // |x| <= 8127 splits into two s8 limbs
@@ -59,8 +60,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // Everything this stream wrote before (its pushes) is complete when the kernel starts; the fence + release
 // order it before the flag.  The spin is bounded: a member that never arrives (a failed launch, a dead
 // process) turns into an error status instead of a hung GPU.
-__global__ void peer_barrier_kernel(PeerPtrs w, int rank, int world, unsigned long long timeout_ns) {
+__global__ void peer_barrier_kernel(PeerPtrs w, int rank, int world, unsigned long long timeout_ns, unsigned long long *dbg) {
   const int t = threadIdx.x;
+  if (dbg && t == 0) dbg[13] = global_ns();
   uint32_t *ep = reinterpret_cast<uint32_t *>(w.p[rank] + OFF_SEQ) + 1;  // barriers so far: device-resident, so that the
   uint32_t epoch = 0;                                                    // launch sequence can be replayed as a CUDA graph
   if (t == 0) { epoch = *ep + 1; *ep = epoch; }
@@ -80,11 +82,18 @@ __global__ void peer_barrier_kernel(PeerPtrs w, int rank, int world, unsigned lo
       break;
     }
   }
+  if (dbg) atomicMax(dbg + 14, global_ns());  // when the last member was seen
 }
 
 // First node of a sharded dist on every member: next sequence number, my hit counter and my pre-pass statistics reset
 // (the cursor of my outlier entries starts at my share of the entry space), the root's gather counter reset.
-__global__ void peer_tick_kernel(uint8_t *W, int rank, int is_root, uint32_t entry_base) {
+__global__ void peer_tick_kernel(uint8_t *W, int rank, int is_root, uint32_t entry_base, int timeline) {
+  if (timeline) {  // stamps 0..15 of this call; [16] keeps the previous call's barrier exit (the members' common time base)
+    unsigned long long *dbg = reinterpret_cast<unsigned long long *>(W + OFF_DBG);
+    if (threadIdx.x == 0) dbg[16] = dbg[14];
+    __syncwarp();
+    if (threadIdx.x < 16) dbg[threadIdx.x] = threadIdx.x == 0 ? global_ns() : 0ull;
+  }
   if (threadIdx.x == 0) {
     uint32_t *seq = reinterpret_cast<uint32_t *>(W + OFF_SEQ);
     *seq = *seq + 1;
@@ -101,8 +110,9 @@ __global__ void peer_tick_kernel(uint8_t *W, int rank, int is_root, uint32_t ent
 // computed) moves to the root in ONE piece: one atomic on the root's counter reserves the room, then coalesced 16-byte
 // stores - over NVLink into the root's gather list, or over this GPU's own PCIe link into a host buffer that every
 // member has mapped.
-__global__ void peer_flush_kernel(const uint8_t *W, unsigned long long *root_total, hg_hit *dst, unsigned long long cap) {
+__global__ void peer_flush_kernel(uint8_t *W, unsigned long long *root_total, hg_hit *dst, unsigned long long cap, int timeline) {
   __shared__ unsigned long long s_base;
+  if (timeline && blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<unsigned long long *>(W + OFF_DBG)[12] = global_ns();
   const unsigned long long cnt = *reinterpret_cast<const unsigned long long *>(W + OFF_COUNT);
   const unsigned long long n = cnt < cap ? cnt : cap;  // records beyond my list's capacity were counted, not stored
   // every block moves a contiguous slice of my list and reserves exactly that much room on the root
@@ -205,6 +215,7 @@ struct hg_peer {
   bool opened[HG_MAX_PEERS] = {};
   bool connected = false;
   unsigned long long timeout_ns = 0;
+  int timeline = 0;  // HG_PEER_TIMELINE=1: the kernels of a sharded dist stamp globaltimer values into the window (hg_peer_timeline)
   uint8_t *h_hdr = nullptr;  // pinned copy of window bytes [OFF_STATUS, OFF_STATUS + 128): status word and hit counters of the
                              // last call, written by the call's last node
   // The launch sequence of a sharded dist with asserted path (same pointers, same shapes, call after call) is captured
@@ -262,6 +273,7 @@ static int peer_alloc(hg_ctx *ctx, int rank, int world, uint64_t window_bytes, h
   p->window_bytes = window_bytes;
   p->timeout_ns = 10ull * 1000000000ull;
   if (const char *e = getenv("HG_PEER_TIMEOUT_MS")) p->timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
+  if (const char *e = getenv("HG_PEER_TIMELINE")) p->timeline = atoi(e) != 0;
   if (cudaStreamCreateWithFlags(&p->push_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_operands, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&p->ev_pushed, cudaEventDisableTiming) != cudaSuccess) {
@@ -367,7 +379,8 @@ extern "C" int hg_peer_rank(const hg_peer *p) { return p ? p->rank : -1; }
 extern "C" int hg_peer_world(const hg_peer *p) { return p ? p->world : 0; }
 
 static int peer_barrier(hg_peer *p) {
-  peer_barrier_kernel<<<1, 32, 0, p->ctx->stream>>>(peer_ptrs(p), p->rank, p->world, p->timeout_ns);
+  peer_barrier_kernel<<<1, 32, 0, p->ctx->stream>>>(peer_ptrs(p), p->rank, p->world, p->timeout_ns,
+                                                    p->timeline ? reinterpret_cast<unsigned long long *>(p->win[p->rank] + OFF_DBG) : nullptr);
   p->ctx->launches++;
   HG_CUDA(cudaGetLastError());
   return HG_OK;
@@ -562,7 +575,7 @@ static int shard_enqueue(hg_peer *p, const ShardCall &a, int use_path) {
   p->ev_n = 0;
   PEER_PROF(p, 0);
   // sequence number + 1, my hit counter and statistics reset, the root's gather counter reset
-  peer_tick_kernel<<<1, 32, 0, c->stream>>>(W, rank, rank == a.root, use_path == 3 ? (uint32_t)rank * lay.set_cap : 0u);
+  peer_tick_kernel<<<1, 32, 0, c->stream>>>(W, rank, rank == a.root, use_path == 3 ? (uint32_t)rank * lay.set_cap : 0u, p->timeline);
   c->launches++;
   HG_CUDA(cudaGetLastError());
   hg_tile_feed feed = {};
@@ -578,6 +591,7 @@ static int shard_enqueue(hg_peer *p, const ShardCall &a, int use_path) {
     feed.seq_ptr = (const uint32_t *)(W + OFF_SEQ);
     feed.status = (uint32_t *)(W + OFF_STATUS);
     feed.timeout_ns = p->timeout_ns;
+    feed.dbg = p->timeline ? reinterpret_cast<unsigned long long *>(W + OFF_DBG) : nullptr;
     if (use_path == 3)  // the pre-pass statistics of every other member travel with its chunk 0
       for (int m = 0; m < world; ++m) if (m != rank) feed.start_need |= 1u << (m * N_CHUNKS);
     // nobody moves hits to the root before the root has reset its gather counter for this call: the root raises its
@@ -621,6 +635,7 @@ static int shard_enqueue(hg_peer *p, const ShardCall &a, int use_path) {
   plan.done = reinterpret_cast<uint32_t *>(W + OFF_DONE);
   plan.ready_off = OFF_READY;
   plan.seq = (const uint32_t *)(W + OFF_SEQ);
+  plan.dbg = p->timeline ? reinterpret_cast<unsigned long long *>(W + OFF_DBG) : nullptr;
   for (int ch = 0; ch < N_CHUNKS && world > 1; ++ch) {
     const uint64_t lo = chunk_lo(a.qb, rank, ch), n = chunk_lo(a.qb, rank, ch + 1) - lo;
     auto add = [&](uint64_t off, uint64_t bytes) {
@@ -690,7 +705,7 @@ static int shard_enqueue(hg_peer *p, const ShardCall &a, int use_path) {
   {  // my hits to the root: its gather list (NVLink), or the host buffer every member has mapped (my own PCIe link)
     hg_hit *dst = a.mapped_hits ? a.mapped_hits : (hg_hit *)(p->win[a.root] + lay.gather);
     unsigned long long *total = (unsigned long long *)(p->win[a.root] + OFF_TOTAL);
-    peer_flush_kernel<<<64, 256, 0, c->stream>>>(W, total, dst, a.cap);
+    peer_flush_kernel<<<64, 256, 0, c->stream>>>(W, total, dst, a.cap, p->timeline);
     c->launches++;
     HG_CUDA(cudaGetLastError());
   }
@@ -711,6 +726,19 @@ extern "C" int hg_peer_stage_ms(hg_peer *p, float out_ms[4]) {
     out_ms[i] = -1.0f;
     if (p->ev_n >= i + 2) HG_CUDA(cudaEventElapsedTime(&out_ms[i], p->ev[i], p->ev[i + 1]));
   }
+  return HG_OK;
+}
+
+// Measurement support (HG_PEER_TIMELINE=1 in the environment when the group is created): globaltimer stamps (ns) of the
+// last sharded dist on this member - [0] first node, [1] dist kernel entry, [2] start flags seen, [3] ns CTA 0's producer
+// waited for rows, [4] last CTA done, [5] longest producer wait, [8..11] my chunk c pushed, [12] hit flush, [13] barrier
+// entry, [14] barrier exit, [16] barrier exit of the call before (all members leave a barrier within about a microsecond:
+// the common time base).  Synchronises the member's stream.
+extern "C" int hg_peer_timeline(hg_peer *p, unsigned long long out[32]) {
+  if (!p || !out) { hg_set_error("hg_peer_timeline: NULL argument"); return HG_E_INVALID; }
+  HG_CUDA(cudaSetDevice(p->ctx->device));
+  HG_CUDA(cudaStreamSynchronize(p->ctx->stream));
+  HG_CUDA(cudaMemcpy(out, p->win[p->rank] + OFF_DBG, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return HG_OK;
 }
 

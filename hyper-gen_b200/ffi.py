@@ -23,7 +23,7 @@ EXPORTS = [
     "hg_dist", "hg_dist_dev", "hg_dist_status", "hg_dist_last_path", "hg_dist_last_reason", "hg_sort_hits_dev", "hg_dist_sorted", "hg_dist_packed",
     "hg_group_create", "hg_group_destroy", "hg_group_size", "hg_group_ctx", "hg_group_sketch_fasta_batch", "hg_group_dist_packed",
     "hg_peer_window_need", "hg_peer_create", "hg_peer_connect", "hg_peer_create_local", "hg_peer_destroy", "hg_peer_rank",
-    "hg_peer_world", "hg_peer_barrier", "hg_peer_stage_ms", "hg_peer_plan_tiles", "hg_dist_sharded_dev", "hg_dist_sharded_hits", "hg_peer_hit_buffers",
+    "hg_peer_world", "hg_peer_barrier", "hg_peer_stage_ms", "hg_peer_timeline", "hg_peer_plan_tiles", "hg_dist_sharded_dev", "hg_dist_sharded_hits", "hg_peer_hit_buffers",
 ]
 HG_MAX_PEERS, HG_IPC_HANDLE_BYTES = 8, 64
 
@@ -118,6 +118,7 @@ def load() -> C.CDLL:
     L.hg_peer_barrier.restype = i32; L.hg_peer_barrier.argtypes = [vp]
     L.hg_peer_plan_tiles.restype = i32; L.hg_peer_plan_tiles.argtypes = [i32, i32, i32, i32, u32, vp, vp, u64, C.POINTER(u64)]
     L.hg_peer_stage_ms.restype = i32; L.hg_peer_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.hg_peer_timeline.restype = i32; L.hg_peer_timeline.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.hg_dist_sharded_dev.restype = i32
     L.hg_dist_sharded_dev.argtypes = [vp, vp, vp, u32, u32, vp, vp, vp, u32, u32, C.c_float, i32, i32, i32, u64, vp]
     L.hg_dist_sharded_hits.restype = i32; L.hg_dist_sharded_hits.argtypes = [vp, i32, vp, vp, u64, C.POINTER(u64)]
@@ -444,6 +445,12 @@ class Peer:
         out = (C.c_float * 4)()
         _check(load().hg_peer_stage_ms(self._h, out))
         return [float(x) for x in out]
+
+    def timeline(self):
+        """globaltimer stamps (ns) of the last sharded dist (HG_PEER_TIMELINE=1); see hg_peer_timeline"""
+        out = (C.c_uint64 * 32)()
+        _check(load().hg_peer_timeline(self._h, out))
+        return [int(x) for x in out]
 
     def hit_buffers(self, root: int = 0):
         dh, dc = C.c_void_p(), C.c_void_p()

@@ -323,6 +323,12 @@ HG_API int hg_peer_plan_tiles(int world, int rank, int symmetric, int path, uint
  * [0] operand form of this member's rows, [1] chunked push to the peers, [2] dist kernel (with its waits for the
  * peers' chunks), [3] final barrier.  Synchronises the member's stream. */
 HG_API int hg_peer_stage_ms(hg_peer *p, float out_ms[4]);
+/* Measurement support, with HG_PEER_TIMELINE=1 in the environment when the member is created: %globaltimer stamps (ns) the
+ * kernels of the last sharded dist left in the member's window: [0] first node, [1] dist kernel entry, [2] start flags seen,
+ * [3] ns CTA 0's producer waited for other members' rows, [4] last CTA done, [5] longest producer wait, [8..11] chunk c pushed,
+ * [12] hit flush, [13] barrier entry, [14] barrier exit, [16] barrier exit of the call before (the members' common time
+ * base).  Synchronises the member's stream.  No counterpart in the reference. */
+HG_API int hg_peer_timeline(hg_peer *p, unsigned long long out_ns[32]);
 /* the root's hit list and counter as this member addresses them (device pointers) */
 HG_API int hg_peer_hit_buffers(hg_peer *p, int root, hg_hit **d_hits, unsigned long long **d_count);
 
