@@ -119,53 +119,75 @@ __device__ __forceinline__ bool feed_poll(const hg_tile_feed &f, uint32_t need, 
   return (have & need) == need;
 }
 
-// One pusher warp's share of this member's chunk pushes (hg_push_plan); `me` of `n_pushers` warps in the grid.
-__device__ __forceinline__ void push_my_chunks(const hg_push_plan *__restrict__ pp, uint32_t me, uint32_t n_pushers) {
+// whole warp, converged: returns once every member in f.start_need has raised its start flag
+__device__ __forceinline__ void feed_wait_start(const hg_tile_feed &f) {
+  const uint32_t lane = threadIdx.x & 31;
+  const unsigned long long t0 = feed_ns();
+  for (;;) {
+    uint32_t v = f.seq;
+    if (lane < HG_MAX_PEERS) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.start + lane) : "memory");
+    const uint32_t have = __ballot_sync(0xffffffffu, (int32_t)(v - f.seq) >= 0);
+    if ((have & f.start_need) == f.start_need) break;
+    if (feed_ns() - t0 > f.timeout_ns) {
+      if (lane == 0) atomicExch(f.status, 1u);
+      break;
+    }
+    __nanosleep(200);
+  }
+}
+
+// One pusher warp's share of this member's pushes (hg_push_plan); `me` of `n_pushers` warps in the grid.
+__device__ __forceinline__ void push_my_units(const hg_push_plan *__restrict__ pp, uint32_t me, uint32_t n_pushers) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t seq = *pp->seq;
   const int rank = pp->rank, world = pp->world;
   const size_t tid = (size_t)me * 32 + lane, nth = (size_t)n_pushers * 32;
-  for (int ch = 0; ch < HG_PUSH_CHUNKS; ++ch) {
-    for (int k = 0; k < pp->n[ch]; ++k) {
-      const uint64_t off = pp->off[ch][k];
-      const uint32_t bytes = pp->bytes[ch][k];
+  for (int u = 0; u < pp->n_units; ++u) {
+    const int set = pp->unit_set[u];
+    const uint32_t dest = pp->unit_dest[u];
+    for (int k = 0; k < pp->n[set]; ++k) {
+      const uint64_t off = pp->off[set][k];
+      const uint32_t bytes = pp->bytes[set][k];
       if (((off | bytes) & 15) == 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(pp->win[rank] + off);
         const size_t n16 = bytes / 16;
-        for (size_t i = tid; i < n16; i += 12 * nth) {  // twelve loads in flight per lane, then their stores to every peer
+        for (size_t i = tid; i < n16; i += 12 * nth) {  // twelve loads in flight per lane, then their stores to the destinations
           uint4 v[12];
 #pragma unroll
-          for (int u = 0; u < 12; ++u)
-            if (i + u * nth < n16) v[u] = src[i + u * nth];
+          for (int t = 0; t < 12; ++t)
+            if (i + t * nth < n16) v[t] = src[i + t * nth];
 #pragma unroll
-          for (int u = 0; u < 12; ++u)
-            if (i + u * nth < n16)
+          for (int t = 0; t < 12; ++t)
+            if (i + t * nth < n16)
               for (int m = 0; m < world; ++m)
-                if (m != rank) reinterpret_cast<uint4 *>(pp->win[m] + off)[i + u * nth] = v[u];
+                if (dest >> m & 1u) reinterpret_cast<uint4 *>(pp->win[m] + off)[i + t * nth] = v[t];
         }
       } else {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(pp->win[rank] + off);
         for (size_t i = tid; i < bytes / 4; i += nth) {
           const uint32_t v = src[i];
           for (int m = 0; m < world; ++m)
-            if (m != rank) reinterpret_cast<uint32_t *>(pp->win[m] + off)[i] = v;
+            if (dest >> m & 1u) reinterpret_cast<uint32_t *>(pp->win[m] + off)[i] = v;
         }
       }
     }
-    // the last pusher warp of the grid through with this chunk raises its arrival flag in every other window
+    // the last pusher warp of the grid through with this unit raises its flag in the destination windows: one lane per
+    // window, all release stores in flight together (one after the other they cost an NVLink round trip each)
     __threadfence_system();
     __syncwarp();
-    if (lane == 0) {
-      const uint32_t prev = atomicAdd(pp->done + ch, 1u);
-      if (prev == n_pushers - 1) {
-        __threadfence_system();
-        pp->done[ch] = 0;
-        feed_stamp(pp->dbg, 8 + ch);
-        for (int m = 0; m < world; ++m)
-          if (m != rank) {
-            uint32_t *f = reinterpret_cast<uint32_t *>(pp->win[m] + pp->ready_off) + (rank * HG_PUSH_CHUNKS + ch);
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
-          }
+    uint32_t prev = 0;
+    if (lane == 0) prev = atomicAdd(pp->done + u, 1u);
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev == n_pushers - 1) {
+      __threadfence_system();
+      if (lane == 0) {
+        pp->done[u] = 0;
+        if (pp->unit_stamp[u] >= 0) feed_stamp(pp->dbg, pp->unit_stamp[u]);
+      }
+      if ((int)lane < world && (dest >> lane & 1u)) {
+        uint32_t *f = set == HG_PUSH_START_SET ? reinterpret_cast<uint32_t *>(pp->win[lane] + pp->start_off) + rank
+                                               : reinterpret_cast<uint32_t *>(pp->win[lane] + pp->ready_off) + (rank * HG_PUSH_CHUNKS + set);
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
       }
     }
     __syncwarp();

@@ -494,11 +494,11 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
 
   if (PUSHW > 0 && warp >= N1_THREADS / 32) {
     // ===== pusher warps (a member of several GPUs): my operand rows to every other window, chunk by chunk =====
-    hg::push_my_chunks(&plan, blockIdx.x * PUSHW + (uint32_t)(warp - N1_THREADS / 32), gridDim.x * PUSHW);
+    hg::push_my_units(&plan, blockIdx.x * PUSHW + (uint32_t)(warp - N1_THREADS / 32), gridDim.x * PUSHW);
   } else {
   uint32_t have = 0;  // arrival flags seen so far (warp 0)
   if (feed.start_need) {  // the other members' pre-pass statistics have arrived, the root has reset its hit counter
-    if (warp == 0) hg::feed_wait(feed, feed.start_need, have);
+    if (warp == 0) hg::feed_wait_start(feed);
     if (warp == 0 && blockIdx.x == 0 && lane == 0) hg::feed_stamp(feed.dbg, 2);
     asm volatile("bar.sync 2, %0;" ::"r"(N1_THREADS) : "memory");
   }

@@ -405,14 +405,14 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
 
   if (PUSHW > 0 && warp >= TC_THREADS / 32) {
     // ===== pusher warps (a member of several GPUs): my limb-plane rows to every other window, chunk by chunk =====
-    hg::push_my_chunks(&plan, blockIdx.x * PUSHW + (uint32_t)(warp - TC_THREADS / 32), gridDim.x * PUSHW);
+    hg::push_my_units(&plan, blockIdx.x * PUSHW + (uint32_t)(warp - TC_THREADS / 32), gridDim.x * PUSHW);
   } else {
   PairTiles tiles;
   tiles.init(ep, feed);
   bool valid = tiles.advance(pair);
   uint32_t have = 0;  // arrival flags seen so far (the producer warp)
   if (feed.start_need) {  // a member of several GPUs: nothing is appended before the root has reset its hit counter
-    if (warp == 0) hg::feed_wait(feed, feed.start_need, have);
+    if (warp == 0) hg::feed_wait_start(feed);
     if (warp == 0 && blockIdx.x == 0 && lane == 0) hg::feed_stamp(feed.dbg, 2);
     asm volatile("bar.sync 2, %0;" ::"r"(TC_THREADS) : "memory");
   }

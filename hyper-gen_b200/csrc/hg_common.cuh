@@ -235,23 +235,35 @@ int hg_launch_dist_simt(hg_ctx *ctx, const int16_t *d_ref, const int32_t *d_ref_
 // arithmetic enumeration, ordered by when the rows they read arrive, and its TMA producer waits for the arrival flags
 // of those rows: the operand exchange over NVLink overlaps the tile computation.
 // What a multi-GPU member pushes to the other members WHILE its dist kernel runs: the kernel carries extra "pusher"
-// warps that copy this member's operand rows (byte ranges of its window, in HG_PUSH_CHUNKS chunks) to the same offsets
-// of every other window with 16-byte stores over NVLink and raise the chunk's arrival flag there when all pusher warps
-// of the grid are through with it.  One kernel computes tiles and moves operands; nothing has to be co-scheduled.
-// TPCs a multi-GPU dist launch leaves free when this member's chunk pushes run as a kernel of their own NEXT TO it (on a
+// warps that copy this member's operand rows (byte ranges of its window) to the same offsets of other windows with
+// 16-byte stores over NVLink.  The work is a list of UNITS, done in order: unit u sends one SET of byte ranges (set
+// 0..3 = a chunk of this member's rows, set 4 = what every member needs before it starts: pre-pass statistics, outlier
+// entries) to the members in its destination mask and then raises a flag in those windows - the chunk's arrival flag,
+// or this member's start flag - when all pusher warps of the grid are through with it.  All-vs-all on three or more
+// GPUs sends a member's rows only to the floor(N/2) members that compute tiles with them, nearest ring neighbour first
+// (csrc/peer.cu); otherwise every chunk goes to everybody.  One kernel computes tiles and moves operands.
+// TPCs a multi-GPU dist launch leaves free when this member's pushes run as kernels of their own NEXT TO it (on a
 // second, lower-priority stream): the dist kernel is resident and waiting for the other members' chunks while they run, so
 // the pushes must never need one of its SMs.
 #define HG_PEER_RESERVED_TPCS 8
 #define HG_PUSH_CHUNKS 4
-#define HG_PUSH_RANGES 10
+#define HG_PUSH_SETS (HG_PUSH_CHUNKS + 1)
+#define HG_PUSH_START_SET HG_PUSH_CHUNKS
+#define HG_PUSH_RANGES 8
+#define HG_PUSH_UNITS (1 + HG_PUSH_CHUNKS * (HG_MAX_PEERS / 2))
 struct hg_push_plan {
   uint8_t *win[HG_MAX_PEERS];  // every member's window as this member addresses it
   int rank, world;
-  uint64_t off[HG_PUSH_CHUNKS][HG_PUSH_RANGES];   // byte ranges (relative to the window base), 4-byte granular
-  uint32_t bytes[HG_PUSH_CHUNKS][HG_PUSH_RANGES];
-  int n[HG_PUSH_CHUNKS];
-  uint32_t *done;       // HG_PUSH_CHUNKS counters in this member's window: pusher warps through with the chunk
+  uint64_t off[HG_PUSH_SETS][HG_PUSH_RANGES];   // byte ranges (relative to the window base), 4-byte granular
+  uint32_t bytes[HG_PUSH_SETS][HG_PUSH_RANGES];
+  int n[HG_PUSH_SETS];
+  int n_units;
+  uint8_t unit_set[HG_PUSH_UNITS];   // which set unit u sends
+  uint8_t unit_dest[HG_PUSH_UNITS];  // bit m: to member m
+  int8_t unit_stamp[HG_PUSH_UNITS];  // timeline stamp this unit's completion writes (-1: none)
+  uint32_t *done;       // HG_PUSH_UNITS counters in this member's window: pusher warps through with the unit
   uint64_t ready_off;   // offset of the arrival flags in every window; chunk c raises flag rank * HG_PUSH_CHUNKS + c
+  uint64_t start_off;   // offset of the start flags in every window; the start set raises flag `rank`
   const uint32_t *seq;  // the call's sequence number lives in device memory (the launch sequence is replayed as a CUDA graph)
   unsigned long long *dbg;  // timeline stamps (HG_PEER_TIMELINE=1, hg_peer_timeline), else NULL
 };
@@ -261,7 +273,9 @@ struct hg_tile_feed {
   const uint32_t *ready;    // 32 arrival flags (in this member's window); a flag is set when (int)(flag - seq) >= 0
   const uint32_t *seq_ptr;  // where the call's sequence number lives (device memory: the launch sequence is replayed as a CUDA graph)
   uint32_t seq;             // filled in by the kernel from *seq_ptr
-  uint32_t start_need;      // flags to wait for before the kernel reads anything (the members' pre-pass statistics)
+  const uint32_t *start;    // HG_MAX_PEERS start flags (in this member's window): member m's start set has landed
+  uint32_t start_need;      // bit m: wait for member m's start flag before anything is read (its pre-pass statistics and
+                            // outlier entries are here; the root has reset its gather counter)
   uint32_t *status;         // set to 1 if a wait times out (the host turns it into an error)
   unsigned long long timeout_ns;
   int reserve_tpcs;         // TPCs the launch leaves free (for the push kernel running next to it)

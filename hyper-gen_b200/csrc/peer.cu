@@ -6,18 +6,22 @@
 // (one process per GPU: cudaIpc handles; one process driving several GPUs: peer access).  A sharded
 // dist then needs no collective library on its data path, and the exchange overlaps the compute:
 //   1. each member turns ITS rows into the operand form of the tensor kernel (one s8 plane + per-row
-//      constants, or two s8 limb planes) inside its own window and PUSHES them, in 4 chunks, with plain
-//      16-byte stores over NVLink to the same offsets of every other window - the "all-gather" of what
-//      the kernel actually reads: 1 byte per element instead of the 2 of the int16 rows, no pre-pass
-//      replicated on every GPU.  The last CTA of a chunk's push raises that chunk's ARRIVAL FLAG in
-//      every window (fence + st.release.sys);
-//   2. every member launches the dist kernel at once.  Its tiles come from a host-built list: the
-//      non-empty tiles of the all-vs-all dealt round-robin (tile t to member t mod N - balances the
-//      triangle to within one tile), each member's share ordered by when the rows it reads arrive (own
-//      rows first, then chunk 0 of everybody, chunk 1 ...).  The kernel's TMA producer waits for the
-//      arrival flags a tile needs (ld.acquire.sys on its own window, bounded) - so tiles are computed
-//      while later chunks are still crossing NVLink.  ref x query: the member's own (resident) ref rows
-//      against all queries, same mechanism on the query side;
+//      constants, or two s8 limb planes) inside its own window and PUSHES them, in up to 4 chunks of
+//      about 2 MB or more, with plain 16-byte stores over NVLink to the same offsets of other windows:
+//      1 byte per element instead of the 2 of the int16 rows, no pre-pass replicated on every GPU.
+//      The last pusher warp through with a chunk raises that chunk's ARRIVAL FLAG in the destination
+//      windows (fence + st.release.sys, one lane per window);
+//   2. every member launches the dist kernel at once.  Its tiles come from a host-built list.
+//      All-vs-all on 3 or more GPUs with row blocks that are multiples of 256 rows ("ring"): the
+//      block pair (a, b) is computed by the member from which the other block is at most N/2 steps
+//      AHEAD on the ring (the pair exactly N/2 apart is split tile by tile), so a member's rows go to
+//      floor(N/2) members instead of N - 1 - half the NVLink bytes - nearest neighbour first, and a
+//      member's tiles are ordered own block, block + 1, block + 2 ... as those arrive.  Otherwise the
+//      non-empty tiles are dealt round-robin (tile t to member t mod N), every chunk goes to everybody,
+//      and a member's share is ordered own rows, chunk 0 of everybody, chunk 1 ...  The kernel's TMA
+//      producer waits for the arrival flags a tile needs (ld.acquire.sys on its own window, bounded) -
+//      tiles are computed while later chunks are still crossing NVLink.  ref x query: the member's own
+//      (resident) ref rows against all queries, same mechanism on the query side;
 //   3. hits are appended straight into the ROOT's hit list - its window, or a host buffer every member
 //      has mapped - with one atomic on the root's counter per evaluated candidate list;
 //   4. one flag barrier at the end (st.release.sys / ld.acquire.sys, bounded spin); the root's stream
@@ -42,9 +46,12 @@ constexpr size_t OFF_TOTAL = 136;    // u64: hits of all members gathered so far
 constexpr size_t OFF_STATS_Q = 256;  // u32[HG_MAX_PEERS][4]: pre-pass statistics of the gathered (query) matrix, one set per member
 constexpr size_t OFF_STATS_R = 384;  // u32[HG_MAX_PEERS][4]: ... of the members' own ref rows (ref x query)
 constexpr size_t OFF_READY = 512;    // u32[32]: arrival flags, flag m * 4 + c = sequence number of the last call for which chunk c of member m's rows is here
-constexpr size_t OFF_DONE = 640;     // u32[4]: CTAs of this member's chunk pushes that have finished (local use)
+constexpr size_t OFF_DONE = 640;     // u32[HG_PUSH_UNITS]: pusher warps / CTAs through with push unit u (local use)
 constexpr size_t OFF_DBG = 768;      // u64[32]: timeline stamps of the last sharded dist (globaltimer ns; HG_PEER_TIMELINE=1)
-constexpr int N_CHUNKS = 4;
+constexpr size_t OFF_START = 1024;   // u32[HG_MAX_PEERS]: start flags, flag m = sequence number of the last call whose start set of member m is here
+constexpr int N_CHUNKS = HG_PUSH_CHUNKS;
+constexpr uint64_t CHUNK_TARGET_BYTES = 2u << 20;  // a member's block is cut into chunks of at least about this much
+static_assert(OFF_DONE + 4 * HG_PUSH_UNITS <= OFF_DBG, "header layout");
 constexpr size_t OFF_HITS = 4096;    // hg_hit[cap]
 constexpr int32_t TC_MAX_ABS = 8127; // |x| <= 8127 splits into two s8 limbs
 
@@ -131,9 +138,9 @@ __global__ void peer_flush_kernel(uint8_t *W, unsigned long long *root_total, hg
 
 // Copies byte ranges of this member's window to the same offsets of every other window.
 struct PushRange { uint64_t off, bytes; };  // 4-byte granular; ranges that are 16-byte aligned go as uint4
-struct PushArgs { PushRange r[10]; int n; };
+struct PushArgs { PushRange r[HG_PUSH_RANGES]; int n; };
 
-__global__ void __launch_bounds__(256) peer_push_kernel(PeerPtrs w, int rank, int world, PushArgs a, uint32_t flag_index, uint32_t *done) {
+__global__ void __launch_bounds__(256) peer_push_kernel(PeerPtrs w, int rank, int world, PushArgs a, uint32_t dest, uint64_t flag_off, uint32_t *done) {
   const uint32_t seq = *reinterpret_cast<const uint32_t *>(w.p[rank] + OFF_SEQ);
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
   for (int k = 0; k < a.n; ++k) {
@@ -150,31 +157,32 @@ __global__ void __launch_bounds__(256) peer_push_kernel(PeerPtrs w, int rank, in
         for (int u = 0; u < 4; ++u)
           if (i + u * nth < n16)
             for (int m = 0; m < world; ++m)
-              if (m != rank) reinterpret_cast<uint4 *>(w.p[m] + off)[i + u * nth] = v[u];
+              if (dest >> m & 1u) reinterpret_cast<uint4 *>(w.p[m] + off)[i + u * nth] = v[u];
       }
     } else {
       const uint32_t *src = reinterpret_cast<const uint32_t *>(w.p[rank] + off);
       for (size_t i = tid; i < bytes / 4; i += nth) {
         const uint32_t v = src[i];
         for (int m = 0; m < world; ++m)
-          if (m != rank) reinterpret_cast<uint32_t *>(w.p[m] + off)[i] = v;
+          if (dest >> m & 1u) reinterpret_cast<uint32_t *>(w.p[m] + off)[i] = v;
       }
     }
   }
-  // the last CTA to finish raises this chunk's arrival flag in every other window
+  // the last CTA to finish raises this chunk's arrival flag in every other window (one thread per window: the release
+  // stores are in flight together)
+  __shared__ uint32_t s_last;
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t prev = atomicAdd(done, 1u);
-    if (prev == gridDim.x - 1) {
-      __threadfence_system();
-      *done = 0;
-      for (int m = 0; m < world; ++m)
-        if (m != rank) {
-          uint32_t *f = reinterpret_cast<uint32_t *>(w.p[m] + OFF_READY) + flag_index;
-          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
-        }
-    }
+    s_last = prev == gridDim.x - 1;
+    if (s_last) *done = 0;
+  }
+  __syncthreads();
+  if (s_last && (int)threadIdx.x < world && (dest >> threadIdx.x & 1u)) {
+    __threadfence_system();
+    uint32_t *f = reinterpret_cast<uint32_t *>(w.p[threadIdx.x] + flag_off);
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
   }
 }
 
@@ -202,7 +210,7 @@ ShardLayout make_layout(int world, uint32_t n_total, uint32_t hv_d, uint64_t cap
 
 struct TileKey {  // what a cached tile list was built for
   int sym, path;
-  uint32_t n_ref, n_qry, tr, tc;
+  uint32_t n_ref, n_qry, tr, tc, hv_d;
   uint32_t qb[HG_MAX_PEERS + 1];
 };
 
@@ -215,6 +223,7 @@ struct hg_peer {
   bool opened[HG_MAX_PEERS] = {};
   bool connected = false;
   unsigned long long timeout_ns = 0;
+  int last_ring = 0;  // the last sharded dist used the ring ownership
   int timeline = 0;  // HG_PEER_TIMELINE=1: the kernels of a sharded dist stamp globaltimer values into the window (hg_peer_timeline)
   uint8_t *h_hdr = nullptr;  // pinned copy of window bytes [OFF_STATUS, OFF_STATUS + 128): status word and hit counters of the
                              // last call, written by the call's last node
@@ -392,15 +401,16 @@ extern "C" int hg_peer_barrier(hg_peer *p) {
   return peer_barrier(p);
 }
 
-// Stand-alone push of one chunk (a member that has rows to contribute but no tile to compute - otherwise the dist
-// kernel's pusher warps do this, see hg_push_plan): the ranges, then arrival flag `flag_index` in every other window
-static int peer_push(hg_peer *p, const PushArgs &a, uint32_t flag_index, cudaStream_t stream, unsigned max_blocks) {
+// Stand-alone push of one unit (a member that has rows to contribute but no tile to compute - otherwise the dist
+// kernel's pusher warps do this, see hg_push_plan): the ranges to the members in `dest`, then the flag at byte offset
+// `flag_off` of those windows
+static int peer_push(hg_peer *p, const PushArgs &a, uint32_t dest, uint64_t flag_off, int unit, cudaStream_t stream, unsigned max_blocks) {
   if (p->world == 1) return HG_OK;
   uint64_t bytes = 0;
   for (int k = 0; k < a.n; ++k) bytes += a.r[k].bytes;
   const unsigned blocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(bytes / (16 * 256 * 4), 1), (uint64_t)max_blocks);
-  uint32_t *done = reinterpret_cast<uint32_t *>(p->win[p->rank] + OFF_DONE) + (flag_index % N_CHUNKS);
-  peer_push_kernel<<<blocks, 256, 0, stream>>>(peer_ptrs(p), p->rank, p->world, a, flag_index, done);
+  uint32_t *done = reinterpret_cast<uint32_t *>(p->win[p->rank] + OFF_DONE) + unit;
+  peer_push_kernel<<<blocks, 256, 0, stream>>>(peer_ptrs(p), p->rank, p->world, a, dest, flag_off, done);
   p->ctx->launches++;
   HG_CUDA(cudaGetLastError());
   return HG_OK;
@@ -419,19 +429,65 @@ struct ShardCall {
   uint32_t n_qry_total(int world) const { return qb[world]; }
 };
 
+// How the members' blocks of the gathered matrix are cut into chunks and who receives them: a pure function of the
+// call's shape, so every member derives the same plan.
+struct XPlan {
+  int world, sym, ring, path;
+  uint32_t hv_d;
+  int n_chunks[HG_MAX_PEERS];
+  uint32_t qb[HG_MAX_PEERS + 1];
+};
+XPlan make_xplan(int world, int symmetric, int path, uint32_t hv_d, const uint32_t *qb) {
+  XPlan x = {};
+  x.world = world; x.sym = symmetric; x.path = path; x.hv_d = hv_d;
+  bool aligned = true, nonempty = true;
+  for (int m = 0; m <= world; ++m) x.qb[m] = qb[m];
+  for (int m = 0; m < world; ++m) {
+    const uint64_t rows = qb[m + 1] - qb[m], bytes = rows * hv_d * (path == 3 ? 1 : 2);
+    x.n_chunks[m] = (int)std::min<uint64_t>(std::max<uint64_t>((bytes + CHUNK_TARGET_BYTES - 1) / CHUNK_TARGET_BYTES, 1), N_CHUNKS);
+    if (rows == 0) nonempty = false;
+    if (m > 0 && qb[m] % 256 != 0) aligned = false;  // a tile (256 rows x 128 or 256 columns) lies inside one block on either side
+  }
+  x.ring = symmetric && world >= 3 && aligned && nonempty && !getenv("HG_PEER_NO_RING");
+  return x;
+}
 // chunk c of member m's block: rows [chunk_lo(c), chunk_lo(c + 1))
-inline uint32_t chunk_lo(const uint32_t *qb, int m, int c) {
-  if (c >= N_CHUNKS) return qb[m + 1];
-  return qb[m] + (uint32_t)(((uint64_t)(qb[m + 1] - qb[m]) * c / N_CHUNKS) & ~3ull);
+inline uint32_t chunk_lo(const XPlan &x, int m, int c) {
+  if (c >= x.n_chunks[m]) return x.qb[m + 1];
+  return x.qb[m] + (uint32_t)(((uint64_t)(x.qb[m + 1] - x.qb[m]) * c / x.n_chunks[m]) & ~3ull);
+}
+// the members that receive member s's rows
+inline uint32_t dest_mask(const XPlan &x, int s) {
+  uint32_t d = 0;
+  if (x.ring) for (int k = 1; k <= x.world / 2; ++k) d |= 1u << ((s - k + x.world) % x.world);
+  else for (int m = 0; m < x.world; ++m) if (m != s) d |= 1u << m;
+  return d;
+}
+inline int block_of(const XPlan &x, uint64_t row) {
+  int m = 0;
+  while (m + 1 < x.world && row >= x.qb[m + 1]) ++m;
+  return m;
+}
+// ring: who computes a tile whose rows lie in block bi and whose columns lie in block bj >= bi
+inline int ring_owner(const XPlan &x, int bi, int bj, uint32_t R, uint32_t C) {
+  const int d = bj - bi;
+  if (2 * d < x.world) return bi;         // bj is d <= N/2 steps ahead of bi
+  if (2 * d > x.world) return bj;         // bi is N - d < N/2 steps ahead of bj
+  return ((R + C) & 1u) ? bi : bj;        // exactly opposite: both hold the other's block, the tiles alternate
+}
+// position of (member m, chunk c) in the order in which chunks arrive at member r
+inline uint32_t arrival_pos(const XPlan &x, int r, int m, int c) {
+  if (x.ring) return (uint32_t)(((m - r + x.world) % x.world - 1) * N_CHUNKS + c);
+  return (uint32_t)c;
 }
 
 // arrival flags (other members' chunks) that rows [x0, x1) of the gathered matrix depend on
-uint32_t need_mask(const uint32_t *qb, int world, int rank, uint64_t x0, uint64_t x1) {
+uint32_t need_mask(const XPlan &x, int rank, uint64_t x0, uint64_t x1) {
   uint32_t m_ = 0;
-  for (int m = 0; m < world; ++m) {
-    if (m == rank || qb[m + 1] <= x0 || qb[m] >= x1) continue;
-    for (int c = 0; c < N_CHUNKS; ++c) {
-      const uint64_t lo = chunk_lo(qb, m, c), hi = chunk_lo(qb, m, c + 1);
+  for (int m = 0; m < x.world; ++m) {
+    if (m == rank || x.qb[m + 1] <= x0 || x.qb[m] >= x1) continue;
+    for (int c = 0; c < x.n_chunks[m]; ++c) {
+      const uint64_t lo = chunk_lo(x, m, c), hi = chunk_lo(x, m, c + 1);
       if (lo < hi && lo < x1 && hi > x0) m_ |= 1u << (m * N_CHUNKS + c);
     }
   }
@@ -462,10 +518,11 @@ static int shard_check(hg_peer *p, const ShardCall &a) {
   return HG_OK;
 }
 
-// Member `rank`'s tiles for a key (pure host logic): the non-empty tiles of the all-vs-all dealt round-robin over the
-// members (ref x query: every tile of the member's own ref rows), each with the mask of arrival flags it reads, ordered
-// by when those arrive.
+// Member `rank`'s tiles for a key (pure host logic): its share of the non-empty tiles of the all-vs-all (see the file
+// header: ring ownership, or dealt round-robin; ref x query: every tile of the member's own ref rows), each with the
+// mask of arrival flags it reads, ordered by when those arrive.
 static void plan_tiles(const TileKey &k, int world, int rank, std::vector<uint2> &out) {
+  const XPlan x = make_xplan(world, k.sym, k.path, k.hv_d, k.qb);
   const uint32_t gx = (k.n_qry + k.tc - 1) / k.tc, gy = (k.n_ref + k.tr - 1) / k.tr;
   struct T { uint2 e; uint32_t key; };
   std::vector<T> v;
@@ -475,26 +532,30 @@ static void plan_tiles(const TileKey &k, int world, int rank, std::vector<uint2>
     uint32_t c0 = 0;
     if (k.sym) c0 = (uint32_t)std::min<uint64_t>(((uint64_t)k.tr * R + 1) / k.tc, gx);
     for (uint32_t C = c0; C < gx; ++C, ++t) {
-      if (k.sym && (int)(t % (uint64_t)world) != rank) continue;
-      uint32_t need = need_mask(k.qb, world, rank, (uint64_t)C * k.tc, std::min<uint64_t>((uint64_t)(C + 1) * k.tc, k.n_qry));
-      if (k.sym) need |= need_mask(k.qb, world, rank, (uint64_t)R * k.tr, std::min<uint64_t>((uint64_t)(R + 1) * k.tr, k.n_ref));
+      if (k.sym) {
+        const int owner = x.ring ? ring_owner(x, block_of(x, (uint64_t)R * k.tr), block_of(x, (uint64_t)C * k.tc), R, C) : (int)(t % (uint64_t)world);
+        if (owner != rank) continue;
+      }
+      uint32_t need = need_mask(x, rank, (uint64_t)C * k.tc, std::min<uint64_t>((uint64_t)(C + 1) * k.tc, k.n_qry));
+      if (k.sym) need |= need_mask(x, rank, (uint64_t)R * k.tr, std::min<uint64_t>((uint64_t)(R + 1) * k.tr, k.n_ref));
       uint32_t key = 0;
-      for (int b = 0; b < 32; ++b) if (need >> b & 1u) key = std::max<uint32_t>(key, 1 + b % N_CHUNKS);
+      for (int b = 0; b < 32; ++b) if (need >> b & 1u) key = std::max<uint32_t>(key, 1 + arrival_pos(x, rank, b / N_CHUNKS, b % N_CHUNKS));
       v.push_back({make_uint2(R | (C << 16), need), key});
     }
   }
   // all-vs-all: tiles that read only my own rows first, then in the order the other members' chunks arrive (row-major
   // within each group).  ref x query stays row-major: the queries are few and arrive early, while a column-wise sweep
   // would stream my whole ref plane from HBM once per query tile column.
-  if (k.sym && !getenv("HG_PEER_NOSORT")) std::stable_sort(v.begin(), v.end(), [](const T &x, const T &y) { return x.key < y.key; });
+  if (k.sym && !getenv("HG_PEER_NOSORT")) std::stable_sort(v.begin(), v.end(), [](const T &a, const T &b) { return a.key < b.key; });
   out.resize(v.size());
   for (size_t i = 0; i < v.size(); ++i) out[i] = v[i].e;
 }
 
-static TileKey tile_key(int world, int symmetric, int use_path, uint32_t n_ref, const uint32_t *qb) {
+static TileKey tile_key(int world, int symmetric, int use_path, uint32_t hv_d, uint32_t n_ref, const uint32_t *qb) {
   TileKey k = {};
   k.sym = symmetric;
   k.path = use_path;
+  k.hv_d = hv_d;
   k.n_ref = symmetric ? qb[world] : n_ref;
   k.n_qry = qb[world];
   if (use_path == 3) hg_narrow_tile_shape(&k.tr, &k.tc); else hg_tc_tile_shape(&k.tr, &k.tc);
@@ -504,7 +565,7 @@ static TileKey tile_key(int world, int symmetric, int use_path, uint32_t n_ref, 
 
 // This member's tiles for kernel `use_path` (3: 256 x 256 tiles, 2: 256 x 128), cached while the shapes stay the same.
 static void build_tiles(hg_peer *p, const ShardCall &a, int use_path) {
-  const TileKey k = tile_key(p->world, a.symmetric, use_path, a.n_ref_local, a.qb);
+  const TileKey k = tile_key(p->world, a.symmetric, use_path, a.hv_d, a.n_ref_local, a.qb);
   if (p->tiles_valid && memcmp(&k, &p->tiles_key, sizeof(k)) == 0) return;
   p->tiles_key = k;
   p->tiles_valid = true;
@@ -514,16 +575,49 @@ static void build_tiles(hg_peer *p, const ShardCall &a, int use_path) {
 
 // The plan above without a GPU (host logic only; tests): tiles_out receives (tile row | tile column << 16, need mask)
 // pairs; *n_tiles the count (HG_E_CAPACITY if it exceeds cap).
-extern "C" int hg_peer_plan_tiles(int world, int rank, int symmetric, int path, uint32_t n_ref_local, const uint32_t *qry_bounds,
-                                  uint32_t *tiles_out, uint64_t cap, uint64_t *n_tiles) {
-  if (!qry_bounds || !n_tiles || world < 1 || world > HG_MAX_PEERS || rank < 0 || rank >= world || (path != 2 && path != 3)) {
+extern "C" int hg_peer_plan_tiles(int world, int rank, int symmetric, int path, uint32_t hv_d, uint32_t n_ref_local,
+                                  const uint32_t *qry_bounds, uint32_t *tiles_out, uint64_t cap, uint64_t *n_tiles) {
+  if (!qry_bounds || !n_tiles || world < 1 || world > HG_MAX_PEERS || rank < 0 || rank >= world || (path != 2 && path != 3) || hv_d == 0) {
     hg_set_error("hg_peer_plan_tiles: bad argument"); return HG_E_INVALID;
   }
   std::vector<uint2> v;
-  plan_tiles(tile_key(world, symmetric, path, n_ref_local, qry_bounds), world, rank, v);
+  plan_tiles(tile_key(world, symmetric, path, hv_d, n_ref_local, qry_bounds), world, rank, v);
   *n_tiles = v.size();
   if (v.size() > cap || (!tiles_out && !v.empty())) { hg_set_error("hg_peer_plan_tiles: %zu tiles", v.size()); return HG_E_CAPACITY; }
   for (size_t i = 0; i < v.size(); ++i) { tiles_out[2 * i] = v[i].x; tiles_out[2 * i + 1] = v[i].y; }
+  return HG_OK;
+}
+
+// The exchange plan of member `rank` without a GPU (host logic only; tests): chunk_rows_out[0 .. HG_PUSH_CHUNKS] = the
+// row boundaries of its chunks (unused chunks are empty), units_out = (chunk index or HG_PUSH_CHUNKS for the start
+// set, destination mask) per push unit in sending order, *ring = 1 if rows go to ring neighbours only.
+static void plan_units(const XPlan &x, int rank, bool have_rows, std::vector<std::pair<int, uint32_t>> &units) {
+  units.clear();
+  uint32_t all = 0;
+  for (int m = 0; m < x.world; ++m) if (m != rank) all |= 1u << m;
+  if (x.world > 1) units.push_back({HG_PUSH_START_SET, all});
+  if (!have_rows || x.world == 1) return;
+  if (x.ring) {
+    for (int d = 1; d <= x.world / 2; ++d)
+      for (int c = 0; c < x.n_chunks[rank]; ++c) units.push_back({c, 1u << ((rank - d + x.world) % x.world)});
+  } else {
+    for (int c = 0; c < x.n_chunks[rank]; ++c) units.push_back({c, all});
+  }
+}
+extern "C" int hg_peer_plan_push(int world, int rank, int symmetric, int path, uint32_t hv_d, const uint32_t *qry_bounds,
+                                 uint32_t chunk_rows_out[HG_PUSH_CHUNKS + 1], uint32_t *units_out, uint64_t cap, uint64_t *n_units,
+                                 int *ring) {
+  if (!qry_bounds || !n_units || !chunk_rows_out || world < 1 || world > HG_MAX_PEERS || rank < 0 || rank >= world || (path != 2 && path != 3) || hv_d == 0) {
+    hg_set_error("hg_peer_plan_push: bad argument"); return HG_E_INVALID;
+  }
+  const XPlan x = make_xplan(world, symmetric, path, hv_d, qry_bounds);
+  for (int c = 0; c <= N_CHUNKS; ++c) chunk_rows_out[c] = chunk_lo(x, rank, c);
+  std::vector<std::pair<int, uint32_t>> u;
+  plan_units(x, rank, qry_bounds[rank + 1] > qry_bounds[rank], u);
+  *n_units = u.size();
+  if (ring) *ring = x.ring;
+  if (u.size() > cap || (!units_out && !u.empty())) { hg_set_error("hg_peer_plan_push: %zu units", u.size()); return HG_E_CAPACITY; }
+  for (size_t i = 0; i < u.size(); ++i) { units_out[2 * i] = (uint32_t)u[i].first; units_out[2 * i + 1] = u[i].second; }
   return HG_OK;
 }
 
@@ -592,11 +686,10 @@ static int shard_enqueue(hg_peer *p, const ShardCall &a, int use_path) {
     feed.status = (uint32_t *)(W + OFF_STATUS);
     feed.timeout_ns = p->timeout_ns;
     feed.dbg = p->timeline ? reinterpret_cast<unsigned long long *>(W + OFF_DBG) : nullptr;
-    if (use_path == 3)  // the pre-pass statistics of every other member travel with its chunk 0
-      for (int m = 0; m < world; ++m) if (m != rank) feed.start_need |= 1u << (m * N_CHUNKS);
-    // nobody moves hits to the root before the root has reset its gather counter for this call: the root raises its
-    // chunk-0 flag (empty chunk or not) after its tick kernel, in stream order
-    if (rank != a.root) feed.start_need |= 1u << (a.root * N_CHUNKS);
+    // every other member's start set has landed: its pre-pass statistics and outlier entries (single plane), and - the
+    // root raises its start flag after its tick kernel, in stream order - the root has reset its gather counter
+    feed.start = (const uint32_t *)(W + OFF_START);
+    for (int m = 0; m < world; ++m) if (m != rank) feed.start_need |= 1u << m;
   }
   if (nl) HG_CUDA(cudaMemcpyAsync(normW + r0, a.d_qry_norm, (size_t)nl * 4, cudaMemcpyDeviceToDevice, c->stream));
   hg_narrow_mat Qn, Rn;
@@ -625,40 +718,52 @@ static int shard_enqueue(hg_peer *p, const ShardCall &a, int use_path) {
     }
   }
   PEER_PROF(p, 1);
-  // ---- what I push to the others, in chunks; every chunk raises its arrival flag in the other windows (also when it is
-  //      empty).  The dist kernel below carries pusher warps that do it while the tiles are computed; a member without a
-  //      tile to compute pushes with a stand-alone kernel instead ----
+  // ---- what I push to the others (hg_push_plan): the start set to everybody, then my rows chunk by chunk to the members
+  //      that compute with them.  The dist kernel below carries pusher warps that do it while the tiles are computed; a
+  //      member without a tile to compute pushes with stand-alone kernels instead ----
+  const XPlan xp = make_xplan(world, a.symmetric, use_path, a.hv_d, a.qb);
+  p->last_ring = xp.ring;
   hg_push_plan plan = {};
   for (int m = 0; m < world; ++m) plan.win[m] = p->win[m];
   plan.rank = rank;
   plan.world = world;
   plan.done = reinterpret_cast<uint32_t *>(W + OFF_DONE);
   plan.ready_off = OFF_READY;
+  plan.start_off = OFF_START;
   plan.seq = (const uint32_t *)(W + OFF_SEQ);
   plan.dbg = p->timeline ? reinterpret_cast<unsigned long long *>(W + OFF_DBG) : nullptr;
-  for (int ch = 0; ch < N_CHUNKS && world > 1; ++ch) {
-    const uint64_t lo = chunk_lo(a.qb, rank, ch), n = chunk_lo(a.qb, rank, ch + 1) - lo;
-    auto add = [&](uint64_t off, uint64_t bytes) {
-      if (bytes) { plan.off[ch][plan.n[ch]] = off; plan.bytes[ch][plan.n[ch]] = (uint32_t)bytes; plan.n[ch]++; }
-    };
-    add(lay.norm + lo * 4, n * 4);
-    add(lay.plane + lo * a.hv_d, n * a.hv_d);
-    if (use_path == 3) {
-      for (int k = 0; k < 5; ++k) add(lay.arrays + ((uint64_t)k * n_total + lo) * 4, n * 4);
-      if (ch == 0) {  // the statistics and the outlier entries of ALL my rows (the pre-pass above is complete) go first
-        if (nl) add(lay.entries + (uint64_t)rank * lay.set_cap * 4, (uint64_t)lay.set_cap * 4);
-        add(OFF_STATS_Q + 16 * (uint64_t)rank, 16);
-        if (!a.symmetric) add(OFF_STATS_R + 16 * (uint64_t)rank, 16);
-      }
-    } else {
-      add(lay.plane + ((uint64_t)n_total + lo) * a.hv_d, n * a.hv_d);
+  auto add = [&](int set, uint64_t off, uint64_t bytes) {
+    if (bytes) { plan.off[set][plan.n[set]] = off; plan.bytes[set][plan.n[set]] = (uint32_t)bytes; plan.n[set]++; }
+  };
+  for (int ch = 0; ch < xp.n_chunks[rank] && world > 1; ++ch) {
+    const uint64_t lo = chunk_lo(xp, rank, ch), n = chunk_lo(xp, rank, ch + 1) - lo;
+    add(ch, lay.norm + lo * 4, n * 4);
+    add(ch, lay.plane + lo * a.hv_d, n * a.hv_d);
+    if (use_path == 3) for (int k = 0; k < 5; ++k) add(ch, lay.arrays + ((uint64_t)k * n_total + lo) * 4, n * 4);
+    else add(ch, lay.plane + ((uint64_t)n_total + lo) * a.hv_d, n * a.hv_d);
+  }
+  if (use_path == 3 && world > 1) {  // the statistics and the outlier entries of ALL my rows (the pre-pass above is complete)
+    if (nl) add(HG_PUSH_START_SET, lay.entries + (uint64_t)rank * lay.set_cap * 4, (uint64_t)lay.set_cap * 4);
+    add(HG_PUSH_START_SET, OFF_STATS_Q + 16 * (uint64_t)rank, 16);
+    if (!a.symmetric) add(HG_PUSH_START_SET, OFF_STATS_R + 16 * (uint64_t)rank, 16);
+  }
+  {
+    std::vector<std::pair<int, uint32_t>> units;
+    plan_units(xp, rank, nl > 0, units);
+    plan.n_units = (int)units.size();
+    for (int u = 0; u < plan.n_units; ++u) {
+      plan.unit_set[u] = (uint8_t)units[u].first;
+      plan.unit_dest[u] = (uint8_t)units[u].second;
+      plan.unit_stamp[u] = -1;
     }
+    // timeline: [8] start set out, [9] my first chunk at its first destination, [10] all chunks at the first destination, [11] all out
+    if (plan.n_units > 0) plan.unit_stamp[0] = 8;
+    if (plan.n_units > 1) { plan.unit_stamp[1] = 9; plan.unit_stamp[std::min(plan.n_units - 1, xp.n_chunks[rank])] = 10; plan.unit_stamp[plan.n_units - 1] = 11; }
   }
   // Who pushes?  mode 1 (default): pusher warps inside the dist kernel - one kernel computes tiles and moves operands, no
-  // SM is given up.  mode 0 (HG_PEER_PUSH=concurrent): a kernel of its own per chunk on the push stream, next to the dist
+  // SM is given up.  mode 0 (HG_PEER_PUSH=concurrent): a kernel of its own per unit on the push stream, next to the dist
   // kernel, which then leaves HG_PEER_RESERVED_TPCS TPCs free for it.  mode 2 (HG_PEER_PUSH=ahead, or a member without a
-  // tile to compute): the push kernels on the main stream, ahead of the dist kernel.  Measured on 4 B200s:
-  // all three deliver about 200 GB/s of egress per GPU; fused wins on configs 3 and 4, concurrent by 5 % on config 5.
+  // tile to compute): the push kernels on the main stream, ahead of the dist kernel.
   const bool have_tiles = world > 1 && !p->tiles.empty() && (a.symmetric || a.n_ref_local > 0);
   int mode = have_tiles ? 1 : 2;
   if (const char *e = getenv("HG_PEER_PUSH")) {
@@ -673,11 +778,13 @@ static int shard_enqueue(hg_peer *p, const ShardCall &a, int use_path) {
       feed.reserve_tpcs = HG_PEER_RESERVED_TPCS;
     }
     const unsigned max_blocks = mode == 0 ? 2u * HG_PEER_RESERVED_TPCS * 8u : (unsigned)c->sm_count * 4u;
-    for (int ch = 0; ch < N_CHUNKS; ++ch) {
+    for (int u = 0; u < plan.n_units; ++u) {
+      const int set = plan.unit_set[u];
       PushArgs pa;
-      pa.n = plan.n[ch];
-      for (int k = 0; k < pa.n; ++k) { pa.r[k].off = plan.off[ch][k]; pa.r[k].bytes = plan.bytes[ch][k]; }
-      if ((rc = peer_push(p, pa, (uint32_t)(rank * N_CHUNKS + ch), ps, max_blocks))) return rc;
+      pa.n = plan.n[set];
+      for (int k = 0; k < pa.n; ++k) { pa.r[k].off = plan.off[set][k]; pa.r[k].bytes = plan.bytes[set][k]; }
+      const uint64_t flag_off = set == HG_PUSH_START_SET ? OFF_START + 4 * (uint64_t)rank : OFF_READY + 4 * (uint64_t)(rank * N_CHUNKS + set);
+      if ((rc = peer_push(p, pa, plan.unit_dest[u], flag_off, u, ps, max_blocks))) return rc;
     }
     if (mode == 0) HG_CUDA(cudaEventRecord(p->ev_pushed, ps));
   }
@@ -776,11 +883,12 @@ static void shard_reason(hg_peer *p, int path, int32_t absmax, bool forced) {
   hg_ctx *c = p->ctx;
   c->dist_path = path;
   if (path == 3)
-    snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor-narrow%s: member %d of %d GPUs, operand planes pushed over NVLink windows in %d chunks, tiles dealt round-robin and ordered by arrival%s",
-             forced ? " (forced)" : "", p->rank, p->world, N_CHUNKS, forced ? "" : "; rows fit one s8 plane as x = 2a + s");
+    snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor-narrow%s: member %d of %d GPUs, operand planes pushed over NVLink windows in chunks, %s, tiles ordered by arrival%s",
+             forced ? " (forced)" : "", p->rank, p->world, p->last_ring ? "block pairs owned along the ring (rows go to N/2 members)" : "tiles dealt round-robin (rows go to every member)",
+             forced ? "" : "; rows fit one s8 plane as x = 2a + s");
   else
-    snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor%s: member %d of %d GPUs, two s8 limb planes pushed over NVLink windows in %d chunks, tiles dealt round-robin and ordered by arrival (max |hv| = %d)",
-             forced ? " (forced)" : "", p->rank, p->world, N_CHUNKS, absmax);
+    snprintf(c->dist_reason, sizeof(c->dist_reason), "tensor%s: member %d of %d GPUs, two s8 limb planes pushed over NVLink windows in chunks, %s, tiles ordered by arrival (max |hv| = %d)",
+             forced ? " (forced)" : "", p->rank, p->world, p->last_ring ? "block pairs owned along the ring (rows go to N/2 members)" : "tiles dealt round-robin (rows go to every member)", absmax);
 }
 
 // Collective over the group (every member calls it with the same scalars and its own rows); see hypergen_b200.h.
@@ -1049,7 +1157,12 @@ extern "C" int hg_group_dist_packed(hg_group *g, const uint8_t *ref_packed, uint
   int rc;
   const int N = g->n;
   if ((rc = group_windows(g, hg_peer_window_need(n_qry, hv_d, cap)))) return rc;
-  auto bound = [&](uint32_t n, int k) -> uint32_t { return k >= N ? n : (uint32_t)(((uint64_t)n * k / N) & ~3ull); };
+  // row blocks: multiples of 256 rows when there are enough rows (what the ring ownership of the all-vs-all needs), else of 4
+  auto bound = [&](uint32_t n, int k) -> uint32_t {
+    if (k >= N) return n;
+    if (n >= 512u * (uint32_t)N) return std::min<uint32_t>(n, 256u * (uint32_t)(((uint64_t)k * ((n + 255) / 256) + N / 2) / N));  // the 256-row tile rows, dealt evenly
+    return (uint32_t)(((uint64_t)n * k / N) & ~3ull);
+  };
   struct Member { uint32_t r0, rn, q0, qn; int16_t *d_ref, *d_qry; int32_t *d_rn, *d_qn; };
   std::vector<Member> M(N);
   auto make_call = [&](const Member &m) {

@@ -23,7 +23,7 @@ EXPORTS = [
     "hg_dist", "hg_dist_dev", "hg_dist_status", "hg_dist_last_path", "hg_dist_last_reason", "hg_sort_hits_dev", "hg_dist_sorted", "hg_dist_packed",
     "hg_group_create", "hg_group_destroy", "hg_group_size", "hg_group_ctx", "hg_group_sketch_fasta_batch", "hg_group_dist_packed",
     "hg_peer_window_need", "hg_peer_create", "hg_peer_connect", "hg_peer_create_local", "hg_peer_destroy", "hg_peer_rank",
-    "hg_peer_world", "hg_peer_barrier", "hg_peer_stage_ms", "hg_peer_timeline", "hg_peer_plan_tiles", "hg_dist_sharded_dev", "hg_dist_sharded_hits", "hg_peer_hit_buffers",
+    "hg_peer_world", "hg_peer_barrier", "hg_peer_stage_ms", "hg_peer_timeline", "hg_peer_plan_tiles", "hg_peer_plan_push", "hg_dist_sharded_dev", "hg_dist_sharded_hits", "hg_peer_hit_buffers",
 ]
 HG_MAX_PEERS, HG_IPC_HANDLE_BYTES = 8, 64
 
@@ -116,7 +116,8 @@ def load() -> C.CDLL:
     L.hg_peer_rank.restype = i32; L.hg_peer_rank.argtypes = [vp]
     L.hg_peer_world.restype = i32; L.hg_peer_world.argtypes = [vp]
     L.hg_peer_barrier.restype = i32; L.hg_peer_barrier.argtypes = [vp]
-    L.hg_peer_plan_tiles.restype = i32; L.hg_peer_plan_tiles.argtypes = [i32, i32, i32, i32, u32, vp, vp, u64, C.POINTER(u64)]
+    L.hg_peer_plan_tiles.restype = i32; L.hg_peer_plan_tiles.argtypes = [i32, i32, i32, i32, u32, u32, vp, vp, u64, C.POINTER(u64)]
+    L.hg_peer_plan_push.restype = i32; L.hg_peer_plan_push.argtypes = [i32, i32, i32, i32, u32, vp, vp, vp, u64, C.POINTER(u64), C.POINTER(C.c_int)]
     L.hg_peer_stage_ms.restype = i32; L.hg_peer_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.hg_peer_timeline.restype = i32; L.hg_peer_timeline.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.hg_dist_sharded_dev.restype = i32
@@ -469,15 +470,26 @@ def host_unregister(arr: np.ndarray) -> None:
     _check(load().hg_host_unregister(arr.ctypes.data))
 
 
-def peer_plan_tiles(world: int, rank: int, symmetric: bool, path: int, n_ref_local: int, qry_bounds):
+def peer_plan_tiles(world: int, rank: int, symmetric: bool, path: int, n_ref_local: int, qry_bounds, hv_d: int = 4096):
     """hg_peer_plan_tiles -> (tile_row, tile_col, need_mask) arrays in walk order (host logic, no GPU)"""
     qb = np.ascontiguousarray(qry_bounds, np.uint32)
     n = C.c_uint64(0)
-    load().hg_peer_plan_tiles(world, rank, int(symmetric), path, n_ref_local, _ptr(qb), None, 0, C.byref(n))
+    load().hg_peer_plan_tiles(world, rank, int(symmetric), path, hv_d, n_ref_local, _ptr(qb), None, 0, C.byref(n))
     out = np.zeros((max(int(n.value), 1), 2), np.uint32)
-    _check(load().hg_peer_plan_tiles(world, rank, int(symmetric), path, n_ref_local, _ptr(qb), _ptr(out), out.shape[0], C.byref(n)))
+    _check(load().hg_peer_plan_tiles(world, rank, int(symmetric), path, hv_d, n_ref_local, _ptr(qb), _ptr(out), out.shape[0], C.byref(n)))
     out = out[: n.value]
     return out[:, 0] & 0xFFFF, out[:, 0] >> 16, out[:, 1]
+
+
+def peer_plan_push(world: int, rank: int, symmetric: bool, path: int, qry_bounds, hv_d: int = 4096):
+    """hg_peer_plan_push -> (chunk row boundaries [5], [(set, destination mask)] in sending order, ring?)"""
+    qb = np.ascontiguousarray(qry_bounds, np.uint32)
+    rows = np.zeros(5, np.uint32)
+    units = np.zeros((40, 2), np.uint32)
+    n, ring = C.c_uint64(0), C.c_int(0)
+    _check(load().hg_peer_plan_push(world, rank, int(symmetric), path, hv_d, _ptr(qb), _ptr(rows), _ptr(units), units.shape[0],
+                                    C.byref(n), C.byref(ring)))
+    return rows.tolist(), [(int(a), int(b)) for a, b in units[: n.value]], bool(ring.value)
 
 
 def peer_window_need(gathered_rows: int, hv_d: int, hit_cap: int) -> int:

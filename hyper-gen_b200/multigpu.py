@@ -251,8 +251,15 @@ def sketch_files_distributed(files, sketch_fn, out_file: str | None = None):
 # ---------------------------------------------------------------------------------------------
 # NVLink-window transport (the product path): hg_peer behind torch.distributed's bootstrap
 # ---------------------------------------------------------------------------------------------
-def block_rows(n: int, n_ranks: int, align: int = 4) -> list[int]:
-    """Boundaries of the contiguous row blocks the ranks hold: as even as `align`-row granularity allows."""
+def block_rows(n: int, n_ranks: int, align: int | None = None) -> list[int]:
+    """Boundaries of the contiguous row blocks the ranks hold (as hg_group_dist_packed deals them): multiples of 256
+    rows when there are at least 512 rows per rank - what the ring ownership of the all-vs-all needs (csrc/peer.cu) -
+    else of 4 rows."""
+    if align is None:
+        if n >= 512 * n_ranks:
+            t = (n + 255) // 256  # the 256-row tile rows, dealt evenly
+            return [n if r == n_ranks else min(n, 256 * ((r * t + n_ranks // 2) // n_ranks)) for r in range(n_ranks + 1)]
+        align = 4
     return [n if r == n_ranks else (n * r // n_ranks) // align * align for r in range(n_ranks + 1)]
 
 
