@@ -699,6 +699,10 @@ def bench_dist_config(cfg, args, ctx, ext, hg, multigpu, synth, dev, rank, world
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(ext):
+            if world > 1:
+                # the GPUs meet at a device-side barrier first: the step is timed from a common start, as in back-to-back
+                # calls, not from whenever each rank's host happened to get its launch out after the host barrier
+                pg.peer.barrier()
             e0.record()
             h = step(path)
             e1.record()
@@ -738,15 +742,19 @@ def bench_dist_config(cfg, args, ctx, ext, hg, multigpu, synth, dev, rank, world
                                       "hit_flush_to_root_and_final_barrier"),
                                      [statistics.mean(x[i] for x in stages) for i in range(4)])) if stages else None),
         "timing": ("ms_per_step: CUDA events around the whole step on the library's stream, max over ranks" +
+                   ("; every rank's stream passes a device-side barrier before the first event (common start, host launch skew excluded)"
+                    if world > 1 else "") +
                    ("; kernel_ms / stages from separate profiled steps (direct launches), the timed steps replay a CUDA graph"
                     if world > 1 else "; kernel_ms from the same steps")),
         "config": {"workload": ("all-vs-all dist over %d synthetic sketches (%s), D=%d, ani_th=85" % (n_ref, cfg["label"], D)) if sym else
                    ("%d ref sketches x %d queries (%s), D=%d, ani_th=85" % (n_ref, n_qry, cfg["label"], D)),
                    "rows_per_rank": ([qb[r + 1] - qb[r] for r in range(world)] if sym else [rb[r + 1] - rb[r] for r in range(world)]),
                    "sharding": ("single GPU; hits written by the kernel into pinned host memory" if world == 1 else
-                                ("rows sharded in blocks; operand planes pushed to every GPU over NVLink windows in 4 chunks with arrival "
-                                 "flags the kernels' TMA producers wait on; output tiles dealt round-robin; hits appended into one host "
-                                 "buffer every GPU has mapped" if sym else
+                                ("rows sharded in blocks of 256-row tile rows; operand planes pushed over NVLink windows in chunks with "
+                                 "arrival flags the kernels' TMA producers wait on; " +
+                                 ("block pairs owned along the ring: a rank's rows go to the N/2 ranks that compute with them"
+                                  if world >= 3 else "output tiles dealt round-robin, rows go to the other rank") +
+                                 "; hits appended into one host buffer every GPU has mapped" if sym else
                                  "ref rows sharded and resident; every rank holds 1/N of the queries and pushes their operand plane to "
                                  "every GPU (chunks + arrival flags); hits appended into one host buffer every GPU has mapped")),
                    "step": "i16 rows resident in HBM -> operand form -> dist kernel -> hit list in rank 0's host memory",

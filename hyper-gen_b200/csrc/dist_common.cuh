@@ -147,7 +147,11 @@ __device__ __forceinline__ void push_my_units(const hg_push_plan *__restrict__ p
     const uint32_t dest = pp->unit_dest[u];
     for (int k = 0; k < pp->n[set]; ++k) {
       const uint64_t off = pp->off[set][k];
-      const uint32_t bytes = pp->bytes[set][k];
+      uint32_t bytes = pp->bytes[set][k];
+      if (set == HG_PUSH_START_SET && k == 0 && pp->dyn_count) {  // only the outlier entries that exist (usually a handful)
+        const uint32_t used = *pp->dyn_count - pp->dyn_base;      // (a cursor past the capacity means "declined": nothing to send)
+        bytes = used * 4u <= bytes ? ((used * 4u + 15u) & ~15u) : 0u;
+      }
       if (((off | bytes) & 15) == 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(pp->win[rank] + off);
         const size_t n16 = bytes / 16;
@@ -179,7 +183,7 @@ __device__ __forceinline__ void push_my_units(const hg_push_plan *__restrict__ p
     if (lane == 0) prev = atomicAdd(pp->done + u, 1u);
     prev = __shfl_sync(0xffffffffu, prev, 0);
     if (prev == n_pushers - 1) {
-      __threadfence_system();
+      __threadfence_system();  // (acquire side of the counter: the other warps' stores are ordered before the flags below)
       if (lane == 0) {
         pp->done[u] = 0;
         if (pp->unit_stamp[u] >= 0) feed_stamp(pp->dbg, pp->unit_stamp[u]);

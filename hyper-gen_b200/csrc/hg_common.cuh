@@ -265,6 +265,8 @@ struct hg_push_plan {
   uint64_t ready_off;   // offset of the arrival flags in every window; chunk c raises flag rank * HG_PUSH_CHUNKS + c
   uint64_t start_off;   // offset of the start flags in every window; the start set raises flag `rank`
   const uint32_t *seq;  // the call's sequence number lives in device memory (the launch sequence is replayed as a CUDA graph)
+  const uint32_t *dyn_count;  // not NULL: range 0 of the start set holds (*dyn_count - dyn_base) 4-byte entries, not its full size
+  uint32_t dyn_base;
   unsigned long long *dbg;  // timeline stamps (HG_PEER_TIMELINE=1, hg_peer_timeline), else NULL
 };
 struct hg_tile_feed {

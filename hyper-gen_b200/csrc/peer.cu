@@ -15,10 +15,9 @@
 //      All-vs-all on 3 or more GPUs with row blocks that are multiples of 256 rows ("ring"): the
 //      block pair (a, b) is computed by the member from which the other block is at most N/2 steps
 //      AHEAD on the ring (the pair exactly N/2 apart is split tile by tile), so a member's rows go to
-//      floor(N/2) members instead of N - 1 - half the NVLink bytes - nearest neighbour first, and a
-//      member's tiles are ordered own block, block + 1, block + 2 ... as those arrive.  Otherwise the
-//      non-empty tiles are dealt round-robin (tile t to member t mod N), every chunk goes to everybody,
-//      and a member's share is ordered own rows, chunk 0 of everybody, chunk 1 ...  The kernel's TMA
+//      floor(N/2) members instead of N - 1 - half the NVLink bytes.  Otherwise the
+//      non-empty tiles are dealt round-robin (tile t to member t mod N) and every chunk goes to
+//      everybody.  A member's tiles are ordered own rows, chunk 0 of everybody, chunk 1 ...  The kernel's TMA
 //      producer waits for the arrival flags a tile needs (ld.acquire.sys on its own window, bounded) -
 //      tiles are computed while later chunks are still crossing NVLink.  ref x query: the member's own
 //      (resident) ref rows against all queries, same mechanism on the query side;
@@ -477,8 +476,8 @@ inline int ring_owner(const XPlan &x, int bi, int bj, uint32_t R, uint32_t C) {
 }
 // position of (member m, chunk c) in the order in which chunks arrive at member r
 inline uint32_t arrival_pos(const XPlan &x, int r, int m, int c) {
-  if (x.ring) return (uint32_t)(((m - r + x.world) % x.world - 1) * N_CHUNKS + c);
-  return (uint32_t)c;
+  (void)x; (void)r; (void)m;
+  return (uint32_t)c;  // every member sends chunk 0 to all its destinations first, then chunk 1, ...
 }
 
 // arrival flags (other members' chunks) that rows [x0, x1) of the gathered matrix depend on
@@ -597,12 +596,10 @@ static void plan_units(const XPlan &x, int rank, bool have_rows, std::vector<std
   for (int m = 0; m < x.world; ++m) if (m != rank) all |= 1u << m;
   if (x.world > 1) units.push_back({HG_PUSH_START_SET, all});
   if (!have_rows || x.world == 1) return;
-  if (x.ring) {
-    for (int d = 1; d <= x.world / 2; ++d)
-      for (int c = 0; c < x.n_chunks[rank]; ++c) units.push_back({c, 1u << ((rank - d + x.world) % x.world)});
-  } else {
-    for (int c = 0; c < x.n_chunks[rank]; ++c) units.push_back({c, all});
-  }
+  // chunk by chunk, every chunk to all its destinations at once: one NVLink destination takes 100-250 GB/s from a
+  // GPU's pusher warps, four or seven together about 500 GB/s (measured)
+  const uint32_t dest = dest_mask(x, rank);
+  for (int c = 0; c < x.n_chunks[rank]; ++c) units.push_back({c, dest});
 }
 extern "C" int hg_peer_plan_push(int world, int rank, int symmetric, int path, uint32_t hv_d, const uint32_t *qry_bounds,
                                  uint32_t chunk_rows_out[HG_PUSH_CHUNKS + 1], uint32_t *units_out, uint64_t cap, uint64_t *n_units,
@@ -743,7 +740,11 @@ static int shard_enqueue(hg_peer *p, const ShardCall &a, int use_path) {
     else add(ch, lay.plane + ((uint64_t)n_total + lo) * a.hv_d, n * a.hv_d);
   }
   if (use_path == 3 && world > 1) {  // the statistics and the outlier entries of ALL my rows (the pre-pass above is complete)
-    if (nl) add(HG_PUSH_START_SET, lay.entries + (uint64_t)rank * lay.set_cap * 4, (uint64_t)lay.set_cap * 4);
+    if (nl) {  // (range 0 of the start set: the pushers cut it down to the entries the pre-pass actually wrote)
+      add(HG_PUSH_START_SET, lay.entries + (uint64_t)rank * lay.set_cap * 4, (uint64_t)lay.set_cap * 4);
+      plan.dyn_count = (const uint32_t *)(W + OFF_STATS_Q) + 4 * rank + 2;
+      plan.dyn_base = (uint32_t)rank * lay.set_cap;
+    }
     add(HG_PUSH_START_SET, OFF_STATS_Q + 16 * (uint64_t)rank, 16);
     if (!a.symmetric) add(HG_PUSH_START_SET, OFF_STATS_R + 16 * (uint64_t)rank, 16);
   }
@@ -758,7 +759,7 @@ static int shard_enqueue(hg_peer *p, const ShardCall &a, int use_path) {
     }
     // timeline: [8] start set out, [9] my first chunk at its first destination, [10] all chunks at the first destination, [11] all out
     if (plan.n_units > 0) plan.unit_stamp[0] = 8;
-    if (plan.n_units > 1) { plan.unit_stamp[1] = 9; plan.unit_stamp[std::min(plan.n_units - 1, xp.n_chunks[rank])] = 10; plan.unit_stamp[plan.n_units - 1] = 11; }
+    if (plan.n_units > 1) { plan.unit_stamp[1] = 9; plan.unit_stamp[plan.n_units - 1] = 11; }
   }
   // Who pushes?  mode 1 (default): pusher warps inside the dist kernel - one kernel computes tiles and moves operands, no
   // SM is given up.  mode 0 (HG_PEER_PUSH=concurrent): a kernel of its own per unit on the push stream, next to the dist

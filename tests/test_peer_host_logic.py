@@ -62,10 +62,7 @@ def test_all_vs_all_tiles_are_dealt_once_and_wait_for_the_right_rows(hg, world, 
             for b in range(32):
                 if nd >> b & 1:
                     assert (b // 4, b % 4) in pos, "member %d waits for chunk %d of member %d, which is never sent to it" % (rank, b % 4, b // 4)
-                    if ring:
-                        k = max(k, 1 + ((b // 4 - rank) % world - 1) * 4 + b % 4)
-                    else:
-                        k = max(k, 1 + b % 4)
+                    k = max(k, 1 + b % 4)
             keys.append(k)
         assert keys == sorted(keys)  # own rows first, then in the order the chunks arrive
         for m in range(world):
@@ -94,9 +91,9 @@ def test_chunks_are_at_least_about_two_megabytes(hg):
     assert all(r[1] == r[4] for r in rows) and not ring
     assert all(len(u) == 2 and u[1][0] == 0 for u in units)  # start set + one chunk, both to everybody
     rows, units, ring = _plans(hg, 8, True, 2, multigpu.block_rows(20000, 8), 8192)
-    assert ring and all(len(set(r)) == 5 for r in rows) and all(len(u) == 1 + 4 * 4 for u in units)
-    # nearest ring neighbour first: member 3's first chunk units go to member 2, the last ones to member 7
-    assert [d for st, d in units[3][1:5]] == [1 << 2] * 4 and [d for st, d in units[3][-4:]] == [1 << 7] * 4
+    assert ring and all(len(set(r)) == 5 for r in rows) and all(len(u) == 1 + 4 for u in units)
+    # member 3's rows go to the four members behind it on the ring (2, 1, 0, 7), chunk by chunk
+    assert units[3][1:] == [(c, 1 << 2 | 1 << 1 | 1 << 0 | 1 << 7) for c in range(4)]
 
 
 def test_ref_x_query_tiles_cover_the_members_rows_row_major(hg):

@@ -67,6 +67,7 @@ for mode in modes:
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(ext):
+            pg.peer.barrier()
             e0.record()
             h = step(path)
             e1.record()
