@@ -726,7 +726,9 @@ static int narrow_attrs(hg_ctx *ctx) {
   if (!ctx->n1_attr_set) {
     HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
     HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
-    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<1, N1_PUSH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_n1_kernel<1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, N1_SMEM_BYTES));
     ctx->n1_attr_set = 1;
   }
   return HG_OK;
@@ -872,8 +874,11 @@ int hg_narrow_launch_ex(hg_ctx *ctx, const hg_narrow_mat *R, uint32_t r0, uint32
   static const hg_push_plan no_push = {};
   if (push) {  // a member of several GPUs: the launch carries pusher warps that send my operand rows while the tiles are computed
     if (nacc != 1) { hg_set_error("pusher warps come with the 256-row tile kernel"); return HG_E_UNSUPPORTED; }
-    cfg.blockDim = dim3(N1_THREADS + 32 * N1_PUSH_WARPS, 1, 1);
-    HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<1, N1_PUSH_WARPS>, tm_ref, tm_qry, r0, q0, ep, na, fd, *push));
+    const int pw = hg_push_warps(N1_PUSH_WARPS);
+    cfg.blockDim = dim3(N1_THREADS + 32 * pw, 1, 1);
+    if (pw == 2) HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<1, 2>, tm_ref, tm_qry, r0, q0, ep, na, fd, *push));
+    else if (pw == 4) HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<1, 4>, tm_ref, tm_qry, r0, q0, ep, na, fd, *push));
+    else HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<1, 6>, tm_ref, tm_qry, r0, q0, ep, na, fd, *push));
   } else if (nacc == 2) {
     HG_CUDA(cudaLaunchKernelEx(&cfg, dist_n1_kernel<2, 0>, tm_ref, tm_qry, r0, q0, ep, na, fd, no_push));
   } else {

@@ -595,7 +595,9 @@ int hg_tc_setup(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_d
   if (!ctx->tc_attr_set) {
     HG_CUDA(cudaFuncSetAttribute(dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<TC_PUSH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
     ctx->tc_attr_set = 1;
   }
   return HG_OK;
@@ -630,7 +632,9 @@ int hg_tc_attach(hg_ctx *ctx, const int16_t *d_hv, uint32_t n_rows, uint32_t hv_
   if (!ctx->tc_attr_set) {
     HG_CUDA(cudaFuncSetAttribute(dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<TC_PUSH_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    HG_CUDA(cudaFuncSetAttribute(dist_tc2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
     ctx->tc_attr_set = 1;
   }
   return HG_OK;
@@ -692,9 +696,11 @@ int hg_tc_launch_ex(hg_ctx *ctx, const hg_tc_mat *R, uint32_t r0, uint32_t n_ref
     attr[0].val.clusterDim.x = 2;
     static const hg_push_plan no_push = {};
     if (push) {  // a member of several GPUs: pusher warps send my limb-plane rows while the tiles are computed
-      cfg.blockDim = dim3(TC_THREADS + 32 * TC_PUSH_WARPS, 1, 1);
-      HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel<TC_PUSH_WARPS>, tm_ref, tm_qry, R->n_rows, r0, Q->n_rows, q0, hv_d, make_ep(0), walk_mul,
-                                 walk_add, fd, *push));
+      const int pw = hg_push_warps(TC_PUSH_WARPS);
+      cfg.blockDim = dim3(TC_THREADS + 32 * pw, 1, 1);
+      if (pw == 2) HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel<2>, tm_ref, tm_qry, R->n_rows, r0, Q->n_rows, q0, hv_d, make_ep(0), walk_mul, walk_add, fd, *push));
+      else if (pw == 4) HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel<4>, tm_ref, tm_qry, R->n_rows, r0, Q->n_rows, q0, hv_d, make_ep(0), walk_mul, walk_add, fd, *push));
+      else HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel<6>, tm_ref, tm_qry, R->n_rows, r0, Q->n_rows, q0, hv_d, make_ep(0), walk_mul, walk_add, fd, *push));
     } else {
       HG_CUDA(cudaLaunchKernelEx(&cfg, dist_tc2_kernel<0>, tm_ref, tm_qry, R->n_rows, r0, Q->n_rows, q0, hv_d, make_ep(0), walk_mul, walk_add,
                                  fd, no_push));

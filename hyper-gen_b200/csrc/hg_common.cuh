@@ -269,6 +269,12 @@ struct hg_push_plan {
   uint32_t dyn_base;
   unsigned long long *dbg;  // timeline stamps (HG_PEER_TIMELINE=1, hg_peer_timeline), else NULL
 };
+// pusher warps per CTA of a multi-GPU dist launch: 2, 4 or 6 (HG_PEER_PUSH_WARPS overrides the kernels' default)
+inline int hg_push_warps(int dflt) {
+  int w = dflt;
+  if (const char *e = getenv("HG_PEER_PUSH_WARPS")) w = atoi(e);
+  return w <= 2 ? 2 : (w <= 4 ? 4 : 6);
+}
 struct hg_tile_feed {
   const uint2 *list;        // x = tile row | tile column << 16, y = mask of the arrival flags the tile needs; NULL: arithmetic walk
   uint32_t n_list;

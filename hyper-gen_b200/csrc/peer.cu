@@ -914,7 +914,7 @@ extern "C" int hg_dist_sharded_dev(hg_peer *p, const int16_t *d_ref_hv, const in
     // The first call runs directly, the second is captured, the following ones are one cudaGraphLaunch each.
     std::vector<uint8_t> key(sizeof(ShardCall) + 4 * sizeof(void *));
     memcpy(key.data(), &a, sizeof(ShardCall));
-    const void *extra[4] = {c->d_scratch[HG_S_REF_LIMBS], c->d_scratch[HG_S_NARROW_META], c->d_scratch[HG_S_TILES], (const void *)(uintptr_t)path};
+    const void *extra[4] = {c->d_scratch[HG_S_REF_LIMBS], c->d_scratch[HG_S_NARROW_META], c->d_scratch[HG_S_TILES], (const void *)(uintptr_t)(path | hg_push_warps(0) << 8)};
     memcpy(key.data() + sizeof(ShardCall), extra, sizeof(extra));
     const bool can_graph = !c->prof && !getenv("HG_PEER_NO_GRAPH");
     if (can_graph && p->graph && key == p->graph_key) {
@@ -927,7 +927,7 @@ extern "C" int hg_dist_sharded_dev(hg_peer *p, const int16_t *d_ref_hv, const in
     if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; p->graph_key.clear(); }
     if ((rc = shard_reserve(p, a, path))) return rc;
     memcpy(key.data() + sizeof(ShardCall), extra, 0);  // (scratch pointers may have changed in shard_reserve: refresh below)
-    const void *extra2[4] = {c->d_scratch[HG_S_REF_LIMBS], c->d_scratch[HG_S_NARROW_META], c->d_scratch[HG_S_TILES], (const void *)(uintptr_t)path};
+    const void *extra2[4] = {c->d_scratch[HG_S_REF_LIMBS], c->d_scratch[HG_S_NARROW_META], c->d_scratch[HG_S_TILES], (const void *)(uintptr_t)(path | hg_push_warps(0) << 8)};
     memcpy(key.data() + sizeof(ShardCall), extra2, sizeof(extra2));
     if (can_graph && key == p->last_key && p->tiles_on_device) {
       HG_CUDA(cudaSetDevice(c->device));

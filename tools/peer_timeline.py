@@ -57,9 +57,11 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 NAMES = {0: "first node", 1: "kernel in", 2: "start flags", 4: "last CTA out", 8: "start set out", 9: "1st chunk out", 10: "1st dest done", 11: "all rows out",
          12: "flush", 13: "barrier in", 14: "barrier out"}
 for mode in modes:
-    if mode == "fused":
-        os.environ.pop("HG_PEER_PUSH", None)
-    else:
+    os.environ.pop("HG_PEER_PUSH", None)
+    os.environ.pop("HG_PEER_PUSH_WARPS", None)
+    if mode.startswith("pw"):  # pusher warps per CTA
+        os.environ["HG_PEER_PUSH_WARPS"] = mode[2:]
+    elif mode != "fused":
         os.environ["HG_PEER_PUSH"] = mode
     rows, ms = [], []
     for it in range(8):
