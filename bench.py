@@ -752,8 +752,7 @@ def bench_dist_config(cfg, args, ctx, ext, hg, multigpu, synth, dev, rank, world
                    "sharding": ("single GPU; hits written by the kernel into pinned host memory" if world == 1 else
                                 ("rows sharded in blocks of 256-row tile rows; operand planes pushed over NVLink windows in chunks with "
                                  "arrival flags the kernels' TMA producers wait on; " +
-                                 ("block pairs owned along the ring: a rank's rows go to the N/2 ranks that compute with them"
-                                  if world >= 3 else "output tiles dealt round-robin, rows go to the other rank") +
+                                 "block pairs owned along the ring: a rank's rows go to the N/2 ranks that compute with them" +
                                  "; hits appended into one host buffer every GPU has mapped" if sym else
                                  "ref rows sharded and resident; every rank holds 1/N of the queries and pushes their operand plane to "
                                  "every GPU (chunks + arrival flags); hits appended into one host buffer every GPU has mapped")),

@@ -12,7 +12,7 @@
 //      The last pusher warp through with a chunk raises that chunk's ARRIVAL FLAG in the destination
 //      windows (fence + st.release.sys, one lane per window);
 //   2. every member launches the dist kernel at once.  Its tiles come from a host-built list.
-//      All-vs-all on 3 or more GPUs with row blocks that are multiples of 256 rows ("ring"): the
+//      All-vs-all with row blocks that are multiples of 256 rows ("ring"): the
 //      block pair (a, b) is computed by the member from which the other block is at most N/2 steps
 //      AHEAD on the ring (the pair exactly N/2 apart is split tile by tile), so a member's rows go to
 //      floor(N/2) members instead of N - 1 - half the NVLink bytes.  Otherwise the
@@ -447,7 +447,7 @@ XPlan make_xplan(int world, int symmetric, int path, uint32_t hv_d, const uint32
     if (rows == 0) nonempty = false;
     if (m > 0 && qb[m] % 256 != 0) aligned = false;  // a tile (256 rows x 128 or 256 columns) lies inside one block on either side
   }
-  x.ring = symmetric && world >= 3 && aligned && nonempty && !getenv("HG_PEER_NO_RING");
+  x.ring = symmetric && world >= 2 && aligned && nonempty && !getenv("HG_PEER_NO_RING");
   return x;
 }
 // chunk c of member m's block: rows [chunk_lo(c), chunk_lo(c + 1))

@@ -322,8 +322,8 @@ HG_API int hg_peer_plan_tiles(int world, int rank, int symmetric, int path, uint
 /* ... and what the member sends: chunk_rows_out[c .. c + 1] = the rows of its chunk c (a block is cut into 1..4 chunks
  * of about 2 MB of operand bytes or more), units_out[2 u] = what push unit u sends (chunk index, or 4 = the start set:
  * pre-pass statistics and outlier entries), units_out[2 u + 1] = mask of the members it goes to, in sending order;
- * *ring = 1 when rows go only to the floor(world / 2) members that compute with them (all-vs-all, world >= 3, block
- * boundaries multiples of 256 rows). */
+ * *ring = 1 when rows go only to the floor(world / 2) members that compute with them (all-vs-all, block boundaries
+ * multiples of 256 rows). */
 HG_API int hg_peer_plan_push(int world, int rank, int symmetric, int path, uint32_t hv_d, const uint32_t *qry_bounds,
                              uint32_t chunk_rows_out[5], uint32_t *units_out, uint64_t cap, uint64_t *n_units, int *ring);
 /* Measurement support (hg_set_profiling on the member's context): device ms of the last sharded dist's stages -

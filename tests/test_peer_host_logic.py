@@ -25,7 +25,7 @@ def test_all_vs_all_tiles_are_dealt_once_and_wait_for_the_right_rows(hg, world, 
     from hypergen_b200 import multigpu
     qb = multigpu.block_rows(n, world)
     rows, units, ring = _plans(hg, world, True, path, qb, hv_d)
-    assert ring == (world >= 3 and n >= 512 * world)  # blocks are multiples of 256 rows from 512 rows per member on
+    assert ring == (world >= 2 and n >= 512 * world)  # blocks are multiples of 256 rows from 512 rows per member on
     tr, tc = 256, (256 if path == 3 else 128)
     seen = {}
     counts = []
