@@ -654,10 +654,12 @@ def bench_dist_config(cfg, args, ctx, ext, hg, multigpu, synth, dev, rank, world
         d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
         cnt_pin = torch.zeros(1, dtype=torch.int64, pin_memory=True)
 
-        def step(path):
+        def step(path, done=None):
             ctx.dist_dev(ref_hv.data_ptr(), ref_norm.data_ptr(), n_ref, 0, qry_hv.data_ptr(), qry_norm.data_ptr(), n_qry, 0, D, K,
                          85.0, sym, path, hits_pin.data_ptr(), cap, d_cnt.data_ptr())  # hits land in host memory as they are found
             cnt_pin.copy_(d_cnt, non_blocking=True)
+            if done is not None:
+                done.record()  # everything of the step, the count's D2H included, is in the stream ahead of this event
             torch.cuda.current_stream().synchronize()
             c = int(cnt_pin.item())
             if c > cap:
@@ -677,13 +679,15 @@ def bench_dist_config(cfg, args, ctx, ext, hg, multigpu, synth, dev, rank, world
         hits_np = np.ndarray((cap,), dtype=hg.ffi.HIT_DTYPE, buffer=shm.buf)
         mapped = hg.ffi.host_register(hits_np)
 
-        def step(path):
+        def step(path, done=None):
             if sym:
                 pg.peer.dist_sharded_dev(None, None, 0, 0, qry_hv[a:b].data_ptr(), qry_norm[a:b].data_ptr(), qb, D, K, 85.0, True, path,
                                          0, cap, mapped)
             else:  # refs: this rank's resident block; queries: every rank holds 1/N of them (as hg_group_dist_packed deals them)
                 pg.peer.dist_sharded_dev(ref_hv[ra:rbb].data_ptr(), ref_norm[ra:rbb].data_ptr(), rbb - ra, ra, qry_hv[a:b].data_ptr(),
                                          qry_norm[a:b].data_ptr(), qb, D, K, 85.0, False, path, 0, cap, mapped)
+            if done is not None:
+                done.record()  # the call's last node (status + hit counters to host memory) is in the stream ahead of this event
             h, _ = pg.peer.dist_sharded_hits(cap, hits=hits_np)
             return h
 
@@ -704,8 +708,7 @@ def bench_dist_config(cfg, args, ctx, ext, hg, multigpu, synth, dev, rank, world
                 # calls, not from whenever each rank's host happened to get its launch out after the host barrier
                 pg.peer.barrier()
             e0.record()
-            h = step(path)
-            e1.record()
+            h = step(path, e1)
         e1.synchronize()
         return h, max_over_ranks(e0.elapsed_time(e1))
 
@@ -741,7 +744,8 @@ def bench_dist_config(cfg, args, ctx, ext, hg, multigpu, synth, dev, rank, world
         "rank0_stages_ms": (dict(zip(("operand_form_of_my_rows", "(unused)", "dist_kernel_with_pusher_warps_and_waits_for_peer_chunks",
                                       "hit_flush_to_root_and_final_barrier"),
                                      [statistics.mean(x[i] for x in stages) for i in range(4)])) if stages else None),
-        "timing": ("ms_per_step: CUDA events around the whole step on the library's stream, max over ranks" +
+        "timing": ("ms_per_step: CUDA events on the library's stream around everything the step enqueues (operand form, kernels, hit "
+                   "records and their count into host memory), max over ranks; the host's wake-up after the stream drains is not in it" +
                    ("; every rank's stream passes a device-side barrier before the first event (common start, host launch skew excluded)"
                     if world > 1 else "") +
                    ("; kernel_ms / stages from separate profiled steps (direct launches), the timed steps replay a CUDA graph"
