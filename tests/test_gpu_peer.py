@@ -165,7 +165,9 @@ a0, a1 = b[rank], b[rank + 1]
 dev = torch.device("cuda", rank)
 d_hv = torch.from_numpy(hv[a0:a1].copy()).to(dev); d_n = torch.from_numpy(norm[a0:a1].copy()).to(dev)
 out = {}
-for name, sym, path in (("sym", True, 0), ("sym3", True, 3), ("refq", False, 0), ("sym2", True, 2), ("mapped", True, 3)):
+hv_o, norm_o = d["hv_o"], d["norm_o"]  # the same rows with a few far-off elements: outlier entries travel in the start set
+d_hv_o = torch.from_numpy(hv_o[a0:a1].copy()).to(dev); d_n_o = torch.from_numpy(norm_o[a0:a1].copy()).to(dev)
+for name, sym, path in (("sym", True, 0), ("sym3", True, 3), ("refq", False, 0), ("sym2", True, 2), ("mapped", True, 3), ("outl", True, 3)):
     mapped = None
     if name == "mapped":  # hits straight into a host buffer both ranks have mapped (POSIX shared memory)
         from multiprocessing import shared_memory
@@ -176,7 +178,9 @@ for name, sym, path in (("sym", True, 0), ("sym3", True, 3), ("refq", False, 0),
             shm = shared_memory.SharedMemory(name="hg_test_hits")
         host_hits = np.ndarray((cap,), dtype=hg.ffi.HIT_DTYPE, buffer=shm.buf)
         mapped = hg.ffi.host_register(host_hits)
-    if sym:
+    if name == "outl":
+        pg.peer.dist_sharded_dev(None, None, 0, 0, d_hv_o.data_ptr(), d_n_o.data_ptr(), b, D, 21, 75.0, True, path, 0, cap, mapped)
+    elif sym:
         pg.peer.dist_sharded_dev(None, None, 0, 0, d_hv.data_ptr(), d_n.data_ptr(), b, D, 21, 75.0, True, path, 0, cap, mapped)
     else:  # refs: this rank's block; queries: all on rank 1 (a "broadcast" from a non-root member)
         q_hv = torch.from_numpy(hv.copy()).to(dev) if rank == 1 else None
@@ -206,12 +210,19 @@ def test_one_process_per_gpu_ipc_windows(hg, oracle, ctx, tmp_path):
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
     hv, norm, _, _ = _sketch_sets(ctx, 1900, 2048, 1700, 1500)
+    rng = np.random.default_rng(5)
+    hv_o = hv.copy()
+    for r in rng.choice(1900, 200, replace=False):  # far elements of the row's parity, in both members' blocks
+        dd = rng.choice(2048, 4, replace=False)
+        hv_o[r, dd] += np.int16(2) * rng.integers(200, 900, 4).astype(np.int16) * rng.choice([-1, 1], 4).astype(np.int16)
+    norm_o = np.array([oracle.hv_l2_norm_sq(v) for v in hv_o], np.int32)
     npz, outp, script = str(tmp_path / "in.npz"), str(tmp_path / "out.npz"), str(tmp_path / "rank.py")
-    np.savez(npz, hv=hv, norm=norm)
+    np.savez(npz, hv=hv, norm=norm, hv_o=hv_o, norm_o=norm_o)
     with open(script, "w") as f:
         f.write(_RANK_SCRIPT % dict(root=ROOT, npz=npz, out=outp))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                        "127.0.0.1", "--master-port", "29533", script], capture_output=True, text=True, timeout=300)
+                        "127.0.0.1", "--master-port", "29533", script], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, HG_NARROW_BUDGET="64"))  # room for the outlier entries of the "outl" case
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     got = np.load(outp)
     from hypergen_b200.ffi import HIT_DTYPE
@@ -228,6 +239,7 @@ def test_one_process_per_gpu_ipc_windows(hg, oracle, ctx, tmp_path):
     same(got["sym2"], got["sym"], "forced two-limb vs auto")
     same(got["mapped"], np.sort(got["sym"], order=["i", "j"]), "hits in mapped host memory vs window")
     _check_hits(oracle, got["refq"].view(HIT_DTYPE), hv, norm, hv, norm, False, 75.0)
+    _check_hits(oracle, got["outl"].view(HIT_DTYPE), hv_o, norm_o, hv_o, norm_o, True, 75.0)
 
 
 def test_cli_all_gpus_writes_the_same_bytes_as_one_gpu(hg, tmp_path):
