@@ -623,7 +623,8 @@ def torch_index(rows, like):
 def bench_dist_config(cfg, args, ctx, ext, hg, multigpu, synth, dev, rank, world, barrier, max_over_ranks, i8_peak, pg, host_pg):
     """One dist configuration at this world size.  N = 1: hg_dist_dev, hits written by the kernel straight into pinned
     host memory.  N > 1: hg_dist_sharded_dev over the NVLink windows (every rank holds a block of the rows, turns it
-    into operand planes, pushes them; tiles dealt round-robin; hits appended into rank 0's list) + the D2H on rank 0."""
+    into operand planes, pushes them to the ranks that compute with them; block pairs owned along the ring; every rank's hits
+    moved into one host buffer all GPUs have mapped, which rank 0 reads in place)."""
     import torch
     import torch.distributed as dist
     D, sym = cfg["hv_d"], cfg["symmetric"]

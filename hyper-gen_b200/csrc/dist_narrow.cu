@@ -493,7 +493,7 @@ dist_n1_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constant
   const uint32_t num_kb = na.hv_d / TC_BK;
 
   if (PUSHW > 0 && warp >= N1_THREADS / 32) {
-    // ===== pusher warps (a member of several GPUs): my operand rows to every other window, chunk by chunk =====
+    // ===== pusher warps (a member of several GPUs): my operand rows to the windows of the members that compute with them, unit by unit =====
     hg::push_my_units(&plan, blockIdx.x * PUSHW + (uint32_t)(warp - N1_THREADS / 32), gridDim.x * PUSHW);
   } else {
   uint32_t have = 0;  // arrival flags seen so far (warp 0)

@@ -404,7 +404,7 @@ dist_tc2_kernel(const __grid_constant__ CUtensorMap tm_ref, const __grid_constan
   const uint32_t num_kb = hv_d / TC_BK;
 
   if (PUSHW > 0 && warp >= TC_THREADS / 32) {
-    // ===== pusher warps (a member of several GPUs): my limb-plane rows to every other window, chunk by chunk =====
+    // ===== pusher warps (a member of several GPUs): my limb-plane rows to the windows of the members that compute with them, unit by unit =====
     hg::push_my_units(&plan, blockIdx.x * PUSHW + (uint32_t)(warp - TC_THREADS / 32), gridDim.x * PUSHW);
   } else {
   PairTiles tiles;

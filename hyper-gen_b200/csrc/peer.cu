@@ -135,7 +135,7 @@ __global__ void peer_flush_kernel(uint8_t *W, unsigned long long *root_total, hg
     if (base + (i - lo) < cap) out[base + (i - lo)] = src[i];
 }
 
-// Copies byte ranges of this member's window to the same offsets of every other window.
+// Copies byte ranges of this member's window to the same offsets of the windows in `dest`.
 struct PushRange { uint64_t off, bytes; };  // 4-byte granular; ranges that are 16-byte aligned go as uint4
 struct PushArgs { PushRange r[HG_PUSH_RANGES]; int n; };
 
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) peer_push_kernel(PeerPtrs w, int rank, in
       }
     }
   }
-  // the last CTA to finish raises this chunk's arrival flag in every other window (one thread per window: the release
+  // the last CTA to finish raises the unit's flag in the destination windows (one thread per window: the release
   // stores are in flight together)
   __shared__ uint32_t s_last;
   __threadfence_system();

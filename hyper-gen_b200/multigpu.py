@@ -10,9 +10,9 @@
 
 Two transports exist for the dist exchange:
   * the product path, `PeerGroup`: NVLink windows inside the library (csrc/peer.cu) - every rank turns its
-    own rows into the kernel's operand form and pushes them into all windows, tiles are dealt round-robin,
-    hits are appended straight into rank 0's list.  torch.distributed only carries the 64-byte window
-    handles once, at start-up;
+    own rows into the kernel's operand form and pushes them into the windows of the ranks that compute with
+    them (block pairs owned along the ring), hits are collected per rank and moved to rank 0's list in one
+    piece.  torch.distributed only carries the 64-byte window handles once, at start-up;
   * `dist_sharded`, collectives of torch.distributed around a `compute` callback (NCCL on GPUs, gloo on
     CPU tensors): the reference formulation of the same sharding, kept for the CPU tests of the host logic.
 """

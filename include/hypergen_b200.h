@@ -295,16 +295,19 @@ HG_API int hg_peer_barrier(hg_peer *p);
  * Every member calls it with the same scalars and ITS rows.  qry_bounds (world + 1 entries, [0] = 0) says which rows
  * of the gathered ("query") matrix each member holds: member m has rows [qry_bounds[m], qry_bounds[m + 1]) - d_qry_hv /
  * d_qry_norm2 point at this member's block (it may be empty; one member may hold everything: a broadcast).
- *   symmetric != 0  all-vs-all (j > i, src/dist.rs:253-265) over that ONE matrix; the ref arguments are ignored.  The
- *                   non-empty output tiles are dealt round-robin to the members;
+ *   symmetric != 0  all-vs-all (j > i, src/dist.rs:253-265) over that ONE matrix; the ref arguments are ignored.  With
+ *                   block boundaries that are multiples of 256 rows a block pair is computed by the member from which
+ *                   the other block is at most world / 2 steps ahead on the ring, and a member's rows travel only to
+ *                   those world / 2 members; otherwise the non-empty output tiles are dealt round-robin and every row
+ *                   goes to every member (hg_peer_plan_tiles / hg_peer_plan_push show the plan);
  *   symmetric == 0  this member's n_ref_local resident ref rows (global index ref_row0 + row) against ALL gathered rows.
  *   path  0 auto (one host read of all members' pre-pass verdict; two-limb kernel if the rows are not narrow),
  *         3 / 2 single-plane / two-limb tensor kernel asserted by the caller: the call only enqueues.
  * Hits carry global (i, j) and go to member `root`: into its window (capacity `cap`, same on every member), or - if
  * mapped_hits is not NULL - into a HOST buffer of `cap` records that every member has mapped (the same physical
  * memory: hg_host_alloc in a one-process group, a shared-memory segment passed through hg_host_register by every
- * process otherwise; each member passes ITS device pointer to it).  The records then cross each GPU's own PCIe link
- * while the kernels run and no copy is left for the end. */
+ * process otherwise; each member passes ITS device pointer to it).  Every member collects its hits in its own window
+ * and moves them to the root's list / the host buffer in one piece after its kernel (over NVLink / its own PCIe link). */
 HG_API int hg_dist_sharded_dev(hg_peer *p, const int16_t *d_ref_hv, const int32_t *d_ref_norm2, uint32_t n_ref_local,
                                uint32_t ref_row0, const int16_t *d_qry_hv, const int32_t *d_qry_norm2, const uint32_t *qry_bounds,
                                uint32_t hv_d, uint32_t ksize, float ani_th, int symmetric, int path, int root, uint64_t cap,
