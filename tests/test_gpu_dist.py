@@ -333,11 +333,12 @@ def test_streamed_dist_declines_midway_and_falls_back(ctx, hg, oracle, monkeypat
     assert np.array_equal(hits["ani"].view(np.uint32), ani[idx].view(np.uint32))
 
 
-def test_full_size_config3_cross_kernel_and_symmetry_properties(ctx, hg):
-    """BASELINE config 3 at full size (10,000 sketches, D=4096, ani_th=85), where the oracle would take minutes:
-    the three kernels must report the same hits bit for bit; the symmetric run must equal the j > i half of the
-    full ref x query run, whose other half must mirror it (dot and ANI are symmetric in the pair); and the ten
-    identical pairs the generator plants must come out at exactly 100."""
+def test_full_size_config3_against_the_oracle_cross_kernel_and_symmetry_properties(ctx, hg, oracle):
+    """BASELINE config 3 at full size (10,000 sketches, D=4096, ani_th=85): the hit list must be the oracle's over all
+    49,995,000 pairs (src/dist.rs:139-161,231-294 + the filter of src/utils.rs:274-285: same set, i32 dots, f32 ANI
+    bits - about two seconds of the C restatement on the box's cores); the three kernels must report the same hits bit
+    for bit; the symmetric run must equal the j > i half of the full ref x query run, whose other half must mirror it
+    (dot and ANI are symmetric in the pair); and every sketch against itself must come out at exactly 100."""
     import torch
     from hypergen_b200 import synth
     n, D = 10_000, 4096
@@ -366,6 +367,16 @@ def test_full_size_config3_cross_kernel_and_symmetry_properties(ctx, hg):
 
     narrow = run(3, True)
     assert ctx.dist_last_path == 3
+    oracle.set_threads(os.cpu_count() or 1)
+    hv_np, norm_np = hv.cpu().numpy(), norm.cpu().numpy()
+    ani, dot = oracle.dist_all(hv_np, norm_np, hv_np, norm_np, symmetric=True)
+    want = np.nonzero(ani >= np.float32(85.0))[0]
+    hi, hj = narrow["i"].astype(np.int64), narrow["j"].astype(np.int64)
+    idx = hi * (n - 1) - hi * (hi - 1) // 2 + (hj - hi - 1)  # (i, j)-sorted hits are in pair-index order
+    assert np.array_equal(idx, want)
+    assert np.array_equal(narrow["dot"], dot[want])
+    assert np.array_equal(narrow["ani"].view(np.uint32), ani[want].view(np.uint32))
+    del ani, dot
     assert np.array_equal(narrow, run(2, True))      # two-limb tensor kernel
     assert np.array_equal(narrow, run(1, True))      # CUDA-core kernel
     assert narrow.size > 100_000 and (narrow["i"] < narrow["j"]).all()
