@@ -39,7 +39,14 @@ constexpr int KH_PPT = 32;                       // k-mer start positions per th
 constexpr int KH_TILE = 32 * KH_PPT;             // start positions per WARP tile
 constexpr int KH_CHUNKS = (KH_TILE + 64) / 16;   // 16-base chunks staged per tile (halo + align)
 constexpr int KH_QCAP = 64;                      // per-warp queue of survivors, flushed once per tile
-constexpr int KH_GROUP = 8;                      // positions hashed back to back before survivors are handled
+#ifndef HG_KH_GROUP
+#define HG_KH_GROUP 4
+#endif
+#ifndef HG_KH_UNROLL
+#define HG_KH_UNROLL 1
+#endif
+constexpr int KH_UNROLL = HG_KH_UNROLL;          // groups of 8 positions unrolled in the per-lane loop
+constexpr int KH_GROUP = HG_KH_GROUP;            // positions hashed back to back before survivors are looked at (measured: 4 beats 8 by 1.2 %, fewer hashes kept live)
 #ifndef HG_KH_MIN_CTAS
 #define HG_KH_MIN_CTAS 8
 #endif
@@ -285,7 +292,7 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
   uint32_t *count = counts + g;
   const uint32_t thr_hi = (uint32_t)(threshold >> 32);
 
-#pragma unroll 1
+#pragma unroll KH_UNROLL
   for (int o = 0; o < KH_PPT / 8; ++o) {
     const uint32_t in32 = window8(nb0 + (K - 1) + 8 * o);  // the 8 incoming bases
     const uint32_t kv8 = kv32 >> (8 * o);
@@ -353,7 +360,7 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
       hs[jj % KH_GROUP] = h;
       min_hi = min(min_hi, (uint32_t)(h >> 32));
       if ((jj % KH_GROUP) == KH_GROUP - 1) {
-        // some hash of the group may be below the threshold (1 group in ~190 at scaled = 1500): the exact 64-bit test
+        // some hash of these KH_GROUP positions may be below the threshold (1 quartet in ~375 at scaled = 1500): the exact 64-bit test
         // and the validity of the position are looked at only here
         if (min_hi <= thr_hi) {
           const uint32_t gm = kv8 >> (jj + 1 - KH_GROUP);
@@ -365,6 +372,7 @@ kmer_hash_kernel(const uint8_t *__restrict__ seq, const hg_genome_desc *__restri
               else table_insert(table, gd.table_mask, hs[e], count, status);  // queue full (tiny `scaled`)
             }
         }
+        min_hi = 0xFFFFFFFFu;
       }
     }
   }
