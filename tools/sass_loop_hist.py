@@ -20,18 +20,19 @@ for a, t in ins:
         if tgt < a and (best is None or a - tgt > best[1] - best[0]):
             best = (tgt, a)
 body = [t for a, t in ins if best[0] <= a <= best[1]]
-# the rare path (survivor handling) is the longest forward-branch span inside the loop: report the main path without it
-skip = None
+# the rare paths (survivor handling) are the long forward-branch spans inside the loop: report the main path without them
+skips = []
 for a, t in ins:
     if best[0] <= a <= best[1]:
         m = re.search(r"BRA(?:\.U)?(?:\.\w+)*\s+(?:\w+,\s*)?`?\(?0x([0-9a-f]+)", t)
         if m and t.startswith("@"):
             tgt = int(m.group(1), 16)
-            if a < tgt <= best[1] and (skip is None or tgt - a > skip[1] - skip[0]):
-                skip = (a, tgt)
-if skip:
-    main = [t for a, t in ins if best[0] <= a <= best[1] and not (skip[0] < a < skip[1])]
-    print("main path (without the 0x%x..0x%x survivor branch): %d instructions, %.1f per k-mer" % (skip[0], skip[1], len(main), len(main) / 8))
+            if a < tgt <= best[1] and tgt - a > 40 * 16 and not any(lo < a < hi for lo, hi in skips):
+                skips.append((a, tgt))
+if skips:
+    main = [t for a, t in ins if best[0] <= a <= best[1] and not any(lo < a < hi for lo, hi in skips)]
+    print("main path (without the survivor branches %s): %d instructions, %.1f per k-mer" % (
+        ", ".join("0x%x..0x%x" % x for x in skips), len(main), len(main) / 8))
     body = main
 ops = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0] for t in body)
 wide = sum(1 for t in body if "IMAD.WIDE" in t)
