@@ -673,7 +673,15 @@ def bench_dist_config(cfg, args, ctx, ext, hg, multigpu, synth, dev, rank, world
         # GPU's own PCIe link while the kernels run, and rank 0 reads them in place
         from multiprocessing import shared_memory
         shm_name = "hg_bench_hits_%s_%s" % (os.environ.get("MASTER_PORT", "0"), cfg["key"])
-        shm = shared_memory.SharedMemory(name=shm_name, create=True, size=cap * 16) if rank == 0 else None
+        shm = None
+        if rank == 0:
+            try:
+                shm = shared_memory.SharedMemory(name=shm_name, create=True, size=cap * 16)
+            except FileExistsError:  # left behind by a run that died: take it over
+                old = shared_memory.SharedMemory(name=shm_name)
+                old.close()
+                old.unlink()
+                shm = shared_memory.SharedMemory(name=shm_name, create=True, size=cap * 16)
         dist.barrier(group=host_pg)
         if rank != 0:
             shm = shared_memory.SharedMemory(name=shm_name)

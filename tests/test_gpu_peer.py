@@ -172,7 +172,11 @@ for name, sym, path in (("sym", True, 0), ("sym3", True, 3), ("refq", False, 0),
     if name == "mapped":  # hits straight into a host buffer both ranks have mapped (POSIX shared memory)
         from multiprocessing import shared_memory
         if rank == 0:
-            shm = shared_memory.SharedMemory(name="hg_test_hits", create=True, size=cap * 16)
+            try:
+                shm = shared_memory.SharedMemory(name="hg_test_hits", create=True, size=cap * 16)
+            except FileExistsError:  # left behind by a run that died
+                old = shared_memory.SharedMemory(name="hg_test_hits"); old.close(); old.unlink()
+                shm = shared_memory.SharedMemory(name="hg_test_hits", create=True, size=cap * 16)
         dist.barrier()
         if rank != 0:
             shm = shared_memory.SharedMemory(name="hg_test_hits")
