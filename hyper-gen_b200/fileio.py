@@ -31,10 +31,11 @@ class FileSketch:
 
 
 def get_fasta_files(path: str) -> list[str]:
-    """*.fna, then *.fa, then *.fasta under `path`, each group in glob (sorted) order."""
+    """*.fna, then *.fa, then *.fasta under `path`, each group in glob (sorted) order; like the glob crate's default
+    MatchOptions (utils.rs get_fasta_files) `*` also matches a leading dot."""
     out = []
     for pat in ("*.fna", "*.fa", "*.fasta"):
-        out += sorted(glob.glob(os.path.join(path, pat)))
+        out += sorted(glob.glob(os.path.join(path, pat), include_hidden=True))
     return out
 
 

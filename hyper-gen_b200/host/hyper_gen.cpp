@@ -85,7 +85,7 @@ std::vector<std::string> get_fasta_files(const std::string &path_in) {
   std::vector<std::string> all;
   for (const char *pat : {"*.fna", "*.fa", "*.fasta"}) {
     glob_t g;
-    if (glob((path + "/" + pat).c_str(), 0, nullptr, &g) == 0)
+    if (glob((path + "/" + pat).c_str(), GLOB_PERIOD, nullptr, &g) == 0)  // the glob crate lets * match a leading dot (MatchOptions default)
       for (size_t i = 0; i < g.gl_pathc; i++) all.emplace_back(g.gl_pathv[i]);  // glob() sorts
     globfree(&g);
   }

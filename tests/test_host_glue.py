@@ -21,10 +21,11 @@ def test_read_merge_seq_matches_oracle(oracle, hg, tmp_path):
 
 def test_get_fasta_files_order(hg, tmp_path):
     from hypergen_b200 import fileio
-    for n in ("b.fna", "a.fna", "z.fa", "c.fasta", "skip.txt"):
+    for n in ("b.fna", "a.fna", "z.fa", "c.fasta", "skip.txt", ".hidden.fna"):
         (tmp_path / n).write_bytes(b">x\nACGT\n")
     got = [os.path.basename(f) for f in fileio.get_fasta_files(str(tmp_path))]
-    assert got == ["a.fna", "b.fna", "z.fa", "c.fasta"]  # *.fna, then *.fa, then *.fasta
+    # *.fna, then *.fa, then *.fasta; the glob crate's default options let * match a leading dot (utils.rs get_fasta_files)
+    assert got == [".hidden.fna", "a.fna", "b.fna", "z.fa", "c.fasta"]
 
 
 def test_sketch_file_is_bincode_of_vec_filesketch(hg, oracle, tmp_path):
